@@ -1,0 +1,125 @@
+/*
+ * ppasr_b200 -- C-ABI of the B200-native PPASR inference hot path
+ * (fbank features -> Conformer encoder -> CTC projection -> greedy / beam-search decode).
+ *
+ * Plain C: opaque handle, raw pointers and sizes, int status codes (0 = ok; message via
+ * ppasr_b200_last_error()). No torch / C++ types cross this boundary. Each entry point cites the
+ * reference interface (yeyupiaoling/PPASR @ c8bb3b96, paths under ppasr/) that it replaces; the
+ * Python binding a PPASR maintainer would add is ppasr_b200/_lib.py (ctypes), see INTEGRATION.md.
+ *
+ * Threading: a context is not re-entrant (like the reference's InferencePredictor, which owns mutable
+ * stream caches: infer_utils/inference_predictor.py:35-39); use one context per CUDA stream.
+ * All `stream` arguments are a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef PPASR_B200_H_
+#define PPASR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ppasr_b200_ctx ppasr_b200_ctx;
+
+/* Model hyper-parameters = the inference-relevant keys of configs/conformer.yml (encoder_conf,
+ * streaming, preprocess_conf.n_mels) plus the vocabulary size. */
+typedef struct ppasr_b200_config {
+  int32_t model_type;      /* 0 = conformer (others: later rounds) */
+  int32_t feat_dim;        /* preprocess_conf.n_mels, 80 */
+  int32_t d_model;         /* encoder_conf.output_size, 256 */
+  int32_t n_heads;         /* encoder_conf.attention_heads, 4 (d_model / n_heads must be 64) */
+  int32_t ffn_dim;         /* encoder_conf.linear_units, 2048 */
+  int32_t n_layers;        /* encoder_conf.num_blocks, 12 */
+  int32_t conv_kernel;     /* encoder_conf.cnn_module_kernel, 15 (7, 15 or 31) */
+  int32_t causal;          /* `streaming: True` => causal depthwise conv (conformer/model.py:35-39) */
+  int32_t conv_norm;       /* 0 = layer_norm (shipped default, conformer/encoder.py:51), 1 = batch_norm */
+  int32_t vocab_size;      /* CTC output size V */
+  int32_t max_len;         /* positional table length, 5000 (conformer/embedding.py:30) */
+  int32_t reserved[5];
+} ppasr_b200_config;
+
+const char* ppasr_b200_last_error(void);
+int ppasr_b200_abi_version(void);
+
+/* ---- life cycle ------------------------------------------------------------------------------
+ * replaces: InferencePredictor.__init__ loading model.pdmodel/.pdiparams
+ *           (infer_utils/inference_predictor.py:12-45). */
+int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out);
+int ppasr_b200_destroy(ppasr_b200_ctx* ctx);
+/* Hands one parameter over by its reference (Paddle) name and layout, fp32, host memory; e.g.
+ * "encoder.encoders.0.self_attn.linear_q.weight" with shape [256,256] = [in,out].
+ * The data is copied. */
+int ppasr_b200_load_tensor(ppasr_b200_ctx* ctx, const char* name, const float* data, int32_t ndim,
+                           const int64_t* shape);
+/* Packs (transposes to K-major bf16, interleaves GLU rows, folds BatchNorm), uploads, and
+ * precomputes the weight-only linear_pos(pos_emb) table. Fails listing any missing parameter. */
+int ppasr_b200_finalize(ppasr_b200_ctx* ctx);
+
+/* ---- offline encoder -------------------------------------------------------------------------
+ * replaces: Model.get_encoder_out up to (not including) the CTC soft-max
+ *           (model_utils/conformer/model.py:148-162 -> conformer/encoder.py:164-206).
+ * feats: fp32 [B, T, feat_dim] row-major, zero padded; on the device if feats_on_device != 0 else in
+ * host memory (copied inside, asynchronously if pinned). lens_host: int64 [B] valid frame counts
+ * (NULL = all T). Leaves the encoder output in the context for the ctc_* calls below. */
+int ppasr_b200_encode(ppasr_b200_ctx* ctx, const float* feats, int32_t feats_on_device, const int64_t* lens_host,
+                      int32_t B, int32_t T, void* stream);
+/* T' = ((T-1)/2 - 1)/2 : output frames for T input frames (conformer/subsampling.py:96-115). */
+int ppasr_b200_out_frames(const ppasr_b200_ctx* ctx, int32_t T);
+
+/* replaces: CTCLoss.softmax (model_utils/loss/ctc.py:62-70) + copy_to_cpu
+ *           (infer_utils/inference_predictor.py:143-145).
+ * probs: fp32 [B, T', V] dense, device or host. */
+int ppasr_b200_ctc_probs(ppasr_b200_ctx* ctx, float* probs, int32_t probs_on_device, void* stream);
+/* fp32 logits [B, T', V] (before the soft-max); for parity tests (CTCLoss.ctc_lo, loss/ctc.py:27). */
+int ppasr_b200_ctc_logits(ppasr_b200_ctx* ctx, float* logits, int32_t on_device, void* stream);
+
+/* Fused CTC head + greedy decode: never materialises [B,T',V].
+ * replaces: CTCLoss.softmax + greedy_decoder / greedy_decoder_batch
+ *           (loss/ctc.py:62-70, decoders/ctc_greedy_decoder.py:6-49).
+ * ids: int32 [B, T'] (collapsed, blank-free token ids; first out_lens[b] entries valid),
+ * out_lens: int32 [B], scores: fp32 [B] = mean max-probability over non-blank frames (x100 on the
+ * host gives the reference score). trim_to_lens != 0 decodes only the valid frames of each utterance;
+ * 0 reproduces the reference's evaluate(), which decodes padded frames too (trainer.py:347).
+ * frame_ids / frame_probs (nullable, device-or-host like the others): per-frame arg-max id and its
+ * probability [B, T']. */
+int ppasr_b200_ctc_greedy(ppasr_b200_ctx* ctx, int32_t* ids, int32_t* out_lens, float* scores, int32_t* frame_ids,
+                          float* frame_probs, int32_t outputs_on_device, int32_t trim_to_lens, int32_t blank_id,
+                          void* stream);
+
+/* ---- stand-alone decoders on a probability tensor (device pointers) --------------------------
+ * replaces: greedy_decoder / greedy_decoder_batch (decoders/ctc_greedy_decoder.py:6-49).
+ * probs: fp32 [B, T, V] dense. frame_lens (nullable): int32 [B]. tmp_idx: int32 [B*T], tmp_maxp: fp32 [B*T]
+ * scratch that afterwards holds the per-frame arg-max ids / probabilities. */
+int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens,
+                             int32_t blank_id, int32_t* ids, int32_t ld_ids, int32_t* out_lens, float* scores,
+                             int32_t* tmp_idx, float* tmp_maxp, void* stream);
+
+/* ---- op-level entry points (parity tests, per-kernel roofline) ------------------------------- */
+/* out = epilogue(A[M,K] bf16 * W[N,K]^T bf16 + bias). epilogue: 0 = bf16 store with act (0 none,
+ * 1 relu, 2 swish); 1 = fp32 x = (residual ? x : 0) + alpha*(acc+bias) with optional pad-row mask
+ * (lens int32 [M/T]); 2 = GLU over interleaved column pairs -> bf16 [M, N/2]; 3 = fp32 logits. */
+int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t w_rows, const float* bias,
+                         void* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t act,
+                         float alpha, int32_t residual, const int32_t* lens, int32_t T, int32_t block_n, void* stream);
+int ppasr_b200_op_layernorm(float* x, void* y_bf16, const float* g1, const float* b1, const float* g2,
+                            const float* b2, const int32_t* lens, int32_t T, int32_t M, int32_t D, float eps,
+                            void* stream);
+int ppasr_b200_op_dwconv(const void* g_bf16, const float* w, const float* bias, const float* pad_left,
+                         const float* gamma, const float* beta, int32_t use_layer_norm, void* out_bf16, int32_t B,
+                         int32_t Tin, int32_t Tout, int32_t C, int32_t K, int32_t lpad, float eps, void* stream);
+int ppasr_b200_op_softmax(const float* logits, int32_t ldl, float* probs, int32_t M, int32_t V, void* stream);
+/* rel-pos attention on packed q2 [B,H,T1,128], kk [B,H,T2,64], vt [B,H,64,T2p], pos [pos_rows, pos_ld]
+ * (all bf16) -> out bf16 [B*T1, H*64]; klens nullable int32 [B]. */
+int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int32_t T2p, const void* pos,
+                            int32_t pos_rows, int32_t pos_ld, int32_t pos_row0, int32_t pos_col0, void* out,
+                            int32_t B, int32_t H, int32_t T1, int32_t T2, const int32_t* klens, void* stream);
+
+/* Debug/inspection: copies an internal activation (fp32 residual stream x [B*T', d_model]) to the
+ * device buffer `dst`. Used by the layer-wise parity tests only. */
+int ppasr_b200_debug_copy_x(ppasr_b200_ctx* ctx, float* dst_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPASR_B200_H_ */

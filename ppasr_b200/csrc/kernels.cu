@@ -1,0 +1,516 @@
+// CUDA-core kernels of the Conformer hot path (everything that is not a tensor-core contraction):
+// fused (double) LayerNorm, CMVN + first subsampling conv, depthwise-conv + norm + Swish,
+// row soft-max, CTC greedy decode. All are HBM-bandwidth bound: coalesced 16-byte accesses,
+// warp-shuffle reductions, no re-reads.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ppasr {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over D=256 channels, one warp per row (8 channels per lane).
+//   single: y_bf16 = LN(x; g1, b1)                      (rows with t >= lens[b] are written as 0)
+//   double: x <- LN(x; g1, b1) (fp32, in place), y_bf16 = LN(x; g2, b2)
+// Reference: the five LayerNorms of ConformerEncoderLayer (ppasr/model_utils/conformer/encoder.py:327-336,
+// 380-429): norm_final of layer i is fused with norm_ff_macaron of layer i+1 (or after_norm).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        const float* __restrict__ g1, const float* __restrict__ b1,
+                                                        const float* __restrict__ g2, const float* __restrict__ b2,
+                                                        const int* __restrict__ lens, int T, int M, float eps) {
+  constexpr int PER = D / 32;
+  static_assert(PER % 4 == 0, "D must be a multiple of 128");
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[PER];
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * D + lane * PER);
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    float4 t = src[i];
+    v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+  }
+  auto norm = [&](const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = (v[i] - mean) * rstd * __ldg(g + lane * PER + i) + __ldg(b + lane * PER + i);
+  };
+  norm(g1, b1);
+  if (g2 != nullptr) {
+    float4* dst = reinterpret_cast<float4*>(x + (size_t)row * D + lane * PER);
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    norm(g2, b2);
+  }
+  bool zero = false;
+  if (lens != nullptr) {
+    const int b = row / T;
+    zero = (row - b * T) >= __ldg(lens + b);
+  }
+  uint32_t pk[PER / 2];
+#pragma unroll
+  for (int i = 0; i < PER / 2; ++i) pk[i] = zero ? 0u : pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  uint4* dy = reinterpret_cast<uint4*>(y + (size_t)row * D + lane * PER);
+#pragma unroll
+  for (int i = 0; i < PER / 8; ++i) dy[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
+
+cudaError_t launch_layernorm(float* x, __nv_bfloat16* y, const float* g1, const float* b1, const float* g2,
+                             const float* b2, const int* lens, int T, int M, int D, float eps, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  const int grid = (M + 7) / 8;
+  if (D == 256)
+    layernorm_kernel<256><<<grid, 256, 0, st>>>(x, y, g1, b1, g2, b2, lens, T, M, eps);
+  else if (D == 512)
+    layernorm_kernel<512><<<grid, 256, 0, st>>>(x, y, g1, b1, g2, b2, lens, T, M, eps);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GlobalCMVN + Conv2d(1 -> C, 3x3, stride 2) + ReLU, written as four stride-phase images so that the
+// second stride-2 conv becomes nine unit-stride shifted GEMM taps (see gemm.cuh, CONV mode).
+//   reference: ppasr/model_utils/utils/cmvn.py:29-32, ppasr/model_utils/conformer/subsampling.py:84-85,110
+//   in : feats fp32 [B, T, F]
+//   out: P[ph][b][th][fh][c] bf16, ph = (t1&1)*2 + (f1&1), th = t1>>1 in [0,Th), fh = f1>>1 in [0,FH)
+//        (slots with t1 >= T1 or f1 >= F1 are written as 0)
+// One block per (b, th): 256 threads = output channels, both time phases, all frequency slots.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(C) conv1_subsample_kernel(const float* __restrict__ feats,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ istd,
+                                                            const float* __restrict__ w,     // [C, 9]
+                                                            const float* __restrict__ bias,  // [C]
+                                                            __nv_bfloat16* __restrict__ out, int B, int T, int F, int T1,
+                                                            int F1, int Th, int FH) {
+  extern __shared__ float xs[];  // [5][F] normalised input rows 4*th .. 4*th+4
+  const int b = blockIdx.x / Th;
+  const int th = blockIdx.x - b * Th;
+  const int c = threadIdx.x;
+  for (int i = threadIdx.x; i < 5 * F; i += C) {
+    const int r = i / F, f = i - r * F;
+    const int t = 4 * th + r;
+    float v = 0.f;
+    if (t < T) v = (feats[((size_t)b * T + t) * F + f] - __ldg(mean + f)) * __ldg(istd + f);
+    xs[i] = v;
+  }
+  float wr[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wr[i] = __ldg(w + c * 9 + i);
+  const float bs = __ldg(bias + c);
+  __syncthreads();
+  const size_t phase_stride = (size_t)B * Th * FH * C;
+#pragma unroll 1
+  for (int pt = 0; pt < 2; ++pt) {
+    const int t1 = 2 * th + pt;
+    const float* r0 = xs + (2 * pt) * F;
+#pragma unroll 1
+    for (int f1 = 0; f1 < 2 * FH; ++f1) {
+      float acc = 0.f;
+      if (t1 < T1 && f1 < F1) {
+        acc = bs;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) acc = fmaf(wr[kh * 3 + kw], r0[kh * F + 2 * f1 + kw], acc);
+        acc = fmaxf(acc, 0.f);
+      }
+      const int ph = pt * 2 + (f1 & 1);
+      out[ph * phase_stride + (((size_t)b * Th + th) * FH + (f1 >> 1)) * C + c] = __float2bfloat16_rn(acc);
+    }
+  }
+}
+
+cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const float* istd, const float* w,
+                                   const float* bias, __nv_bfloat16* out, int B, int T, int F, int C, int T1, int F1,
+                                   int Th, int FH, cudaStream_t st) {
+  if (C != 256) return cudaErrorInvalidValue;
+  const size_t smem = 5 * F * sizeof(float);
+  conv1_subsample_kernel<256><<<B * Th, 256, smem, st>>>(feats, mean, istd, w, bias, out, B, T, F, T1, F1, Th, FH);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise Conv1d(k) over time + (LayerNorm over channels | folded BatchNorm) + Swish.
+//   reference: ppasr/model_utils/conformer/convolution.py:125-131
+//   in : g bf16 [B, Tin, C] (GLU output);  out: bf16 [B, Tout, C]
+//   out[t, c] = swish(norm(bias[c] + sum_j w[c, j] * in[t - lpad + j, c]))
+//   rows with index < 0 read pad_left[c] (causal offline: the value GLU produces for a zero input
+//   row, because the reference left-pads *before* pointwise_conv1, convolution.py:108-110),
+//   rows >= Tin read 0 (symmetric padding of the depthwise conv itself, convolution.py:47-54).
+//   Chunk mode passes Tin = lorder + Tout with lpad = 0 ("valid" convolution over [cache ; chunk]).
+// One block per (b, 32-frame tile); thread = channel for the conv, warp = row for the norm.
+// ------------------------------------------------------------------------------------------------
+template <int C, int TT, int K>
+__global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat16* __restrict__ g,
+                                                              const float* __restrict__ w,  // [C, K]
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ pad_left,  // [C] or null
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int use_layer_norm,
+                                                              __nv_bfloat16* __restrict__ out, int Tin, int Tout,
+                                                              int lpad, float eps) {
+  extern __shared__ uint8_t dsm[];
+  __nv_bfloat16* sin = reinterpret_cast<__nv_bfloat16*>(dsm);                       // [TT + K - 1][C]
+  float* sout = reinterpret_cast<float*>(dsm + (size_t)(TT + 32) * C * 2);          // [TT][C]
+  const int tiles = (Tout + TT - 1) / TT;
+  const int b = blockIdx.x / tiles;
+  const int t0 = (blockIdx.x - b * tiles) * TT;
+  const int c = threadIdx.x;
+  const int rows = TT + K - 1;
+  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + rows)
+  for (int i = threadIdx.x; i < rows * (C / 8); i += C) {
+    const int r = i / (C / 8), seg = i - r * (C / 8);
+    const int ti = t0 - lpad + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ti >= 0 && ti < Tin) {
+      v = *reinterpret_cast<const uint4*>(g + ((size_t)b * Tin + ti) * C + seg * 8);
+    } else if (ti < 0 && pad_left != nullptr) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pad_left + seg * 8));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pad_left + seg * 8) + 1);
+      v = make_uint4(pack_bf16x2(p0.x, p0.y), pack_bf16x2(p0.z, p0.w), pack_bf16x2(p1.x, p1.y),
+                     pack_bf16x2(p1.z, p1.w));
+    }
+    *reinterpret_cast<uint4*>(sin + (size_t)r * C + seg * 8) = v;
+  }
+  __syncthreads();
+  // depthwise conv, thread = channel, sliding over time
+  float wk[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wk[j] = __ldg(w + c * K + j);
+  const float bs = __ldg(bias + c);
+  const float sc = use_layer_norm ? 1.f : __ldg(gamma + c);
+  const float sh = use_layer_norm ? 0.f : __ldg(beta + c);
+#pragma unroll 1
+  for (int t = 0; t < TT; ++t) {
+    float acc = bs;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fmaf(wk[j], __bfloat162float(sin[(size_t)(t + j) * C + c]), acc);
+    sout[t * C + c] = acc * sc + sh;
+  }
+  __syncthreads();
+  // norm + swish, warp = row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PER = C / 32;
+  for (int t = warp; t < TT; t += C / 32) {
+    if (t0 + t >= Tout) break;
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = sout[t * C + lane * PER + i];
+    if (use_layer_norm) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) s += v[i];
+      const float mean = warp_sum(s) * (1.0f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const float d = v[i] - mean;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+        v[i] = (v[i] - mean) * rstd * __ldg(gamma + lane * PER + i) + __ldg(beta + lane * PER + i);
+    }
+    uint32_t pk[PER / 2];
+#pragma unroll
+    for (int i = 0; i < PER / 2; ++i) pk[i] = pack_bf16x2(swish_precise(v[2 * i]), swish_precise(v[2 * i + 1]));
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * Tout + t0 + t) * C + lane * PER);
+#pragma unroll
+    for (int i = 0; i < PER / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  }
+}
+
+cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
+                                     const float* gamma, const float* beta, int use_layer_norm, __nv_bfloat16* out,
+                                     int B, int Tin, int Tout, int C, int K, int lpad, float eps, cudaStream_t st) {
+  if (C != 256) return cudaErrorInvalidValue;
+  constexpr int TT = 32;
+  const size_t smem = (size_t)(TT + 32) * C * 2 + (size_t)TT * C * 4;
+  const int tiles = (Tout + TT - 1) / TT;
+#define PPASR_DW_LAUNCH(KK)                                                                                   \
+  {                                                                                                           \
+    auto kern = dwconv_norm_swish_kernel<256, TT, KK>;                                                        \
+    static bool configured = false;                                                                           \
+    if (!configured) {                                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return e;                                                                         \
+      configured = true;                                                                                      \
+    }                                                                                                         \
+    kern<<<B * tiles, 256, smem, st>>>(g, w, bias, pad_left, gamma, beta, use_layer_norm, out, Tin, Tout, lpad, \
+                                       eps);                                                                  \
+  }
+  if (K == 15) PPASR_DW_LAUNCH(15) else if (K == 31) PPASR_DW_LAUNCH(31) else if (K == 7) PPASR_DW_LAUNCH(7) else return cudaErrorInvalidValue;
+#undef PPASR_DW_LAUNCH
+  return cudaGetLastError();
+}
+
+// pad_left[c] = bf16(GLU(bias_a[c], bias_g[c])) computed with exactly the epilogue's arithmetic
+// (interleaved bias layout: [2c] = a, [2c+1] = gate).
+__global__ void glu_pad_kernel(const float* __restrict__ bias_il, float* __restrict__ pad, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) pad[c] = __bfloat162float(__float2bfloat16_rn(bias_il[2 * c] * sigmoid_f(bias_il[2 * c + 1])));
+}
+cudaError_t launch_glu_pad(const float* bias_il, float* pad, int C, cudaStream_t st) {
+  glu_pad_kernel<<<(C + 127) / 128, 128, 0, st>>>(bias_il, pad, C);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row soft-max of the CTC logits: probs[row, 0:V] (dense) = softmax(logits[row, 0:V]) (ld = ldl)
+//   reference: ppasr/model_utils/loss/ctc.py:62-70
+// One block per row; values stay in registers between the passes.
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int MAXPER>
+__global__ void __launch_bounds__(THREADS) softmax_rows_kernel(const float* __restrict__ logits, int ldl,
+                                                               float* __restrict__ probs, int V) {
+  __shared__ float red[THREADS / 32];
+  __shared__ float bcast;
+  const size_t row = blockIdx.x;
+  const float* src = logits + row * ldl;
+  float v[MAXPER];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const int j = threadIdx.x + i * THREADS;
+    v[i] = (j < V) ? src[j] : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < THREADS / 32) ? red[threadIdx.x] : -INFINITY;
+    t = warp_max(t);
+    if (threadIdx.x == 0) bcast = t;
+  }
+  __syncthreads();
+  m = bcast;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    v[i] = expf(v[i] - m);  // exp(-inf) = 0 for the tail
+    s += v[i];
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < THREADS / 32) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) bcast = t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bcast;
+  float* dst = probs + row * V;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const int j = threadIdx.x + i * THREADS;
+    if (j < V) dst[j] = v[i] * inv;
+  }
+}
+
+cudaError_t launch_softmax_rows(const float* logits, int ldl, float* probs, int M, int V, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  if (V <= 256 * 8)
+    softmax_rows_kernel<256, 8><<<M, 256, 0, st>>>(logits, ldl, probs, V);
+  else if (V <= 256 * 20)
+    softmax_rows_kernel<256, 20><<<M, 256, 0, st>>>(logits, ldl, probs, V);
+  else if (V <= 512 * 32)
+    softmax_rows_kernel<512, 32><<<M, 512, 0, st>>>(logits, ldl, probs, V);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTC greedy decode
+//   reference: ppasr/decoders/ctc_greedy_decoder.py:21-31 (argmax -> collapse repeats -> drop blank;
+//   score = mean of the max-probabilities of the non-blank frames)
+// ------------------------------------------------------------------------------------------------
+// (a) frame arg-max over a dense probability matrix probs[rows, V] (first maximum wins, like np.argmax).
+//     One warp per frame, 4 frames per block; the row is streamed once with 16-byte loads where the
+//     row start allows (rows are only 4-byte aligned because V is odd in general).
+__global__ void __launch_bounds__(128) argmax_rows_kernel(const float* __restrict__ probs, int V, int rows,
+                                                          int* __restrict__ idx, float* __restrict__ maxp) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = probs + (size_t)row * V;
+  float bm = -INFINITY;
+  int bi = 0x7fffffff;
+  auto upd = [&](float v, int j) {
+    if (v > bm || (v == bm && j < bi)) {
+      bm = v;
+      bi = j;
+    }
+  };
+  // peel to 16-byte alignment
+  const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+  const int head = mis ? min(4 - mis, V) : 0;
+  if (lane < head) upd(src[lane], lane);
+  const float4* v4 = reinterpret_cast<const float4*>(src + head);
+  const int n4 = (V - head) >> 2;
+  int i = lane;
+  for (; i + 96 < n4; i += 128) {  // 4 independent 16-byte loads in flight per lane
+    const float4 a = __ldcs(v4 + i), b = __ldcs(v4 + i + 32), c = __ldcs(v4 + i + 64), d = __ldcs(v4 + i + 96);
+    int j = head + 4 * i;
+    upd(a.x, j), upd(a.y, j + 1), upd(a.z, j + 2), upd(a.w, j + 3);
+    j += 128;
+    upd(b.x, j), upd(b.y, j + 1), upd(b.z, j + 2), upd(b.w, j + 3);
+    j += 128;
+    upd(c.x, j), upd(c.y, j + 1), upd(c.z, j + 2), upd(c.w, j + 3);
+    j += 128;
+    upd(d.x, j), upd(d.y, j + 1), upd(d.z, j + 2), upd(d.w, j + 3);
+  }
+  for (; i < n4; i += 32) {
+    const float4 a = __ldcs(v4 + i);
+    const int j = head + 4 * i;
+    upd(a.x, j), upd(a.y, j + 1), upd(a.z, j + 2), upd(a.w, j + 3);
+  }
+  const int tail0 = head + 4 * n4;
+  if (tail0 + lane < V) upd(src[tail0 + lane], tail0 + lane);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (om > bm || (om == bm && oi < bi)) {
+      bm = om;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    idx[row] = bi;
+    maxp[row] = bm;
+  }
+}
+
+cudaError_t launch_argmax_rows(const float* probs, int V, int rows, int* idx, float* maxp, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  argmax_rows_kernel<<<(rows + 3) / 4, 128, 0, st>>>(probs, V, rows, idx, maxp);
+  return cudaGetLastError();
+}
+
+// (b) fused-head variant: combine the per-tile partial statistics written by EpiCtcStats.
+//     idx = arg-max of the logits (first maximum), maxp = softmax probability of it = 1 / sum exp(l - max).
+__global__ void ctc_stats_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ parg,
+                                          const float* __restrict__ psum, int parts, int rows, int* __restrict__ idx,
+                                          float* __restrict__ maxp) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float bm = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int p = lane; p < parts; p += 32) {
+    const float m = pmax[(size_t)row * parts + p];
+    const int a = parg[(size_t)row * parts + p];
+    if (m > bm || (m == bm && a < bi)) {
+      bm = m;
+      bi = a;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (om > bm || (om == bm && oi < bi)) {
+      bm = om;
+      bi = oi;
+    }
+  }
+  float s = 0.f;
+  for (int p = lane; p < parts; p += 32) {
+    const float m = pmax[(size_t)row * parts + p];
+    if (m > -INFINITY) s += psum[(size_t)row * parts + p] * expf(m - bm);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    idx[row] = bi;
+    maxp[row] = 1.0f / s;
+  }
+}
+
+cudaError_t launch_ctc_stats_finalize(const float* pmax, const int* parg, const float* psum, int parts, int rows,
+                                      int* idx, float* maxp, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  ctc_stats_finalize_kernel<<<(rows + 3) / 4, 128, 0, st>>>(pmax, parg, psum, parts, rows, idx, maxp);
+  return cudaGetLastError();
+}
+
+// (c) blank-collapse: one warp per utterance. ids_out[b, 0:n] = collapsed non-blank ids, out_len[b] = n,
+//     score[b] = (sequential fp32 sum of maxp over non-blank frames) / count   (0 if none); the
+//     sequential order reproduces Python's sum() over np.float32 values bit-for-bit.
+//     prev_id (nullable): last frame id of the previous chunk for streaming collapse (-1 = none).
+__global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ maxp, int B, int T,
+                                    const int* __restrict__ frame_lens, int blank, int* __restrict__ ids_out,
+                                    int ld_out, int* __restrict__ out_len, float* __restrict__ score,
+                                    float* __restrict__ score_sum, int* __restrict__ score_cnt) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int n_frames = frame_lens ? min(T, frame_lens[b]) : T;
+  const int* id = idx + (size_t)b * T;
+  int n_out = 0;
+  for (int t0 = 0; t0 < n_frames; t0 += 32) {
+    const int t = t0 + lane;
+    int cur = blank, prev = -1;
+    if (t < n_frames) {
+      cur = id[t];
+      prev = (t > 0) ? id[t - 1] : -1;
+    }
+    const bool keep = (t < n_frames) && (cur != blank) && (cur != prev);
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) ids_out[(size_t)b * ld_out + n_out + __popc(mask & ((1u << lane) - 1))] = cur;
+    n_out += __popc(mask);
+  }
+  // sequential (in frame order) fp32 sum, computed redundantly by every lane from warp-wide loads
+  float s = 0.f;
+  int cnt = 0;
+  const float* mp = maxp + (size_t)b * T;
+  for (int t0 = 0; t0 < n_frames; t0 += 32) {
+    const int t = t0 + lane;
+    const float pv = (t < n_frames) ? mp[t] : 0.f;
+    const bool nb = (t < n_frames) && (id[t] != blank);
+    const unsigned nbmask = __ballot_sync(0xffffffffu, nb);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float v = __shfl_sync(0xffffffffu, pv, k);
+      if ((nbmask >> k) & 1u) {
+        s += v;
+        ++cnt;
+      }
+    }
+  }
+  if (lane == 0) {
+    out_len[b] = n_out;
+    score[b] = cnt > 0 ? s / (float)cnt : 0.f;
+    if (score_sum) score_sum[b] = s;
+    if (score_cnt) score_cnt[b] = cnt;
+  }
+}
+
+cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T, const int* frame_lens, int blank,
+                                int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
+                                int* score_cnt, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  ctc_collapse_kernel<<<(B + 3) / 4, 128, 0, st>>>(idx, maxp, B, T, frame_lens, blank, ids_out, ld_out, out_len, score,
+                                                   score_sum, score_cnt);
+  return cudaGetLastError();
+}
+
+}  // namespace ppasr

@@ -1,0 +1,51 @@
+// Launchers of the non-GEMM hot-path kernels (defined in kernels.cu / attention.cu). All take raw
+// device pointers and a stream; none allocate.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ppasr {
+
+cudaError_t launch_layernorm(float* x, __nv_bfloat16* y, const float* g1, const float* b1, const float* g2,
+                             const float* b2, const int* lens, int T, int M, int D, float eps, cudaStream_t st);
+
+cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const float* istd, const float* w,
+                                   const float* bias, __nv_bfloat16* out, int B, int T, int F, int C, int T1, int F1,
+                                   int Th, int FH, cudaStream_t st);
+
+cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
+                                     const float* gamma, const float* beta, int use_layer_norm, __nv_bfloat16* out,
+                                     int B, int Tin, int Tout, int C, int K, int lpad, float eps, cudaStream_t st);
+
+cudaError_t launch_glu_pad(const float* bias_il, float* pad, int C, cudaStream_t st);
+
+cudaError_t launch_softmax_rows(const float* logits, int ldl, float* probs, int M, int V, cudaStream_t st);
+
+cudaError_t launch_argmax_rows(const float* probs, int V, int rows, int* idx, float* maxp, cudaStream_t st);
+
+cudaError_t launch_ctc_stats_finalize(const float* pmax, const int* parg, const float* psum, int parts, int rows,
+                                      int* idx, float* maxp, cudaStream_t st);
+
+cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T, const int* frame_lens, int blank,
+                                int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
+                                int* score_cnt, cudaStream_t st);
+
+// Relative-position attention (attention.cu). Tensor maps are built by the caller.
+struct AttnParams {
+  int B, H;
+  int T1;        // query frames per utterance
+  int T2;        // key frames per utterance (cache + new)
+  int q_rows_per_bh;   // rows of q2 per (b,h)  (= T1)
+  int k_rows_per_bh;   // rows of kk per (b,h)
+  int pos_row0;  // first row of the positional table used for key 0
+  int pos_col0;  // first column (layer * D) of this layer's slice in the positional table
+  int D;         // H * 64
+  const int* klens;  // per-utterance valid key count (nullable = all T2 valid)
+  __nv_bfloat16* out;  // [B*T1, D]
+};
+cudaError_t launch_rel_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_p,
+                                 const CUtensorMap& tm_vt, const AttnParams& p, cudaStream_t st);
+
+}  // namespace ppasr

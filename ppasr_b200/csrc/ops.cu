@@ -1,0 +1,131 @@
+// Op-level C-ABI entry points: each hot-path kernel callable on raw device pointers.
+// Used by the parity tests (kernel vs oracle) and by bench.py's per-kernel roofline leg.
+// The model-level entry points (ppasr_b200_create / encode / decode ...) live in runtime.cu.
+#include "common.h"
+#include "gemm.cuh"
+#include "kernels.h"
+#include "ppasr_b200.h"
+#include "tmap.h"
+
+#include <mutex>
+
+namespace ppasr {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    sms = prop.multiProcessorCount;
+  }
+  return sms;
+}
+
+GemmShape make_shape(int M, int N, int K, int block_n) {
+  GemmShape s;
+  s.M = M;
+  s.N = N;
+  s.num_k_blocks = K / GEMM_BLOCK_K;
+  s.num_m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  s.num_n_tiles = (N + block_n - 1) / block_n;
+  s.conv_pitch = 0;
+  s.conv_kc = 1;
+  return s;
+}
+
+}  // namespace ppasr
+
+using namespace ppasr;
+
+extern "C" {
+
+const char* ppasr_b200_last_error(void) { return get_last_error(); }
+
+int ppasr_b200_abi_version(void) { return 1; }
+
+// C = epilogue(A[M,K] * W[N,K]^T + bias).  See include/ppasr_b200.h for the epilogue codes.
+int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t w_rows, const float* bias,
+                         void* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t act,
+                         float alpha, int32_t residual, const int32_t* lens, int32_t T, int32_t block_n, void* stream) {
+  PPASR_REQUIRE(a_bf16 && w_bf16 && bias && out, "null pointer");
+  PPASR_REQUIRE(M > 0 && N > 0 && K > 0 && K % GEMM_BLOCK_K == 0, "K must be a positive multiple of 64");
+  PPASR_REQUIRE(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+  PPASR_REQUIRE(w_rows >= ((N + block_n - 1) / block_n) * (int64_t)block_n, "weight rows must be padded to block_n");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::string err;
+  CUtensorMap ta, tb;
+  if (!make_tmap_2d(&ta, a_bf16, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BLOCK_M, &err) ||
+      !make_tmap_2d(&tb, w_bf16, (uint64_t)K, (uint64_t)w_rows, (uint64_t)K * 2, (uint32_t)block_n, &err)) {
+    set_last_error(err);
+    return PPASR_ERR_CUDA;
+  }
+  GemmShape s = make_shape(M, N, K, block_n);
+  const int sms = device_sm_count();
+  cudaError_t e = cudaSuccess;
+  switch (epilogue) {
+    case 0: {  // bf16 store with activation
+      if (block_n == 256) {
+#define LAUNCH_STORE(ACT)                                                                       \
+  {                                                                                             \
+    EpiStoreBF16<256, ACT> epi{(__nv_bfloat16*)out, bias, (int)ldo, M, N};                      \
+    e = launch_gemm<256, 4, false>(ta, tb, s, epi, sms, st);                                    \
+  }
+        if (act == ACT_NONE) LAUNCH_STORE(ACT_NONE) else if (act == ACT_RELU) LAUNCH_STORE(ACT_RELU) else LAUNCH_STORE(ACT_SWISH)
+#undef LAUNCH_STORE
+      } else {
+#define LAUNCH_STORE(ACT)                                                                       \
+  {                                                                                             \
+    EpiStoreBF16<128, ACT> epi{(__nv_bfloat16*)out, bias, (int)ldo, M, N};                      \
+    e = launch_gemm<128, 6, false>(ta, tb, s, epi, sms, st);                                    \
+  }
+        if (act == ACT_NONE) LAUNCH_STORE(ACT_NONE) else if (act == ACT_RELU) LAUNCH_STORE(ACT_RELU) else LAUNCH_STORE(ACT_SWISH)
+#undef LAUNCH_STORE
+      }
+      break;
+    }
+    case 1: {  // fp32 residual update
+      if (block_n == 256) {
+        EpiResidF32<256> epi{(float*)out, bias, (int)ldo, M, N, alpha, residual, lens, T};
+        e = launch_gemm<256, 4, false>(ta, tb, s, epi, sms, st);
+      } else {
+        EpiResidF32<128> epi{(float*)out, bias, (int)ldo, M, N, alpha, residual, lens, T};
+        e = launch_gemm<128, 6, false>(ta, tb, s, epi, sms, st);
+      }
+      break;
+    }
+    case 2: {  // GLU over interleaved columns
+      if (block_n == 256) {
+        EpiGLU<256> epi{(__nv_bfloat16*)out, bias, (int)ldo, M, N};
+        e = launch_gemm<256, 4, false>(ta, tb, s, epi, sms, st);
+      } else {
+        EpiGLU<128> epi{(__nv_bfloat16*)out, bias, (int)ldo, M, N};
+        e = launch_gemm<128, 6, false>(ta, tb, s, epi, sms, st);
+      }
+      break;
+    }
+    case 3: {  // fp32 logits
+      PPASR_REQUIRE(ldo % 4 == 0, "ldo must be a multiple of 4 for fp32 logits");
+      if (block_n == 256) {
+        EpiLogitsF32<256> epi{(float*)out, bias, (int)ldo, M, N};
+        e = launch_gemm<256, 4, false>(ta, tb, s, epi, sms, st);
+      } else {
+        EpiLogitsF32<128> epi{(float*)out, bias, (int)ldo, M, N};
+        e = launch_gemm<128, 6, false>(ta, tb, s, epi, sms, st);
+      }
+      break;
+    }
+    default:
+      set_last_error("unknown epilogue code");
+      return PPASR_ERR_INVALID;
+  }
+  PPASR_CUDA_CHECK(e);
+  return PPASR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,796 @@
+// Model-level runtime behind the C-ABI (include/ppasr_b200.h): parameter packing, workspace,
+// the Conformer encoder launch sequence and the CTC head / greedy decode.
+//
+// Reference call path being replaced (yeyupiaoling/PPASR @ c8bb3b96):
+//   InferencePredictor.predict (ppasr/infer_utils/inference_predictor.py:103-145)
+//   -> ConformerModel.get_encoder_out (ppasr/model_utils/conformer/model.py:148-162)
+//   -> ConformerEncoder.forward (ppasr/model_utils/conformer/encoder.py:164-206)
+//   -> CTCLoss.softmax (ppasr/model_utils/loss/ctc.py:62-70) -> greedy_decoder (ppasr/decoders/ctc_greedy_decoder.py)
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "gemm.cuh"
+#include "kernels.h"
+#include "ppasr_b200.h"
+#include "tmap.h"
+
+namespace ppasr {
+
+GemmShape make_shape(int M, int N, int K, int block_n);
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// simple bump allocator over one cudaMalloc'ed slab (weights) / growable slab (workspace)
+struct DeviceSlab {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&base, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  template <class T>
+  T* take(size_t count) {
+    size_t off = (used + 255) & ~size_t(255);
+    used = off + count * sizeof(T);
+    return reinterpret_cast<T*>(base + off);
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = used = 0;
+  }
+};
+
+struct LayerW {
+  // layer norms (gamma, beta) fp32 [D]
+  const float *ln_ffm_g, *ln_ffm_b, *ln_mha_g, *ln_mha_b, *ln_conv_g, *ln_conv_b, *ln_ff_g, *ln_ff_b, *ln_fin_g,
+      *ln_fin_b;
+  // feed-forward (macaron, final): K-major bf16
+  const __nv_bfloat16 *ffm_w1, *ffm_w2, *ff_w1, *ff_w2;
+  const float *ffm_b1, *ffm_b2, *ff_b1, *ff_b2;
+  // attention
+  const __nv_bfloat16 *wqkv, *wo;
+  const float *bqkv, *bo, *pos_u, *pos_v;
+  // conv module
+  const __nv_bfloat16 *pw1, *pw2;
+  const float *pw1_b, *pw2_b, *dw_w, *dw_b, *cn_g, *cn_b, *glu_pad;
+};
+
+struct Plan {  // everything that depends on (B, T)
+  int B = 0, T = 0, T1 = 0, Tp = 0, Th = 0, M = 0, Mr = 0, Tkp = 0;
+  // activations
+  float* feats = nullptr;
+  int* vlen = nullptr;
+  __nv_bfloat16 *phase = nullptr, *c2 = nullptr, *y = nullptr, *h = nullptr, *q2 = nullptr, *kk = nullptr,
+                *vt = nullptr, *att = nullptr, *g = nullptr, *z = nullptr;
+  float *x = nullptr, *logits = nullptr, *pmax = nullptr, *psum = nullptr, *maxp = nullptr, *score = nullptr,
+        *probs = nullptr;
+  int *parg = nullptr, *idx = nullptr, *ids = nullptr, *out_len = nullptr;
+  // tensor maps (A operands)
+  CUtensorMap tm_phase, tm_c2, tm_y, tm_h, tm_att, tm_g, tm_z, tm_q, tm_k, tm_vt;
+};
+
+}  // namespace ppasr
+
+using namespace ppasr;
+
+struct ppasr_b200_ctx {
+  ppasr_b200_config cfg;
+  std::map<std::string, HostTensor> host;
+  bool finalized = false;
+  int F1 = 0, F2 = 0, FH = 0, Kemb = 0, Vpad = 0, Vld = 0, ctc_parts = 0;
+  DeviceSlab wslab, aslab;
+  // global weights
+  const float *cmvn_mean = nullptr, *cmvn_istd = nullptr, *conv1_w = nullptr, *conv1_b = nullptr, *conv2_b = nullptr,
+              *emb_b = nullptr, *after_g = nullptr, *after_b = nullptr, *ctc_b = nullptr, *zero_bias = nullptr;
+  const __nv_bfloat16 *conv2_w = nullptr, *emb_w = nullptr, *ctc_w = nullptr, *pos_tab = nullptr;
+  std::vector<LayerW> layers;
+  // weight tensor maps (B operands)
+  CUtensorMap tm_conv2_w, tm_emb_w, tm_ctc_w, tm_pos;
+  struct LayerMaps {
+    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2;
+  };
+  std::vector<LayerMaps> lmaps;
+  Plan plan;
+  int sms = 148;
+};
+
+namespace {
+
+constexpr int BN_WIDE = 256, ST_WIDE = 4;    // N >= 512 outputs
+constexpr int BN_NARROW = 128, ST_NARROW = 6;  // N = 256 outputs (fills 124 of 148 SMs at M = 7936)
+
+const HostTensor* find(ppasr_b200_ctx* c, const std::string& name, std::string* missing) {
+  auto it = c->host.find(name);
+  if (it == c->host.end()) {
+    if (missing) *missing += (missing->empty() ? "" : ", ") + name;
+    return nullptr;
+  }
+  return &it->second;
+}
+
+std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+  std::vector<__nv_bfloat16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+  return o;
+}
+
+// Paddle Linear weight [in, out] -> K-major [rows_pad, in] (row = output feature)
+std::vector<float> transpose_in_out(const HostTensor& w, int rows_pad = 0) {
+  const int64_t in = w.shape[0], out = w.shape[1];
+  const int64_t rows = rows_pad > out ? rows_pad : out;
+  std::vector<float> o((size_t)rows * in, 0.f);
+  for (int64_t i = 0; i < in; ++i)
+    for (int64_t j = 0; j < out; ++j) o[(size_t)j * in + i] = w.data[(size_t)i * out + j];
+  return o;
+}
+
+template <class T>
+const T* upload(ppasr_b200_ctx* c, const std::vector<T>& v) {
+  T* d = c->wslab.take<T>(v.size());
+  cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
+  PPASR_REQUIRE(cfg && out, "null pointer");
+  PPASR_REQUIRE(cfg->model_type == 0, "only model_type 0 (conformer) is implemented");
+  PPASR_REQUIRE(cfg->d_model == 256, "d_model must be 256 in this build");
+  PPASR_REQUIRE(cfg->n_heads * 64 == cfg->d_model, "head dim must be 64");
+  PPASR_REQUIRE(cfg->ffn_dim % 256 == 0 && cfg->ffn_dim > 0, "ffn_dim must be a multiple of 256");
+  PPASR_REQUIRE(cfg->conv_kernel == 7 || cfg->conv_kernel == 15 || cfg->conv_kernel == 31, "conv_kernel 7/15/31");
+  PPASR_REQUIRE(cfg->feat_dim >= 7 && cfg->vocab_size > 1 && cfg->n_layers > 0 && cfg->max_len > 16, "bad config");
+  auto* c = new ppasr_b200_ctx();
+  c->cfg = *cfg;
+  c->F1 = (cfg->feat_dim - 1) / 2;
+  c->F2 = (c->F1 - 1) / 2;
+  c->FH = (c->F1 + 1) / 2;
+  c->Kemb = c->F2 * cfg->d_model;
+  if (c->Kemb % GEMM_BLOCK_K != 0) {
+    delete c;
+    set_last_error("subsampled feature size * d_model must be a multiple of 64");
+    return PPASR_ERR_INVALID;
+  }
+  c->Vpad = (cfg->vocab_size + BN_NARROW - 1) / BN_NARROW * BN_NARROW;
+  c->Vld = (cfg->vocab_size + 3) / 4 * 4;
+  c->ctc_parts = 2 * (c->Vpad / BN_NARROW);
+  *out = c;
+  return PPASR_OK;
+}
+
+int ppasr_b200_destroy(ppasr_b200_ctx* ctx) {
+  if (!ctx) return PPASR_OK;
+  ctx->wslab.release();
+  ctx->aslab.release();
+  delete ctx;
+  return PPASR_OK;
+}
+
+int ppasr_b200_load_tensor(ppasr_b200_ctx* ctx, const char* name, const float* data, int32_t ndim,
+                           const int64_t* shape) {
+  PPASR_REQUIRE(ctx && name && data && shape && ndim >= 1 && ndim <= 4, "bad arguments");
+  if (ctx->finalized) {
+    set_last_error("context already finalized");
+    return PPASR_ERR_STATE;
+  }
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.assign(data, data + t.numel());
+  ctx->host[name] = std::move(t);
+  return PPASR_OK;
+}
+
+int ppasr_b200_finalize(ppasr_b200_ctx* c) {
+  PPASR_REQUIRE(c, "null ctx");
+  if (c->finalized) return PPASR_OK;
+  const auto& cfg = c->cfg;
+  const int D = cfg.d_model, L = cfg.n_layers, FF = cfg.ffn_dim, K = cfg.conv_kernel, V = cfg.vocab_size;
+  int dev = 0;
+  PPASR_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  PPASR_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_last_error("ppasr_b200 requires an sm_100 (Blackwell B200) device; found sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor));
+    return PPASR_ERR_CUDA;
+  }
+  c->sms = prop.multiProcessorCount;
+
+  std::string missing;
+  auto need = [&](const std::string& n) { return find(c, n, &missing); };
+  // ---- presence check first, so the error lists everything -------------------------------------
+  std::vector<std::string> names = {"encoder.global_cmvn.mean", "encoder.global_cmvn.istd",
+                                    "encoder.embed.conv.0.weight", "encoder.embed.conv.0.bias",
+                                    "encoder.embed.conv.2.weight", "encoder.embed.conv.2.bias",
+                                    "encoder.embed.out.0.weight", "encoder.embed.out.0.bias",
+                                    "encoder.after_norm.weight", "encoder.after_norm.bias",
+                                    "ctc.ctc_lo.weight", "ctc.ctc_lo.bias"};
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "encoder.encoders." + std::to_string(l) + ".";
+    for (const char* s : {"norm_ff_macaron", "norm_mha", "norm_conv", "norm_ff", "norm_final"}) {
+      names.push_back(p + s + ".weight");
+      names.push_back(p + s + ".bias");
+    }
+    for (const char* s : {"feed_forward_macaron", "feed_forward"})
+      for (const char* t : {".w_1.weight", ".w_1.bias", ".w_2.weight", ".w_2.bias"}) names.push_back(p + s + t);
+    for (const char* s : {"linear_q", "linear_k", "linear_v", "linear_out"}) {
+      names.push_back(p + "self_attn." + s + ".weight");
+      names.push_back(p + "self_attn." + s + ".bias");
+    }
+    names.push_back(p + "self_attn.linear_pos.weight");
+    names.push_back(p + "self_attn.pos_bias_u");
+    names.push_back(p + "self_attn.pos_bias_v");
+    for (const char* s : {"pointwise_conv1", "depthwise_conv", "pointwise_conv2", "norm"}) {
+      names.push_back(p + "conv_module." + s + ".weight");
+      names.push_back(p + "conv_module." + s + ".bias");
+    }
+    if (cfg.conv_norm == 1) {
+      names.push_back(p + "conv_module.norm._mean");
+      names.push_back(p + "conv_module.norm._variance");
+    }
+  }
+  for (auto& n : names) need(n);
+  if (!missing.empty()) {
+    set_last_error("missing parameters: " + missing);
+    return PPASR_ERR_STATE;
+  }
+
+  // ---- size the weight slab ----------------------------------------------------------------------
+  size_t bytes = 0;
+  bytes += (size_t)L * ((size_t)4 * D * FF + 3 * D * D + D * D + 2 * D * D + D * D) * 2;  // bf16 matrices
+  bytes += (size_t)D * 9 * D * 2 + (size_t)D * c->Kemb * 2 + (size_t)c->Vpad * D * 2;
+  bytes += (size_t)cfg.max_len * L * D * 2 + (size_t)cfg.max_len * D * 2 + (size_t)L * D * D * 2;
+  bytes += (size_t)L * (20 * D + 2 * FF + 3 * D + 2 * D + D * K + 64) * 4 + (size_t)(c->Vpad + 4 * D + L * D + 4096) * 4;
+  bytes += 4u << 20;  // alignment slack
+  PPASR_CUDA_CHECK(c->wslab.reserve(bytes));
+  c->wslab.used = 0;
+
+  std::string err;
+  auto vecf = [&](const std::string& n) -> const float* { return upload(c, c->host[n].data); };
+
+  // ---- front end ------------------------------------------------------------------------------
+  c->cmvn_mean = vecf("encoder.global_cmvn.mean");
+  c->cmvn_istd = vecf("encoder.global_cmvn.istd");
+  {
+    const HostTensor& w = c->host["encoder.embed.conv.0.weight"];  // [D,1,3,3]
+    PPASR_REQUIRE(w.numel() == (int64_t)D * 9, "conv.0.weight shape");
+    c->conv1_w = upload(c, w.data);
+    c->conv1_b = vecf("encoder.embed.conv.0.bias");
+  }
+  {
+    // conv.2.weight [O, I, 3, 3] -> K-major [O, (kh*3+kw)*I + i]
+    const HostTensor& w = c->host["encoder.embed.conv.2.weight"];
+    PPASR_REQUIRE(w.numel() == (int64_t)D * D * 9, "conv.2.weight shape");
+    std::vector<float> p((size_t)D * 9 * D);
+    for (int o = 0; o < D; ++o)
+      for (int i = 0; i < D; ++i)
+        for (int t = 0; t < 9; ++t) p[(size_t)o * 9 * D + (size_t)t * D + i] = w.data[((size_t)o * D + i) * 9 + t];
+    c->conv2_w = upload(c, to_bf16(p));
+    c->conv2_b = vecf("encoder.embed.conv.2.bias");
+  }
+  {
+    // out.0.weight [C*F2 (c*F2+f), D] -> K-major [D, f*D + c]
+    const HostTensor& w = c->host["encoder.embed.out.0.weight"];
+    PPASR_REQUIRE(w.shape.size() == 2 && w.shape[0] == (int64_t)D * c->F2 && w.shape[1] == D, "embed.out.0.weight shape");
+    std::vector<float> p((size_t)D * c->Kemb);
+    for (int ch = 0; ch < D; ++ch)
+      for (int f = 0; f < c->F2; ++f)
+        for (int o = 0; o < D; ++o) p[(size_t)o * c->Kemb + (size_t)f * D + ch] = w.data[((size_t)ch * c->F2 + f) * D + o];
+    c->emb_w = upload(c, to_bf16(p));
+    c->emb_b = vecf("encoder.embed.out.0.bias");
+  }
+  c->after_g = vecf("encoder.after_norm.weight");
+  c->after_b = vecf("encoder.after_norm.bias");
+  {
+    const HostTensor& w = c->host["ctc.ctc_lo.weight"];  // [D, V]
+    PPASR_REQUIRE(w.shape.size() == 2 && w.shape[0] == D && w.shape[1] == V, "ctc_lo.weight shape");
+    c->ctc_w = upload(c, to_bf16(transpose_in_out(w, c->Vpad)));
+    std::vector<float> b(c->Vpad, 0.f);
+    std::memcpy(b.data(), c->host["ctc.ctc_lo.bias"].data.data(), sizeof(float) * V);
+    c->ctc_b = upload(c, b);
+  }
+  {
+    std::vector<float> z((size_t)std::max(L * D, 4096), 0.f);
+    c->zero_bias = upload(c, z);
+  }
+
+  // ---- encoder layers -------------------------------------------------------------------------
+  c->layers.resize(L);
+  c->lmaps.resize(L);
+  std::vector<float> wpos_all((size_t)L * D * D);
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "encoder.encoders." + std::to_string(l) + ".";
+    LayerW& w = c->layers[l];
+    w.ln_ffm_g = vecf(p + "norm_ff_macaron.weight"), w.ln_ffm_b = vecf(p + "norm_ff_macaron.bias");
+    w.ln_mha_g = vecf(p + "norm_mha.weight"), w.ln_mha_b = vecf(p + "norm_mha.bias");
+    w.ln_conv_g = vecf(p + "norm_conv.weight"), w.ln_conv_b = vecf(p + "norm_conv.bias");
+    w.ln_ff_g = vecf(p + "norm_ff.weight"), w.ln_ff_b = vecf(p + "norm_ff.bias");
+    w.ln_fin_g = vecf(p + "norm_final.weight"), w.ln_fin_b = vecf(p + "norm_final.bias");
+    w.ffm_w1 = upload(c, to_bf16(transpose_in_out(c->host[p + "feed_forward_macaron.w_1.weight"])));
+    w.ffm_w2 = upload(c, to_bf16(transpose_in_out(c->host[p + "feed_forward_macaron.w_2.weight"])));
+    w.ff_w1 = upload(c, to_bf16(transpose_in_out(c->host[p + "feed_forward.w_1.weight"])));
+    w.ff_w2 = upload(c, to_bf16(transpose_in_out(c->host[p + "feed_forward.w_2.weight"])));
+    w.ffm_b1 = vecf(p + "feed_forward_macaron.w_1.bias"), w.ffm_b2 = vecf(p + "feed_forward_macaron.w_2.bias");
+    w.ff_b1 = vecf(p + "feed_forward.w_1.bias"), w.ff_b2 = vecf(p + "feed_forward.w_2.bias");
+    {
+      std::vector<float> qkv((size_t)3 * D * D), bq((size_t)3 * D);
+      const char* nm[3] = {"linear_q", "linear_k", "linear_v"};
+      for (int s = 0; s < 3; ++s) {
+        auto t = transpose_in_out(c->host[p + "self_attn." + nm[s] + ".weight"]);
+        std::memcpy(qkv.data() + (size_t)s * D * D, t.data(), sizeof(float) * D * D);
+        std::memcpy(bq.data() + (size_t)s * D, c->host[p + "self_attn." + nm[s] + ".bias"].data.data(), sizeof(float) * D);
+      }
+      w.wqkv = upload(c, to_bf16(qkv));
+      w.bqkv = upload(c, bq);
+    }
+    w.wo = upload(c, to_bf16(transpose_in_out(c->host[p + "self_attn.linear_out.weight"])));
+    w.bo = vecf(p + "self_attn.linear_out.bias");
+    w.pos_u = vecf(p + "self_attn.pos_bias_u");
+    w.pos_v = vecf(p + "self_attn.pos_bias_v");
+    {
+      auto t = transpose_in_out(c->host[p + "self_attn.linear_pos.weight"]);
+      std::memcpy(wpos_all.data() + (size_t)l * D * D, t.data(), sizeof(float) * D * D);
+    }
+    {
+      // pointwise_conv1.weight [2D, D, 1]: rows [0,D) = "a", [D,2D) = gate -> interleave (2c, 2c+1)
+      const HostTensor& pw = c->host[p + "conv_module.pointwise_conv1.weight"];
+      const HostTensor& pb = c->host[p + "conv_module.pointwise_conv1.bias"];
+      PPASR_REQUIRE(pw.numel() == (int64_t)2 * D * D, "pointwise_conv1.weight shape");
+      std::vector<float> wi((size_t)2 * D * D), bi((size_t)2 * D);
+      for (int ch = 0; ch < D; ++ch) {
+        std::memcpy(&wi[(size_t)(2 * ch) * D], &pw.data[(size_t)ch * D], sizeof(float) * D);
+        std::memcpy(&wi[(size_t)(2 * ch + 1) * D], &pw.data[(size_t)(ch + D) * D], sizeof(float) * D);
+        bi[2 * ch] = pb.data[ch];
+        bi[2 * ch + 1] = pb.data[ch + D];
+      }
+      w.pw1 = upload(c, to_bf16(wi));
+      w.pw1_b = upload(c, bi);
+      float* pad = c->wslab.take<float>(D);
+      PPASR_CUDA_CHECK(launch_glu_pad(w.pw1_b, pad, D, 0));
+      w.glu_pad = pad;
+    }
+    {
+      const HostTensor& dw = c->host[p + "conv_module.depthwise_conv.weight"];  // [D,1,K]
+      PPASR_REQUIRE(dw.numel() == (int64_t)D * K, "depthwise_conv.weight shape");
+      w.dw_w = upload(c, dw.data);
+      w.dw_b = vecf(p + "conv_module.depthwise_conv.bias");
+    }
+    if (cfg.conv_norm == 0) {
+      w.cn_g = vecf(p + "conv_module.norm.weight");
+      w.cn_b = vecf(p + "conv_module.norm.bias");
+    } else {
+      // eval-mode BatchNorm1D folded to scale/shift (epsilon 1e-5)
+      const auto& g = c->host[p + "conv_module.norm.weight"].data;
+      const auto& b = c->host[p + "conv_module.norm.bias"].data;
+      const auto& mu = c->host[p + "conv_module.norm._mean"].data;
+      const auto& var = c->host[p + "conv_module.norm._variance"].data;
+      std::vector<float> sc(D), sh(D);
+      for (int i = 0; i < D; ++i) {
+        sc[i] = g[i] / std::sqrt(var[i] + 1e-5f);
+        sh[i] = b[i] - mu[i] * sc[i];
+      }
+      w.cn_g = upload(c, sc);
+      w.cn_b = upload(c, sh);
+    }
+    {
+      const HostTensor& pw = c->host[p + "conv_module.pointwise_conv2.weight"];  // [D, D, 1] = [out, in]
+      PPASR_REQUIRE(pw.numel() == (int64_t)D * D, "pointwise_conv2.weight shape");
+      w.pw2 = upload(c, to_bf16(pw.data));
+      w.pw2_b = vecf(p + "conv_module.pointwise_conv2.bias");
+    }
+    auto& m = c->lmaps[l];
+    bool ok = make_tmap_2d(&m.ffm_w1, w.ffm_w1, D, FF, (uint64_t)D * 2, BN_WIDE, &err) &&
+              make_tmap_2d(&m.ffm_w2, w.ffm_w2, FF, D, (uint64_t)FF * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.ff_w1, w.ff_w1, D, FF, (uint64_t)D * 2, BN_WIDE, &err) &&
+              make_tmap_2d(&m.ff_w2, w.ff_w2, FF, D, (uint64_t)FF * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.wqkv, w.wqkv, D, 3 * D, (uint64_t)D * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.wo, w.wo, D, D, (uint64_t)D * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.pw1, w.pw1, D, 2 * D, (uint64_t)D * 2, BN_WIDE, &err) &&
+              make_tmap_2d(&m.pw2, w.pw2, D, D, (uint64_t)D * 2, BN_NARROW, &err);
+    if (!ok) {
+      set_last_error(err);
+      return PPASR_ERR_CUDA;
+    }
+  }
+  if (!make_tmap_2d(&c->tm_conv2_w, c->conv2_w, (uint64_t)9 * D, D, (uint64_t)9 * D * 2, BN_WIDE, &err) ||
+      !make_tmap_2d(&c->tm_emb_w, c->emb_w, c->Kemb, D, (uint64_t)c->Kemb * 2, BN_NARROW, &err) ||
+      !make_tmap_2d(&c->tm_ctc_w, c->ctc_w, D, c->Vpad, (uint64_t)D * 2, BN_NARROW, &err)) {
+    set_last_error(err);
+    return PPASR_ERR_CUDA;
+  }
+
+  // ---- weight-only precompute: pos_tab[pos, l*D + h*64 + d] = linear_pos_l(pe[pos]) --------------
+  // (reference: conformer/embedding.py:41-53 table, attention.py:234-236 projection; the projection
+  //  of a constant table by a constant matrix is folded here, like BatchNorm folding)
+  {
+    const int ML = cfg.max_len;
+    std::vector<float> pe((size_t)ML * D);
+    for (int pos = 0; pos < ML; ++pos)
+      for (int i = 0; i < D / 2; ++i) {
+        const float div = std::exp((float)(2 * i) * -(std::log(10000.0f) / (float)D));
+        pe[(size_t)pos * D + 2 * i] = std::sin((float)pos * div);
+        pe[(size_t)pos * D + 2 * i + 1] = std::cos((float)pos * div);
+      }
+    const __nv_bfloat16* pe_d = upload(c, to_bf16(pe));
+    const __nv_bfloat16* wpos_d = upload(c, to_bf16(wpos_all));
+    __nv_bfloat16* tab = c->wslab.take<__nv_bfloat16>((size_t)ML * L * D);
+    CUtensorMap ta, tb;
+    if (!make_tmap_2d(&ta, pe_d, D, ML, (uint64_t)D * 2, GEMM_BLOCK_M, &err) ||
+        !make_tmap_2d(&tb, wpos_d, D, (uint64_t)L * D, (uint64_t)D * 2, BN_WIDE, &err) ||
+        !make_tmap_2d(&c->tm_pos, tab, (uint64_t)L * D, ML, (uint64_t)L * D * 2, 128, &err)) {
+      set_last_error(err);
+      return PPASR_ERR_CUDA;
+    }
+    GemmShape s = make_shape(ML, L * D, D, BN_WIDE);
+    EpiStoreBF16<BN_WIDE, ACT_NONE> epi{tab, c->zero_bias, L * D, ML, L * D};
+    PPASR_CUDA_CHECK((launch_gemm<BN_WIDE, ST_WIDE, false>(ta, tb, s, epi, c->sms, 0)));
+    c->pos_tab = tab;
+  }
+  PPASR_CUDA_CHECK(cudaDeviceSynchronize());
+  if (c->wslab.used > c->wslab.cap) {
+    set_last_error("internal error: weight slab overflow");
+    return PPASR_ERR_STATE;
+  }
+  c->host.clear();
+  c->finalized = true;
+  return PPASR_OK;
+}
+
+int ppasr_b200_out_frames(const ppasr_b200_ctx*, int32_t T) {
+  if (T < 7) return 0;
+  return ((T - 1) / 2 - 1) / 2;
+}
+
+}  // extern "C"
+
+namespace {
+
+// (re)builds the activation workspace and A-operand tensor maps for a (B, T) problem
+int build_plan(ppasr_b200_ctx* c, int B, int T) {
+  Plan& p = c->plan;
+  if (p.B == B && p.T == T) return PPASR_OK;
+  const auto& cfg = c->cfg;
+  const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, F = cfg.feat_dim;
+  PPASR_REQUIRE(T >= 7, "need at least 7 feature frames (subsampling right context, predict.py:288)");
+  Plan n;
+  n.B = B, n.T = T;
+  n.T1 = (T - 1) / 2;
+  n.Tp = (n.T1 - 1) / 2;
+  n.Th = (n.T1 + 1) / 2;
+  n.M = B * n.Tp;
+  n.Mr = B * n.Th * c->FH;
+  n.Tkp = (n.Tp + 63) / 64 * 64;
+  PPASR_REQUIRE(n.Tp >= 1 && n.Tp < cfg.max_len, "sequence too long for the positional table (embedding.py:110-112)");
+  const size_t M = n.M;
+  size_t bytes = 0;
+  auto acc = [&](size_t b) { bytes += ((b + 255) & ~size_t(255)) + 256; };
+  acc((size_t)B * T * F * 4);
+  acc(B * 4);
+  acc((size_t)4 * n.Mr * D * 2);
+  acc(M * c->Kemb * 2);
+  acc(M * D * 4);                                   // x
+  acc(M * D * 2 * 4);                               // y, att, g, z
+  acc(M * FF * 2);                                  // h
+  acc((size_t)B * H * n.Tp * 128 * 2);              // q2
+  acc((size_t)B * H * n.Tp * 64 * 2);               // kk
+  acc((size_t)B * H * 64 * n.Tkp * 2);              // vt
+  acc(M * c->Vld * 4);                              // logits
+  acc(M * (size_t)cfg.vocab_size * 4);              // probs
+  acc(M * c->ctc_parts * 4 * 3);                    // partial stats
+  acc(M * 4 * 3 + (size_t)B * 4 * 3);
+  bytes += 1u << 20;
+  if (bytes > c->aslab.cap) {
+    PPASR_CUDA_CHECK(cudaDeviceSynchronize());
+    PPASR_CUDA_CHECK(c->aslab.reserve(bytes));
+    // q2/kk/vt padding regions must be finite for masked-out MMA operands
+    PPASR_CUDA_CHECK(cudaMemset(c->aslab.base, 0, c->aslab.cap));
+  }
+  c->aslab.used = 0;
+  auto& a = c->aslab;
+  n.feats = a.take<float>((size_t)B * T * F);
+  n.vlen = a.take<int>(B);
+  n.phase = a.take<__nv_bfloat16>((size_t)4 * n.Mr * D);
+  n.c2 = a.take<__nv_bfloat16>(M * c->Kemb);
+  n.x = a.take<float>(M * D);
+  n.y = a.take<__nv_bfloat16>(M * D);
+  n.att = a.take<__nv_bfloat16>(M * D);
+  n.g = a.take<__nv_bfloat16>(M * D);
+  n.z = a.take<__nv_bfloat16>(M * D);
+  n.h = a.take<__nv_bfloat16>(M * FF);
+  n.q2 = a.take<__nv_bfloat16>((size_t)B * H * n.Tp * 128);
+  n.kk = a.take<__nv_bfloat16>((size_t)B * H * n.Tp * 64);
+  n.vt = a.take<__nv_bfloat16>((size_t)B * H * 64 * n.Tkp);
+  n.logits = a.take<float>(M * c->Vld);
+  n.probs = a.take<float>(M * (size_t)cfg.vocab_size);
+  n.pmax = a.take<float>(M * c->ctc_parts);
+  n.psum = a.take<float>(M * c->ctc_parts);
+  n.parg = a.take<int>(M * c->ctc_parts);
+  n.idx = a.take<int>(M);
+  n.maxp = a.take<float>(M);
+  n.ids = a.take<int>(M);
+  n.out_len = a.take<int>(B);
+  n.score = a.take<float>(B);
+  if (a.used > a.cap) {
+    set_last_error("internal error: activation slab overflow");
+    return PPASR_ERR_STATE;
+  }
+  std::string err;
+  bool ok = make_tmap_3d(&n.tm_phase, n.phase, D, n.Mr, 4, (uint64_t)D * 2, (uint64_t)n.Mr * D * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_c2, n.c2, c->Kemb, M, (uint64_t)c->Kemb * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_y, n.y, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_h, n.h, FF, M, (uint64_t)FF * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_att, n.att, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_g, n.g, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_z, n.z, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_q, n.q2, 128, (uint64_t)B * H * n.Tp, 256, 128, &err) &&
+            make_tmap_2d(&n.tm_k, n.kk, 64, (uint64_t)B * H * n.Tp, 128, 128, &err) &&
+            make_tmap_2d(&n.tm_vt, n.vt, n.Tp, (uint64_t)B * H * 64, (uint64_t)n.Tkp * 2, 64, &err);
+  if (!ok) {
+    set_last_error(err);
+    return PPASR_ERR_CUDA;
+  }
+  p = n;
+  return PPASR_OK;
+}
+
+template <int BN, int ST, class Epi>
+cudaError_t gemm(ppasr_b200_ctx* c, const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K, const Epi& epi,
+                 cudaStream_t st) {
+  GemmShape s = make_shape(M, N, K, BN);
+  return launch_gemm<BN, ST, false>(a, b, s, epi, c->sms, st);
+}
+
+int run_encoder(ppasr_b200_ctx* c, cudaStream_t st) {
+  Plan& p = c->plan;
+  const auto& cfg = c->cfg;
+  const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, L = cfg.n_layers, M = p.M;
+  const float eps = 1e-5f;
+  // CMVN + conv1 + ReLU -> stride-phase images
+  PPASR_CUDA_CHECK(launch_conv1_subsample(p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.phase, p.B,
+                                          p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st));
+  // conv2 + ReLU as 9 shifted GEMM taps -> c2 [M, F2*D]
+  {
+    GemmShape s = make_shape(p.Mr, D, 9 * D, BN_WIDE);
+    s.conv_pitch = c->FH;
+    s.conv_kc = D / GEMM_BLOCK_K;
+    EpiConv2<BN_WIDE> epi{p.c2, c->conv2_b, p.Mr, D, p.Th, c->FH, p.Tp, c->F2};
+    PPASR_CUDA_CHECK((launch_gemm<BN_WIDE, ST_WIDE, true>(p.tm_phase, c->tm_conv2_w, s, epi, c->sms, st)));
+  }
+  // Linear(F2*D -> D) then x * sqrt(D)   (subsampling.py:113, embedding.py:113)
+  {
+    EpiResidF32<BN_NARROW> epi{p.x, c->emb_b, D, M, D, std::sqrt((float)D), 0, nullptr, p.Tp};
+    PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_c2, c->tm_emb_w, M, D, c->Kemb, epi, st)));
+  }
+  PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, c->layers[0].ln_ffm_g, c->layers[0].ln_ffm_b, nullptr, nullptr, nullptr,
+                                    p.Tp, M, D, eps, st));
+  for (int l = 0; l < L; ++l) {
+    const LayerW& w = c->layers[l];
+    const auto& m = c->lmaps[l];
+    // ---- macaron FFN: x += 0.5 * W2 swish(W1 LN(x))           (encoder.py:380-386)
+    {
+      EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ffm_b1, FF, M, FF};
+      PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ffm_w1, M, FF, D, e1, st)));
+      EpiResidF32<BN_NARROW> e2{p.x, w.ffm_b2, D, M, D, 0.5f, 1, nullptr, p.Tp};
+      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ffm_w2, M, D, FF, e2, st)));
+    }
+    // ---- rel-pos MHA: x += Wo attn(LN(x))                      (encoder.py:389-402)
+    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st));
+    {
+      EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
+      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st)));
+      AttnParams ap;
+      ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.T2 = p.Tp, ap.q_rows_per_bh = p.Tp, ap.k_rows_per_bh = p.Tp;
+      ap.pos_row0 = 0, ap.pos_col0 = l * D, ap.D = D, ap.klens = p.vlen, ap.out = p.att;
+      PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st));
+      EpiResidF32<BN_NARROW> eo{p.x, w.bo, D, M, D, 1.0f, 1, nullptr, p.Tp};
+      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_att, m.wo, M, D, D, eo, st)));
+    }
+    // ---- conv module: x += mask * pw2 swish(norm(dw(glu(pw1(mask * LN(x))))))   (encoder.py:407-416)
+    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, p.vlen, p.Tp, M, D, eps, st));
+    {
+      EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, M, 2 * D};
+      PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st)));
+      const int K = cfg.conv_kernel;
+      const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
+      PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
+                                                cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, st));
+      EpiResidF32<BN_NARROW> e2{p.x, w.pw2_b, D, M, D, 1.0f, 1, p.vlen, p.Tp};
+      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_z, m.pw2, M, D, D, e2, st)));
+    }
+    // ---- FFN: x += 0.5 * W2 swish(W1 LN(x))                    (encoder.py:419-426)
+    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st));
+    {
+      EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ff_b1, FF, M, FF};
+      PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st)));
+      EpiResidF32<BN_NARROW> e2{p.x, w.ff_b2, D, M, D, 0.5f, 1, nullptr, p.Tp};
+      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ff_w2, M, D, FF, e2, st)));
+    }
+    // ---- x = norm_final(x); y = next block's first LayerNorm (or after_norm)   (encoder.py:428-429, 201-202)
+    const float* g2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_g : c->after_g;
+    const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
+    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_fin_g, w.ln_fin_b, g2, b2, nullptr, p.Tp, M, D, eps, st));
+  }
+  return PPASR_OK;
+}
+
+int copy_out(void* dst, const void* src_dev, size_t bytes, int on_device, cudaStream_t st) {
+  if (!dst) return PPASR_OK;
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(dst, src_dev, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  return PPASR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_device, const int64_t* lens_host,
+                      int32_t B, int32_t T, void* stream) {
+  PPASR_REQUIRE(c && feats && B > 0 && T > 0, "bad arguments");
+  if (!c->finalized) {
+    set_last_error("ppasr_b200_finalize has not been called");
+    return PPASR_ERR_STATE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(c, B, T);
+  if (rc != PPASR_OK) return rc;
+  Plan& p = c->plan;
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(p.feats, feats, (size_t)B * T * c->cfg.feat_dim * sizeof(float),
+                                   feats_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  // valid subsampled frames: mask[:, :, :-2:2][:, :, :-2:2] keeps frame j iff 4*j < len (subsampling.py:115)
+  std::vector<int> vlen(B);
+  for (int b = 0; b < B; ++b) {
+    const int64_t len = lens_host ? lens_host[b] : T;
+    int64_t v = (len + 3) / 4;
+    if (v > p.Tp) v = p.Tp;
+    if (v < 0) v = 0;
+    vlen[b] = (int)v;
+  }
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  return run_encoder(c, st);
+}
+
+static int run_ctc_logits(ppasr_b200_ctx* c, cudaStream_t st) {
+  Plan& p = c->plan;
+  EpiLogitsF32<BN_NARROW> e{p.logits, c->ctc_b, c->Vld, p.M, c->cfg.vocab_size};
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, c->cfg.vocab_size, c->cfg.d_model, e, st)));
+  return PPASR_OK;
+}
+
+int ppasr_b200_ctc_logits(ppasr_b200_ctx* c, float* logits, int32_t on_device, void* stream) {
+  PPASR_REQUIRE(c && logits && c->plan.M > 0, "encode first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = run_ctc_logits(c, st);
+  if (rc) return rc;
+  Plan& p = c->plan;
+  PPASR_CUDA_CHECK(cudaMemcpy2DAsync(logits, (size_t)c->cfg.vocab_size * 4, p.logits, (size_t)c->Vld * 4,
+                                     (size_t)c->cfg.vocab_size * 4, p.M,
+                                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!on_device) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
+  return PPASR_OK;
+}
+
+int ppasr_b200_ctc_probs(ppasr_b200_ctx* c, float* probs, int32_t probs_on_device, void* stream) {
+  PPASR_REQUIRE(c && probs && c->plan.M > 0, "encode first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = run_ctc_logits(c, st);
+  if (rc) return rc;
+  Plan& p = c->plan;
+  float* dst = probs_on_device ? probs : p.probs;
+  PPASR_CUDA_CHECK(launch_softmax_rows(p.logits, c->Vld, dst, p.M, c->cfg.vocab_size, st));
+  if (!probs_on_device) {
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(probs, p.probs, (size_t)p.M * c->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, st));
+    PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return PPASR_OK;
+}
+
+int ppasr_b200_ctc_greedy(ppasr_b200_ctx* c, int32_t* ids, int32_t* out_lens, float* scores, int32_t* frame_ids,
+                          float* frame_probs, int32_t outputs_on_device, int32_t trim_to_lens, int32_t blank_id,
+                          void* stream) {
+  PPASR_REQUIRE(c && c->plan.M > 0, "encode first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Plan& p = c->plan;
+  const int V = c->cfg.vocab_size;
+  EpiCtcStats<BN_NARROW> e{p.pmax, p.parg, p.psum, c->ctc_b, p.M, V, c->ctc_parts};
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, V, c->cfg.d_model, e, st)));
+  PPASR_CUDA_CHECK(launch_ctc_stats_finalize(p.pmax, p.parg, p.psum, c->ctc_parts, p.M, p.idx, p.maxp, st));
+  PPASR_CUDA_CHECK(launch_ctc_collapse(p.idx, p.maxp, p.B, p.Tp, trim_to_lens ? p.vlen : nullptr, blank_id, p.ids, p.Tp,
+                                       p.out_len, p.score, nullptr, nullptr, st));
+  int rc;
+  if ((rc = copy_out(ids, p.ids, (size_t)p.M * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(out_lens, p.out_len, (size_t)p.B * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(scores, p.score, (size_t)p.B * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(frame_ids, p.idx, (size_t)p.M * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(frame_probs, p.maxp, (size_t)p.M * 4, outputs_on_device, st))) return rc;
+  if (!outputs_on_device) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
+  return PPASR_OK;
+}
+
+int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens,
+                             int32_t blank_id, int32_t* ids, int32_t ld_ids, int32_t* out_lens, float* scores,
+                             int32_t* tmp_idx, float* tmp_maxp, void* stream) {
+  PPASR_REQUIRE(probs && ids && out_lens && scores && tmp_idx && tmp_maxp, "null pointer");
+  PPASR_REQUIRE(B > 0 && T > 0 && V > 0 && ld_ids >= T, "bad sizes");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PPASR_CUDA_CHECK(launch_argmax_rows(probs, V, B * T, tmp_idx, tmp_maxp, st));
+  PPASR_CUDA_CHECK(launch_ctc_collapse(tmp_idx, tmp_maxp, B, T, frame_lens, blank_id, ids, ld_ids, out_lens, scores,
+                                       nullptr, nullptr, st));
+  return PPASR_OK;
+}
+
+int ppasr_b200_debug_copy_x(ppasr_b200_ctx* c, float* dst_device, void* stream) {
+  PPASR_REQUIRE(c && dst_device && c->plan.M > 0, "encode first");
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(dst_device, c->plan.x, (size_t)c->plan.M * c->cfg.d_model * 4,
+                                   cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+// ---- op-level wrappers ------------------------------------------------------------------------
+int ppasr_b200_op_layernorm(float* x, void* y_bf16, const float* g1, const float* b1, const float* g2,
+                            const float* b2, const int32_t* lens, int32_t T, int32_t M, int32_t D, float eps,
+                            void* stream) {
+  PPASR_REQUIRE(x && y_bf16 && g1 && b1, "null pointer");
+  PPASR_CUDA_CHECK(launch_layernorm(x, (__nv_bfloat16*)y_bf16, g1, b1, g2, b2, lens, T, M, D, eps,
+                                    reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+int ppasr_b200_op_dwconv(const void* g_bf16, const float* w, const float* bias, const float* pad_left,
+                         const float* gamma, const float* beta, int32_t use_layer_norm, void* out_bf16, int32_t B,
+                         int32_t Tin, int32_t Tout, int32_t C, int32_t K, int32_t lpad, float eps, void* stream) {
+  PPASR_REQUIRE(g_bf16 && w && bias && gamma && beta && out_bf16, "null pointer");
+  PPASR_CUDA_CHECK(launch_dwconv_norm_swish((const __nv_bfloat16*)g_bf16, w, bias, pad_left, gamma, beta, use_layer_norm,
+                                            (__nv_bfloat16*)out_bf16, B, Tin, Tout, C, K, lpad, eps,
+                                            reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+int ppasr_b200_op_softmax(const float* logits, int32_t ldl, float* probs, int32_t M, int32_t V, void* stream) {
+  PPASR_REQUIRE(logits && probs, "null pointer");
+  PPASR_CUDA_CHECK(launch_softmax_rows(logits, ldl, probs, M, V, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int32_t T2p, const void* pos,
+                            int32_t pos_rows, int32_t pos_ld, int32_t pos_row0, int32_t pos_col0, void* out,
+                            int32_t B, int32_t H, int32_t T1, int32_t T2, const int32_t* klens, void* stream) {
+  PPASR_REQUIRE(q2 && kk && vt && pos && out, "null pointer");
+  PPASR_REQUIRE(T2p % 8 == 0 && T2p >= T2 && pos_ld % 8 == 0, "T2p / pos_ld must be multiples of 8");
+  std::string err;
+  CUtensorMap tq, tk, tp, tv;
+  if (!make_tmap_2d(&tq, q2, 128, (uint64_t)B * H * T1, 256, 128, &err) ||
+      !make_tmap_2d(&tk, kk, 64, (uint64_t)B * H * T2, 128, 128, &err) ||
+      !make_tmap_2d(&tp, pos, pos_ld, pos_rows, (uint64_t)pos_ld * 2, 128, &err) ||
+      !make_tmap_2d(&tv, vt, T2, (uint64_t)B * H * 64, (uint64_t)T2p * 2, 64, &err)) {
+    set_last_error(err);
+    return PPASR_ERR_CUDA;
+  }
+  AttnParams ap;
+  ap.B = B, ap.H = H, ap.T1 = T1, ap.T2 = T2, ap.q_rows_per_bh = T1, ap.k_rows_per_bh = T2;
+  ap.pos_row0 = pos_row0, ap.pos_col0 = pos_col0, ap.D = H * 64, ap.klens = klens, ap.out = (__nv_bfloat16*)out;
+  PPASR_CUDA_CHECK(launch_rel_attention(tq, tk, tp, tv, ap, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+}  // extern "C"

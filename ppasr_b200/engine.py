@@ -1,0 +1,139 @@
+"""Thin Python handle over the C-ABI context (include/ppasr_b200.h).
+
+torch is used only as a container for device memory and for streams; all compute happens in
+libppasr_b200.so. There is no CPU path: constructing an engine without a B200 raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+from .weights import ConformerConfig
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("model_type", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("d_model", ctypes.c_int32),
+                ("n_heads", ctypes.c_int32), ("ffn_dim", ctypes.c_int32), ("n_layers", ctypes.c_int32),
+                ("conv_kernel", ctypes.c_int32), ("causal", ctypes.c_int32), ("conv_norm", ctypes.c_int32),
+                ("vocab_size", ctypes.c_int32), ("max_len", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5)]
+
+
+def out_frames(T: int) -> int:
+    """Encoder output frames for T fbank frames (two k3/s2 convs, conformer/subsampling.py:96-115)."""
+    return ((T - 1) // 2 - 1) // 2 if T >= 7 else 0
+
+
+class ConformerEngine:
+    """Owns one ppasr_b200_ctx: packed weights, workspace and (later) streaming caches."""
+
+    def __init__(self, cfg: ConformerConfig, weights, device: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise L.PPASRB200Error("ppasr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.lib = L.load()
+        c = Config()
+        c.model_type = 0
+        c.feat_dim = cfg.input_dim
+        c.d_model = cfg.output_size
+        c.n_heads = cfg.attention_heads
+        c.ffn_dim = cfg.linear_units
+        c.n_layers = cfg.num_blocks
+        c.conv_kernel = cfg.cnn_module_kernel
+        c.causal = int(cfg.causal)
+        c.conv_norm = 0 if cfg.cnn_module_norm == "layer_norm" else 1
+        c.vocab_size = cfg.vocab_size
+        c.max_len = cfg.max_len
+        self._ctx = ctypes.c_void_p()
+        L.check(self.lib.ppasr_b200_create(ctypes.byref(c), ctypes.byref(self._ctx)))
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            L.check(self.lib.ppasr_b200_load_tensor(self._ctx, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                    a.ndim, shape))
+        L.check(self.lib.ppasr_b200_finalize(self._ctx))
+        self.B = 0
+        self.Tp = 0
+
+    def close(self):
+        if self._ctx:
+            self.lib.ppasr_b200_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------------
+    def encode(self, feats, lens=None, stream=None):
+        """feats: float32 [B,T,F], torch CUDA tensor or host numpy/torch tensor. lens: int64 [B] (host)."""
+        torch = self.torch
+        if isinstance(feats, np.ndarray):
+            feats = np.ascontiguousarray(feats, dtype=np.float32)
+            B, T, _ = feats.shape
+            ptr, on_dev = ctypes.c_void_p(feats.ctypes.data), 0
+        else:
+            feats = feats.contiguous()
+            assert feats.dtype == torch.float32
+            B, T, _ = feats.shape
+            ptr, on_dev = ctypes.c_void_p(feats.data_ptr()), int(feats.is_cuda)
+        lens_p = None
+        if lens is not None:
+            lens = np.ascontiguousarray(np.asarray(lens), dtype=np.int64)
+            lens_p = ctypes.c_void_p(lens.ctypes.data)
+        L.check(self.lib.ppasr_b200_encode(self._ctx, ptr, on_dev, lens_p, B, T, L.stream_ptr(stream)))
+        self.B, self.Tp = B, out_frames(T)
+        return self
+
+    def ctc_probs(self, to_host=False, stream=None):
+        torch = self.torch
+        V = self.cfg.vocab_size
+        if to_host:
+            out = np.empty((self.B, self.Tp, V), dtype=np.float32)
+            L.check(self.lib.ppasr_b200_ctc_probs(self._ctx, ctypes.c_void_p(out.ctypes.data), 0, L.stream_ptr(stream)))
+            return out
+        out = torch.empty((self.B, self.Tp, V), dtype=torch.float32, device=self.device)
+        L.check(self.lib.ppasr_b200_ctc_probs(self._ctx, L.ptr(out), 1, L.stream_ptr(stream)))
+        return out
+
+    def ctc_logits(self, stream=None):
+        torch = self.torch
+        out = torch.empty((self.B, self.Tp, self.cfg.vocab_size), dtype=torch.float32, device=self.device)
+        L.check(self.lib.ppasr_b200_ctc_logits(self._ctx, L.ptr(out), 1, L.stream_ptr(stream)))
+        return out
+
+    def ctc_greedy(self, to_host=True, trim_to_lens=False, blank_id=0, with_frames=False, stream=None):
+        """Fused CTC head + greedy decode. Returns (ids [B,T'], out_lens [B], scores [B][, frame_ids, frame_probs])."""
+        torch = self.torch
+        B, Tp = self.B, self.Tp
+        if to_host:
+            ids = np.empty((B, Tp), dtype=np.int32)
+            ol = np.empty((B,), dtype=np.int32)
+            sc = np.empty((B,), dtype=np.float32)
+            fi = np.empty((B, Tp), dtype=np.int32) if with_frames else None
+            fp = np.empty((B, Tp), dtype=np.float32) if with_frames else None
+            p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+            L.check(self.lib.ppasr_b200_ctc_greedy(self._ctx, p(ids), p(ol), p(sc), p(fi), p(fp), 0,
+                                                   int(trim_to_lens), blank_id, L.stream_ptr(stream)))
+        else:
+            ids = torch.empty((B, Tp), dtype=torch.int32, device=self.device)
+            ol = torch.empty((B,), dtype=torch.int32, device=self.device)
+            sc = torch.empty((B,), dtype=torch.float32, device=self.device)
+            fi = torch.empty((B, Tp), dtype=torch.int32, device=self.device) if with_frames else None
+            fp = torch.empty((B, Tp), dtype=torch.float32, device=self.device) if with_frames else None
+            L.check(self.lib.ppasr_b200_ctc_greedy(self._ctx, L.ptr(ids), L.ptr(ol), L.ptr(sc), L.ptr(fi), L.ptr(fp), 1,
+                                                   int(trim_to_lens), blank_id, L.stream_ptr(stream)))
+        if with_frames:
+            return ids, ol, sc, fi, fp
+        return ids, ol, sc
+
+    def debug_x(self):
+        torch = self.torch
+        out = torch.empty((self.B * self.Tp, self.cfg.output_size), dtype=torch.float32, device=self.device)
+        L.check(self.lib.ppasr_b200_debug_copy_x(self._ctx, L.ptr(out), L.stream_ptr()))
+        return out

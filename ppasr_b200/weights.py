@@ -1,0 +1,200 @@
+"""Parameter containers for the hot path: synthetic initialisation and file I/O.
+
+Parameters are kept as a dict  name -> float32 numpy array  using the reference's own (Paddle)
+parameter names and layouts (`Linear.weight` is [in, out], `Conv*.weight` is [out, in/groups, k...];
+SURVEY.md Appendix A), i.e. exactly what `paddle.load("model.pdparams")` yields after `.numpy()`.
+The C library repacks them (ppasr_b200_finalize).
+
+No pretrained PPASR weights are reachable offline, so tests and the benchmark use seeded synthetic
+weights drawn with the reference's initialisers (ppasr/model_utils/utils/base.py:58-138: Kaiming-uniform
+with negative_slope sqrt(5) => U(-1/sqrt(fan_in), 1/sqrt(fan_in)); LayerNorm 1/0; pos_bias_u/v
+Xavier-uniform, conformer/attention.py:193-196). The CTC projection is scaled by `ctc_gain` so the
+posteriors are peaked (arg-max margins far above bf16 noise), as documented in SURVEY.md §8d.
+"""
+import json
+import math
+import os
+import pickle
+from typing import Dict
+
+import numpy as np
+
+
+class ConformerConfig:
+    """Inference-relevant keys of configs/conformer.yml (`encoder_conf`, `streaming`, n_mels)."""
+
+    def __init__(self, input_dim=80, vocab_size=4233, output_size=256, attention_heads=4, linear_units=2048,
+                 num_blocks=12, cnn_module_kernel=15, streaming=True, cnn_module_norm="layer_norm", max_len=5000,
+                 **_ignored):
+        self.input_dim = int(input_dim)
+        self.vocab_size = int(vocab_size)
+        self.output_size = int(output_size)
+        self.attention_heads = int(attention_heads)
+        self.linear_units = int(linear_units)
+        self.num_blocks = int(num_blocks)
+        self.cnn_module_kernel = int(cnn_module_kernel)
+        self.streaming = bool(streaming)
+        self.causal = bool(streaming)            # conformer/model.py:35-39
+        self.use_dynamic_chunk = bool(streaming)
+        self.cnn_module_norm = cnn_module_norm
+        self.max_len = int(max_len)
+
+    def to_dict(self):
+        return dict(input_dim=self.input_dim, vocab_size=self.vocab_size, output_size=self.output_size,
+                    attention_heads=self.attention_heads, linear_units=self.linear_units,
+                    num_blocks=self.num_blocks, cnn_module_kernel=self.cnn_module_kernel, streaming=self.streaming,
+                    cnn_module_norm=self.cnn_module_norm, max_len=self.max_len)
+
+
+def conformer_param_shapes(cfg: ConformerConfig) -> Dict[str, tuple]:
+    D, FF, K, V, F = cfg.output_size, cfg.linear_units, cfg.cnn_module_kernel, cfg.vocab_size, cfg.input_dim
+    H = cfg.attention_heads
+    f2 = ((F - 1) // 2 - 1) // 2
+    s = {
+        "encoder.global_cmvn.mean": (F,), "encoder.global_cmvn.istd": (F,),
+        "encoder.embed.conv.0.weight": (D, 1, 3, 3), "encoder.embed.conv.0.bias": (D,),
+        "encoder.embed.conv.2.weight": (D, D, 3, 3), "encoder.embed.conv.2.bias": (D,),
+        "encoder.embed.out.0.weight": (D * f2, D), "encoder.embed.out.0.bias": (D,),
+        "encoder.after_norm.weight": (D,), "encoder.after_norm.bias": (D,),
+        "ctc.ctc_lo.weight": (D, V), "ctc.ctc_lo.bias": (V,),
+    }
+    for i in range(cfg.num_blocks):
+        p = f"encoder.encoders.{i}."
+        for n in ("norm_ff_macaron", "norm_mha", "norm_conv", "norm_ff", "norm_final"):
+            s[p + n + ".weight"] = (D,)
+            s[p + n + ".bias"] = (D,)
+        for n in ("feed_forward_macaron", "feed_forward"):
+            s[p + n + ".w_1.weight"] = (D, FF)
+            s[p + n + ".w_1.bias"] = (FF,)
+            s[p + n + ".w_2.weight"] = (FF, D)
+            s[p + n + ".w_2.bias"] = (D,)
+        for n in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            s[p + f"self_attn.{n}.weight"] = (D, D)
+            s[p + f"self_attn.{n}.bias"] = (D,)
+        s[p + "self_attn.linear_pos.weight"] = (D, D)
+        s[p + "self_attn.pos_bias_u"] = (H, D // H)
+        s[p + "self_attn.pos_bias_v"] = (H, D // H)
+        s[p + "conv_module.pointwise_conv1.weight"] = (2 * D, D, 1)
+        s[p + "conv_module.pointwise_conv1.bias"] = (2 * D,)
+        s[p + "conv_module.depthwise_conv.weight"] = (D, 1, K)
+        s[p + "conv_module.depthwise_conv.bias"] = (D,)
+        s[p + "conv_module.norm.weight"] = (D,)
+        s[p + "conv_module.norm.bias"] = (D,)
+        if cfg.cnn_module_norm == "batch_norm":
+            s[p + "conv_module.norm._mean"] = (D,)
+            s[p + "conv_module.norm._variance"] = (D,)
+        s[p + "conv_module.pointwise_conv2.weight"] = (D, D, 1)
+        s[p + "conv_module.pointwise_conv2.bias"] = (D,)
+    return s
+
+
+def _fan_in(name, shape):
+    if len(shape) == 1:
+        return shape[0]
+    if len(shape) == 2:  # Paddle Linear [in, out]
+        return shape[0]
+    return int(np.prod(shape[1:]))  # conv [out, in/groups, k...]
+
+
+def init_conformer_weights(cfg: ConformerConfig, seed: int = 1000, ctc_gain: float = 8.0,
+                           perturb_norms: bool = True) -> Dict[str, np.ndarray]:
+    """Seeded synthetic parameters (seed 1000 mirrors ppasr/trainer.py:518).
+
+    perturb_norms: LayerNorm gains/biases are 1/0 at initialisation in the reference; a trained model has
+    non-trivial values, so by default they are perturbed (gain U(0.8,1.2), bias U(-0.1,0.1)) to make the
+    parity tests sensitive to them."""
+    rng = np.random.RandomState(seed)
+    w = {}
+    for name, shape in conformer_param_shapes(cfg).items():
+        if name.endswith("global_cmvn.mean"):
+            a = rng.uniform(-1.0, 1.0, shape) + 10.0  # fbank log-mel energies sit around 5..15
+        elif name.endswith("global_cmvn.istd"):
+            a = rng.uniform(0.2, 0.5, shape)
+        elif ".norm" in name and name.endswith("_mean"):
+            a = rng.uniform(-0.1, 0.1, shape)
+        elif ".norm" in name and name.endswith("_variance"):
+            a = rng.uniform(0.5, 1.5, shape)
+        elif ("norm" in name.split(".")[-2]) and name.endswith(".weight"):
+            a = rng.uniform(0.8, 1.2, shape) if perturb_norms else np.ones(shape)
+        elif ("norm" in name.split(".")[-2]) and name.endswith(".bias"):
+            a = rng.uniform(-0.1, 0.1, shape) if perturb_norms else np.zeros(shape)
+        elif name.endswith("pos_bias_u") or name.endswith("pos_bias_v"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            a = rng.uniform(-lim, lim, shape)
+        elif name.startswith("ctc.ctc_lo"):
+            if name.endswith("weight"):  # paddle.nn.Linear default: Xavier-uniform, zero bias
+                lim = math.sqrt(6.0 / (shape[0] + shape[1])) * ctc_gain
+                a = rng.uniform(-lim, lim, shape)
+            else:
+                a = np.zeros(shape)
+        else:
+            lim = 1.0 / math.sqrt(_fan_in(name, shape))
+            a = rng.uniform(-lim, lim, shape)
+        w[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return w
+
+
+def save_npz(path: str, weights: Dict[str, np.ndarray], cfg: ConformerConfig = None):
+    extra = {}
+    if cfg is not None:
+        extra["__config_json__"] = np.frombuffer(json.dumps(cfg.to_dict()).encode(), dtype=np.uint8)
+    np.savez(path, **weights, **extra)
+
+
+def load_npz(path: str):
+    z = np.load(path)
+    cfg = None
+    w = {}
+    for k in z.files:
+        if k == "__config_json__":
+            cfg = ConformerConfig(**json.loads(bytes(z[k]).decode()))
+        else:
+            w[k] = np.asarray(z[k], dtype=np.float32)
+    return w, cfg
+
+
+def load_pdparams(path: str) -> Dict[str, np.ndarray]:
+    """`model.pdparams` as written by paddle.save (ppasr/trainer.py:311): a pickle of name -> ndarray
+    (Paddle >= 2.1 stores plain numpy arrays; tuples (name, ndarray) from older versions are unwrapped)."""
+    with open(path, "rb") as f:
+        obj = pickle.load(f, encoding="latin1")
+    out = {}
+    for k, v in obj.items():
+        if isinstance(v, tuple) and len(v) == 2:
+            v = v[1]
+        if isinstance(v, np.ndarray):
+            out[k] = np.asarray(v, dtype=np.float32)
+    return out
+
+
+def make_vocab(vocab_size: int):
+    """Synthetic vocabulary in the reference's order (ppasr/trainer.py:479-487): <blank>, <unk>, chars, <eos>."""
+    chars = [chr(0x4E00 + i) for i in range(vocab_size - 3)]
+    return ["<blank>", "<unk>"] + chars + ["<eos>"]
+
+
+def read_vocab_file(path: str):
+    """ppasr/data_utils/featurizer/text_featurizer.py:52-59: one `token\\tcount` per line."""
+    with open(path, "r", encoding="utf-8") as f:
+        return [line.split("\t")[0].replace("\n", "") for line in f.readlines()]
+
+
+def read_mean_istd(path: str, eps: float = 1e-20):
+    """ppasr/data_utils/normalizer.py:27-41."""
+    with open(path, "r", encoding="utf-8") as f:
+        data = json.load(f)
+    mean = np.array(data["mean"], dtype=np.float32)
+    istd = np.maximum(np.array(data["istd"], dtype=np.float32), eps)
+    return mean, istd
+
+
+def synthetic_fbank(batch: int, frames: int, n_mels: int = 80, seed: int = 1234) -> np.ndarray:
+    """Seeded stand-in for kaldi fbank features of 16 kHz audio (log-mel energies, roughly 5..15 with
+    temporal and spectral correlation). Shapes follow audio_featurizer.py:125-136: frames = 1 + (N-400)//160."""
+    rng = np.random.RandomState(seed)
+    t = np.arange(frames, dtype=np.float32)[None, :, None]
+    f = np.arange(n_mels, dtype=np.float32)[None, None, :]
+    phase = rng.uniform(0, 2 * np.pi, (batch, 1, 1)).astype(np.float32)
+    x = 10.0 + 2.0 * np.sin(0.05 * t + phase) * np.cos(0.11 * f + phase) + 1.5 * np.sin(0.31 * t + 0.07 * f)
+    x = x + rng.normal(0.0, 1.0, (batch, frames, n_mels))
+    return np.ascontiguousarray(x, dtype=np.float32)
