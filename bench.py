@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native PPASR hot path (contract: see the task statement / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1]): conformer.yml streaming model, batch 32 x 10 s synthetic fbank
+([32, 998, 80] fp32) per GPU, fused CTC head + ctc_greedy. A "step" = one pass of the hot path over one
+batch: encoder forward -> CTC projection -> greedy decode (-> one NCCL all-gather of the decoded ids
+when N > 1). Weak scaling: every GPU processes its own 32 utterances.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (torchrun for N > 1)
+  python bench.py --impl reference [--steps K] [--warmup W]      # CPU reference arm (oracle port, all host threads)
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 32
+SECONDS = 10
+FRAMES = 1 + (16000 * SECONDS - 400) // 160  # 998 (kaldi snip-edges, audio_featurizer.py:125-136)
+VOCAB = 4233
+GFLOP_PER_UTT = 23.17  # SURVEY.md §8d algorithmic FLOPs of the conformer path at 10 s
+METRIC = "utterances_per_sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit and (r & bit):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_step(orc, feats, lens, vocab):
+    """One pass of the reference-equivalent CPU path (oracle restatement; Paddle is not installable here):
+    get_encoder_out -> greedy_decoder_batch."""
+    import torch
+    from oracle import decoders_oracle as DO
+    probs = orc.get_encoder_out(torch.from_numpy(feats), torch.tensor(lens))
+    return DO.greedy_decoder_batch([p for p in probs.numpy()], vocab)
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.conformer_oracle import ConformerConf, ConformerOracle
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab, synthetic_fbank
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ConformerConfig(vocab_size=VOCAB)
+    w = init_conformer_weights(cfg)
+    orc = ConformerOracle(ConformerConf(**cfg.to_dict()), w)
+    vocab = make_vocab(VOCAB)
+    sample_b = 8  # bounded sample of the 32-utterance batch per step
+    feats = synthetic_fbank(sample_b, FRAMES)
+    lens = [FRAMES] * sample_b
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_step(orc, feats, lens, vocab)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(orc, feats, lens, vocab)
+    dt = (time.perf_counter() - t0) / steps
+    value = sample_b / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (BATCH_PER_GPU / sample_b), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "conformer-streaming b32x10s fbank[32,998,80] ctc_greedy (BASELINE configs[1])",
+                   "rtf": dt / (sample_b * SECONDS)},
+        "cpu_baseline": {"value": value, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample_b} of 32 utterances x 10 s per step, PyTorch-CPU fp32 oracle restatement "
+                                   "of the reference Paddle graph + reference greedy restatement (Paddle not installable)"},
+        "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ppasr_b200 import _lib as L
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.parallel import all_gather_results, detokenize
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab, synthetic_fbank
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    cfg = ConformerConfig(vocab_size=VOCAB)
+    weights = init_conformer_weights(cfg)
+    vocab = make_vocab(VOCAB)
+    configs = {"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}
+    pred = InferencePredictor(configs, "conformer", streaming=True, weights=weights, device=local_rank)
+    eng = pred.engine
+    lib = L.load()
+
+    B = BATCH_PER_GPU
+    total_utts = B * world
+    feats_host = torch.from_numpy(synthetic_fbank(B, FRAMES, seed=1234 + rank)).pin_memory()
+    feats_dev = feats_host.to(dev)
+    Tp = eng.encode(feats_dev).Tp
+    lmax = Tp
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        eng.encode(feats_dev)
+        ids, ol, sc = eng.ctc_greedy(to_host=False)
+        if world > 1:
+            ids, ol, sc = all_gather_results(ids, ol, sc, total_utts, lmax)
+        return ids, ol, sc
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = lib.ppasr_b200_launch_count()
+    for k in range(K):
+        flush.zero_()  # L2 flush between timed iterations (not inside the timed events)
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    launches1 = lib.ppasr_b200_launch_count()
+    sampler.stop_flag = True
+    if world > 1:
+        dist.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total_utts / (ms * 1e-3)
+
+    # ---- e2e through the public API with host buffers (H2D of the features, D2H of ids/lens/scores) ----
+    def e2e_step():
+        ids, ol, scores = pred.predict_decode(feats_host)  # pinned host in, host results out (synchronous)
+        if world > 1:
+            ids_d = torch.from_numpy(ids).to(dev)
+            g = all_gather_results(ids_d, torch.from_numpy(ol).to(dev), torch.tensor(scores, dtype=torch.float32,
+                                                                                      device=dev), total_utts, lmax)
+            ids, ol = g[0].cpu().numpy(), g[1].cpu().numpy()
+        return detokenize(ids, ol, vocab)
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ke = max(5, min(K, 30))
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        texts = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / ke * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = B * FRAMES * 80 * 4
+    d2h = B * Tp * 4 + B * 4 + B * 4
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events around every launch ----
+    pk = peaks()
+    roof = None
+    prof_table = None
+    if rank == 0:
+        eng.profile_enable(True)
+        reps = 5
+        for _ in range(reps):
+            flush.zero_()
+            eng.encode(feats_dev)
+            eng.ctc_greedy(to_host=False)
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        M = B * Tp
+        D, FF = cfg.output_size, cfg.linear_units
+        T1 = (FRAMES - 1) // 2
+        Th = (T1 + 1) // 2
+        flops = {  # algorithmic FLOPs per launch (2*M*N*K)
+            "ffn1_gemm": 2.0 * M * FF * D, "ffn2_gemm": 2.0 * M * D * FF, "qkv_gemm": 2.0 * M * 3 * D * D,
+            "outproj_gemm": 2.0 * M * D * D, "pw1_glu_gemm": 2.0 * M * 2 * D * D, "pw2_gemm": 2.0 * M * D * D,
+            "conv2_gemm": 2.0 * (B * Tp * 19) * D * 9 * D, "embed_gemm": 2.0 * M * D * 19 * D,
+            "ctc_stats_gemm": 2.0 * M * VOCAB * D, "attention": 2.0 * B * 4 * Tp * Tp * (128 + 64),
+        }
+        total = sum(v[1] for v in prof.values())
+        prof_table = {k: {"launches_per_step": v[0] // reps, "us_per_launch": v[1] / v[0] * 1e3,
+                          "share": v[1] / total} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        top = max((k for k in prof if k in flops), key=lambda k: prof[k][1])
+        us = prof[top][1] / prof[top][0] * 1e3
+        ach = flops[top] / (us * 1e-6) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + " (burst cuBLAS bf16)",
+                "us_per_launch": us, "share_of_step": prof[top][1] / total,
+                "step_tensor_frac_sustained": (GFLOP_PER_UTT * B / ms) / pk["bf16_tflops_sustained"]}
+
+    # ---- CPU baseline: oracle restatement on the host cores, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.conformer_oracle import ConformerConf, ConformerOracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        orc = ConformerOracle(ConformerConf(**cfg.to_dict()), weights)
+        sb = 4
+        f = feats_host[:sb].numpy()
+        cpu_reference_step(orc, f, [FRAMES] * sb, vocab)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 10.0:
+            ref_texts = cpu_reference_step(orc, f, [FRAMES] * sb, vocab)
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        cpu = {"value": sb / dt, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{sb} of 32 utterances x 10 s, {n} passes (~10 s): PyTorch-CPU fp32 oracle restatement of the "
+                         "reference Paddle graph + greedy restatement (Paddle not installable offline)",
+               "rtf": dt / (sb * SECONDS)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "conformer-streaming b32x10s fbank[32,998,80] per GPU, fused CTC head + ctc_greedy "
+                                   "(BASELINE configs[1])",
+                       "global_batch": total_utts, "frames": FRAMES, "out_frames": Tp, "vocab": VOCAB,
+                       "parallelism": f"dp{world} (batch sharded, one all-gather of ids)" if world > 1 else "single GPU",
+                       "l2": "256 MiB memset between timed steps (outside the CUDA-event brackets)",
+                       "rtf": ms * 1e-3 / (B * SECONDS), "gflop_per_step_per_gpu": GFLOP_PER_UTT * B},
+            "clocks": sampler.result(),
+            "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "InferencePredictor.predict_decode(host fbank) + host detokenisation"},
+            "gpu_launches": int(launches1 - launches0),
+            "roofline": roof, "cpu_baseline": cpu, "kernel_profile": prof_table,
+            "sample_text_len": len(texts[0]) if texts else 0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,8 @@ typedef struct ppasr_b200_config {
 
 const char* ppasr_b200_last_error(void);
 int ppasr_b200_abi_version(void);
+/* Number of CUDA kernels this library has launched so far in this process (bench.py "gpu_launches"). */
+int64_t ppasr_b200_launch_count(void);
 
 /* ---- life cycle ------------------------------------------------------------------------------
  * replaces: InferencePredictor.__init__ loading model.pdmodel/.pdiparams
@@ -114,6 +116,14 @@ int ppasr_b200_op_softmax(const float* logits, int32_t ldl, float* probs, int32_
 int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int32_t T2p, const void* pos,
                             int32_t pos_rows, int32_t pos_ld, int32_t pos_row0, int32_t pos_col0, void* out,
                             int32_t B, int32_t H, int32_t T1, int32_t T2, const int32_t* klens, void* stream);
+
+/* Per-kernel-class device timing of the model-level calls (cudaEvent pairs around every launch).
+ * enable, run encode/ctc_* once, then read: counts[i] launches and total_ms[i] for class i in
+ * [0, ppasr_b200_profile_num_classes()). Used by bench.py for the live roofline figure. */
+int ppasr_b200_profile_enable(ppasr_b200_ctx* ctx, int32_t enable);
+int ppasr_b200_profile_num_classes(void);
+const char* ppasr_b200_profile_class_name(int32_t cls);
+int ppasr_b200_profile_read(ppasr_b200_ctx* ctx, int32_t* counts, float* total_ms);
 
 /* Debug/inspection: copies an internal activation (fp32 residual stream x [B*T', d_model]) to the
  * device buffer `dst`. Used by the layer-wise parity tests only. */

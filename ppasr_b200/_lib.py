@@ -50,6 +50,7 @@ c_int32 = ctypes.c_int32
 P = c_void_p
 I = c_int32
 PROTOTYPES = {
+    "ppasr_b200_launch_count": (c_int64, []),
     "ppasr_b200_create": (c_int, [P, ctypes.POINTER(P)]),
     "ppasr_b200_destroy": (c_int, [P]),
     "ppasr_b200_load_tensor": (c_int, [P, c_char_p, P, I, P]),
@@ -66,6 +67,10 @@ PROTOTYPES = {
     "ppasr_b200_op_softmax": (c_int, [P, I, P, I, I, P]),
     "ppasr_b200_op_attention": (c_int, [P, P, P, I, P, I, I, I, I, P, I, I, I, I, P, P]),
     "ppasr_b200_debug_copy_x": (c_int, [P, P, P]),
+    "ppasr_b200_profile_enable": (c_int, [P, I]),
+    "ppasr_b200_profile_num_classes": (c_int, []),
+    "ppasr_b200_profile_class_name": (c_char_p, [I]),
+    "ppasr_b200_profile_read": (c_int, [P, P, P]),
 }
 
 

@@ -18,6 +18,8 @@
 
 namespace ppasr {
 
+void count_launch();
+
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 128;
 constexpr int ATT_THREADS = 160;  // warps 0..3 softmax (TMEM lane quadrants), warp 4 control
@@ -231,6 +233,7 @@ cudaError_t launch_rel_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_
   }
   dim3 grid((p.T1 + ATT_BM - 1) / ATT_BM, p.H, p.B);
   rel_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, st>>>(tm_q, tm_k, tm_p, tm_vt, p);
+  count_launch();
   return cudaGetLastError();
 }
 

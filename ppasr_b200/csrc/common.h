@@ -12,6 +12,10 @@ const char* get_last_error();
 
 int device_sm_count();
 
+// number of kernels launched by this library (all contexts); read by bench.py for "gpu_launches"
+void count_launch();
+long long launch_count();
+
 }  // namespace ppasr
 
 #define PPASR_OK 0

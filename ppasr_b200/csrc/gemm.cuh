@@ -19,6 +19,8 @@
 
 namespace ppasr {
 
+void count_launch();
+
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int GEMM_UMMA_K = 16;
@@ -550,6 +552,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tma
   if (num_tiles <= 0) return cudaSuccess;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(tmap_a, tmap_b, shape, epi);
+  count_launch();
   return cudaGetLastError();
 }
 

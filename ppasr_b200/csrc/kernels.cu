@@ -7,6 +7,8 @@
 
 namespace ppasr {
 
+void count_launch();
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over D=256 channels, one warp per row (8 channels per lane).
 //   single: y_bf16 = LN(x; g1, b1)                      (rows with t >= lens[b] are written as 0)
@@ -76,6 +78,7 @@ cudaError_t launch_layernorm(float* x, __nv_bfloat16* y, const float* g1, const 
     layernorm_kernel<512><<<grid, 256, 0, st>>>(x, y, g1, b1, g2, b2, lens, T, M, eps);
   else
     return cudaErrorInvalidValue;
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -140,6 +143,7 @@ cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const 
   if (C != 256) return cudaErrorInvalidValue;
   const size_t smem = 5 * F * sizeof(float);
   conv1_subsample_kernel<256><<<B * Th, 256, smem, st>>>(feats, mean, istd, w, bias, out, B, T, F, T1, F1, Th, FH);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -256,6 +260,7 @@ cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, con
   }
   if (K == 15) PPASR_DW_LAUNCH(15) else if (K == 31) PPASR_DW_LAUNCH(31) else if (K == 7) PPASR_DW_LAUNCH(7) else return cudaErrorInvalidValue;
 #undef PPASR_DW_LAUNCH
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -267,6 +272,7 @@ __global__ void glu_pad_kernel(const float* __restrict__ bias_il, float* __restr
 }
 cudaError_t launch_glu_pad(const float* bias_il, float* pad, int C, cudaStream_t st) {
   glu_pad_kernel<<<(C + 127) / 128, 128, 0, st>>>(bias_il, pad, C);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -335,6 +341,7 @@ cudaError_t launch_softmax_rows(const float* logits, int ldl, float* probs, int 
     softmax_rows_kernel<512, 32><<<M, 512, 0, st>>>(logits, ldl, probs, V);
   else
     return cudaErrorInvalidValue;
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -403,6 +410,7 @@ __global__ void __launch_bounds__(128) argmax_rows_kernel(const float* __restric
 cudaError_t launch_argmax_rows(const float* probs, int V, int rows, int* idx, float* maxp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   argmax_rows_kernel<<<(rows + 3) / 4, 128, 0, st>>>(probs, V, rows, idx, maxp);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -449,6 +457,7 @@ cudaError_t launch_ctc_stats_finalize(const float* pmax, const int* parg, const 
                                       int* idx, float* maxp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   ctc_stats_finalize_kernel<<<(rows + 3) / 4, 128, 0, st>>>(pmax, parg, psum, parts, rows, idx, maxp);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -510,6 +519,7 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
   if (B <= 0) return cudaSuccess;
   ctc_collapse_kernel<<<(B + 3) / 4, 128, 0, st>>>(idx, maxp, B, T, frame_lens, blank, ids_out, ld_out, out_len, score,
                                                    score_sum, score_cnt);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 #include "ppasr_b200.h"
 #include "tmap.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace ppasr {
@@ -14,6 +15,10 @@ namespace ppasr {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int device_sm_count() {
   static int sms = 0;
@@ -48,6 +53,8 @@ extern "C" {
 const char* ppasr_b200_last_error(void) { return get_last_error(); }
 
 int ppasr_b200_abi_version(void) { return 1; }
+
+int64_t ppasr_b200_launch_count(void) { return (int64_t)launch_count(); }
 
 // C = epilogue(A[M,K] * W[N,K]^T + bias).  See include/ppasr_b200.h for the epilogue codes.
 int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t w_rows, const float* bias,

@@ -110,9 +110,50 @@ struct ppasr_b200_ctx {
   std::vector<LayerMaps> lmaps;
   Plan plan;
   int sms = 148;
+  // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
+  bool profiling = false;
+  struct ProfRec {
+    int cls;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<ProfRec> prof;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+  size_t prof_used = 0;
 };
 
 namespace {
+
+enum ProfClass : int {
+  PC_CONV1 = 0, PC_CONV2, PC_EMBED, PC_LAYERNORM, PC_FFN1, PC_FFN2, PC_QKV, PC_ATTENTION, PC_OUTPROJ, PC_PW1_GLU,
+  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_COUNT
+};
+const char* const kProfNames[PC_COUNT] = {"conv1_subsample", "conv2_gemm", "embed_gemm", "layernorm", "ffn1_gemm",
+                                          "ffn2_gemm", "qkv_gemm", "attention", "outproj_gemm", "pw1_glu_gemm",
+                                          "dwconv_norm_swish", "pw2_gemm", "ctc_stats_gemm", "ctc_finalize",
+                                          "ctc_collapse", "ctc_logits_gemm", "softmax"};
+
+struct ProfScope {
+  ppasr_b200_ctx* c;
+  cudaStream_t st;
+  cudaEvent_t e1 = nullptr;
+  ProfScope(ppasr_b200_ctx* c_, int cls, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->profiling) return;
+    if (c->prof_used == c->prof_pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      c->prof_pool.emplace_back(a, b);
+    }
+    auto& pr = c->prof_pool[c->prof_used++];
+    c->prof.push_back({cls, pr.first, pr.second});
+    e1 = pr.second;
+    cudaEventRecord(pr.first, st);
+  }
+  ~ProfScope() {
+    if (e1) cudaEventRecord(e1, st);
+  }
+};
+#define PROF(cls) ProfScope _prof_scope(c, cls, st)
 
 constexpr int BN_WIDE = 256, ST_WIDE = 4;    // N >= 512 outputs
 constexpr int BN_NARROW = 128, ST_NARROW = 6;  // N = 256 outputs (fills 124 of 148 SMs at M = 7936)
@@ -567,69 +608,72 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st) {
   const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, L = cfg.n_layers, M = p.M;
   const float eps = 1e-5f;
   // CMVN + conv1 + ReLU -> stride-phase images
+  { PROF(PC_CONV1);
   PPASR_CUDA_CHECK(launch_conv1_subsample(p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.phase, p.B,
-                                          p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st));
+                                          p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st)); }
   // conv2 + ReLU as 9 shifted GEMM taps -> c2 [M, F2*D]
   {
     GemmShape s = make_shape(p.Mr, D, 9 * D, BN_WIDE);
     s.conv_pitch = c->FH;
     s.conv_kc = D / GEMM_BLOCK_K;
     EpiConv2<BN_WIDE> epi{p.c2, c->conv2_b, p.Mr, D, p.Th, c->FH, p.Tp, c->F2};
+    PROF(PC_CONV2);
     PPASR_CUDA_CHECK((launch_gemm<BN_WIDE, ST_WIDE, true>(p.tm_phase, c->tm_conv2_w, s, epi, c->sms, st)));
   }
   // Linear(F2*D -> D) then x * sqrt(D)   (subsampling.py:113, embedding.py:113)
   {
     EpiResidF32<BN_NARROW> epi{p.x, c->emb_b, D, M, D, std::sqrt((float)D), 0, nullptr, p.Tp};
+    PROF(PC_EMBED);
     PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_c2, c->tm_emb_w, M, D, c->Kemb, epi, st)));
   }
-  PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, c->layers[0].ln_ffm_g, c->layers[0].ln_ffm_b, nullptr, nullptr, nullptr,
-                                    p.Tp, M, D, eps, st));
+  { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, c->layers[0].ln_ffm_g, c->layers[0].ln_ffm_b, nullptr, nullptr, nullptr,
+                                    p.Tp, M, D, eps, st)); }
   for (int l = 0; l < L; ++l) {
     const LayerW& w = c->layers[l];
     const auto& m = c->lmaps[l];
     // ---- macaron FFN: x += 0.5 * W2 swish(W1 LN(x))           (encoder.py:380-386)
     {
       EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ffm_b1, FF, M, FF};
-      PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ffm_w1, M, FF, D, e1, st)));
+      { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ffm_w1, M, FF, D, e1, st))); }
       EpiResidF32<BN_NARROW> e2{p.x, w.ffm_b2, D, M, D, 0.5f, 1, nullptr, p.Tp};
-      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ffm_w2, M, D, FF, e2, st)));
+      { PROF(PC_FFN2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ffm_w2, M, D, FF, e2, st))); }
     }
     // ---- rel-pos MHA: x += Wo attn(LN(x))                      (encoder.py:389-402)
-    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st));
+    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st)); }
     {
       EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
-      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st)));
+      { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st))); }
       AttnParams ap;
       ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.T2 = p.Tp, ap.q_rows_per_bh = p.Tp, ap.k_rows_per_bh = p.Tp;
       ap.pos_row0 = 0, ap.pos_col0 = l * D, ap.D = D, ap.klens = p.vlen, ap.out = p.att;
-      PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st));
+      { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st)); }
       EpiResidF32<BN_NARROW> eo{p.x, w.bo, D, M, D, 1.0f, 1, nullptr, p.Tp};
-      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_att, m.wo, M, D, D, eo, st)));
+      { PROF(PC_OUTPROJ); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_att, m.wo, M, D, D, eo, st))); }
     }
     // ---- conv module: x += mask * pw2 swish(norm(dw(glu(pw1(mask * LN(x))))))   (encoder.py:407-416)
-    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, p.vlen, p.Tp, M, D, eps, st));
+    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, p.vlen, p.Tp, M, D, eps, st)); }
     {
       EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, M, 2 * D};
-      PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st)));
+      { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st))); }
       const int K = cfg.conv_kernel;
       const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
-      PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
-                                                cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, st));
+      { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
+                                                cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, st)); }
       EpiResidF32<BN_NARROW> e2{p.x, w.pw2_b, D, M, D, 1.0f, 1, p.vlen, p.Tp};
-      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_z, m.pw2, M, D, D, e2, st)));
+      { PROF(PC_PW2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_z, m.pw2, M, D, D, e2, st))); }
     }
     // ---- FFN: x += 0.5 * W2 swish(W1 LN(x))                    (encoder.py:419-426)
-    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st));
+    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st)); }
     {
       EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ff_b1, FF, M, FF};
-      PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st)));
+      { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st))); }
       EpiResidF32<BN_NARROW> e2{p.x, w.ff_b2, D, M, D, 0.5f, 1, nullptr, p.Tp};
-      PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ff_w2, M, D, FF, e2, st)));
+      { PROF(PC_FFN2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ff_w2, M, D, FF, e2, st))); }
     }
     // ---- x = norm_final(x); y = next block's first LayerNorm (or after_norm)   (encoder.py:428-429, 201-202)
     const float* g2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_g : c->after_g;
     const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
-    PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_fin_g, w.ln_fin_b, g2, b2, nullptr, p.Tp, M, D, eps, st));
+    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_fin_g, w.ln_fin_b, g2, b2, nullptr, p.Tp, M, D, eps, st)); }
   }
   return PPASR_OK;
 }
@@ -673,6 +717,7 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
 static int run_ctc_logits(ppasr_b200_ctx* c, cudaStream_t st) {
   Plan& p = c->plan;
   EpiLogitsF32<BN_NARROW> e{p.logits, c->ctc_b, c->Vld, p.M, c->cfg.vocab_size};
+  PROF(PC_CTC_LOGITS);
   PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, c->cfg.vocab_size, c->cfg.d_model, e, st)));
   return PPASR_OK;
 }
@@ -697,7 +742,8 @@ int ppasr_b200_ctc_probs(ppasr_b200_ctx* c, float* probs, int32_t probs_on_devic
   if (rc) return rc;
   Plan& p = c->plan;
   float* dst = probs_on_device ? probs : p.probs;
-  PPASR_CUDA_CHECK(launch_softmax_rows(p.logits, c->Vld, dst, p.M, c->cfg.vocab_size, st));
+  { PROF(PC_SOFTMAX);
+  PPASR_CUDA_CHECK(launch_softmax_rows(p.logits, c->Vld, dst, p.M, c->cfg.vocab_size, st)); }
   if (!probs_on_device) {
     PPASR_CUDA_CHECK(cudaMemcpyAsync(probs, p.probs, (size_t)p.M * c->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, st));
     PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -713,8 +759,11 @@ int ppasr_b200_ctc_greedy(ppasr_b200_ctx* c, int32_t* ids, int32_t* out_lens, fl
   Plan& p = c->plan;
   const int V = c->cfg.vocab_size;
   EpiCtcStats<BN_NARROW> e{p.pmax, p.parg, p.psum, c->ctc_b, p.M, V, c->ctc_parts};
-  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, V, c->cfg.d_model, e, st)));
-  PPASR_CUDA_CHECK(launch_ctc_stats_finalize(p.pmax, p.parg, p.psum, c->ctc_parts, p.M, p.idx, p.maxp, st));
+  { PROF(PC_CTC_STATS);
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, V, c->cfg.d_model, e, st))); }
+  { PROF(PC_CTC_FINALIZE);
+  PPASR_CUDA_CHECK(launch_ctc_stats_finalize(p.pmax, p.parg, p.psum, c->ctc_parts, p.M, p.idx, p.maxp, st)); }
+  PROF(PC_CTC_COLLAPSE);
   PPASR_CUDA_CHECK(launch_ctc_collapse(p.idx, p.maxp, p.B, p.Tp, trim_to_lens ? p.vlen : nullptr, blank_id, p.ids, p.Tp,
                                        p.out_len, p.score, nullptr, nullptr, st));
   int rc;
@@ -736,6 +785,32 @@ int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V
   PPASR_CUDA_CHECK(launch_argmax_rows(probs, V, B * T, tmp_idx, tmp_maxp, st));
   PPASR_CUDA_CHECK(launch_ctc_collapse(tmp_idx, tmp_maxp, B, T, frame_lens, blank_id, ids, ld_ids, out_lens, scores,
                                        nullptr, nullptr, st));
+  return PPASR_OK;
+}
+
+int ppasr_b200_profile_enable(ppasr_b200_ctx* c, int32_t enable) {
+  PPASR_REQUIRE(c, "null ctx");
+  c->profiling = enable != 0;
+  c->prof.clear();
+  c->prof_used = 0;
+  return PPASR_OK;
+}
+
+int ppasr_b200_profile_num_classes(void) { return PC_COUNT; }
+const char* ppasr_b200_profile_class_name(int32_t cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : ""; }
+
+int ppasr_b200_profile_read(ppasr_b200_ctx* c, int32_t* counts, float* total_ms) {
+  PPASR_REQUIRE(c && counts && total_ms, "null pointer");
+  PPASR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < PC_COUNT; ++i) counts[i] = 0, total_ms[i] = 0.f;
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    PPASR_CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    counts[r.cls] += 1;
+    total_ms[r.cls] += ms;
+  }
+  c->prof.clear();
+  c->prof_used = 0;
   return PPASR_OK;
 }
 

@@ -132,6 +132,18 @@ class ConformerEngine:
             return ids, ol, sc, fi, fp
         return ids, ol, sc
 
+    def profile_enable(self, on=True):
+        L.check(self.lib.ppasr_b200_profile_enable(self._ctx, int(on)))
+
+    def profile_read(self):
+        """Returns {class_name: (launches, total_ms)} for the launches since profile_enable(True)."""
+        n = self.lib.ppasr_b200_profile_num_classes()
+        counts = (ctypes.c_int32 * n)()
+        ms = (ctypes.c_float * n)()
+        L.check(self.lib.ppasr_b200_profile_read(self._ctx, counts, ms))
+        return {self.lib.ppasr_b200_profile_class_name(i).decode(): (int(counts[i]), float(ms[i]))
+                for i in range(n) if counts[i] > 0}
+
     def debug_x(self):
         torch = self.torch
         out = torch.empty((self.B * self.Tp, self.cfg.output_size), dtype=torch.float32, device=self.device)

@@ -1,0 +1,126 @@
+"""Drop-in for ppasr/infer_utils/inference_predictor.py::InferencePredictor on a B200.
+
+Same constructor signature, method names, NumPy array contracts and error behaviour as the reference
+class (infer_utils/inference_predictor.py:11-220); the Paddle static graph behind `predictor.run()` is
+replaced by the sm_100a kernels of libppasr_b200.so. Differences, all additive:
+  * `model_dir` holds `model.npz` (or `model.pdparams`) with the reference's own parameter names, not an
+    exported `.pdmodel/.pdiparams` pair;
+  * `predict` accepts any batch size for every model type (the reference's streaming export is B=1);
+  * `predict_decode` runs the fused CTC-head + greedy decode and returns ids / texts without ever
+    materialising the [B, T', V] posterior (the reference copies it to the host, :143-145);
+  * `weights=` lets tests/bench pass an in-memory parameter dict.
+There is no CPU mode: `use_gpu=False` raises (the reference's CPU path is what bench.py times as the
+baseline through the oracle).
+"""
+import os
+
+import numpy as np
+
+from .. import _lib as L
+from ..engine import ConformerEngine, out_frames
+from ..parallel import detokenize
+from ..weights import ConformerConfig, load_npz, load_pdparams, read_mean_istd
+
+
+def _get(obj, key, default=None):
+    if obj is None:
+        return default
+    if isinstance(obj, dict):
+        return obj.get(key, default)
+    return getattr(obj, key, default)
+
+
+class InferencePredictor:
+    def __init__(self,
+                 configs,
+                 use_model,
+                 streaming=True,
+                 model_dir='models/conformer_streaming_fbank/infer/',
+                 use_gpu=True,
+                 use_tensorrt=False,
+                 gpu_mem=1000,
+                 num_threads=10,
+                 weights=None,
+                 vocab_size=None,
+                 device=0):
+        if not use_gpu:
+            raise Exception("ppasr_b200 only runs on a B200 GPU (use_gpu=False is not supported)")
+        if use_model != 'conformer':
+            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 round 1 implements conformer)')
+        self.configs = configs
+        self.use_model = use_model
+        self.streaming = streaming
+        # streaming state, mirrors inference_predictor.py:35-39
+        self.output_state_h = None
+        self.output_state_c = None
+        self.cnn_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
+        self.att_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
+        self.offset = np.array([0], dtype=np.int32)
+
+        enc = _get(configs, 'encoder_conf', {}) or {}
+        enc = dict(enc) if isinstance(enc, dict) else {k: getattr(enc, k) for k in vars(enc)}
+        pre = _get(configs, 'preprocess_conf', {}) or {}
+        n_mels = _get(pre, 'n_mels', 80)
+        if weights is None:
+            npz = os.path.join(model_dir, 'model.npz')
+            pdp = os.path.join(model_dir, 'model.pdparams')
+            if os.path.exists(npz):
+                weights, _ = load_npz(npz)
+            elif os.path.exists(pdp):
+                weights = load_pdparams(pdp)
+            else:
+                # same failure mode as inference_predictor.py:43-44
+                raise Exception("模型文件不存在，请检查%s和%s是否存在！" % (npz, pdp))
+            mi = os.path.join(model_dir, 'mean_istd.json')
+            if 'encoder.global_cmvn.mean' not in weights and os.path.exists(mi):
+                mean, istd = read_mean_istd(mi)
+                weights['encoder.global_cmvn.mean'] = mean
+                weights['encoder.global_cmvn.istd'] = istd
+        if vocab_size is None:
+            vocab_size = int(weights['ctc.ctc_lo.weight'].shape[1])
+        allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
+                   'cnn_module_norm', 'max_len')
+        kw = {k: enc[k] for k in allowed if k in enc}
+        self.model_config = ConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        self.engine = ConformerEngine(self.model_config, weights, device=device)
+
+    # ---------------------------------------------------------------------------------------------
+    def predict(self, speech, speech_lengths):
+        """inference_predictor.py:103-145: speech f32 [B,T,n_mels], speech_lengths i64 [B] -> probs f32 [B,T',V]
+        (host NumPy). For streaming *former models the reference resets the caches and runs the whole
+        utterance with full attention (:127-137); the batched engine path is that computation."""
+        speech = np.ascontiguousarray(speech, dtype=np.float32)
+        if 'former' in self.use_model and self.streaming:
+            self.reset_stream()
+        self.engine.encode(speech, speech_lengths)
+        return self.engine.ctc_probs(to_host=True)
+
+    def predict_decode(self, speech, speech_lengths=None, vocabulary=None, trim_to_lens=False, blank_id=0):
+        """Extension: fused encoder + CTC head + greedy decode. speech may be host NumPy (copied H2D inside) or
+        a CUDA tensor. Returns (ids [B,T'] int32, out_lens [B], scores [B] in the reference's 0..100 scale)
+        or, when `vocabulary` is given, a list of (score, text) like greedy_decoder."""
+        self.engine.encode(speech, speech_lengths)
+        ids, ol, sc = self.engine.ctc_greedy(to_host=True, trim_to_lens=trim_to_lens, blank_id=blank_id)
+        scores = [float(s) * 100.0 if n > 0 else 0 for s, n in zip(sc, ol)]
+        if vocabulary is None:
+            return ids, ol, scores
+        texts = detokenize(ids, ol, vocabulary)
+        return list(zip(scores, texts))
+
+    def predict_chunk_deepspeech(self, x_chunk):
+        # inference_predictor.py:147-149
+        raise Exception(f'当前模型不支持该方法，当前模型为：{self.use_model}')
+
+    def predict_chunk_conformer(self, x_chunk, required_cache_size):
+        """inference_predictor.py:184-212."""
+        if not ('former' in self.use_model and self.streaming):
+            raise Exception(f'当前模型不支持该方法，当前模型为：{self.use_model}')
+        raise Exception("predict_chunk_conformer: chunk streaming kernels are not built yet in this round")
+
+    def reset_stream(self):
+        """inference_predictor.py:215-220."""
+        self.output_state_h = None
+        self.output_state_c = None
+        self.att_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
+        self.cnn_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
+        self.offset = np.array([0], dtype=np.int32)

@@ -1,0 +1,144 @@
+"""CPU tests: the C-ABI library loads and exports every symbol of include/ppasr_b200.h, fails loudly
+without a GPU, and the host-side logic (weights, sharding, gloo all-gather) behaves."""
+import ctypes
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "ppasr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ppasr_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    from ppasr_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ppasr_b200.h but not exported"
+    for s in syms:
+        if s in ("ppasr_b200_last_error", "ppasr_b200_abi_version"):
+            continue
+        assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype in ppasr_b200/_lib.py"
+    assert lib.ppasr_b200_abi_version() == 1
+
+
+def test_config_struct_matches_header():
+    from ppasr_b200.engine import Config
+    assert ctypes.sizeof(Config) == 16 * 4
+
+
+def test_create_validates_and_finalize_reports_missing(lib):
+    from ppasr_b200 import _lib
+    from ppasr_b200.engine import Config
+    c = Config(model_type=0, feat_dim=80, d_model=256, n_heads=4, ffn_dim=2048, n_layers=1, conv_kernel=15, causal=1,
+               conv_norm=0, vocab_size=100, max_len=5000)
+    ctx = ctypes.c_void_p()
+    assert lib.ppasr_b200_create(ctypes.byref(c), ctypes.byref(ctx)) == 0
+    bad = Config(model_type=3, feat_dim=80, d_model=256, n_heads=4, ffn_dim=2048, n_layers=1, conv_kernel=15,
+                 vocab_size=100, max_len=5000)
+    ctx2 = ctypes.c_void_p()
+    assert lib.ppasr_b200_create(ctypes.byref(bad), ctypes.byref(ctx2)) != 0
+    assert b"model_type" in lib.ppasr_b200_last_error()
+    if not torch.cuda.is_available():
+        # no device: must fail loudly, never fall back
+        rc = lib.ppasr_b200_finalize(ctx)
+        assert rc != 0 and len(lib.ppasr_b200_last_error()) > 0
+        with pytest.raises(_lib.PPASRB200Error):
+            _lib.check(rc)
+    lib.ppasr_b200_destroy(ctx)
+
+
+def test_engine_refuses_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ppasr_b200 import _lib
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200.weights import ConformerConfig
+    with pytest.raises(_lib.PPASRB200Error):
+        ConformerEngine(ConformerConfig(num_blocks=1, vocab_size=10), {})
+    from ppasr_b200.decoders.ctc_greedy_decoder import greedy_decoder
+    with pytest.raises(_lib.PPASRB200Error):
+        greedy_decoder(np.ones((3, 4), dtype=np.float32) / 4, ["a", "b", "c", "d"])
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ppasr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_weight_shapes_and_counts():
+    from ppasr_b200.weights import ConformerConfig, conformer_param_shapes, init_conformer_weights, make_vocab
+    cfg = ConformerConfig()
+    shapes = conformer_param_shapes(cfg)
+    enc = sum(int(np.prod(s)) for n, s in shapes.items() if n.startswith("encoder.") and "global_cmvn" not in n)
+    assert enc == 33_464_576 - 0 or abs(enc - 33.46e6) < 0.02e6  # 33.46 M encoder params
+    w = init_conformer_weights(ConformerConfig(num_blocks=1, vocab_size=50))
+    assert w["encoder.embed.out.0.weight"].shape == (256 * 19, 256)
+    assert w["encoder.encoders.0.feed_forward.w_1.weight"].shape == (256, 2048)
+    v = make_vocab(4233)
+    assert len(v) == 4233 and v[0] == "<blank>" and v[-1] == "<eos>"
+
+
+def test_out_frames_and_shard_range():
+    from ppasr_b200.engine import out_frames
+    from ppasr_b200.parallel import shard_range
+    assert [out_frames(t) for t in (498, 998, 2998, 67, 7, 6)] == [123, 248, 748, 16, 1, 0]
+    for n, w in ((256, 8), (33, 4), (5, 8)):
+        cover = []
+        for r in range(w):
+            s, e = shard_range(n, w, r)
+            cover += list(range(s, e))
+        assert cover == list(range(n))
+    assert shard_range(256, 8, 3) == (96, 128)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from ppasr_b200.parallel import shard_range, all_gather_results
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+N, L = 7, 6
+g = torch.Generator().manual_seed(0)
+ids_all = torch.randint(1, 50, (N, L), generator=g, dtype=torch.int32)
+lens_all = torch.randint(0, L + 1, (N,), generator=g, dtype=torch.int32)
+sc_all = torch.rand(N, generator=g)
+s, e = shard_range(N, world, rank)
+ids, ol, sc = all_gather_results(ids_all[s:e].clone(), lens_all[s:e].clone(), sc_all[s:e].clone(), N, L)
+assert torch.equal(ids, ids_all) and torch.equal(ol, lens_all) and torch.equal(sc, sc_all), "gather mismatch"
+dist.barrier(); dist.destroy_process_group()
+print("RANK_OK", rank)
+'''
+
+
+def test_gloo_world2_all_gather(tmp_path):
+    """The N>1 path: contiguous shards + ONE all-gather reproduce the single-process result (gloo, world 2)."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0 and "RANK_OK" in out, out

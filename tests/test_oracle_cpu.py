@@ -1,0 +1,184 @@
+"""CPU tests of the oracle (test infrastructure) against the reference's known answers and golden vectors."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conformer_oracle as CO
+from oracle import decoders_oracle as DO
+from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold_vocab(V):
+    v = ["<blank>", "<unk>"] + [chr(0x4E00 + i) for i in range(V - 4)] + ["<space>", "<eos>"]
+    return v[:V]
+
+
+# ---- docstring known answers of ppasr/model_utils/utils/mask.py ------------------------------------
+def test_make_pad_mask_kat():
+    # mask.py:30-35
+    m = CO.make_pad_mask(torch.tensor([5, 3, 2]))
+    assert m.int().tolist() == [[0, 0, 0, 0, 0], [0, 0, 0, 1, 1], [0, 0, 1, 1, 1]]
+    assert CO.make_non_pad_mask(torch.tensor([5, 3, 2])).int().tolist() == [[1, 1, 1, 1, 1], [1, 1, 1, 0, 0],
+                                                                          [1, 1, 0, 0, 0]]
+
+
+def test_subsequent_chunk_mask_kat():
+    # mask.py:107-112
+    assert CO.subsequent_chunk_mask(4, 2).int().tolist() == [[1, 1, 0, 0], [1, 1, 0, 0], [1, 1, 1, 1], [1, 1, 1, 1]]
+    m = CO.subsequent_chunk_mask(6, 2, 1).int().tolist()
+    assert m[4] == [0, 0, 1, 1, 1, 1] and m[0] == [1, 1, 0, 0, 0, 0]
+
+
+def test_subsampled_mask_rule():
+    """mask[:, :, :-2:2][:, :, :-2:2] keeps output frame j iff 4*j < len (conformer/subsampling.py:115)."""
+    for T in (7, 8, 67, 131, 998):
+        for L in (1, 3, 4, 5, T - 1, T):
+            m = CO.make_non_pad_mask(torch.tensor([T, L]))[:, None, :]
+            sub = m[:, :, :-2:2][:, :, :-2:2][1, 0]
+            Tp = ((T - 1) // 2 - 1) // 2
+            assert sub.shape[0] == Tp
+            assert sub.tolist() == [4 * j < L for j in range(Tp)]
+
+
+# ---- greedy decoder restatement pinned on the reference's own outputs ------------------------------
+def _gold():
+    z = np.load(os.path.join(GOLD, "greedy_golden.npz"))
+    meta = json.load(open(os.path.join(GOLD, "greedy_golden.json"), encoding="utf-8"))
+    return z, meta
+
+
+def test_greedy_oracle_matches_reference_golden():
+    z, meta = _gold()
+    for m in meta:
+        if m["name"] == "__batch__":
+            continue
+        probs = z[m["name"] + "_probs"]
+        score, text = DO.greedy_decoder(probs, gold_vocab(m["V"]))
+        assert text == m["text"], m["name"]
+        assert repr(float(score)) == m["score"], m["name"]
+
+
+def test_greedy_chunk_oracle_matches_reference_golden():
+    z, meta = _gold()
+    for m in meta:
+        if m["name"] == "__batch__":
+            continue
+        probs = z[m["name"] + "_probs"]
+        lp, li = None, None
+        for c, s in enumerate(range(0, m["T"], 16)):
+            sc, tx, lp, li = DO.greedy_decoder_chunk(probs[s:s + 16], gold_vocab(m["V"]), lp, li)
+            assert tx == m["chunks"][c]["text"]
+            assert repr(float(sc)) == m["chunks"][c]["score"]
+
+
+def test_greedy_batch_oracle_matches_reference_golden():
+    z, meta = _gold()
+    m = [x for x in meta if x["name"] == "__batch__"][0]
+    p = z["long_probs"]
+    assert DO.greedy_decoder_batch([p, p[:100]], gold_vocab(97)) == m["texts"]
+
+
+# ---- encoder oracle self-consistency (parity of the encoder is unpinned: no Paddle, no reference tests) ----
+@pytest.fixture(scope="module")
+def small():
+    cfg = ConformerConfig(num_blocks=2, vocab_size=61)
+    w = init_conformer_weights(cfg)
+    return cfg, w
+
+
+def test_chunked_equals_chunk_masked_offline(small):
+    """forward(decoding_chunk_size=16, left=-1) == concat of forward_chunk over 67/64 windows."""
+    cfg, w = small
+    o = CO.ConformerOracle(CO.ConformerConf(**cfg.to_dict()), w)
+    T = 195
+    x = torch.from_numpy(synthetic_fbank(1, T))
+    enc, _ = o.encoder_forward(x, torch.tensor([T]), decoding_chunk_size=16, num_decoding_left_chunks=-1)
+    att = torch.zeros(0, 0, 0, 0)
+    cnn = torch.zeros(0, 0, 0, 0)
+    off, outs = 0, []
+    for (s, e) in CO.stream_windows(T, is_end=True):
+        y, att, cnn = o.encoder_forward_chunk(x[:, s:e], off, -16, att, cnn)
+        off += y.shape[1]
+        outs.append(y)
+    yc = torch.cat(outs, 1)
+    assert yc.shape[1] == enc.shape[1]
+    assert (enc - yc).abs().max() < 2e-5
+    assert att.shape == (cfg.num_blocks, cfg.attention_heads, yc.shape[1], 128)
+    assert cnn.shape == (cfg.num_blocks, 1, cfg.output_size, cfg.cnn_module_kernel - 1)
+
+
+def test_batch_invariance(small):
+    """An utterance that fills the batch tensor is independent of its batch mates. (A *padded* utterance is
+    not equal to its stand-alone run in the reference: the subsampled mask keeps frame j iff 4*j < len, i.e.
+    one or two frames more than the stand-alone T', and those frames are attended to -- replicated as is.)"""
+    cfg, w = small
+    o = CO.ConformerOracle(CO.ConformerConf(**cfg.to_dict()), w)
+    x = torch.from_numpy(synthetic_fbank(2, 131))
+    x[1, 99:] = 0
+    pb = o.get_encoder_out(x, torch.tensor([131, 99]))
+    p0 = o.get_encoder_out(x[:1], torch.tensor([131]))
+    assert (pb[0] - p0[0]).abs().max() < 1e-5
+    # same padded utterance next to a different neighbour: unchanged
+    x2 = x.clone()
+    x2[0] = torch.from_numpy(synthetic_fbank(1, 131, seed=77))[0]
+    pb2 = o.get_encoder_out(x2, torch.tensor([131, 99]))
+    assert (pb[1] - pb2[1]).abs().max() < 1e-5
+
+
+def test_fp64_noise_floor(small):
+    cfg, w = small
+    x = torch.from_numpy(synthetic_fbank(1, 131))
+    l32 = CO.ConformerOracle(CO.ConformerConf(**cfg.to_dict()), w).get_encoder_out(x, torch.tensor([131]), True)
+    l64 = CO.ConformerOracle(CO.ConformerConf(**cfg.to_dict()), w, torch.float64).get_encoder_out(x, torch.tensor([131]), True)
+    rel = (l32.double() - l64).abs().max() / l64.abs().max()
+    assert rel < 1e-4
+
+
+def test_batchnorm_variant_runs():
+    cfg = ConformerConfig(num_blocks=1, vocab_size=31, streaming=False, cnn_module_norm="batch_norm")
+    w = init_conformer_weights(cfg)
+    o = CO.ConformerOracle(CO.ConformerConf(**cfg.to_dict()), w)
+    p = o.get_encoder_out(torch.from_numpy(synthetic_fbank(1, 67)), torch.tensor([67]))
+    assert p.shape == (1, 16, 31) and torch.allclose(p.sum(-1), torch.ones(1, 16), atol=1e-5)
+
+
+# ---- beam search restatement: properties (parity unpinned, see oracle/decoders_oracle.py) ----------
+def test_beam_search_equals_bruteforce_on_tiny():
+    rng = np.random.RandomState(3)
+    for _ in range(5):
+        T, V = 4, 3
+        p = rng.dirichlet(np.ones(V), size=T).astype(np.float32)
+        res = DO.ctc_beam_search_ids(p, beam_size=100, cutoff_prob=1.0, cutoff_top_n=V)
+        brute = DO.ctc_prefix_total_logprob_bruteforce(p)
+        got = {tuple(ids): s for s, ids in res}
+        for lab, lp in brute.items():
+            assert lab in got
+            assert abs(got[lab] - lp) < 1e-4
+        best = max(brute.items(), key=lambda kv: kv[1])[0]
+        assert tuple(res[0][1]) == best
+
+
+def test_beam1_equals_greedy_on_peaked():
+    rng = np.random.RandomState(5)
+    T, V = 30, 12
+    logits = rng.randn(T, V) * 8
+    p = np.exp(logits - logits.max(-1, keepdims=True))
+    p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
+    _, coll, _ = DO.greedy_ids(p)
+    res = DO.ctc_beam_search_ids(p, beam_size=1, cutoff_prob=1.0, cutoff_top_n=V)
+    assert res[0][1] == coll
+
+
+def test_pruned_log_probs():
+    p = np.array([0.05, 0.6, 0.25, 0.1], dtype=np.float32)
+    r = DO.get_pruned_log_probs(p, 0.8, 40)
+    assert [i for i, _ in r] == [1, 2]
+    r = DO.get_pruned_log_probs(p, 1.0, 3)
+    assert [i for i, _ in r] == [1, 2, 3]
+    assert abs(r[0][1] - math.log(0.6 + DO.NUM_FLT_MIN)) < 1e-7
