@@ -304,7 +304,7 @@ def test_inference_predictor_api(lib, cuda):
     feats = synthetic_fbank(3, 211)
     lens = np.array([211, 211, 211], dtype=np.int64)
     probs = pred.predict(feats, lens)
-    assert probs.shape == (3, 51, 300) and probs.dtype == np.float32
+    assert probs.shape == (3, 52, 300) and probs.dtype == np.float32
     vocab = make_vocab(300)
     res = pred.predict_decode(feats, lens, vocabulary=vocab)
     ref = [DO.greedy_decoder(probs[b], vocab) for b in range(3)]
