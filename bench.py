@@ -39,6 +39,19 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def host_cores():
+    """Usable host cores: CPU affinity capped by the cgroup CPU quota (the GPU boxes expose 128 logical CPUs
+    but a 16-CPU quota; running the CPU arm with 128 threads is 100x slower than with 16)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
@@ -107,7 +120,7 @@ def run_reference(args):
         return
     from oracle.conformer_oracle import ConformerConf, ConformerOracle
     from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab, synthetic_fbank
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg = ConformerConfig(vocab_size=VOCAB)
     w = init_conformer_weights(cfg)
@@ -283,7 +296,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.conformer_oracle import ConformerConf, ConformerOracle
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(host_cores())
         orc = ConformerOracle(ConformerConf(**cfg.to_dict()), weights)
         sb = 4
         f = feats_host[:sb].numpy()
