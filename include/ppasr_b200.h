@@ -89,6 +89,25 @@ int ppasr_b200_ctc_greedy(ppasr_b200_ctx* ctx, int32_t* ids, int32_t* out_lens, 
                           float* frame_probs, int32_t outputs_on_device, int32_t trim_to_lens, int32_t blank_id,
                           void* stream);
 
+/* ---- chunk streaming ---------------------------------------------------------------------------
+ * replaces: Model.get_encoder_out_chunk / ConformerEncoder.forward_chunk
+ *           (model_utils/conformer/model.py:164-184, conformer/encoder.py:208-283) and the stream state of
+ *           InferencePredictor (infer_utils/inference_predictor.py:35-39,184-220).
+ * The attention K/V cache and the conv-module cache stay on the device inside the context (the reference
+ * round-trips both through host NumPy every chunk). B lock-step streams are supported (reference: B=1).
+ * stream_reset == InferencePredictor.reset_stream. encode_chunk consumes feats fp32 [B, t, feat_dim]
+ * (t = 67 for a full window, predict.py:277-300), appends ((t-1)/2-1)/2 output frames, applies
+ * required_cache_size exactly like encoder.py:255-260 (<0 keep all, 0 drop, >0 keep last n) and leaves the
+ * chunk's encoder output for ppasr_b200_ctc_probs / ctc_greedy. */
+int ppasr_b200_stream_reset(ppasr_b200_ctx* ctx, int32_t B);
+int ppasr_b200_encode_chunk(ppasr_b200_ctx* ctx, const float* feats, int32_t feats_on_device, int32_t B, int32_t t,
+                            int32_t required_cache_size, void* stream);
+/* offset = encoder frames produced so far (== self.offset of the reference), cache_t = cached keys. */
+int ppasr_b200_stream_info(ppasr_b200_ctx* ctx, int32_t* offset, int32_t* cache_t);
+/* fp32 copies of stream 0's caches in the reference layouts: att_cache [L, H, cache_t, 128] (k | v),
+ * cnn_cache [L, 1, d_model, conv_kernel-1]; either pointer may be NULL. */
+int ppasr_b200_stream_export(ppasr_b200_ctx* ctx, float* att_cache, float* cnn_cache, int32_t on_device, void* stream);
+
 /* ---- stand-alone decoders on a probability tensor (device pointers) --------------------------
  * replaces: greedy_decoder / greedy_decoder_batch (decoders/ctc_greedy_decoder.py:6-49).
  * probs: fp32 [B, T, V] dense. frame_lens (nullable): int32 [B]. tmp_idx: int32 [B*T], tmp_maxp: fp32 [B*T]

@@ -60,6 +60,10 @@ PROTOTYPES = {
     "ppasr_b200_ctc_probs": (c_int, [P, P, I, P]),
     "ppasr_b200_ctc_logits": (c_int, [P, P, I, P]),
     "ppasr_b200_ctc_greedy": (c_int, [P, P, P, P, P, P, I, I, I, P]),
+    "ppasr_b200_stream_reset": (c_int, [P, I]),
+    "ppasr_b200_encode_chunk": (c_int, [P, P, I, I, I, I, P]),
+    "ppasr_b200_stream_info": (c_int, [P, P, P]),
+    "ppasr_b200_stream_export": (c_int, [P, P, P, I, P]),
     "ppasr_b200_greedy_decode": (c_int, [P, I, I, I, P, I, P, I, P, P, P, P, P]),
     "ppasr_b200_op_linear": (c_int, [P, c_int64, P, c_int64, P, P, c_int64, I, I, I, I, I, c_float, I, P, I, I, P]),
     "ppasr_b200_op_layernorm": (c_int, [P, P, P, P, P, P, P, I, I, I, c_float, P]),

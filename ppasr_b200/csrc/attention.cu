@@ -95,10 +95,10 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           mbar_wait(bar_o_full, (j - 1) & 1);  // PV(j-1) finished: probabilities + V^T smem are free
         }
         mbar_arrive_expect_tx(bar_kv_full, 3 * ATT_TILE_BYTES);
-        tma_load_2d(s_kp, &tm_k, bar_kv_full, 0, bh * p.k_rows_per_bh + k0);
+        tma_load_2d(s_kp, &tm_k, bar_kv_full, 0, bh * p.k_rows_per_bh + p.k_row0 + k0);
         tma_load_2d(s_kp + ATT_TILE_BYTES, &tm_p, bar_kv_full, p.pos_col0 + h * 64, p.pos_row0 + k0);
-        tma_load_2d(s_v, &tm_vt, bar_kv_full, k0, bh * 64);
-        tma_load_2d(s_v + ATT_TILE_BYTES / 2, &tm_vt, bar_kv_full, k0 + 64, bh * 64);
+        tma_load_2d(s_v, &tm_vt, bar_kv_full, p.k_row0 + k0, bh * 64);
+        tma_load_2d(s_v + ATT_TILE_BYTES / 2, &tm_vt, bar_kv_full, p.k_row0 + k0 + 64, bh * 64);
         if (j == 0) mbar_wait(bar_q_full, 0);
         mbar_wait(bar_kv_full, j & 1);
         tc_fence_after();

@@ -277,6 +277,70 @@ cudaError_t launch_glu_pad(const float* bias_il, float* pad, int C, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Streaming conv cache: one block per stream. ycat[b] = [cache[b] ; y[b]] ; cache[b] <- tail(ycat[b], lorder)
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_cache_concat_kernel(__nv_bfloat16* __restrict__ cache, const __nv_bfloat16* __restrict__ y,
+                                         __nv_bfloat16* __restrict__ ycat, int T, int lorder, int C) {
+  extern __shared__ uint4 s_old[];  // lorder * C / 8
+  const int b = blockIdx.x;
+  const int vec = C / 8;
+  uint4* cb = reinterpret_cast<uint4*>(cache + (size_t)b * lorder * C);
+  const uint4* yb = reinterpret_cast<const uint4*>(y + (size_t)b * T * C);
+  uint4* ob = reinterpret_cast<uint4*>(ycat + (size_t)b * (lorder + T) * C);
+  for (int i = threadIdx.x; i < lorder * vec; i += blockDim.x) s_old[i] = cb[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < (lorder + T) * vec; i += blockDim.x) {
+    const int r = i / vec;
+    const uint4 v = (r < lorder) ? s_old[i] : yb[i - lorder * vec];
+    ob[i] = v;
+    const int cr = r - T;  // row of the new cache = ycat row T + cr
+    if (cr >= 0) cb[cr * vec + (i - r * vec)] = v;
+  }
+}
+cudaError_t launch_conv_cache_concat(__nv_bfloat16* cache, const __nv_bfloat16* y, __nv_bfloat16* ycat, int B, int T,
+                                     int lorder, int C, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  conv_cache_concat_kernel<<<B, 256, (size_t)lorder * C * 2, st>>>(cache, y, ycat, T, lorder, C);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// att_cache export: out[h, j, 0:64] = k[h, k0 + j, :], out[h, j, 64:128] = v[h, :, k0 + j]  (fp32, stream 0 of the batch)
+__global__ void export_att_cache_kernel(const __nv_bfloat16* __restrict__ kk, const __nv_bfloat16* __restrict__ vt,
+                                        float* __restrict__ out, int H, int Tcap, int Tcapp, int k0, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * t * 128) return;
+  const int d = i & 127, j = (i >> 7) % t, h = (i >> 7) / t;
+  float v;
+  if (d < 64)
+    v = __bfloat162float(kk[((size_t)h * Tcap + k0 + j) * 64 + d]);
+  else
+    v = __bfloat162float(vt[((size_t)h * 64 + (d - 64)) * Tcapp + k0 + j]);
+  out[i] = v;
+}
+cudaError_t launch_export_att_cache(const __nv_bfloat16* kk, const __nv_bfloat16* vt, float* out, int H, int Tcap,
+                                    int Tcapp, int k0, int t, cudaStream_t st) {
+  const int n = H * t * 128;
+  if (n <= 0) return cudaSuccess;
+  export_att_cache_kernel<<<(n + 255) / 256, 256, 0, st>>>(kk, vt, out, H, Tcap, Tcapp, k0, t);
+  count_launch();
+  return cudaGetLastError();
+}
+// cnn_cache export: out[c, j] = cache[j, c]   (reference layout [1, C, lorder])
+__global__ void export_cnn_cache_kernel(const __nv_bfloat16* __restrict__ cache, float* __restrict__ out, int lorder,
+                                        int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lorder * C) return;
+  const int j = i % lorder, c = i / lorder;
+  out[i] = __bfloat162float(cache[(size_t)j * C + c]);
+}
+cudaError_t launch_export_cnn_cache(const __nv_bfloat16* cache, float* out, int lorder, int C, cudaStream_t st) {
+  export_cnn_cache_kernel<<<(lorder * C + 255) / 256, 256, 0, st>>>(cache, out, lorder, C);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row soft-max of the CTC logits: probs[row, 0:V] (dense) = softmax(logits[row, 0:V]) (ld = ldl)
 //   reference: ppasr/model_utils/loss/ctc.py:62-70
 // One block per row; values stay in registers between the passes.

@@ -28,6 +28,15 @@ cudaError_t launch_argmax_rows(const float* probs, int V, int rows, int* idx, fl
 cudaError_t launch_ctc_stats_finalize(const float* pmax, const int* parg, const float* psum, int parts, int rows,
                                       int* idx, float* maxp, cudaStream_t st);
 
+// Streaming conv-module cache (reference: conformer/convolution.py:108-117): ycat[b] = [cache[b] ; y[b]],
+// then cache[b] <- last `lorder` rows of ycat[b]. cache: bf16 [B, lorder, C]; y: [B, T, C]; ycat: [B, lorder+T, C].
+cudaError_t launch_conv_cache_concat(__nv_bfloat16* cache, const __nv_bfloat16* y, __nv_bfloat16* ycat, int B, int T,
+                                     int lorder, int C, cudaStream_t st);
+// fp32 export of the device-resident caches in the reference's layouts.
+cudaError_t launch_export_att_cache(const __nv_bfloat16* kk, const __nv_bfloat16* vt, float* out, int H, int Tcap,
+                                    int Tcapp, int k0, int t, cudaStream_t st);
+cudaError_t launch_export_cnn_cache(const __nv_bfloat16* cache, float* out, int lorder, int C, cudaStream_t st);
+
 cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T, const int* frame_lens, int blank,
                                 int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
                                 int* score_cnt, cudaStream_t st);
@@ -39,6 +48,7 @@ struct AttnParams {
   int T2;        // key frames per utterance (cache + new)
   int q_rows_per_bh;   // rows of q2 per (b,h)  (= T1)
   int k_rows_per_bh;   // rows of kk per (b,h)
+  int k_row0;    // first key row inside each (b,h) block of kk / first key column of vt (cache start)
   int pos_row0;  // first row of the positional table used for key 0
   int pos_col0;  // first column (layer * D) of this layer's slice in the positional table
   int D;         // H * 64

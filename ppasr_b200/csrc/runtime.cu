@@ -83,8 +83,11 @@ struct Plan {  // everything that depends on (B, T)
   float *x = nullptr, *logits = nullptr, *pmax = nullptr, *psum = nullptr, *maxp = nullptr, *score = nullptr,
         *probs = nullptr;
   int *parg = nullptr, *idx = nullptr, *ids = nullptr, *out_len = nullptr;
+  // streaming conv module: [cache ; chunk] rows
+  int Tcat = 0, Mcat = 0;
+  __nv_bfloat16 *ycat = nullptr, *gcat = nullptr;
   // tensor maps (A operands)
-  CUtensorMap tm_phase, tm_c2, tm_y, tm_h, tm_att, tm_g, tm_z, tm_q, tm_k, tm_vt;
+  CUtensorMap tm_phase, tm_c2, tm_y, tm_h, tm_att, tm_g, tm_z, tm_q, tm_k, tm_vt, tm_ycat;
 };
 
 }  // namespace ppasr
@@ -110,6 +113,18 @@ struct ppasr_b200_ctx {
   std::vector<LayerMaps> lmaps;
   Plan plan;
   int sms = 148;
+  // ---- streaming state (reference: inference_predictor.py:35-39,215-220; device resident here) ----
+  struct StreamState {
+    int B = 0;          // lock-step streams
+    int Tcap = 0;       // key capacity per (b,h)
+    int kstart = 0;     // first cached key kept (required_cache_size trimming)
+    int kend = 0;       // one past the last cached key
+    int offset = 0;     // encoder output frames produced so far
+    __nv_bfloat16* kk = nullptr;   // [L][B,H,Tcap,64]
+    __nv_bfloat16* vt = nullptr;   // [L][B,H,64,Tcap]
+    __nv_bfloat16* cnn = nullptr;  // [L][B,lorder,D]
+    std::vector<CUtensorMap> tm_k, tm_vt;  // per layer, rebuilt every chunk (extent = kend)
+  } ss;
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool profiling = false;
   struct ProfRec {
@@ -224,6 +239,9 @@ int ppasr_b200_destroy(ppasr_b200_ctx* ctx) {
   if (!ctx) return PPASR_OK;
   ctx->wslab.release();
   ctx->aslab.release();
+  if (ctx->ss.kk) cudaFree(ctx->ss.kk);
+  if (ctx->ss.vt) cudaFree(ctx->ss.vt);
+  if (ctx->ss.cnn) cudaFree(ctx->ss.cnn);
   delete ctx;
   return PPASR_OK;
 }
@@ -522,6 +540,8 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   n.M = B * n.Tp;
   n.Mr = B * n.Th * c->FH;
   n.Tkp = (n.Tp + 63) / 64 * 64;
+  n.Tcat = n.Tp + cfg.conv_kernel - 1;
+  n.Mcat = B * n.Tcat;
   PPASR_REQUIRE(n.Tp >= 1 && n.Tp < cfg.max_len, "sequence too long for the positional table (embedding.py:110-112)");
   const size_t M = n.M;
   size_t bytes = 0;
@@ -532,6 +552,7 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   acc(M * c->Kemb * 2);
   acc(M * D * 4);                                   // x
   acc(M * D * 2 * 4);                               // y, att, g, z
+  acc((size_t)n.Mcat * D * 2 * 2);                  // ycat, gcat
   acc(M * FF * 2);                                  // h
   acc((size_t)B * H * n.Tp * 128 * 2);              // q2
   acc((size_t)B * H * n.Tp * 64 * 2);               // kk
@@ -558,6 +579,8 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   n.att = a.take<__nv_bfloat16>(M * D);
   n.g = a.take<__nv_bfloat16>(M * D);
   n.z = a.take<__nv_bfloat16>(M * D);
+  n.ycat = a.take<__nv_bfloat16>((size_t)n.Mcat * D);
+  n.gcat = a.take<__nv_bfloat16>((size_t)n.Mcat * D);
   n.h = a.take<__nv_bfloat16>(M * FF);
   n.q2 = a.take<__nv_bfloat16>((size_t)B * H * n.Tp * 128);
   n.kk = a.take<__nv_bfloat16>((size_t)B * H * n.Tp * 64);
@@ -584,6 +607,7 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
             make_tmap_2d(&n.tm_att, n.att, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
             make_tmap_2d(&n.tm_g, n.g, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
             make_tmap_2d(&n.tm_z, n.z, D, M, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
+            make_tmap_2d(&n.tm_ycat, n.ycat, D, n.Mcat, (uint64_t)D * 2, GEMM_BLOCK_M, &err) &&
             make_tmap_2d(&n.tm_q, n.q2, 128, (uint64_t)B * H * n.Tp, 256, 128, &err) &&
             make_tmap_2d(&n.tm_k, n.kk, 64, (uint64_t)B * H * n.Tp, 128, 128, &err) &&
             make_tmap_2d(&n.tm_vt, n.vt, n.Tp, (uint64_t)B * H * 64, (uint64_t)n.Tkp * 2, 64, &err);
@@ -602,8 +626,9 @@ cudaError_t gemm(ppasr_b200_ctx* c, const CUtensorMap& a, const CUtensorMap& b, 
   return launch_gemm<BN, ST, false>(a, b, s, epi, c->sms, st);
 }
 
-int run_encoder(ppasr_b200_ctx* c, cudaStream_t st) {
+int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
   Plan& p = c->plan;
+  auto& ss = c->ss;
   const auto& cfg = c->cfg;
   const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, L = cfg.n_layers, M = p.M;
   const float eps = 1e-5f;
@@ -641,25 +666,47 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st) {
     // ---- rel-pos MHA: x += Wo attn(LN(x))                      (encoder.py:389-402)
     { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st)); }
     {
-      EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
-      { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st))); }
       AttnParams ap;
-      ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.T2 = p.Tp, ap.q_rows_per_bh = p.Tp, ap.k_rows_per_bh = p.Tp;
-      ap.pos_row0 = 0, ap.pos_col0 = l * D, ap.D = D, ap.klens = p.vlen, ap.out = p.att;
-      { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st)); }
+      ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.D = D, ap.pos_col0 = l * D, ap.out = p.att, ap.q_rows_per_bh = p.Tp;
+      if (!chunk) {
+        EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
+        { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st))); }
+        ap.T2 = p.Tp, ap.k_rows_per_bh = p.Tp, ap.k_row0 = 0, ap.pos_row0 = 0, ap.klens = p.vlen;
+        { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st)); }
+      } else {
+        // K/V of this chunk are appended to the device-resident cache at row kend (attention.py:225-232);
+        // keys kstart .. kend+chunk are attended, positions offset-cache_t .. (encoder.py:253)
+        const size_t lk = (size_t)l * ss.B * H * ss.Tcap * 64;
+        EpiQKV<BN_NARROW> e{p.q2, ss.kk + lk, ss.vt + lk, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, ss.Tcap, ss.Tcap, ss.kend};
+        { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st))); }
+        const int cache_t = ss.kend - ss.kstart;
+        ap.T2 = cache_t + p.Tp, ap.k_rows_per_bh = ss.Tcap, ap.k_row0 = ss.kstart, ap.pos_row0 = ss.offset - cache_t;
+        ap.klens = nullptr;
+        { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, ss.tm_k[l], c->tm_pos, ss.tm_vt[l], ap, st)); }
+      }
       EpiResidF32<BN_NARROW> eo{p.x, w.bo, D, M, D, 1.0f, 1, nullptr, p.Tp};
       { PROF(PC_OUTPROJ); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_att, m.wo, M, D, D, eo, st))); }
     }
     // ---- conv module: x += mask * pw2 swish(norm(dw(glu(pw1(mask * LN(x))))))   (encoder.py:407-416)
-    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, p.vlen, p.Tp, M, D, eps, st)); }
+    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, chunk ? nullptr : p.vlen, p.Tp, M, D, eps, st)); }
     {
-      EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, M, 2 * D};
-      { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st))); }
       const int K = cfg.conv_kernel;
-      const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
-      { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
-                                                cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, st)); }
-      EpiResidF32<BN_NARROW> e2{p.x, w.pw2_b, D, M, D, 1.0f, 1, p.vlen, p.Tp};
+      if (!chunk) {
+        EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, M, 2 * D};
+        { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st))); }
+        const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
+        { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
+                                                  cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, st)); }
+      } else {
+        // [cnn_cache ; chunk] -> pw1 + GLU -> "valid" depthwise conv; cache <- last K-1 input rows (convolution.py:108-117)
+        const int lorder = K - 1;
+        PPASR_CUDA_CHECK(launch_conv_cache_concat(ss.cnn + (size_t)l * ss.B * lorder * D, p.y, p.ycat, p.B, p.Tp, lorder, D, st));
+        EpiGLU<BN_WIDE> eg{p.gcat, w.pw1_b, D, p.Mcat, 2 * D};
+        { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_ycat, m.pw1, p.Mcat, 2 * D, D, eg, st))); }
+        { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.gcat, w.dw_w, w.dw_b, nullptr, w.cn_g, w.cn_b, cfg.conv_norm == 0,
+                                                  p.z, p.B, p.Tcat, p.Tp, D, K, 0, eps, st)); }
+      }
+      EpiResidF32<BN_NARROW> e2{p.x, w.pw2_b, D, M, D, 1.0f, 1, chunk ? nullptr : p.vlen, p.Tp};
       { PROF(PC_PW2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_z, m.pw2, M, D, D, e2, st))); }
     }
     // ---- FFN: x += 0.5 * W2 swish(W1 LN(x))                    (encoder.py:419-426)
@@ -711,7 +758,127 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
     vlen[b] = (int)v;
   }
   PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-  return run_encoder(c, st);
+  return run_encoder(c, st, false);
+}
+
+// ---- streaming ------------------------------------------------------------------------------------
+int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
+  PPASR_REQUIRE(c && B > 0 && B <= 1024, "bad arguments");
+  if (!c->finalized) {
+    set_last_error("ppasr_b200_finalize has not been called");
+    return PPASR_ERR_STATE;
+  }
+  if (!c->cfg.causal) {
+    set_last_error("chunk streaming needs a streaming (causal) model");
+    return PPASR_ERR_STATE;
+  }
+  auto& ss = c->ss;
+  const auto& cfg = c->cfg;
+  const int L = cfg.n_layers, H = cfg.n_heads, D = cfg.d_model, lorder = cfg.conv_kernel - 1;
+  if (ss.B != B || !ss.kk) {
+    PPASR_CUDA_CHECK(cudaDeviceSynchronize());
+    if (ss.kk) cudaFree(ss.kk);
+    if (ss.vt) cudaFree(ss.vt);
+    if (ss.cnn) cudaFree(ss.cnn);
+    ss.kk = ss.vt = ss.cnn = nullptr;
+    ss.Tcap = (cfg.max_len + 63) / 64 * 64;
+    const size_t n = (size_t)L * B * H * ss.Tcap * 64;
+    PPASR_CUDA_CHECK(cudaMalloc(&ss.kk, n * 2));
+    PPASR_CUDA_CHECK(cudaMalloc(&ss.vt, n * 2));
+    PPASR_CUDA_CHECK(cudaMalloc(&ss.cnn, (size_t)L * B * lorder * D * 2));
+    PPASR_CUDA_CHECK(cudaMemset(ss.kk, 0, n * 2));
+    PPASR_CUDA_CHECK(cudaMemset(ss.vt, 0, n * 2));
+    ss.B = B;
+    ss.tm_k.resize(L);
+    ss.tm_vt.resize(L);
+  }
+  // empty conv cache == the reference's zero left padding of the first chunk (convolution.py:109-110)
+  PPASR_CUDA_CHECK(cudaMemset(ss.cnn, 0, (size_t)L * B * lorder * D * 2));
+  ss.kstart = ss.kend = ss.offset = 0;
+  return PPASR_OK;
+}
+
+int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_device, int32_t B, int32_t t,
+                            int32_t required_cache_size, void* stream) {
+  PPASR_REQUIRE(c && feats && B > 0 && t > 0, "bad arguments");
+  auto& ss = c->ss;
+  if (ss.B != B || !ss.kk) {
+    int rc = ppasr_b200_stream_reset(c, B);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(c, B, t);
+  if (rc != PPASR_OK) return rc;
+  Plan& p = c->plan;
+  const auto& cfg = c->cfg;
+  const int H = cfg.n_heads, L = cfg.n_layers;
+  if (ss.kend + p.Tp > ss.Tcap || ss.offset + p.Tp >= cfg.max_len) {
+    set_last_error("stream longer than the positional table (max_len); call reset_stream (embedding.py:64-66)");
+    return PPASR_ERR_STATE;
+  }
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(p.feats, feats, (size_t)B * t * cfg.feat_dim * sizeof(float),
+                                   feats_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  {
+    std::vector<int> vlen(B, p.Tp);
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  }
+  // per-layer cache maps with extent = keys valid after this chunk (TMA zero-fills beyond)
+  std::string err;
+  const int kend_new = ss.kend + p.Tp;
+  for (int l = 0; l < L; ++l) {
+    const size_t lk = (size_t)l * B * H * ss.Tcap * 64;
+    if (!make_tmap_2d(&ss.tm_k[l], ss.kk + lk, 64, (uint64_t)B * H * ss.Tcap, 128, 128, &err) ||
+        !make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, kend_new, (uint64_t)B * H * 64, (uint64_t)ss.Tcap * 2, 64, &err)) {
+      set_last_error(err);
+      return PPASR_ERR_CUDA;
+    }
+  }
+  rc = run_encoder(c, st, true);
+  if (rc) return rc;
+  // cache bookkeeping (encoder.py:255-260,272): keep everything (<0), nothing (0) or the last `required` keys
+  ss.kend = kend_new;
+  ss.offset += p.Tp;
+  if (required_cache_size == 0)
+    ss.kstart = ss.kend;
+  else if (required_cache_size > 0 && ss.kend - ss.kstart > required_cache_size)
+    ss.kstart = ss.kend - required_cache_size;
+  return PPASR_OK;
+}
+
+int ppasr_b200_stream_info(ppasr_b200_ctx* c, int32_t* offset, int32_t* cache_t) {
+  PPASR_REQUIRE(c, "null ctx");
+  if (offset) *offset = c->ss.offset;
+  if (cache_t) *cache_t = c->ss.kend - c->ss.kstart;
+  return PPASR_OK;
+}
+
+int ppasr_b200_stream_export(ppasr_b200_ctx* c, float* att_cache, float* cnn_cache, int32_t on_device, void* stream) {
+  PPASR_REQUIRE(c && c->ss.kk, "no stream state");
+  auto& ss = c->ss;
+  const auto& cfg = c->cfg;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int L = cfg.n_layers, H = cfg.n_heads, D = cfg.d_model, lorder = cfg.conv_kernel - 1;
+  const int t = ss.kend - ss.kstart;
+  float* tmp = nullptr;
+  const size_t na = (size_t)L * H * t * 128, nc = (size_t)L * D * lorder;
+  if (!on_device) PPASR_CUDA_CHECK(cudaMalloc(&tmp, (na + nc) * 4 + 16));
+  float* da = on_device ? att_cache : tmp;
+  float* dc = on_device ? cnn_cache : tmp + na;
+  for (int l = 0; l < L; ++l) {
+    const size_t lk = (size_t)l * ss.B * H * ss.Tcap * 64;
+    if (att_cache && t > 0)
+      PPASR_CUDA_CHECK(launch_export_att_cache(ss.kk + lk, ss.vt + lk, da + (size_t)l * H * t * 128, H, ss.Tcap, ss.Tcap,
+                                               ss.kstart, t, st));
+    if (cnn_cache)
+      PPASR_CUDA_CHECK(launch_export_cnn_cache(ss.cnn + (size_t)l * ss.B * lorder * D, dc + (size_t)l * D * lorder, lorder, D, st));
+  }
+  if (!on_device) {
+    if (att_cache && t > 0) PPASR_CUDA_CHECK(cudaMemcpyAsync(att_cache, da, na * 4, cudaMemcpyDeviceToHost, st));
+    if (cnn_cache) PPASR_CUDA_CHECK(cudaMemcpyAsync(cnn_cache, dc, nc * 4, cudaMemcpyDeviceToHost, st));
+    PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  return PPASR_OK;
 }
 
 static int run_ctc_logits(ppasr_b200_ctx* c, cudaStream_t st) {

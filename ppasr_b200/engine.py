@@ -90,6 +90,42 @@ class ConformerEngine:
         self.B, self.Tp = B, out_frames(T)
         return self
 
+    # ---- chunk streaming -------------------------------------------------------------------------
+    def stream_reset(self, B=1):
+        L.check(self.lib.ppasr_b200_stream_reset(self._ctx, int(B)))
+
+    def encode_chunk(self, feats, required_cache_size=-1, stream=None):
+        """feats: float32 [B,t,F] (host numpy / torch, or CUDA tensor). Appends out_frames(t) frames to the stream."""
+        torch = self.torch
+        if isinstance(feats, np.ndarray):
+            feats = np.ascontiguousarray(feats, dtype=np.float32)
+            B, T, _ = feats.shape
+            ptr, on_dev = ctypes.c_void_p(feats.ctypes.data), 0
+        else:
+            feats = feats.contiguous()
+            B, T, _ = feats.shape
+            ptr, on_dev = ctypes.c_void_p(feats.data_ptr()), int(feats.is_cuda)
+        L.check(self.lib.ppasr_b200_encode_chunk(self._ctx, ptr, on_dev, B, T, int(required_cache_size),
+                                                 L.stream_ptr(stream)))
+        self.B, self.Tp = B, out_frames(T)
+        return self
+
+    def stream_info(self):
+        off, ct = ctypes.c_int32(), ctypes.c_int32()
+        L.check(self.lib.ppasr_b200_stream_info(self._ctx, ctypes.byref(off), ctypes.byref(ct)))
+        return off.value, ct.value
+
+    def stream_export(self):
+        """(att_cache [L,H,t,128], cnn_cache [L,1,D,K-1]) fp32 host copies in the reference layouts (stream 0)."""
+        cfg = self.cfg
+        _, ct = self.stream_info()
+        att = np.zeros((cfg.num_blocks, cfg.attention_heads, ct, 2 * (cfg.output_size // cfg.attention_heads)),
+                       dtype=np.float32)
+        cnn = np.zeros((cfg.num_blocks, 1, cfg.output_size, cfg.cnn_module_kernel - 1), dtype=np.float32)
+        L.check(self.lib.ppasr_b200_stream_export(self._ctx, ctypes.c_void_p(att.ctypes.data),
+                                                  ctypes.c_void_p(cnn.ctypes.data), 0, L.stream_ptr()))
+        return att, cnn
+
     def ctc_probs(self, to_host=False, stream=None):
         torch = self.torch
         V = self.cfg.vocab_size

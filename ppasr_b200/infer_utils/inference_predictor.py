@@ -53,6 +53,9 @@ class InferencePredictor:
         # streaming state, mirrors inference_predictor.py:35-39
         self.output_state_h = None
         self.output_state_c = None
+        self._stream_active = False
+        self._stream_batch = 0
+        self._caches_stale = False
         self.cnn_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
         self.att_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
         self.offset = np.array([0], dtype=np.int32)
@@ -112,15 +115,51 @@ class InferencePredictor:
         raise Exception(f'当前模型不支持该方法，当前模型为：{self.use_model}')
 
     def predict_chunk_conformer(self, x_chunk, required_cache_size):
-        """inference_predictor.py:184-212."""
+        """inference_predictor.py:184-212: x_chunk f32 [1, <=67, n_mels] -> probs f32 [1, chunk, V]; advances
+        self.offset. The attention / conv caches stay on the device between calls; `self.att_cache` and
+        `self.cnn_cache` are exported lazily in the reference layouts when read. Batched lock-step streams
+        ([B, t, n_mels]) are accepted as an extension."""
         if not ('former' in self.use_model and self.streaming):
             raise Exception(f'当前模型不支持该方法，当前模型为：{self.use_model}')
-        raise Exception("predict_chunk_conformer: chunk streaming kernels are not built yet in this round")
+        x_chunk = np.ascontiguousarray(x_chunk, dtype=np.float32)
+        if not self._stream_active or self._stream_batch != x_chunk.shape[0]:
+            self.engine.stream_reset(x_chunk.shape[0])
+            self._stream_active, self._stream_batch = True, x_chunk.shape[0]
+        self.engine.encode_chunk(x_chunk, int(required_cache_size))
+        output_chunk_probs = self.engine.ctc_probs(to_host=True)
+        self.offset += output_chunk_probs.shape[1]
+        self._caches_stale = True
+        return output_chunk_probs
+
+    def _refresh_caches(self):
+        if self._stream_active and self._caches_stale:
+            self._att_cache, self._cnn_cache = self.engine.stream_export()
+            self._caches_stale = False
+
+    @property
+    def att_cache(self):
+        self._refresh_caches()
+        return self._att_cache
+
+    @att_cache.setter
+    def att_cache(self, v):
+        self._att_cache = v
+
+    @property
+    def cnn_cache(self):
+        self._refresh_caches()
+        return self._cnn_cache
+
+    @cnn_cache.setter
+    def cnn_cache(self, v):
+        self._cnn_cache = v
 
     def reset_stream(self):
         """inference_predictor.py:215-220."""
         self.output_state_h = None
         self.output_state_c = None
+        self._stream_active = False
+        self._caches_stale = False
         self.att_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
         self.cnn_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
         self.offset = np.array([0], dtype=np.int32)

@@ -1,0 +1,185 @@
+"""Drop-in for the hot-path part of ppasr/predict.py::PPASRPredictor on a B200.
+
+Mirrors `predict`, `predict_stream`, `reset_stream` and `decode` (predict.py:114-140,163-187,232-347): same
+arguments, same `{'text', 'score'}` results, same window logic (67-frame window, stride 64, 3 cached
+frames), same `None` returns when too few frames are buffered, same exceptions. The encoder + decode call
+path runs in libppasr_b200.so; only the audio front end (outside the hot path) is host code:
+`AudioFeaturizer` below restates audio_featurizer.py:37-69,120-138 with torchaudio's kaldi fbank, the CPU
+twin of paddleaudio's.
+
+Not mirrored (out of scope): predict_long (VAD), punctuation, ITN — passing
+`use_pun=True` / `is_itn=True` raises.
+"""
+import numpy as np
+
+from .decoders.ctc_greedy_decoder import greedy_decoder, greedy_decoder_chunk
+from .infer_utils.inference_predictor import InferencePredictor, _get
+from .weights import read_vocab_file
+
+
+class AudioFeaturizer:
+    """ppasr/data_utils/featurizer/audio_featurizer.py:13-138 for feature_method='fbank' (the shipped default)."""
+
+    def __init__(self, feature_method='fbank', n_mels=80, n_mfcc=40, sample_rate=16000, use_dB_normalization=True,
+                 target_dB=-20, train=False):
+        if feature_method != 'fbank':
+            raise Exception('没有{}预处理方法'.format(feature_method))
+        self._n_mels = n_mels
+        self._target_sample_rate = sample_rate
+        self._use_dB_normalization = use_dB_normalization
+        self._target_dB = target_dB
+
+    @staticmethod
+    def _rms_db(samples):
+        mean_square = np.mean(samples.astype(np.float64) ** 2)
+        return 10 * np.log10(max(mean_square, 1e-20))  # audio.py rms_db
+
+    def featurize(self, samples, sample_rate=16000):
+        """samples: float32 in [-1, 1]. Returns fbank [T, n_mels] float32."""
+        import torch
+        import torchaudio
+        samples = np.asarray(samples, dtype=np.float32)
+        if sample_rate != self._target_sample_rate:
+            raise Exception("resampling is outside the hot path: feed audio at %d Hz" % self._target_sample_rate)
+        if self._use_dB_normalization:  # audio.py:287-304 normalize(), gain_db()
+            gain = self._target_dB - self._rms_db(samples)
+            if gain > 300.0:
+                raise ValueError(f"无法将段规范化到{self._target_dB}dB，音频增益{gain}增益已经超过max_gain_db (300.0dB)")
+            samples = samples * (10.0 ** (gain / 20.0))
+        # audio.py:549-574 to('int16'): scale by 2^15 and clip
+        s16 = np.clip(samples * 32768.0, -32768, 32767).astype(np.int16)
+        wav = torch.from_numpy(s16.astype(np.float32)).unsqueeze(0)
+        if wav.shape[1] < 400:
+            return np.zeros((0, self._n_mels), dtype=np.float32)
+        mat = torchaudio.compliance.kaldi.fbank(wav, num_mel_bins=self._n_mels, frame_length=25, frame_shift=10,
+                                                dither=0.0, sample_frequency=float(self._target_sample_rate))
+        return mat.numpy().astype(np.float32)
+
+
+class PPASRPredictor:
+    def __init__(self, configs, model_path='models/conformer_streaming_fbank/infer/', use_pun=False, use_gpu=True,
+                 vocab_list=None, weights=None, device=0):
+        """configs: dict (or attribute object) with the reference's yaml keys: use_model, streaming, decoder,
+        encoder_conf, preprocess_conf, dataset_conf.dataset_vocab. `vocab_list` / `weights` let tests pass
+        in-memory objects instead of files."""
+        if use_pun:
+            raise Exception("punctuation restoration is outside the ppasr_b200 hot path")
+        self.configs = configs
+        self.use_model = _get(configs, 'use_model', 'conformer')
+        self.streaming = bool(_get(configs, 'streaming', True))
+        self.decoder = _get(configs, 'decoder', 'ctc_greedy')
+        pre = _get(configs, 'preprocess_conf', {}) or {}
+        pre = dict(pre) if isinstance(pre, dict) else vars(pre)
+        self._audio_featurizer = AudioFeaturizer(**pre)
+        if vocab_list is None:
+            vocab_list = read_vocab_file(_get(_get(configs, 'dataset_conf', {}), 'dataset_vocab'))
+        self.vocab_list = vocab_list
+        self.running = False
+        # streaming state (predict.py:69-72)
+        self.remained_wav = None
+        self.cached_feat = None
+        self.greedy_last_max_prob_list = None
+        self.greedy_last_max_index_list = None
+        if self.decoder == 'ctc_beam_search':
+            from .decoders.beam_search_decoder import BeamSearchDecoder
+            bconf = _get(configs, 'ctc_beam_search_decoder_conf', {}) or {}
+            bconf = dict(bconf) if isinstance(bconf, dict) else vars(bconf)
+            self.beam_search_decoder = BeamSearchDecoder(vocab_list=vocab_list, **bconf)
+        self.predictor = InferencePredictor(configs=configs, use_model=self.use_model, streaming=self.streaming,
+                                            model_dir=model_path, use_gpu=use_gpu, weights=weights,
+                                            vocab_size=len(vocab_list), device=device)
+
+    # predict.py:114-140
+    def decode(self, output_data, use_pun=False, is_itn=False):
+        if use_pun or is_itn:
+            raise Exception("punctuation / ITN are outside the ppasr_b200 hot path")
+        if self.decoder == 'ctc_beam_search':
+            result = self.beam_search_decoder.decode_beam_search_offline(probs_split=output_data)
+        else:
+            result = greedy_decoder(probs_seq=output_data, vocabulary=self.vocab_list)
+        return result[0], result[1]
+
+    # predict.py:163-187
+    def predict(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000):
+        if not isinstance(audio_data, np.ndarray):
+            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+        audio_feature = self._audio_featurizer.featurize(audio_data, sample_rate)
+        return self.predict_features(audio_feature, use_pun=use_pun, is_itn=is_itn)
+
+    def predict_features(self, audio_feature, use_pun=False, is_itn=False):
+        """Same as predict() from the featurizer output on ([T, n_mels] fp32)."""
+        input_data = np.array(audio_feature).astype(np.float32)[np.newaxis, :]
+        audio_len = np.array([input_data.shape[1]]).astype(np.int64)
+        output_data = self.predictor.predict(input_data, audio_len)[0]
+        score, text = self.decode(output_data=output_data, use_pun=use_pun, is_itn=is_itn)
+        return {'text': text, 'score': score}
+
+    # predict.py:232-337
+    def predict_stream(self, audio_data, is_end=False, use_pun=False, is_itn=False, channels=1, samp_width=2,
+                       sample_rate=16000):
+        if not self.streaming:
+            raise Exception(f"不支持改该模型流式识别，当前模型：{self.use_model}")
+        if isinstance(audio_data, bytes):
+            if samp_width != 2 or channels != 1:
+                raise Exception("only 16-bit mono PCM bytes are supported")
+            audio_data = np.frombuffer(audio_data, dtype=np.int16).astype(np.float32) / 32768.0
+        elif not isinstance(audio_data, np.ndarray):
+            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+        audio_data = np.asarray(audio_data, dtype=np.float32)
+        if self.remained_wav is None:
+            self.remained_wav = audio_data
+        else:
+            self.remained_wav = np.concatenate([self.remained_wav, audio_data])
+        # featurise ALL remaining audio, then drop the consumed samples (predict.py:268-274)
+        x_chunk = self._audio_featurizer.featurize(self.remained_wav, sample_rate)
+        x_chunk = np.array(x_chunk).astype(np.float32)[np.newaxis, :]
+        self.remained_wav = self.remained_wav[160 * x_chunk.shape[1]:]
+        return self.predict_stream_features(x_chunk, is_end=is_end, use_pun=use_pun, is_itn=is_itn)
+
+    def predict_stream_features(self, x_chunk, is_end=False, use_pun=False, is_itn=False):
+        """predict.py:269-337 from the featurizer output on: x_chunk [1, n, n_mels] new frames."""
+        if use_pun or is_itn:
+            raise Exception("punctuation / ITN are outside the ppasr_b200 hot path")
+        if self.cached_feat is None:
+            self.cached_feat = x_chunk
+        else:
+            self.cached_feat = np.concatenate([self.cached_feat, x_chunk], axis=1)
+        decoding_chunk_size = 16
+        context = 7
+        subsampling = 4
+        cached_feature_num = context - subsampling
+        decoding_window = (decoding_chunk_size - 1) * subsampling + context
+        stride = subsampling * decoding_chunk_size
+        num_frames = self.cached_feat.shape[1]
+        if num_frames < decoding_window and not is_end:
+            return None
+        if num_frames < context:
+            return None
+        left_frames = context if is_end else decoding_window
+        score, text, end = None, None, None
+        for cur in range(0, num_frames - left_frames + 1, stride):
+            end = min(cur + decoding_window, num_frames)
+            x = self.cached_feat[:, cur:end, :]
+            num_decoding_left_chunks = -1
+            required_cache_size = decoding_chunk_size * num_decoding_left_chunks
+            output_chunk_probs = self.predictor.predict_chunk_conformer(x_chunk=x, required_cache_size=required_cache_size)
+            output_lens = np.array([output_chunk_probs.shape[1]])
+            if self.decoder == 'ctc_beam_search':
+                score, text = self.beam_search_decoder.decode_chunk(probs=output_chunk_probs, logits_lens=output_lens)
+            else:
+                score, text, self.greedy_last_max_prob_list, self.greedy_last_max_index_list = \
+                    greedy_decoder_chunk(probs_seq=output_chunk_probs[0], vocabulary=self.vocab_list,
+                                         last_max_index_list=self.greedy_last_max_index_list,
+                                         last_max_prob_list=self.greedy_last_max_prob_list)
+        self.cached_feat = self.cached_feat[:, end - cached_feature_num:, :]
+        return {'text': text, 'score': score}
+
+    # predict.py:340-347
+    def reset_stream(self):
+        self.predictor.reset_stream()
+        self.remained_wav = None
+        self.cached_feat = None
+        self.greedy_last_max_prob_list = None
+        self.greedy_last_max_index_list = None
+        if self.decoder == 'ctc_beam_search':
+            self.beam_search_decoder.reset_decoder()

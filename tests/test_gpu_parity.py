@@ -313,3 +313,77 @@ def test_inference_predictor_api(lib, cuda):
         InferencePredictor({}, "deepspeech2", weights=w)
     with pytest.raises(Exception):
         InferencePredictor({}, "conformer", model_dir="/nonexistent/dir")
+
+
+# ------------------------------------------------------------------------------------------------
+# chunk streaming (forward_chunk / predict_chunk_conformer / predict_stream)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("required", [-16, 32, 0])
+def test_chunk_streaming_matches_oracle(lib, cuda, required):
+    from oracle.conformer_oracle import ConformerConf, ConformerOracle, stream_windows
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+    cfg = ConformerConfig(num_blocks=2, vocab_size=211)
+    w = init_conformer_weights(cfg)
+    T = 215  # 3 full 67-frame windows + a short tail consumed at is_end
+    feats = synthetic_fbank(1, T)
+    orc = ConformerOracle(ConformerConf(**cfg.to_dict()), w)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "conformer",
+                              streaming=True, weights=w)
+    att = torch.zeros(0, 0, 0, 0)
+    cnn = torch.zeros(0, 0, 0, 0)
+    off = 0
+    for (s, e) in stream_windows(T, is_end=True):
+        ref, att, cnn = orc.get_encoder_out_chunk(torch.from_numpy(feats[:, s:e]), off, required, att, cnn)
+        off += ref.shape[1]
+        got = pred.predict_chunk_conformer(feats[:, s:e], required)
+        assert got.shape == tuple(ref.shape)
+        assert np.abs(got - ref.numpy()).max() < 3e-2, (s, e)
+        assert int(pred.offset[0]) == off
+    a, c = pred.att_cache, pred.cnn_cache
+    assert a.shape == tuple(att.shape) and c.shape == tuple(cnn.shape)
+    if att.numel():
+        assert rel_err(torch.from_numpy(a), att) < 2e-2
+    assert rel_err(torch.from_numpy(c), cnn) < 2e-2
+    pred.reset_stream()
+    assert pred.att_cache.shape == (0, 0, 0, 0) and int(pred.offset[0]) == 0
+    # a second stream after reset reproduces the first chunk bit-for-bit
+    s, e = stream_windows(T, is_end=True)[0]
+    g1 = pred.predict_chunk_conformer(feats[:, s:e], required)
+    pred.reset_stream()
+    g2 = pred.predict_chunk_conformer(feats[:, s:e], required)
+    assert np.array_equal(g1, g2)
+
+
+def test_predict_stream_window_logic(lib, cuda):
+    """PPASRPredictor.predict_stream_features: arbitrary feed sizes give the same transcript as feeding the
+    reference's 67/64 windows by hand; None while fewer than a window is buffered (predict.py:287-288)."""
+    from oracle import decoders_oracle as DO
+    from oracle.conformer_oracle import stream_windows
+    from ppasr_b200.predict import PPASRPredictor
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab, synthetic_fbank
+    cfg = ConformerConfig(num_blocks=2, vocab_size=150)
+    w = init_conformer_weights(cfg)
+    vocab = make_vocab(150)
+    configs = {"use_model": "conformer", "streaming": True, "decoder": "ctc_greedy", "encoder_conf": cfg.to_dict(),
+               "preprocess_conf": {"feature_method": "fbank", "n_mels": 80}}
+    p = PPASRPredictor(configs, vocab_list=vocab, weights=w)
+    T = 300
+    feats = synthetic_fbank(1, T)
+    assert p.predict_stream_features(feats[:, :30]) is None
+    res = None
+    pos = 30
+    for n in (50, 10, 130, 80):
+        r = p.predict_stream_features(feats[:, pos:pos + n], is_end=(pos + n >= T))
+        pos += n
+        res = r if r is not None else res
+    assert pos == T and res is not None
+    # by hand through the InferencePredictor with the reference windows
+    p.reset_stream()
+    chunks = [p.predictor.predict_chunk_conformer(feats[:, s:e], -16)[0] for (s, e) in stream_windows(T, is_end=True)]
+    score, text = DO.greedy_decoder(np.concatenate(chunks, 0), vocab)
+    assert res["text"] == text
+    assert abs(res["score"] - score) < 1e-3
+    # offline predict on the same features returns a dict with the same keys
+    out = p.predict_features(feats[0])
+    assert set(out) == {"text", "score"}
