@@ -666,7 +666,7 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
     // ---- rel-pos MHA: x += Wo attn(LN(x))                      (encoder.py:389-402)
     { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st)); }
     {
-      AttnParams ap;
+      AttnParams ap{};
       ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.D = D, ap.pos_col0 = l * D, ap.out = p.att, ap.q_rows_per_bh = p.Tp;
       if (!chunk) {
         EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
@@ -1028,8 +1028,8 @@ int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int3
     set_last_error(err);
     return PPASR_ERR_CUDA;
   }
-  AttnParams ap;
-  ap.B = B, ap.H = H, ap.T1 = T1, ap.T2 = T2, ap.q_rows_per_bh = T1, ap.k_rows_per_bh = T2;
+  AttnParams ap{};
+  ap.B = B, ap.H = H, ap.T1 = T1, ap.T2 = T2, ap.q_rows_per_bh = T1, ap.k_rows_per_bh = T2, ap.k_row0 = 0;
   ap.pos_row0 = pos_row0, ap.pos_col0 = pos_col0, ap.D = H * 64, ap.klens = klens, ap.out = (__nv_bfloat16*)out;
   PPASR_CUDA_CHECK(launch_rel_attention(tq, tk, tp, tv, ap, reinterpret_cast<cudaStream_t>(stream)));
   return PPASR_OK;
