@@ -116,6 +116,26 @@ int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V
                              int32_t blank_id, int32_t* ids, int32_t ld_ids, int32_t* out_lens, float* scores,
                              int32_t* tmp_idx, float* tmp_maxp, void* stream);
 
+/* ---- CTC prefix beam search without external scorer (device pointers) ---------------------------
+ * replaces: ctc_beam_search_decoding / ctc_beam_search_decoding_batch / CtcBeamSearchDecoderBatch.next+decode
+ *           (decoders/swig_wrapper.py:35-121 -> paddlespeech_ctcdecoders, ext_scoring_func=None).
+ * `states` (ppasr_b200_beam_state_bytes) holds the beam and the prefix table of B utterances across calls,
+ * so advance() can be fed chunk by chunk (decode_chunk) or once (offline). probs: fp32 [B,T,V] dense
+ * probabilities (not logs), like the reference. beam <= 128, cutoff_top_n is capped at 64.
+ * result(): out_ids int32 [B, beam, lmax], out_lens int32 [B, beam] (-1 = no such entry), out_scores fp32
+ * [B, beam] = log P(prefix) sorted best first (the reference returns -score to Python). */
+int64_t ppasr_b200_beam_state_bytes(int32_t B, int32_t max_frames, int32_t beam);
+int64_t ppasr_b200_beam_workspace_bytes(int32_t B, int32_t T);
+int ppasr_b200_beam_reset(void* states, int32_t B, int32_t max_frames, int32_t beam, void* stream);
+int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens,
+                            int32_t beam, float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states,
+                            int32_t max_frames, void* workspace, void* stream);
+int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
+                           int32_t lmax, int32_t* out_lens, float* out_scores, void* stream);
+/* The pruning scan of the posterior alone (decoder_utils.cpp get_pruned_log_probs), for the HBM roofline. */
+int ppasr_b200_op_ctc_prune(const float* probs, int32_t rows, int32_t V, float cutoff_prob, int32_t cutoff_top_n,
+                            void* workspace, void* stream);
+
 /* ---- op-level entry points (parity tests, per-kernel roofline) ------------------------------- */
 /* out = epilogue(A[M,K] bf16 * W[N,K]^T bf16 + bias). epilogue: 0 = bf16 store with act (0 none,
  * 1 relu, 2 swish); 1 = fp32 x = (residual ? x : 0) + alpha*(acc+bias) with optional pad-row mask

@@ -208,9 +208,11 @@ def ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob=1.0, cutoff_top_n=40, 
 
 
 def ctc_beam_search_decoding(probs_seq, vocabulary, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0):
-    """Mirror of ppasr/decoders/swig_wrapper.py:35-64 (ext_scoring_func=None)."""
+    """Mirror of ppasr/decoders/swig_wrapper.py:35-64 (ext_scoring_func=None). The published
+    decoder_utils.cpp get_beam_search_result returns `-approx_ctc` (a positive negative-log-probability),
+    best hypothesis first; without a scorer approx_ctc is the prefix score itself."""
     res = ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob, cutoff_top_n, blank_id)
-    return [(s, "".join(vocabulary[i] for i in ids).replace("<space>", " ")) for s, ids in res]
+    return [(-s, "".join(vocabulary[i] for i in ids)) for s, ids in res]
 
 
 def ctc_prefix_total_logprob_bruteforce(probs_seq, blank_id=0):

@@ -64,6 +64,12 @@ PROTOTYPES = {
     "ppasr_b200_encode_chunk": (c_int, [P, P, I, I, I, I, P]),
     "ppasr_b200_stream_info": (c_int, [P, P, P]),
     "ppasr_b200_stream_export": (c_int, [P, P, P, I, P]),
+    "ppasr_b200_beam_state_bytes": (c_int64, [I, I, I]),
+    "ppasr_b200_beam_workspace_bytes": (c_int64, [I, I]),
+    "ppasr_b200_beam_reset": (c_int, [P, I, I, I, P]),
+    "ppasr_b200_beam_advance": (c_int, [P, I, I, I, P, I, c_float, I, I, P, I, P, P]),
+    "ppasr_b200_beam_result": (c_int, [P, I, I, I, P, I, P, P, P]),
+    "ppasr_b200_op_ctc_prune": (c_int, [P, I, I, c_float, I, P, P]),
     "ppasr_b200_greedy_decode": (c_int, [P, I, I, I, P, I, P, I, P, P, P, P, P]),
     "ppasr_b200_op_linear": (c_int, [P, c_int64, P, c_int64, P, P, c_int64, I, I, I, I, I, c_float, I, P, I, I, P]),
     "ppasr_b200_op_layernorm": (c_int, [P, P, P, P, P, P, P, I, I, I, c_float, P]),

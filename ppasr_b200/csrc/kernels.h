@@ -41,6 +41,30 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
                                 int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
                                 int* score_cnt, cudaStream_t st);
 
+// CTC prefix beam search (beam.cu)
+struct BeamStateHeader {
+  int nb;       // entries in the beam
+  int next_id;  // next free prefix id (0 = root)
+  int frames;   // frames consumed so far
+  int pad;
+};
+struct BeamEntry {
+  unsigned long long hash;  // identity of the prefix string
+  int id, parent_id, last, len;
+  float b_prev, nb_prev, score;
+  int pad;
+};
+size_t beam_state_stride(int node_cap);
+cudaError_t launch_ctc_prune(const float* probs, int V, int rows, float cutoff_prob, int top_n, int* cnt, int* cid,
+                             float* clp, cudaStream_t st);
+cudaError_t launch_beam_reset(void* states, int B, int node_cap, cudaStream_t st);
+cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp, int B, int T, const int* frame_lens,
+                                int beam, int blank, void* states, int node_cap, cudaStream_t st);
+cudaError_t launch_beam_result(const void* states, int B, int node_cap, int beam, int* out_ids, int lmax, int* out_lens,
+                               float* out_scores, cudaStream_t st);
+constexpr int BEAM_MAX_TOPN = 64;
+constexpr int BEAM_MAX_BEAM = 128;
+
 // Relative-position attention (attention.cu). Tensor maps are built by the caller.
 struct AttnParams {
   int B, H;

@@ -135,4 +135,51 @@ int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, in
   return PPASR_OK;
 }
 
+// ---- CTC prefix beam search (no external scorer) ---------------------------------------------------
+int64_t ppasr_b200_beam_state_bytes(int32_t B, int32_t max_frames, int32_t beam) {
+  return (int64_t)beam_state_stride(max_frames * beam + 1) * B;
+}
+int64_t ppasr_b200_beam_workspace_bytes(int32_t B, int32_t T) {
+  return (int64_t)B * T * (4 + 8 * BEAM_MAX_TOPN) + 1024;
+}
+int ppasr_b200_beam_reset(void* states, int32_t B, int32_t max_frames, int32_t beam, void* stream) {
+  PPASR_REQUIRE(states && B > 0 && max_frames > 0 && beam >= 1 && beam <= BEAM_MAX_BEAM, "bad arguments");
+  PPASR_CUDA_CHECK(launch_beam_reset(states, B, max_frames * beam + 1, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens,
+                            int32_t beam, float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states,
+                            int32_t max_frames, void* workspace, void* stream) {
+  PPASR_REQUIRE(probs && states && workspace, "null pointer");
+  PPASR_REQUIRE(B > 0 && T > 0 && V > 1, "bad sizes");
+  PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,128] in this build");
+  PPASR_REQUIRE(cutoff_top_n >= 1, "cutoff_top_n must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int top_n = cutoff_top_n < BEAM_MAX_TOPN ? cutoff_top_n : BEAM_MAX_TOPN;
+  int* cnt = reinterpret_cast<int*>(workspace);
+  int* cid = cnt + (((size_t)B * T + 63) & ~size_t(63));
+  float* clp = reinterpret_cast<float*>(cid + (size_t)B * T * BEAM_MAX_TOPN);
+  PPASR_CUDA_CHECK(launch_ctc_prune(probs, V, B * T, cutoff_prob, top_n, cnt, cid, clp, st));
+  PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, blank_id, states, max_frames * beam + 1, st));
+  return PPASR_OK;
+}
+int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
+                           int32_t lmax, int32_t* out_lens, float* out_scores, void* stream) {
+  PPASR_REQUIRE(states && out_ids && out_lens && out_scores && lmax > 0, "bad arguments");
+  PPASR_CUDA_CHECK(launch_beam_result(states, B, max_frames * beam + 1, beam, out_ids, lmax, out_lens, out_scores,
+                                      reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+// pruning scan alone (per-kernel roofline: reads B*T*V*4 bytes once)
+int ppasr_b200_op_ctc_prune(const float* probs, int32_t rows, int32_t V, float cutoff_prob, int32_t cutoff_top_n,
+                            void* workspace, void* stream) {
+  PPASR_REQUIRE(probs && workspace && rows > 0, "bad arguments");
+  const int top_n = cutoff_top_n < BEAM_MAX_TOPN ? cutoff_top_n : BEAM_MAX_TOPN;
+  int* cnt = reinterpret_cast<int*>(workspace);
+  int* cid = cnt + (((size_t)rows + 63) & ~size_t(63));
+  float* clp = reinterpret_cast<float*>(cid + (size_t)rows * BEAM_MAX_TOPN);
+  PPASR_CUDA_CHECK(launch_ctc_prune(probs, V, rows, cutoff_prob, top_n, cnt, cid, clp, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,156 @@
+"""Drop-in for ppasr/decoders/beam_search_decoder.py::BeamSearchDecoder (and the swig_wrapper functions)
+running the CTC prefix beam search on the B200 (ppasr_b200/csrc/beam.cu) instead of the
+`paddlespeech_ctcdecoders` C++ library.
+
+Same constructor arguments and methods (beam_search_decoder.py:9-96). Differences:
+  * `language_model_path=None` (default here) decodes without an external scorer -- which the upstream C++
+    supports via ext_scoring_func=None (swig_wrapper.py:35-41). A KenLM scorer is a "next" row
+    (SURVEY §8f-4): passing a path raises instead of silently ignoring alpha/beta.
+  * beam_size <= 128 and cutoff_top_n <= 64 in this build; larger values raise.
+  * `num_processes` is accepted and ignored (utterances are decoded by one CTA each, all in parallel).
+Returned scores follow the upstream convention: -log P(prefix) of the total CTC probability
+(decoder_utils.cpp get_beam_search_result, `-approx_ctc`), best first.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib as L
+
+
+class BeamSearchDecoder:
+    def __init__(self, alpha=2.2, beta=4.3, beam_size=300, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=None,
+                 num_processes=10, blank_id=0, language_model_path=None, max_frames=5000):
+        if language_model_path is not None:
+            raise Exception("ppasr_b200 BeamSearchDecoder: external KenLM scorer is not implemented in this round; "
+                            "pass language_model_path=None to decode without a scorer")
+        if beam_size > 128:
+            raise Exception(f"beam_size {beam_size} > 128 is not supported by the GPU decoder in this build")
+        if cutoff_top_n > 64:
+            raise Exception(f"cutoff_top_n {cutoff_top_n} > 64 is not supported by the GPU decoder in this build")
+        import torch
+        if not torch.cuda.is_available():
+            raise L.PPASRB200Error("ppasr_b200 decoders need a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.alpha = alpha
+        self.beta = beta
+        self.beam_size = int(beam_size)
+        self.cutoff_prob = float(cutoff_prob)
+        self.cutoff_top_n = int(cutoff_top_n)
+        self.vocab_list = vocab_list
+        self.num_processes = num_processes
+        self.blank_id = int(blank_id)
+        self.max_frames = int(max_frames)
+        self.lib = L.load()
+        self._ext_scorer = None
+        self._stream_state = None  # persistent state of the streaming decoder (batch 1)
+        self.reset_decoder()
+
+    # ---- device helpers -------------------------------------------------------------------------
+    def _alloc_state(self, B, max_frames):
+        torch = self.torch
+        n = self.lib.ppasr_b200_beam_state_bytes(B, max_frames, self.beam_size)
+        st = torch.empty(n, dtype=torch.uint8, device="cuda")
+        L.check(self.lib.ppasr_b200_beam_reset(L.ptr(st), B, max_frames, self.beam_size, L.stream_ptr()))
+        return st
+
+    def _advance(self, state, probs, frame_lens, max_frames):
+        torch = self.torch
+        B, T, V = probs.shape
+        ws = torch.empty(self.lib.ppasr_b200_beam_workspace_bytes(B, T), dtype=torch.uint8, device="cuda")
+        fl = None
+        if frame_lens is not None:
+            fl = torch.as_tensor(np.asarray(frame_lens), dtype=torch.int32).cuda()
+        L.check(self.lib.ppasr_b200_beam_advance(L.ptr(probs), B, T, V, L.ptr(fl), self.beam_size,
+                                                 ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
+                                                 L.ptr(state), max_frames, L.ptr(ws), L.stream_ptr()))
+
+    def _results(self, state, B, max_frames, lmax):
+        torch = self.torch
+        ids = torch.zeros((B, self.beam_size, lmax), dtype=torch.int32, device="cuda")
+        lens = torch.zeros((B, self.beam_size), dtype=torch.int32, device="cuda")
+        sc = torch.zeros((B, self.beam_size), dtype=torch.float32, device="cuda")
+        L.check(self.lib.ppasr_b200_beam_result(L.ptr(state), B, max_frames, self.beam_size, L.ptr(ids), lmax,
+                                                L.ptr(lens), L.ptr(sc), L.stream_ptr()))
+        ids, lens, sc = ids.cpu().numpy(), lens.cpu().numpy(), sc.cpu().numpy()
+        out = []
+        for b in range(B):
+            res = []
+            for k in range(self.beam_size):
+                if lens[b, k] < 0:
+                    continue
+                text = "".join(self.vocab_list[i] for i in ids[b, k, :lens[b, k]])
+                res.append((-float(sc[b, k]), text))
+            out.append(res)
+        return out
+
+    def _to_cuda(self, probs):
+        torch = self.torch
+        t = probs if isinstance(probs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(probs, dtype=np.float32))
+        return t.to(device="cuda", dtype=torch.float32).contiguous()
+
+    def decode_ids_batch(self, probs, frame_lens=None):
+        """probs [B,T,V] -> per utterance list of (score, text), best first (all beam entries)."""
+        p = self._to_cuda(probs)
+        B, T, V = p.shape
+        st = self._alloc_state(B, T)
+        self._advance(st, p, frame_lens, T)
+        return self._results(st, B, T, T)
+
+    # ---- reference API --------------------------------------------------------------------------
+    def decode_beam_search_offline(self, probs_split):
+        """beam_search_decoder.py:45-56 -> (score, text) of the best hypothesis."""
+        p = self._to_cuda(probs_split)
+        return self.decode_ids_batch(p.unsqueeze(0))[0][0]
+
+    def decode_batch_beam_search_offline(self, probs_split):
+        """beam_search_decoder.py:59-73 -> [text]; probs_split: list of [T_i,V] arrays or a [B,T,V] tensor."""
+        torch = self.torch
+        if isinstance(probs_split, (list, tuple)):
+            lens = [int(p.shape[0]) for p in probs_split]
+            V = int(probs_split[0].shape[1])
+            batch = torch.zeros((len(lens), max(lens), V), dtype=torch.float32)
+            for i, p in enumerate(probs_split):
+                batch[i, :lens[i]] = torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p.cpu())
+            res = self.decode_ids_batch(batch, lens)
+        else:
+            res = self.decode_ids_batch(probs_split)
+        return [r[0][1] for r in res]
+
+    def decode_chunk(self, probs, logits_lens):
+        """beam_search_decoder.py:75-91: feed one chunk [1,t,V] to the persistent decoder, return the current best."""
+        p = self._to_cuda(probs)
+        if p.dim() == 2:
+            p = p.unsqueeze(0)
+        lens = np.asarray(logits_lens).astype(np.int32)
+        self._advance(self._stream_state, p[:1], lens[:1], self.max_frames)
+        return self._results(self._stream_state, 1, self.max_frames, self.max_frames)[0][0]
+
+    def reset_decoder(self):
+        """beam_search_decoder.py:93-96."""
+        self._stream_state = self._alloc_state(1, self.max_frames)
+
+
+def ctc_beam_search_decoding(probs_seq, vocabulary, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0,
+                             ext_scoring_func=None):
+    """swig_wrapper.py:35-64 -> [(score, text)] best first."""
+    if ext_scoring_func is not None:
+        raise Exception("external scorer is not supported")
+    d = BeamSearchDecoder(beam_size=beam_size, cutoff_prob=cutoff_prob, cutoff_top_n=cutoff_top_n, vocab_list=vocabulary,
+                          blank_id=blank_id, max_frames=8)
+    return d.decode_ids_batch(d._to_cuda(probs_seq).unsqueeze(0))[0]
+
+
+def ctc_beam_search_decoding_batch(probs_split, vocabulary, beam_size, num_processes, cutoff_prob=1.0, cutoff_top_n=40,
+                                   blank_id=0, ext_scoring_func=None):
+    """swig_wrapper.py:67-103 -> [[(score, text)]]."""
+    if ext_scoring_func is not None:
+        raise Exception("external scorer is not supported")
+    d = BeamSearchDecoder(beam_size=beam_size, cutoff_prob=cutoff_prob, cutoff_top_n=cutoff_top_n, vocab_list=vocabulary,
+                          blank_id=blank_id, max_frames=8)
+    import torch
+    lens = [int(p.shape[0]) for p in probs_split]
+    batch = torch.zeros((len(lens), max(lens), int(probs_split[0].shape[1])), dtype=torch.float32)
+    for i, p in enumerate(probs_split):
+        batch[i, :lens[i]] = torch.as_tensor(np.asarray(p))
+    return d.decode_ids_batch(batch, lens)

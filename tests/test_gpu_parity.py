@@ -387,3 +387,72 @@ def test_predict_stream_window_logic(lib, cuda):
     # offline predict on the same features returns a dict with the same keys
     out = p.predict_features(feats[0])
     assert set(out) == {"text", "score"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CTC prefix beam search (no scorer) vs the oracle restatement (parity unpinned: see oracle header)
+# ------------------------------------------------------------------------------------------------
+def _peaky_probs(rng, T, V, temp, blank_boost=0.0):
+    logits = rng.randn(T, V).astype(np.float32) * temp
+    logits[:, 0] += blank_boost
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    return (e / e.sum(-1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("T,V,beam,cp,topn,temp", [
+    (12, 5, 100, 1.0, 5, 1.0), (40, 30, 10, 0.99, 40, 3.0), (60, 97, 20, 0.99, 40, 4.0), (248, 300, 10, 1.0, 40, 5.0),
+    (30, 50, 1, 1.0, 50, 6.0), (25, 10, 16, 0.9, 3, 1.5),
+])
+def test_beam_search_matches_oracle(lib, cuda, T, V, beam, cp, topn, temp):
+    from oracle import decoders_oracle as DO
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    rng = np.random.RandomState(T * 31 + V)
+    vocab = [f"<{i}>" for i in range(V)]
+    dec = BeamSearchDecoder(beam_size=beam, cutoff_prob=cp, cutoff_top_n=topn, vocab_list=vocab)
+    probs = np.stack([_peaky_probs(rng, T, V, temp, bb) for bb in (0.0, 2.0, 0.5)])
+    got = dec.decode_ids_batch(probs)
+    for b in range(probs.shape[0]):
+        ref = DO.ctc_beam_search_decoding(probs[b], vocab, beam, cp, topn)
+        assert got[b][0][1] == ref[0][1], f"best hypothesis differs (utt {b})"
+        assert abs(got[b][0][0] - ref[0][0]) < 1e-3 * max(1.0, abs(ref[0][0]))
+        # the whole beam agrees as a set of (text -> score), up to fp32 near-ties at the beam edge
+        rd = dict((t, s) for s, t in ref)
+        hits = sum(1 for s, t in got[b] if t in rd and abs(rd[t] - s) < 1e-3 * max(1.0, abs(s)))
+        assert hits >= max(1, int(0.8 * min(len(ref), len(got[b]))))
+    # single-utterance API and batch API
+    s1, t1 = dec.decode_beam_search_offline(probs[0])
+    assert t1 == got[0][0][1]
+    assert dec.decode_batch_beam_search_offline([probs[0], probs[1][: T // 2]])[0] == t1
+
+
+def test_beam_search_streaming_equals_offline(lib, cuda):
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    rng = np.random.RandomState(9)
+    V, T = 80, 96
+    vocab = [f"<{i}>" for i in range(V)]
+    probs = _peaky_probs(rng, T, V, 4.0, 1.0)
+    dec = BeamSearchDecoder(beam_size=10, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=vocab, max_frames=200)
+    off = dec.decode_beam_search_offline(probs)
+    res = None
+    for s in range(0, T, 16):
+        res = dec.decode_chunk(probs[None, s:s + 16], np.array([16]))
+    assert res[1] == off[1] and abs(res[0] - off[0]) < 1e-4
+    dec.reset_decoder()
+    r2 = dec.decode_chunk(probs[None, :16], np.array([16]))
+    d2 = BeamSearchDecoder(beam_size=10, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=vocab, max_frames=200)
+    assert r2 == d2.decode_chunk(probs[None, :16], np.array([16]))
+
+
+def test_beam_search_full_size_vs_greedy(lib, cuda):
+    """BASELINE configs[2]-like posterior [8,748,4233], beam 10: on peaked posteriors the best beam equals greedy."""
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    from ppasr_b200.decoders.ctc_greedy_decoder import greedy_decode_ids
+    torch.manual_seed(3)
+    V = 4233
+    probs = torch.softmax(torch.randn(8, 748, V, device=cuda) * 8, -1)
+    vocab = [f"<{i}>" for i in range(V)]
+    dec = BeamSearchDecoder(beam_size=10, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=vocab)
+    res = dec.decode_ids_batch(probs)
+    ids, ol, _, _, _ = greedy_decode_ids(probs)
+    for b in range(8):
+        assert res[b][0][1] == "".join(vocab[i] for i in ids[b, :ol[b]])
