@@ -43,7 +43,9 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES;       // 2 x BLOCK_N floats
-  static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * BLOCK_N * 4;
+  static constexpr int SCRATCH_OFFSET = BIAS_OFFSET + 2 * BLOCK_N * 4;  // epilogue exchange area (LayerNorm stats)
+  static constexpr int SCRATCH_BYTES = 2 * 128 * 2 * 16;
+  static constexpr int BAR_OFFSET = SCRATCH_OFFSET + SCRATCH_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;           // + barriers + alignment slack
 };
 
@@ -59,7 +61,7 @@ struct GemmAcc {
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue helpers. Every epilogue functor implements
-//   __device__ void tile(uint32_t taddr, int row, int n0, int n_tile, int half, const float* sbias) const
+//   __device__ void tile(uint32_t taddr, int row, int n0, int n_tile, int half, const float* sbias, float4* scratch) const
 // where taddr addresses (this thread's TMEM lane, first column of the accumulator stage), `row` is
 // the global output row owned by this thread, n0 the first output column of the tile, `half`
 // selects which BLOCK_N/2 columns this warp handles and sbias[j] is the bias of column n0 + j.
@@ -96,7 +98,7 @@ struct EpiStoreBF16 {
   const float* bias;
   int ldo;  // elements
   int M, N;
-  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
       const int col = n0 + cc;
       if (row < M && col < N) {
@@ -130,7 +132,7 @@ struct EpiResidF32 {
   int residual;
   const int* lens;  // per-utterance valid frame count (nullable)
   int T;            // frames per utterance (row = b*T + t)
-  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     bool masked = false;
     if (lens != nullptr && row < M) {
       int b = row / T;
@@ -164,6 +166,202 @@ struct EpiResidF32 {
   }
 };
 
+// Residual update fused with the LayerNorm(s) that follow it. Requires BLOCK_N == N == 256: the CTA owns
+// complete rows (two epilogue threads per row, 128 columns each; statistics are combined through shared
+// memory with Chan's parallel mean/M2 update, so the variance is as robust as a two-pass LayerNorm).
+//   x_new = (residual ? x : 0) + alpha * (acc + bias)         (rows t >= lens[b] keep x when mask_resid)
+//   single (g2 == null): y = LN(x_new; g1, b1)                (rows t >= lens[b] -> 0 when zero_y_pad)
+//   double            : x <- LN(x_new; g1, b1),  y = LN(x; g2, b2)
+// TMEM plan (kXbuf): one accumulator stage in columns [0,256) and a 256-column "X buffer" in [256,512).
+// While the mainloop runs, the epilogue threads prefetch the fp32 residual tile into the X buffer; pass 1
+// writes x_new back over the accumulator columns, so the later passes read TMEM instead of re-reading HBM.
+// Reference: the LayerNorms of ConformerEncoderLayer (conformer/encoder.py:327-336, 380-429) following
+// feed_forward_macaron / self_attn / conv_module / feed_forward, and `after_norm` (encoder.py:201-202).
+template <int BLOCK_N>
+struct EpiResidLN {
+  static constexpr int kXbuf = 1;
+  float* x;
+  const float* bias;
+  int ldx;
+  int M, N;
+  float alpha;
+  int residual;
+  const int* lens;
+  int T;
+  int mask_resid;
+  int zero_y_pad;
+  const float *g1, *b1, *g2, *b2;
+  __nv_bfloat16* y;
+  float eps;
+
+  struct Stat {
+    float n, mean, m2;
+  };
+  static DEVINL void chan(Stat& a, float nb, float mb, float m2b) {
+    const float n = a.n + nb;
+    const float d = mb - a.mean;
+    a.mean += d * (nb / n);
+    a.m2 += m2b + d * d * (a.n * nb / n);
+    a.n = n;
+  }
+  static DEVINL void add_chunk(Stat& a, const float (&v)[32]) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j];
+    const float m = s * (1.0f / 32.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) q += (v[j] - m) * (v[j] - m);
+    if (a.n == 0.f) {
+      a.n = 32.f, a.mean = m, a.m2 = q;
+    } else {
+      chan(a, 32.f, m, q);
+    }
+  }
+  // combine with the partner thread that owns the other 128 columns of this row
+  static DEVINL void exchange(Stat& a, float4* scratch, int r, int half) {
+    scratch[r * 2 + half] = make_float4(a.n, a.mean, a.m2, 0.f);
+    named_bar_sync(2, GEMM_EPI_WARPS * 32);
+    const float4 o = scratch[r * 2 + (half ^ 1)];
+    // fixed combination order (half 0 then half 1) so both partner threads get bit-identical statistics
+    const float4 lo = half ? o : make_float4(a.n, a.mean, a.m2, 0.f);
+    const float4 hi = half ? make_float4(a.n, a.mean, a.m2, 0.f) : o;
+    Stat t{lo.x, lo.y, lo.z};
+    chan(t, hi.x, hi.y, hi.z);
+    a = t;
+  }
+
+  // residual tile -> TMEM X buffer (runs while the MMAs of this tile are in flight)
+  DEVINL void prefetch(uint32_t taddr_x, int row, int half) const {
+    if (!residual) return;
+    constexpr int NCH = BLOCK_N / 64;
+    const bool in = row < M;
+    const float* xr = x + (size_t)(in ? row : 0) * ldx;
+#pragma unroll
+    for (int c = 0; c < NCH; c += 2) {
+      uint32_t v[2][32];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int cc = (half * NCH + c + u) * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = in ? __ldcg(reinterpret_cast<const float4*>(xr + cc) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u][4 * j] = __float_as_uint(t.x), v[u][4 * j + 1] = __float_as_uint(t.y);
+          v[u][4 * j + 2] = __float_as_uint(t.z), v[u][4 * j + 3] = __float_as_uint(t.w);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) tmem_st_32x32b_x32(taddr_x + (half * NCH + c + u) * 32, v[u]);
+    }
+    tmem_st_wait();
+  }
+
+  // taddr: accumulator columns of this thread's lane; taddr + BLOCK_N: the X buffer
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4* scratch) const {
+    static_assert(BLOCK_N == 256, "EpiResidLN needs the whole 256-wide row in one CTA");
+    constexpr int NCH = BLOCK_N / 64;
+    const int r = row & (GEMM_BLOCK_M - 1);
+    const bool in = row < M;
+    bool pad = false;
+    if (lens != nullptr && in) {
+      const int b = row / T;
+      pad = (row - b * T) >= __ldg(lens + b);
+    }
+    const float a = (pad && mask_resid) ? 0.f : alpha;
+    float* xr = x + (size_t)row * ldx;
+    Stat st{0.f, 0.f, 0.f};
+    // pass 1: x_new = x_old + a * (acc + bias) -> TMEM (over the accumulator) [+ global when it is final]
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int cc = (half * NCH + c) * 32;
+      uint32_t ra[32], rx[32];
+      tmem_ld_32x32b_x32(taddr + cc, ra);
+      if (residual) tmem_ld_32x32b_x32(taddr + BLOCK_N + cc, rx);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float xo = residual ? __uint_as_float(rx[j]) : 0.f;
+        v[j] = fmaf(a, __uint_as_float(ra[j]) + sbias[cc + j], xo);
+        ra[j] = __float_as_uint(v[j]);
+      }
+      tmem_st_32x32b_x32(taddr + cc, ra);
+      if (in && g2 == nullptr) {
+        float4* dst = reinterpret_cast<float4*>(xr + cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      add_chunk(st, v);
+    }
+    tmem_st_wait();
+    exchange(st, scratch, r, half);
+    float mean = st.mean;
+    float rstd = rsqrtf(st.m2 * (1.0f / 256.0f) + eps);
+    if (g2 != nullptr) {
+      // pass 2: x <- LN1(x_new) (final residual stream value) -> global + TMEM, statistics of the result
+      Stat s2{0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int cc = (half * NCH + c) * 32;
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(taddr + cc, ra);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(g1 + cc) + j);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(b1 + cc) + j);
+          v[4 * j + 0] = (__uint_as_float(ra[4 * j + 0]) - mean) * rstd * gv.x + bv.x;
+          v[4 * j + 1] = (__uint_as_float(ra[4 * j + 1]) - mean) * rstd * gv.y + bv.y;
+          v[4 * j + 2] = (__uint_as_float(ra[4 * j + 2]) - mean) * rstd * gv.z + bv.z;
+          v[4 * j + 3] = (__uint_as_float(ra[4 * j + 3]) - mean) * rstd * gv.w + bv.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(v[j]);
+        tmem_st_32x32b_x32(taddr + cc, ra);
+        if (in) {
+          float4* dst = reinterpret_cast<float4*>(xr + cc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        add_chunk(s2, v);
+      }
+      tmem_st_wait();
+      exchange(s2, scratch + 2 * GEMM_BLOCK_M, r, half);
+      mean = s2.mean;
+      rstd = rsqrtf(s2.m2 * (1.0f / 256.0f) + eps);
+    }
+    // final pass: y = LN(x; gl, bl) as bf16
+    const float* gl = g2 ? g2 : g1;
+    const float* bl = g2 ? b2 : b1;
+    const bool zero = pad && zero_y_pad;
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int cc = (half * NCH + c) * 32;
+      uint32_t ra[32];
+      tmem_ld_32x32b_x32(taddr + cc, ra);
+      tmem_ld_wait();
+      if (in) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(gl + cc) + j);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bl + cc) + j);
+          const float y0 = (__uint_as_float(ra[4 * j + 0]) - mean) * rstd * gv.x + bv.x;
+          const float y1 = (__uint_as_float(ra[4 * j + 1]) - mean) * rstd * gv.y + bv.y;
+          const float y2 = (__uint_as_float(ra[4 * j + 2]) - mean) * rstd * gv.z + bv.z;
+          const float y3 = (__uint_as_float(ra[4 * j + 3]) - mean) * rstd * gv.w + bv.w;
+          pk[2 * j] = zero ? 0u : pack_bf16x2(y0, y1);
+          pk[2 * j + 1] = zero ? 0u : pack_bf16x2(y2, y3);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(y + (size_t)row * BLOCK_N + cc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+    }
+  }
+};
+
 // GLU over interleaved columns: packed column 2c = "a" channel c, 2c+1 = gate channel c.
 // out_bf16[row, c] = (acc_a + bias_a) * sigmoid(acc_b + bias_b)
 // (reference: ppasr/model_utils/conformer/convolution.py:121-123, paddle glu = a * sigmoid(b))
@@ -173,7 +371,7 @@ struct EpiGLU {
   const float* bias;  // interleaved like the weight rows
   int ldo;
   int M, N;  // N = 2 * channels
-  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
       const int col = n0 + cc;
       if (row < M && col < N) {
@@ -215,7 +413,7 @@ struct EpiQKV {
   int Tk;               // rows per (b,h) in kk
   int Tkp;              // padded key pitch of vt
   int kofs;             // first key position written
-  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     const int D = H * 64;
     int b = 0, t = 0;
     if (row < M) {
@@ -278,7 +476,7 @@ struct EpiConv2 {
   int pitch;  // 20
   int Tout;   // valid output frames per utterance
   int Fout;   // valid output freq bins (19)
-  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     bool valid = false;
     size_t orow = 0;
     if (row < M) {
@@ -316,7 +514,7 @@ struct EpiLogitsF32 {
   const float* bias;  // padded to num_n_tiles*BLOCK_N
   int ldo;
   int M, N;
-  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
       const int col = n0 + cc;
       if (row < M && col < ldo) {
@@ -345,7 +543,7 @@ struct EpiCtcStats {
   const float* bias;  // padded
   int M, N;           // N = vocab size (valid columns)
   int num_parts;      // 2 * num_n_tiles
-  DEVINL void tile(uint32_t taddr, int row, int n0, int n_tile, int half, const float* sbias) const {
+  DEVINL void tile(uint32_t taddr, int row, int n0, int n_tile, int half, const float* sbias, float4*) const {
     float m = -INFINITY, s = 0.f;
     int am = 0;
     epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
@@ -381,6 +579,16 @@ struct EpiCtcStats {
   }
 };
 
+// epilogues that keep a second TMEM buffer (kXbuf) run with one accumulator stage
+template <class Epi, class = void>
+struct EpiUsesXbuf {
+  static constexpr bool value = false;
+};
+template <class Epi>
+struct EpiUsesXbuf<Epi, decltype((void)Epi::kXbuf)> {
+  static constexpr bool value = Epi::kXbuf != 0;
+};
+
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
@@ -390,7 +598,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const GemmShape shape, const Epi epi) {
   using SM = GemmSmem<BLOCK_N, STAGES>;
   using ACC = GemmAcc<BLOCK_N>;
-  constexpr int ACC_STAGES = ACC::ACC_STAGES;
+  constexpr bool XBUF = EpiUsesXbuf<Epi>::value;
+  constexpr int ACC_STAGES = XBUF ? 1 : ACC::ACC_STAGES;
+  static_assert(!XBUF || BLOCK_N == 256, "X buffer layout assumes 2 x 256 TMEM columns");
   static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -398,6 +608,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * SM::A_BYTES;
   float* smem_bias = reinterpret_cast<float*>(smem + SM::BIAS_OFFSET);
+  float4* smem_scratch = reinterpret_cast<float4*>(smem + SM::SCRATCH_OFFSET);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -514,10 +725,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       float* sbias = smem_bias + (it & 1) * BLOCK_N;
       if (etid < BLOCK_N) sbias[etid] = __ldg(epi.bias + n_tile * BLOCK_N + etid);
       named_bar_sync(1, GEMM_EPI_WARPS * 32);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N;
+      if constexpr (XBUF) epi.prefetch(taddr + BLOCK_N, m_tile * GEMM_BLOCK_M + quad * 32 + lane, half);
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N;
-      epi.tile(taddr, m_tile * GEMM_BLOCK_M + quad * 32 + lane, n_tile * BLOCK_N, n_tile, half, sbias);
+      epi.tile(taddr, m_tile * GEMM_BLOCK_M + quad * 32 + lane, n_tile * BLOCK_N, n_tile, half, sbias, smem_scratch);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[as]);
       if (++as == ACC_STAGES) {

@@ -89,50 +89,74 @@ cudaError_t launch_layernorm(float* x, __nv_bfloat16* y, const float* g1, const 
 //   in : feats fp32 [B, T, F]
 //   out: P[ph][b][th][fh][c] bf16, ph = (t1&1)*2 + (f1&1), th = t1>>1 in [0,Th), fh = f1>>1 in [0,FH)
 //        (slots with t1 >= T1 or f1 >= F1 are written as 0)
-// One block per (b, th): 256 threads = output channels, both time phases, all frequency slots.
+// One block per (b, th), both time phases, all frequency slots.
 // ------------------------------------------------------------------------------------------------
+// Thread = (channel octet, frequency group): 8 output channels per thread so every store is 16 bytes and a
+// warp writes 512 contiguous bytes; the 3x3 input window is a shared-memory broadcast. A block covers
+// CONV1_THB consecutive `th` so the 72 weight registers and the input window are set up once per 8x more work.
+constexpr int CONV1_THB = 8;
 template <int C>
-__global__ void __launch_bounds__(C) conv1_subsample_kernel(const float* __restrict__ feats,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ istd,
-                                                            const float* __restrict__ w,     // [C, 9]
-                                                            const float* __restrict__ bias,  // [C]
-                                                            __nv_bfloat16* __restrict__ out, int B, int T, int F, int T1,
-                                                            int F1, int Th, int FH) {
-  extern __shared__ float xs[];  // [5][F] normalised input rows 4*th .. 4*th+4
-  const int b = blockIdx.x / Th;
-  const int th = blockIdx.x - b * Th;
-  const int c = threadIdx.x;
-  for (int i = threadIdx.x; i < 5 * F; i += C) {
+__global__ void __launch_bounds__(256) conv1_subsample_kernel(const float* __restrict__ feats,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ istd,
+                                                              const float* __restrict__ w,     // [C, 9]
+                                                              const float* __restrict__ bias,  // [C]
+                                                              __nv_bfloat16* __restrict__ out, int B, int T, int F,
+                                                              int T1, int F1, int Th, int FH) {
+  static_assert(C == 256, "one warp spans the 256 channels as 32 octets");
+  extern __shared__ float xs[];  // [4*CONV1_THB + 1][F] normalised input rows 4*th0 ..
+  const int tiles = (Th + CONV1_THB - 1) / CONV1_THB;
+  const int b = blockIdx.x / tiles;
+  const int th0 = (blockIdx.x - b * tiles) * CONV1_THB;
+  const int nrows = 4 * CONV1_THB + 1;
+  for (int i = threadIdx.x; i < nrows * F; i += 256) {
     const int r = i / F, f = i - r * F;
-    const int t = 4 * th + r;
+    const int t = 4 * th0 + r;
     float v = 0.f;
     if (t < T) v = (feats[((size_t)b * T + t) * F + f] - __ldg(mean + f)) * __ldg(istd + f);
     xs[i] = v;
   }
-  float wr[9];
+  const int co = (threadIdx.x & 31) * 8;  // first of this thread's 8 channels
+  const int fg = threadIdx.x >> 5;        // 0..7
+  float wr[8][9];
+  float bs[8];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) wr[i] = __ldg(w + c * 9 + i);
-  const float bs = __ldg(bias + c);
+  for (int c = 0; c < 8; ++c) {
+    bs[c] = __ldg(bias + co + c);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wr[c][i] = __ldg(w + (co + c) * 9 + i);
+  }
   __syncthreads();
   const size_t phase_stride = (size_t)B * Th * FH * C;
 #pragma unroll 1
-  for (int pt = 0; pt < 2; ++pt) {
+  for (int dt = 0; dt < 2 * CONV1_THB; ++dt) {
+    const int th = th0 + (dt >> 1), pt = dt & 1;
+    if (th >= Th) break;
     const int t1 = 2 * th + pt;
-    const float* r0 = xs + (2 * pt) * F;
+    const float* r0 = xs + (2 * dt) * F;  // input row 2*t1 - 4*th0 = 2*dt
 #pragma unroll 1
-    for (int f1 = 0; f1 < 2 * FH; ++f1) {
-      float acc = 0.f;
+    for (int f1 = fg; f1 < 2 * FH; f1 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = 0.f;
       if (t1 < T1 && f1 < F1) {
-        acc = bs;
+        float xv[9];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) acc = fmaf(wr[kh * 3 + kw], r0[kh * F + 2 * f1 + kw], acc);
-        acc = fmaxf(acc, 0.f);
+          for (int kw = 0; kw < 3; ++kw) xv[kh * 3 + kw] = r0[kh * F + 2 * f1 + kw];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a = bs[c];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) a = fmaf(wr[c][i], xv[i], a);
+          acc[c] = fmaxf(a, 0.f);
+        }
       }
       const int ph = pt * 2 + (f1 & 1);
-      out[ph * phase_stride + (((size_t)b * Th + th) * FH + (f1 >> 1)) * C + c] = __float2bfloat16_rn(acc);
+      uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                           pack_bf16x2(acc[6], acc[7]));
+      *reinterpret_cast<uint4*>(out + ph * phase_stride + (((size_t)b * Th + th) * FH + (f1 >> 1)) * C + co) = o;
     }
   }
 }
@@ -141,8 +165,9 @@ cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const 
                                    const float* bias, __nv_bfloat16* out, int B, int T, int F, int C, int T1, int F1,
                                    int Th, int FH, cudaStream_t st) {
   if (C != 256) return cudaErrorInvalidValue;
-  const size_t smem = 5 * F * sizeof(float);
-  conv1_subsample_kernel<256><<<B * Th, 256, smem, st>>>(feats, mean, istd, w, bias, out, B, T, F, T1, F1, Th, FH);
+  const size_t smem = (size_t)(4 * CONV1_THB + 1) * F * sizeof(float);
+  const int tiles = (Th + CONV1_THB - 1) / CONV1_THB;
+  conv1_subsample_kernel<256><<<B * tiles, 256, smem, st>>>(feats, mean, istd, w, bias, out, B, T, F, T1, F1, Th, FH);
   count_launch();
   return cudaGetLastError();
 }

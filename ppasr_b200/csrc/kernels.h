@@ -41,6 +41,11 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
                                 int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
                                 int* score_cnt, cudaStream_t st);
 
+// Fused feed-forward block (fused_ffn.cu): x += alpha * W2 swish(W1 y + b1) + b2 ; trailing LayerNorm(s)
+cudaError_t launch_fused_ffn(const CUtensorMap& tm_y, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2, int M, int FF,
+                             float alpha, float* x, __nv_bfloat16* y, const float* b1, const float* b2, const float* g1,
+                             const float* bn1, const float* g2, const float* bn2, float eps, cudaStream_t st);
+
 // CTC prefix beam search (beam.cu)
 struct BeamStateHeader {
   int nb;       // entries in the beam

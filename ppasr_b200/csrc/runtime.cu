@@ -108,7 +108,7 @@ struct ppasr_b200_ctx {
   // weight tensor maps (B operands)
   CUtensorMap tm_conv2_w, tm_emb_w, tm_ctc_w, tm_pos;
   struct LayerMaps {
-    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2;
+    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2, ffm_w1_128, ff_w1_128;
   };
   std::vector<LayerMaps> lmaps;
   Plan plan;
@@ -126,6 +126,7 @@ struct ppasr_b200_ctx {
     std::vector<CUtensorMap> tm_k, tm_vt;  // per layer, rebuilt every chunk (extent = kend)
   } ss;
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
+  bool fused_ffn = true;
   bool profiling = false;
   struct ProfRec {
     int cls;
@@ -140,12 +141,12 @@ namespace {
 
 enum ProfClass : int {
   PC_CONV1 = 0, PC_CONV2, PC_EMBED, PC_LAYERNORM, PC_FFN1, PC_FFN2, PC_QKV, PC_ATTENTION, PC_OUTPROJ, PC_PW1_GLU,
-  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_COUNT
+  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_FUSED_FFN, PC_COUNT
 };
 const char* const kProfNames[PC_COUNT] = {"conv1_subsample", "conv2_gemm", "embed_gemm", "layernorm", "ffn1_gemm",
                                           "ffn2_gemm", "qkv_gemm", "attention", "outproj_gemm", "pw1_glu_gemm",
                                           "dwconv_norm_swish", "pw2_gemm", "ctc_stats_gemm", "ctc_finalize",
-                                          "ctc_collapse", "ctc_logits_gemm", "softmax"};
+                                          "ctc_collapse", "ctc_logits_gemm", "softmax", "fused_ffn"};
 
 struct ProfScope {
   ppasr_b200_ctx* c;
@@ -460,20 +461,22 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
     }
     auto& m = c->lmaps[l];
     bool ok = make_tmap_2d(&m.ffm_w1, w.ffm_w1, D, FF, (uint64_t)D * 2, BN_WIDE, &err) &&
-              make_tmap_2d(&m.ffm_w2, w.ffm_w2, FF, D, (uint64_t)FF * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.ffm_w2, w.ffm_w2, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.ff_w1, w.ff_w1, D, FF, (uint64_t)D * 2, BN_WIDE, &err) &&
-              make_tmap_2d(&m.ff_w2, w.ff_w2, FF, D, (uint64_t)FF * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.ffm_w1_128, w.ffm_w1, D, FF, (uint64_t)D * 2, 128, &err) &&
+              make_tmap_2d(&m.ff_w1_128, w.ff_w1, D, FF, (uint64_t)D * 2, 128, &err) &&
+              make_tmap_2d(&m.ff_w2, w.ff_w2, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.wqkv, w.wqkv, D, 3 * D, (uint64_t)D * 2, BN_NARROW, &err) &&
-              make_tmap_2d(&m.wo, w.wo, D, D, (uint64_t)D * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.wo, w.wo, D, D, (uint64_t)D * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.pw1, w.pw1, D, 2 * D, (uint64_t)D * 2, BN_WIDE, &err) &&
-              make_tmap_2d(&m.pw2, w.pw2, D, D, (uint64_t)D * 2, BN_NARROW, &err);
+              make_tmap_2d(&m.pw2, w.pw2, D, D, (uint64_t)D * 2, BN_WIDE, &err);
     if (!ok) {
       set_last_error(err);
       return PPASR_ERR_CUDA;
     }
   }
   if (!make_tmap_2d(&c->tm_conv2_w, c->conv2_w, (uint64_t)9 * D, D, (uint64_t)9 * D * 2, BN_WIDE, &err) ||
-      !make_tmap_2d(&c->tm_emb_w, c->emb_w, c->Kemb, D, (uint64_t)c->Kemb * 2, BN_NARROW, &err) ||
+      !make_tmap_2d(&c->tm_emb_w, c->emb_w, c->Kemb, D, (uint64_t)c->Kemb * 2, BN_WIDE, &err) ||
       !make_tmap_2d(&c->tm_ctc_w, c->ctc_w, D, c->Vpad, (uint64_t)D * 2, BN_NARROW, &err)) {
     set_last_error(err);
     return PPASR_ERR_CUDA;
@@ -645,26 +648,35 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
     PROF(PC_CONV2);
     PPASR_CUDA_CHECK((launch_gemm<BN_WIDE, ST_WIDE, true>(p.tm_phase, c->tm_conv2_w, s, epi, c->sms, st)));
   }
-  // Linear(F2*D -> D) then x * sqrt(D)   (subsampling.py:113, embedding.py:113)
-  {
-    EpiResidF32<BN_NARROW> epi{p.x, c->emb_b, D, M, D, std::sqrt((float)D), 0, nullptr, p.Tp};
-    PROF(PC_EMBED);
-    PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_c2, c->tm_emb_w, M, D, c->Kemb, epi, st)));
-  }
-  { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, c->layers[0].ln_ffm_g, c->layers[0].ln_ffm_b, nullptr, nullptr, nullptr,
-                                    p.Tp, M, D, eps, st)); }
+  // Linear(F2*D -> D) then x * sqrt(D) (subsampling.py:113, embedding.py:113), fused with block 0's first LayerNorm
+  auto resid_ln = [&](int cls, const CUtensorMap& ta, const CUtensorMap& tb, int K, const float* bias, float alpha,
+                      int residual, const int* lens, int mask_resid, int zero_y_pad, const float* g1, const float* b1,
+                      const float* g2, const float* b2) -> int {
+    EpiResidLN<BN_WIDE> e{p.x, bias, D, M, D, alpha, residual, lens, p.Tp, mask_resid, zero_y_pad, g1, b1, g2, b2, p.y, eps};
+    PROF(cls);
+    PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, ta, tb, M, D, K, e, st)));
+    return PPASR_OK;
+  };
+  int rc;
+  if ((rc = resid_ln(PC_EMBED, p.tm_c2, c->tm_emb_w, c->Kemb, c->emb_b, std::sqrt((float)D), 0, nullptr, 0, 0,
+                     c->layers[0].ln_ffm_g, c->layers[0].ln_ffm_b, nullptr, nullptr)))
+    return rc;
+  const int* vl = chunk ? nullptr : p.vlen;
   for (int l = 0; l < L; ++l) {
     const LayerW& w = c->layers[l];
     const auto& m = c->lmaps[l];
-    // ---- macaron FFN: x += 0.5 * W2 swish(W1 LN(x))           (encoder.py:380-386)
-    {
+    // ---- macaron FFN: x += 0.5 * W2 swish(W1 LN(x)); then y = norm_mha(x)        (encoder.py:380-390)
+    if (c->fused_ffn) {
+      PROF(PC_FUSED_FFN);
+      PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, m.ffm_w1_128, m.ffm_w2, M, FF, 0.5f, p.x, p.y, w.ffm_b1, w.ffm_b2, w.ln_mha_g,
+                                        w.ln_mha_b, nullptr, nullptr, eps, st));
+    } else {
       EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ffm_b1, FF, M, FF};
       { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ffm_w1, M, FF, D, e1, st))); }
-      EpiResidF32<BN_NARROW> e2{p.x, w.ffm_b2, D, M, D, 0.5f, 1, nullptr, p.Tp};
-      { PROF(PC_FFN2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ffm_w2, M, D, FF, e2, st))); }
+      if ((rc = resid_ln(PC_FFN2, p.tm_h, m.ffm_w2, FF, w.ffm_b2, 0.5f, 1, nullptr, 0, 0, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr)))
+        return rc;
     }
-    // ---- rel-pos MHA: x += Wo attn(LN(x))                      (encoder.py:389-402)
-    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st)); }
+    // ---- rel-pos MHA: x += Wo attn(y); then y = mask(norm_conv(x))                (encoder.py:389-409)
     {
       AttnParams ap{};
       ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.D = D, ap.pos_col0 = l * D, ap.out = p.att, ap.q_rows_per_bh = p.Tp;
@@ -684,11 +696,11 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
         ap.klens = nullptr;
         { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, ss.tm_k[l], c->tm_pos, ss.tm_vt[l], ap, st)); }
       }
-      EpiResidF32<BN_NARROW> eo{p.x, w.bo, D, M, D, 1.0f, 1, nullptr, p.Tp};
-      { PROF(PC_OUTPROJ); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_att, m.wo, M, D, D, eo, st))); }
+      // pad frames of the conv-module input are zeroed (convolution.py:104-106 with the caller's inverted mask)
+      if ((rc = resid_ln(PC_OUTPROJ, p.tm_att, m.wo, D, w.bo, 1.0f, 1, vl, 0, 1, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr)))
+        return rc;
     }
-    // ---- conv module: x += mask * pw2 swish(norm(dw(glu(pw1(mask * LN(x))))))   (encoder.py:407-416)
-    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, chunk ? nullptr : p.vlen, p.Tp, M, D, eps, st)); }
+    // ---- conv module: x += mask * pw2 swish(norm(dw(glu(pw1(y))))); then y = norm_ff(x)   (encoder.py:407-421)
     {
       const int K = cfg.conv_kernel;
       if (!chunk) {
@@ -706,21 +718,25 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
         { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.gcat, w.dw_w, w.dw_b, nullptr, w.cn_g, w.cn_b, cfg.conv_norm == 0,
                                                   p.z, p.B, p.Tcat, p.Tp, D, K, 0, eps, st)); }
       }
-      EpiResidF32<BN_NARROW> e2{p.x, w.pw2_b, D, M, D, 1.0f, 1, chunk ? nullptr : p.vlen, p.Tp};
-      { PROF(PC_PW2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_z, m.pw2, M, D, D, e2, st))); }
+      if ((rc = resid_ln(PC_PW2, p.tm_z, m.pw2, D, w.pw2_b, 1.0f, 1, vl, 1, 0, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr)))
+        return rc;
     }
-    // ---- FFN: x += 0.5 * W2 swish(W1 LN(x))                    (encoder.py:419-426)
-    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr, nullptr, p.Tp, M, D, eps, st)); }
+    // ---- FFN: x += 0.5 * W2 swish(W1 y); x = norm_final(x); y = next block's first LayerNorm (or after_norm)
+    //      (encoder.py:419-429, 201-202)
     {
-      EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ff_b1, FF, M, FF};
-      { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st))); }
-      EpiResidF32<BN_NARROW> e2{p.x, w.ff_b2, D, M, D, 0.5f, 1, nullptr, p.Tp};
-      { PROF(PC_FFN2); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_h, m.ff_w2, M, D, FF, e2, st))); }
+      const float* g2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_g : c->after_g;
+      const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
+      if (c->fused_ffn) {
+        PROF(PC_FUSED_FFN);
+        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, m.ff_w1_128, m.ff_w2, M, FF, 0.5f, p.x, p.y, w.ff_b1, w.ff_b2, w.ln_fin_g,
+                                          w.ln_fin_b, g2, b2, eps, st));
+      } else {
+        EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ff_b1, FF, M, FF};
+        { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st))); }
+        if ((rc = resid_ln(PC_FFN2, p.tm_h, m.ff_w2, FF, w.ff_b2, 0.5f, 1, nullptr, 0, 0, w.ln_fin_g, w.ln_fin_b, g2, b2)))
+          return rc;
+      }
     }
-    // ---- x = norm_final(x); y = next block's first LayerNorm (or after_norm)   (encoder.py:428-429, 201-202)
-    const float* g2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_g : c->after_g;
-    const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
-    { PROF(PC_LAYERNORM); PPASR_CUDA_CHECK(launch_layernorm(p.x, p.y, w.ln_fin_g, w.ln_fin_b, g2, b2, nullptr, p.Tp, M, D, eps, st)); }
   }
   return PPASR_OK;
 }
@@ -953,6 +969,17 @@ int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V
   PPASR_CUDA_CHECK(launch_ctc_collapse(tmp_idx, tmp_maxp, B, T, frame_lens, blank_id, ids, ld_ids, out_lens, scores,
                                        nullptr, nullptr, st));
   return PPASR_OK;
+}
+
+int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
+  PPASR_REQUIRE(c && name, "null pointer");
+  const std::string n(name);
+  if (n == "fused_ffn") {
+    c->fused_ffn = value != 0;
+    return PPASR_OK;
+  }
+  set_last_error("unknown option: " + n);
+  return PPASR_ERR_INVALID;
 }
 
 int ppasr_b200_profile_enable(ppasr_b200_ctx* c, int32_t enable) {

@@ -168,6 +168,9 @@ class ConformerEngine:
             return ids, ol, sc, fi, fp
         return ids, ol, sc
 
+    def set_option(self, name, value):
+        L.check(self.lib.ppasr_b200_set_option(self._ctx, name.encode(), int(value)))
+
     def profile_enable(self, on=True):
         L.check(self.lib.ppasr_b200_profile_enable(self._ctx, int(on)))
 
