@@ -1,20 +1,26 @@
-// Fused position-wise feed-forward block for sm_100a (tcgen05 + TMEM + TMA), one CTA per 128 rows:
+// Fused position-wise feed-forward block for sm_100a (tcgen05 + TMEM + TMA), one CTA per 128 rows.
 //
-//   x <- x + alpha * (W2 . swish(W1 . y + b1) + b2)          y = LayerNorm'd input tile (bf16, from the producer)
-//   single:  y_out = LN(x; g1, b1n)
-//   double:  x <- LN(x; g1, b1n) ; y_out = LN(x; g2, b2n)    (norm_final followed by the next block's first LN)
+//   plain  :  x <- x + W2s . swish(W1 . y + b1) + b2s                      (W2s = alpha*W2, b2s = alpha*b2)
+//   chained:  x <- x + mask * (Wp . z + bp)        (conv module's pointwise_conv2 + residual, pad rows masked)
+//             y  = LN(x; gp, bp_n)                 (norm_ff)             -- never leaves shared memory
+//             x <- x + W2s . swish(W1 . y + b1) + b2s
+//   then   single:  y_out = LN(x; g1, bn1)     or  double:  x <- LN(x; g1, bn1) ; y_out = LN(x; g2, bn2)
 //
-// Reference: PositionwiseFeedForward.forward (ppasr/model_utils/conformer/positionwise.py:30-39) inside
-// ConformerEncoderLayer.forward (conformer/encoder.py:380-386, 419-429).
+// Reference: PositionwiseFeedForward.forward (ppasr/model_utils/conformer/positionwise.py:30-39) and the
+// surrounding residual / LayerNorm code of ConformerEncoderLayer.forward (conformer/encoder.py:380-386,
+// 407-429); chained mode additionally covers convolution.py:133-140 (pointwise_conv2 + pad masking).
 //
-// The 2048-wide hidden activation never leaves the SM: the hidden dimension is processed in 16 chunks of 128.
-//   GEMM1(j): S[j&1] (TMEM, 128 cols)  = Y[128x256] . W1_j^T        16 x tcgen05.mma 128x128x16
-//   swish(j): 256 threads read S from TMEM, add b1, swish, write bf16 H[j&1] into 128B-swizzled smem
-//   GEMM2(j): O (TMEM, 256 cols)      += H[j&1][128x128] . W2_j^T     8 x tcgen05.mma 128x256x16
-// The MMA warp issues GEMM1(j+2) right after GEMM2(j), so the tensor pipe always has queued work while the
-// swish of chunk j+1 runs. Weights stream through a 3 x 32 KB TMA ring (2 MB per CTA, L2 resident).
-// Epilogue: every smem buffer is free by then; the fp32 residual tile is staged in smem with coalesced loads,
-// updated by the row-owner threads straight from TMEM, normalised, and written back with coalesced stores.
+// TMEM plan: S double buffer in columns [0,256), output accumulator O in [256,512).
+//  * The fp32 residual tile is preloaded INTO O (coalesced global loads -> smem slab -> tcgen05.st) while the
+//    first weight tiles stream in, and every MMA that produces a residual-branch term accumulates on top of it,
+//    so the residual add costs nothing and the epilogue never re-reads x.
+//  * The 2048-wide hidden activation never leaves the SM: 16 chunks of 128,
+//      GEMM1(j): S[j&1] = Y[128x256] . W1_j^T                 16 x tcgen05.mma 128x128x16
+//      swish(j): 256 threads: TMEM -> +b1 -> swish -> bf16 -> 128B-swizzled smem H[j&1]
+//      GEMM2(j): O += H[j&1][128x128] . W2s_j^T                8 x tcgen05.mma 128x256x16
+//    GEMM1(j+2) is issued right after GEMM2(j) so the tensor pipe always has queued work.
+//  * Weights stream through a 3 x 32 KB TMA ring (2 MB per CTA per call, L2 resident).
+//  * Epilogue: x/y tiles are staged in the (by then free) smem and written with coalesced 16-byte stores.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -24,44 +30,89 @@ void count_launch();
 
 constexpr int FFN_THREADS = 384;             // warps 0..3 control, 4..11 compute
 constexpr int FFN_TILE = 128 * 64 * 2;       // 16 KB: [128 rows x 64 bf16] swizzled tile
-constexpr int FFN_SMEM_A = 0;                // 4 tiles (Y, K = 256)
-constexpr int FFN_SMEM_H = 4 * FFN_TILE;     // 2 buffers x 2 tiles
+constexpr int FFN_SMEM_A = 0;                // 4 tiles (Y or Z, K = 256)
+constexpr int FFN_SMEM_H = 4 * FFN_TILE;     // 2 buffers x 2 tiles (also: residual preload slab)
 constexpr int FFN_SMEM_W = 8 * FFN_TILE;     // ring: 3 big slots x 32 KB
 constexpr int FFN_RING = 3;
 constexpr int FFN_SMEM_BAR = 14 * FFN_TILE;  // 229376
 constexpr int FFN_SMEM_TOTAL = FFN_SMEM_BAR + 512 + 1024;
-constexpr int FFN_XS_PITCH = 257;            // fp32 staging tile [128][257] (conflict-free for row owners)
+constexpr int FFN_XS_PITCH = 260;            // fp32 staging tile [128][260]: 16B-aligned rows, float4 access conflict-free
+constexpr int FFN_SLAB_PITCH = 68;           // residual preload slab [128][68] fp32 (64 columns at a time)
 
 struct FfnParams {
-  int M;            // rows
-  int nchunks;      // FF / 128
-  float alpha;      // 0.5 (macaron scale)
-  float* x;         // fp32 residual stream [M, 256]
-  __nv_bfloat16* y; // bf16 output of the trailing LayerNorm [M, 256]
-  const float* b1;  // [FF]
-  const float* b2;  // [256]
-  const float *g1, *bn1, *g2, *bn2;  // LayerNorm params (g2 null = single)
+  int M;             // rows
+  int nchunks;       // FF / 128
+  float* x;          // fp32 residual stream [M, 256]
+  __nv_bfloat16* y;  // bf16 output of the trailing LayerNorm [M, 256]
+  const float* b1;   // [FF]
+  const float* b2s;  // [256] already scaled by alpha
+  const float *g1, *bn1, *g2, *bn2;  // trailing LayerNorm params (g2 null = single)
   float eps;
+  // chained pre-GEMM (null bp = plain mode)
+  const float* bp;        // [256] bias of the pre-GEMM
+  const float *gp, *bpn;  // LayerNorm between pre-GEMM and FFN
+  const int* lens;        // valid frames per utterance (pad rows: pre-GEMM branch contributes 0)
+  int T;
 };
 
+struct FfnStat {
+  float n, mean, m2;
+};
+DEVINL void ffn_chan(FfnStat& a, float nb, float mb, float m2b) {
+  const float n = a.n + nb;
+  const float d = mb - a.mean;
+  a.mean += d * (nb / n);
+  a.m2 += m2b + d * d * (a.n * nb / n);
+  a.n = n;
+}
+DEVINL void ffn_add_chunk(FfnStat& a, const float (&v)[32]) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s += v[j];
+  const float m = s * (1.0f / 32.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) q += (v[j] - m) * (v[j] - m);
+  if (a.n == 0.f)
+    a.n = 32.f, a.mean = m, a.m2 = q;
+  else
+    ffn_chan(a, 32.f, m, q);
+}
+// combine with the partner thread that owns the other 128 columns of the row (fixed order: bit-identical on both)
+DEVINL void ffn_exchange(FfnStat& a, float4* sc, int r, int half, int barrier_id) {
+  sc[r * 2 + half] = make_float4(a.n, a.mean, a.m2, 0.f);
+  named_bar_sync(barrier_id, 256);
+  const float4 o = sc[r * 2 + (half ^ 1)];
+  const float4 lo = half ? o : make_float4(a.n, a.mean, a.m2, 0.f);
+  const float4 hi = half ? make_float4(a.n, a.mean, a.m2, 0.f) : o;
+  FfnStat t{lo.x, lo.y, lo.z};
+  ffn_chan(t, hi.x, hi.y, hi.z);
+  a = t;
+}
+
+template <bool PRE>
 __global__ void __launch_bounds__(FFN_THREADS, 1)
-fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w1,
-                 const __grid_constant__ CUtensorMap tm_w2, const FfnParams p) {
+fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_wp,
+                 const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+                 const FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_a = smem + FFN_SMEM_A;
   uint8_t* s_h = smem + FFN_SMEM_H;
   uint8_t* s_w = smem + FFN_SMEM_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FFN_SMEM_BAR);
-  uint64_t* a_full = bars;            // 1
-  uint64_t* w_full = bars + 1;        // 3
-  uint64_t* w_empty = bars + 4;       // 3
-  uint64_t* s_full = bars + 7;        // 2
-  uint64_t* s_free = bars + 9;        // 2
-  uint64_t* h_full = bars + 11;       // 2
-  uint64_t* h_free = bars + 13;       // 2
-  uint64_t* o_full = bars + 15;       // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* a_full = bars;       // TMA: A-operand tile (y, or z in chained mode)
+  uint64_t* w_full = bars + 1;   // [3]
+  uint64_t* w_empty = bars + 4;  // [3]
+  uint64_t* s_full = bars + 7;   // [2]
+  uint64_t* s_free = bars + 9;   // [2]
+  uint64_t* h_full = bars + 11;  // [2]
+  uint64_t* h_free = bars + 13;  // [2]
+  uint64_t* o_full = bars + 15;
+  uint64_t* x_loaded = bars + 16;  // residual tile is in TMEM O (256 arrivals)
+  uint64_t* pre_full = bars + 17;  // chained: pre-GEMM accumulated into O
+  uint64_t* a_ready = bars + 18;   // chained: LN output written to the A tiles (256 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,9 +120,10 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   const int NCH = p.nchunks;
 
   if (warp_idx == 0 && elect_one()) {
-    tma_prefetch_desc(&tm_y);
+    tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w1);
     tma_prefetch_desc(&tm_w2);
+    if (PRE) tma_prefetch_desc(&tm_wp);
   }
   if (warp_idx == 1 && elect_one()) {
     mbar_init(a_full, 1);
@@ -86,6 +138,9 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       mbar_init(&h_free[i], 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(x_loaded, 256);
+    mbar_init(pre_full, 1);
+    mbar_init(a_ready, 256);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -100,9 +155,15 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     // ============================ TMA producer ============================
     if (elect_one()) {
       mbar_arrive_expect_tx(a_full, 4 * FFN_TILE);
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * FFN_TILE, &tm_y, a_full, kb * 64, m0);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * FFN_TILE, &tm_a, a_full, kb * 64, m0);
       int slot = 0;
       uint32_t phase = 0;
+      auto load_rows256 = [&](const CUtensorMap* tm, int k0) {  // one big slot: [256 rows x 64 K]
+        mbar_wait(&w_empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&w_full[slot], 2 * FFN_TILE);
+        tma_load_2d(s_w + slot * 2 * FFN_TILE, tm, &w_full[slot], k0, 0);
+        if (++slot == FFN_RING) slot = 0, phase ^= 1;
+      };
       auto load_w1 = [&](int j) {  // two big slots: k-blocks (0,1) and (2,3) of W1 rows [j*128, +128)
         for (int s = 0; s < 2; ++s) {
           mbar_wait(&w_empty[slot], phase ^ 1);
@@ -112,18 +173,13 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           if (++slot == FFN_RING) slot = 0, phase ^= 1;
         }
       };
-      auto load_w2 = [&](int j) {  // two big slots: W2[0:256, j*128 + kb*64 .. +64), kb = 0, 1
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(&w_empty[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&w_full[slot], 2 * FFN_TILE);
-          tma_load_2d(s_w + slot * 2 * FFN_TILE, &tm_w2, &w_full[slot], j * 128 + kb * 64, 0);
-          if (++slot == FFN_RING) slot = 0, phase ^= 1;
-        }
-      };
+      if (PRE)
+        for (int kb = 0; kb < 4; ++kb) load_rows256(&tm_wp, kb * 64);
       load_w1(0);
       if (NCH > 1) load_w1(1);
       for (int j = 0; j < NCH; ++j) {
-        load_w2(j);
+        load_rows256(&tm_w2, j * 128);
+        load_rows256(&tm_w2, j * 128 + 64);
         if (j + 2 < NCH) load_w1(j + 2);
       }
     }
@@ -137,6 +193,25 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       const uint32_t a_addr = smem_u32(s_a);
       mbar_wait(a_full, 0);
       tc_fence_after();
+      if (PRE) {
+        // O (= x + mask*bp, preloaded) += Z . Wp^T
+        mbar_wait(x_loaded, 0);
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&w_full[slot], phase);
+          tc_fence_after();
+          const uint32_t w_addr = smem_u32(s_w + slot * 2 * FFN_TILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_o, umma_desc_k_sw128(a_addr + kb * FFN_TILE + k * 32), umma_desc_k_sw128(w_addr + k * 32),
+                      idesc_g2, 1u);
+          umma_commit(&w_empty[slot]);
+          if (++slot == FFN_RING) slot = 0, phase ^= 1;
+        }
+        umma_commit(pre_full);
+        mbar_wait(a_ready, 0);  // LN(x) has replaced Z in the A tiles
+        tc_fence_after();
+      }
       auto gemm1 = [&](int j) {
         const int b = j & 1;
         if (j >= 2) {
@@ -173,7 +248,7 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem_o, umma_desc_k_sw128(h_addr + kb * FFN_TILE + k * 32), umma_desc_k_sw128(w_addr + k * 32),
-                      idesc_g2, (j | kb | k) != 0);
+                      idesc_g2, 1u);  // always accumulate: O holds the residual
           umma_commit(&w_empty[slot]);
           if (++slot == FFN_RING) slot = 0, phase ^= 1;
         }
@@ -181,6 +256,10 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       };
       gemm1(0);
       if (NCH > 1) gemm1(1);
+      if (!PRE) {
+        mbar_wait(x_loaded, 0);
+        tc_fence_after();
+      }
       for (int j = 0; j < NCH; ++j) {
         gemm2(j);
         if (j + 2 < NCH) gemm1(j + 2);
@@ -193,7 +272,101 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     const int quad = ew & 3;
     const int half = ew >> 2;
     const int r = quad * 32 + lane;  // tile row owned by this thread (with its partner in the other half)
+    const int ct = threadIdx.x - 128;
     const uint32_t lane_base = ((uint32_t)(quad * 32)) << 16;
+    const int row_g = m0 + r;
+    bool pad = false;
+    if (PRE && p.lens != nullptr && row_g < p.M) {
+      const int b = row_g / p.T;
+      pad = (row_g - b * p.T) >= __ldg(p.lens + b);
+    }
+    // ---- residual tile -> TMEM O, 64 columns at a time through a coalesced smem slab (the H region is idle) ----
+    {
+      float* slab = reinterpret_cast<float*>(s_h);
+      for (int s = 0; s < 4; ++s) {
+        // coalesced: 16 threads per row (16 B each), 16 rows per pass
+        for (int rr = ct >> 4; rr < 128; rr += 16) {
+          const int cq = ct & 15;
+          const bool in = (m0 + rr) < p.M;
+          const float4 v = in ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)(m0 + rr) * 256 + s * 64) + cq)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(slab + rr * FFN_SLAB_PITCH + cq * 4) = v;
+        }
+        named_bar_sync(1, 256);
+        if (half == (s >> 1)) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            const int col0 = s * 64 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = *reinterpret_cast<const float4*>(slab + r * FFN_SLAB_PITCH + c * 32 + 4 * j);
+              if (PRE && !pad) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bp + col0) + j);
+                t.x += bb.x, t.y += bb.y, t.z += bb.z, t.w += bb.w;
+              }
+              v[4 * j] = __float_as_uint(t.x), v[4 * j + 1] = __float_as_uint(t.y);
+              v[4 * j + 2] = __float_as_uint(t.z), v[4 * j + 3] = __float_as_uint(t.w);
+            }
+            tmem_st_32x32b_x32(tmem_o + lane_base + col0, v);
+          }
+          tmem_st_wait();
+        }
+        named_bar_sync(1, 256);
+      }
+      tc_fence_before();
+      mbar_arrive(x_loaded);
+    }
+    float4* scratch = reinterpret_cast<float4*>(smem + 128 * FFN_XS_PITCH * 4);  // [2][256] exchange slots (ring region)
+    if (PRE) {
+      // ---- y = LN(x_mid) -> A tiles (bf16, 128B swizzle); x_mid stays in TMEM O ----
+      mbar_wait(pre_full, 0);
+      tc_fence_after();
+      float4* sc = reinterpret_cast<float4*>(s_h);  // H region is idle until the first swish
+      FfnStat st{0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ro[32];
+        tmem_ld_32x32b_x32(tmem_o + lane_base + half * 128 + c * 32, ro);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ro[j]);
+        ffn_add_chunk(st, v);
+      }
+      ffn_exchange(st, sc, r, half, 2);
+      const float mean = st.mean;
+      const float rstd = rsqrtf(st.m2 * (1.0f / 256.0f) + p.eps);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int cc = half * 128 + c * 32;
+        uint32_t ro[32];
+        tmem_ld_32x32b_x32(tmem_o + lane_base + cc, ro);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(p.gp + cc) + j);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bpn + cc) + j);
+          const float y0 = (__uint_as_float(ro[4 * j + 0]) - mean) * rstd * gg.x + bb.x;
+          const float y1 = (__uint_as_float(ro[4 * j + 1]) - mean) * rstd * gg.y + bb.y;
+          const float y2 = (__uint_as_float(ro[4 * j + 2]) - mean) * rstd * gg.z + bb.z;
+          const float y3 = (__uint_as_float(ro[4 * j + 3]) - mean) * rstd * gg.w + bb.w;
+          pk[2 * j] = pack_bf16x2(y0, y1);
+          pk[2 * j + 1] = pack_bf16x2(y2, y3);
+        }
+        // columns cc .. cc+31 live in k-block cc/64, 16-byte chunks (cc%64)/8 .. +3
+        uint8_t* atile = s_a + (cc >> 6) * FFN_TILE + r * 128;
+        const int ch0 = (cc & 63) >> 3;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(atile + (((ch0 + q4) ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(a_ready);
+    }
     // ---- swish between the two GEMMs ----
     for (int j = 0; j < NCH; ++j) {
       const int b = j & 1;
@@ -202,11 +375,13 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       if (j >= 2) mbar_wait(&h_free[b], ((j >> 1) + 1) & 1);  // GEMM2(j-2) has consumed H[b]
       uint8_t* htile = s_h + b * 2 * FFN_TILE + half * FFN_TILE + r * 128;
       const float* b1p = p.b1 + j * 128 + half * 64;
+      uint32_t rr2[2][32];
+      tmem_ld_32x32b_x32(tmem_base + lane_base + b * 128 + half * 64, rr2[0]);
+      tmem_ld_32x32b_x32(tmem_base + lane_base + b * 128 + half * 64 + 32, rr2[1]);
+      tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + b * 128 + half * 64 + c * 32, rr);
-        tmem_ld_wait();
+        const uint32_t(&rr)[32] = rr2[c];
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -227,124 +402,96 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       fence_proxy_async_smem();
       mbar_arrive(&h_full[b]);
     }
-    // ---- epilogue: residual + LayerNorm(s) with a coalesced fp32 staging tile in the (now free) smem ----
+    // ---- epilogue: x_new = O + b2s, LayerNorm(s), coalesced write-out through an fp32 staging tile ----
     mbar_wait(o_full, 0);
     tc_fence_after();
-    float* xs = reinterpret_cast<float*>(smem);  // [128][FFN_XS_PITCH]
-    float4* scratch = reinterpret_cast<float4*>(smem + 128 * FFN_XS_PITCH * 4);  // [2][256] exchange slots
-    float2* stats = reinterpret_cast<float2*>(scratch + 512);                    // [128] (mean, rstd) of the last LN
-    // E1: coalesced load of the residual rows (warp = row, lane = column mod 32)
-    for (int rr0 = ew; rr0 < 128; rr0 += 32) {
-      float v[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int row = rr0 + u * 8;
-        const bool in = (m0 + row) < p.M;
-        const float* src = p.x + (size_t)(m0 + row) * 256;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[u][i] = in ? __ldcg(src + lane + 32 * i) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xs[(rr0 + u * 8) * FFN_XS_PITCH + lane + 32 * i] = v[u][i];
+    float* xs = reinterpret_cast<float*>(smem);  // [128][FFN_XS_PITCH]  (A + H + part of the ring: all idle now)
+    float2* stats = reinterpret_cast<float2*>(scratch + 512);  // [128] (mean, rstd) of the last LN
+    float* prm = reinterpret_cast<float*>(stats + 128);        // [5][256]: b2s, g1, bn1, g2, bn2
+    prm[ct] = __ldg(p.b2s + ct);
+    prm[256 + ct] = __ldg(p.g1 + ct);
+    prm[512 + ct] = __ldg(p.bn1 + ct);
+    if (p.g2 != nullptr) {
+      prm[768 + ct] = __ldg(p.g2 + ct);
+      prm[1024 + ct] = __ldg(p.bn2 + ct);
     }
     named_bar_sync(1, 256);
-    // E2: row owners: x_new = x + alpha * (O + b2), statistics (Chan), optional first LayerNorm in place
-    struct Stat {
-      float n, mean, m2;
-    };
-    auto chan = [](Stat& a, float nb, float mb, float m2b) {
-      const float n = a.n + nb;
-      const float d = mb - a.mean;
-      a.mean += d * (nb / n);
-      a.m2 += m2b + d * d * (a.n * nb / n);
-      a.n = n;
-    };
-    auto add_chunk = [&](Stat& a, const float(&v)[32]) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) s += v[j];
-      const float m = s * (1.0f / 32.0f);
-      float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) q += (v[j] - m) * (v[j] - m);
-      if (a.n == 0.f)
-        a.n = 32.f, a.mean = m, a.m2 = q;
-      else
-        chan(a, 32.f, m, q);
-    };
-    auto exchange = [&](Stat& a, float4* sc, int barrier_id) {
-      sc[r * 2 + half] = make_float4(a.n, a.mean, a.m2, 0.f);
-      named_bar_sync(barrier_id, 256);
-      const float4 o = sc[r * 2 + (half ^ 1)];
-      const float4 lo = half ? o : make_float4(a.n, a.mean, a.m2, 0.f);
-      const float4 hi = half ? make_float4(a.n, a.mean, a.m2, 0.f) : o;
-      Stat t{lo.x, lo.y, lo.z};
-      chan(t, hi.x, hi.y, hi.z);
-      a = t;
-    };
     float* xrow = xs + r * FFN_XS_PITCH;
-    Stat st{0.f, 0.f, 0.f};
+    FfnStat st{0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int cc = half * 128 + c * 32;
-      uint32_t ro[32];
-      tmem_ld_32x32b_x32(tmem_o + lane_base + cc, ro);
+    for (int c = 0; c < 4; c += 2) {
+      uint32_t ro[2][32];
+      tmem_ld_32x32b_x32(tmem_o + lane_base + half * 128 + c * 32, ro[0]);
+      tmem_ld_32x32b_x32(tmem_o + lane_base + half * 128 + c * 32 + 32, ro[1]);
       tmem_ld_wait();
-      float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = fmaf(p.alpha, __uint_as_float(ro[j]) + __ldg(p.b2 + cc + j), xrow[cc + j]);
-        xrow[cc + j] = v[j];
+      for (int u = 0; u < 2; ++u) {
+        const int cc = half * 128 + (c + u) * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(prm + cc + 4 * j);
+          v[4 * j + 0] = __uint_as_float(ro[u][4 * j + 0]) + bb.x;
+          v[4 * j + 1] = __uint_as_float(ro[u][4 * j + 1]) + bb.y;
+          v[4 * j + 2] = __uint_as_float(ro[u][4 * j + 2]) + bb.z;
+          v[4 * j + 3] = __uint_as_float(ro[u][4 * j + 3]) + bb.w;
+          *reinterpret_cast<float4*>(xrow + cc + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        ffn_add_chunk(st, v);
       }
-      add_chunk(st, v);
     }
-    exchange(st, scratch, 2);
+    ffn_exchange(st, scratch, r, half, 2);
     float mean = st.mean;
     float rstd = rsqrtf(st.m2 * (1.0f / 256.0f) + p.eps);
     if (p.g2 != nullptr) {
-      Stat s2{0.f, 0.f, 0.f};
+      FfnStat s2{0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int cc = half * 128 + c * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = (xrow[cc + j] - mean) * rstd * __ldg(p.g1 + cc + j) + __ldg(p.bn1 + cc + j);
-          xrow[cc + j] = v[j];
+        for (int j = 0; j < 8; ++j) {
+          const float4 xo = *reinterpret_cast<const float4*>(xrow + cc + 4 * j);
+          const float4 gg = *reinterpret_cast<const float4*>(prm + 256 + cc + 4 * j);
+          const float4 bb = *reinterpret_cast<const float4*>(prm + 512 + cc + 4 * j);
+          v[4 * j + 0] = (xo.x - mean) * rstd * gg.x + bb.x;
+          v[4 * j + 1] = (xo.y - mean) * rstd * gg.y + bb.y;
+          v[4 * j + 2] = (xo.z - mean) * rstd * gg.z + bb.z;
+          v[4 * j + 3] = (xo.w - mean) * rstd * gg.w + bb.w;
+          *reinterpret_cast<float4*>(xrow + cc + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        add_chunk(s2, v);
+        ffn_add_chunk(s2, v);
       }
-      exchange(s2, scratch + 256, 3);
+      ffn_exchange(s2, scratch + 256, r, half, 3);
       mean = s2.mean;
       rstd = rsqrtf(s2.m2 * (1.0f / 256.0f) + p.eps);
     }
     if (half == 0) stats[r] = make_float2(mean, rstd);
     named_bar_sync(1, 256);
-    // E3: coalesced write-out of x (fp32) and y = LN(x) (bf16); lane owns columns 2*lane + 64*i (+1)
-    const float* gl = p.g2 ? p.g2 : p.g1;
-    const float* bl = p.g2 ? p.bn2 : p.bn1;
-    float2 gv[4], bv[4];
+    // coalesced write-out of x (fp32, 16 B per lane) and y = LN(x) (bf16, 8 B per lane)
+    const float* gl = prm + (p.g2 ? 768 : 256);
+    const float* bl = prm + (p.g2 ? 1024 : 512);
+    float4 gv[2], bv[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      gv[i] = __ldg(reinterpret_cast<const float2*>(gl + 2 * lane + 64 * i));
-      bv[i] = __ldg(reinterpret_cast<const float2*>(bl + 2 * lane + 64 * i));
+    for (int i = 0; i < 2; ++i) {
+      gv[i] = *reinterpret_cast<const float4*>(gl + 4 * lane + 128 * i);
+      bv[i] = *reinterpret_cast<const float4*>(bl + 4 * lane + 128 * i);
     }
     for (int row = ew; row < 128; row += 8) {
       if (m0 + row >= p.M) break;
       const float2 ms = stats[row];
-      const float* src = xs + row * FFN_XS_PITCH;
-      float* dx = p.x + (size_t)(m0 + row) * 256;
-      __nv_bfloat16* dy = p.y + (size_t)(m0 + row) * 256;
+      const float4* src = reinterpret_cast<const float4*>(xs + row * FFN_XS_PITCH);
+      float4* dx = reinterpret_cast<float4*>(p.x + (size_t)(m0 + row) * 256);
+      uint2* dy = reinterpret_cast<uint2*>(p.y + (size_t)(m0 + row) * 256);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = 2 * lane + 64 * i;
-        const float v0 = src[col], v1 = src[col + 1];
-        *reinterpret_cast<float2*>(dx + col) = make_float2(v0, v1);
-        const float y0 = (v0 - ms.x) * ms.y * gv[i].x + bv[i].x;
-        const float y1 = (v1 - ms.x) * ms.y * gv[i].y + bv[i].y;
-        *reinterpret_cast<uint32_t*>(dy + col) = pack_bf16x2(y0, y1);
+      for (int i = 0; i < 2; ++i) {
+        const float4 v = src[lane + 32 * i];
+        dx[lane + 32 * i] = v;
+        const float y0 = (v.x - ms.x) * ms.y * gv[i].x + bv[i].x;
+        const float y1 = (v.y - ms.x) * ms.y * gv[i].y + bv[i].y;
+        const float y2 = (v.z - ms.x) * ms.y * gv[i].z + bv[i].z;
+        const float y3 = (v.w - ms.x) * ms.y * gv[i].w + bv[i].w;
+        dy[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
       }
     }
   }
@@ -357,20 +504,29 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   }
 }
 
-cudaError_t launch_fused_ffn(const CUtensorMap& tm_y, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2, int M, int FF,
-                             float alpha, float* x, __nv_bfloat16* y, const float* b1, const float* b2, const float* g1,
-                             const float* bn1, const float* g2, const float* bn2, float eps, cudaStream_t st) {
+cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, const CUtensorMap& tm_w1,
+                             const CUtensorMap& tm_w2, int M, int FF, float* x, __nv_bfloat16* y, const float* b1,
+                             const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
+                             float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
+                             cudaStream_t st) {
   if (FF % 128 != 0 || M <= 0) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fused_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fused_ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fused_ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   FfnParams p;
-  p.M = M, p.nchunks = FF / 128, p.alpha = alpha, p.x = x, p.y = y, p.b1 = b1, p.b2 = b2;
+  p.M = M, p.nchunks = FF / 128, p.x = x, p.y = y, p.b1 = b1, p.b2s = b2s;
   p.g1 = g1, p.bn1 = bn1, p.g2 = g2, p.bn2 = bn2, p.eps = eps;
-  fused_ffn_kernel<<<(M + 127) / 128, FFN_THREADS, FFN_SMEM_TOTAL, st>>>(tm_y, tm_w1, tm_w2, p);
+  p.bp = bp, p.gp = gp, p.bpn = bpn, p.lens = lens, p.T = T;
+  const int grid = (M + 127) / 128;
+  if (tm_wp != nullptr)
+    fused_ffn_kernel<true><<<grid, FFN_THREADS, FFN_SMEM_TOTAL, st>>>(tm_a, *tm_wp, tm_w1, tm_w2, p);
+  else
+    fused_ffn_kernel<false><<<grid, FFN_THREADS, FFN_SMEM_TOTAL, st>>>(tm_a, tm_w1, tm_w1, tm_w2, p);
   count_launch();
   return cudaGetLastError();
 }

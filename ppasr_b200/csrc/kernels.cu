@@ -191,17 +191,18 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int use_layer_norm,
                                                               __nv_bfloat16* __restrict__ out, int Tin, int Tout,
-                                                              int lpad, float eps) {
+                                                              int lpad, float eps, const int* __restrict__ zero_lens) {
   extern __shared__ uint8_t dsm[];
-  __nv_bfloat16* sin = reinterpret_cast<__nv_bfloat16*>(dsm);                       // [TT + K - 1][C]
-  float* sout = reinterpret_cast<float*>(dsm + (size_t)(TT + 32) * C * 2);          // [TT][C]
+  constexpr int ROWS = TT + K - 1;
+  __nv_bfloat16* sin = reinterpret_cast<__nv_bfloat16*>(dsm);                 // [ROWS][C]
+  float* sout = reinterpret_cast<float*>(dsm + (size_t)ROWS * C * 2);         // [TT][C]
+  float* sw = sout + TT * C;                                                  // [C][K] staged weights
   const int tiles = (Tout + TT - 1) / TT;
   const int b = blockIdx.x / tiles;
   const int t0 = (blockIdx.x - b * tiles) * TT;
   const int c = threadIdx.x;
-  const int rows = TT + K - 1;
-  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + rows)
-  for (int i = threadIdx.x; i < rows * (C / 8); i += C) {
+  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + ROWS) and of the weights
+  for (int i = threadIdx.x; i < ROWS * (C / 8); i += C) {
     const int r = i / (C / 8), seg = i - r * (C / 8);
     const int ti = t0 - lpad + r;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -215,20 +216,31 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
     }
     *reinterpret_cast<uint4*>(sin + (size_t)r * C + seg * 8) = v;
   }
+  for (int i = threadIdx.x; i < C * K; i += C) sw[i] = __ldg(w + i);
   __syncthreads();
-  // depthwise conv, thread = channel, sliding over time
+  // depthwise conv: thread = channel, sliding K-wide register window over time (one smem read per output)
   float wk[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) wk[j] = __ldg(w + c * K + j);
+  for (int j = 0; j < K; ++j) wk[j] = sw[c * K + j];  // stride K (odd): conflict-free
   const float bs = __ldg(bias + c);
   const float sc = use_layer_norm ? 1.f : __ldg(gamma + c);
   const float sh = use_layer_norm ? 0.f : __ldg(beta + c);
-#pragma unroll 1
-  for (int t = 0; t < TT; ++t) {
-    float acc = bs;
+  float win[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) acc = fmaf(wk[j], __bfloat162float(sin[(size_t)(t + j) * C + c]), acc);
-    sout[t * C + c] = acc * sc + sh;
+  for (int j = 0; j < K - 1; ++j) win[j] = __bfloat162float(sin[(size_t)j * C + c]);
+#pragma unroll
+  for (int tb = 0; tb < TT; tb += K) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int t = tb + u;
+      if (t < TT) {
+        win[(u + K - 1) % K] = __bfloat162float(sin[(size_t)(t + K - 1) * C + c]);
+        float acc = bs;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = fmaf(wk[j], win[(u + j) % K], acc);
+        sout[t * C + c] = acc * sc + sh;
+      }
+    }
   }
   __syncthreads();
   // norm + swish, warp = row
@@ -255,9 +267,10 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
       for (int i = 0; i < PER; ++i)
         v[i] = (v[i] - mean) * rstd * __ldg(gamma + lane * PER + i) + __ldg(beta + lane * PER + i);
     }
+    const bool zero = zero_lens != nullptr && (t0 + t) >= __ldg(zero_lens + b);
     uint32_t pk[PER / 2];
 #pragma unroll
-    for (int i = 0; i < PER / 2; ++i) pk[i] = pack_bf16x2(swish_precise(v[2 * i]), swish_precise(v[2 * i + 1]));
+    for (int i = 0; i < PER / 2; ++i) pk[i] = zero ? 0u : pack_bf16x2(swish_precise(v[2 * i]), swish_precise(v[2 * i + 1]));
     uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * Tout + t0 + t) * C + lane * PER);
 #pragma unroll
     for (int i = 0; i < PER / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
@@ -266,13 +279,14 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
 
 cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
                                      const float* gamma, const float* beta, int use_layer_norm, __nv_bfloat16* out,
-                                     int B, int Tin, int Tout, int C, int K, int lpad, float eps, cudaStream_t st) {
+                                     int B, int Tin, int Tout, int C, int K, int lpad, float eps, const int* zero_lens,
+                                     cudaStream_t st) {
   if (C != 256) return cudaErrorInvalidValue;
-  constexpr int TT = 32;
-  const size_t smem = (size_t)(TT + 32) * C * 2 + (size_t)TT * C * 4;
+  constexpr int TT = 16;
   const int tiles = (Tout + TT - 1) / TT;
 #define PPASR_DW_LAUNCH(KK)                                                                                   \
   {                                                                                                           \
+    const size_t smem = (size_t)(TT + KK - 1) * C * 2 + (size_t)TT * C * 4 + (size_t)C * KK * 4;             \
     auto kern = dwconv_norm_swish_kernel<256, TT, KK>;                                                        \
     static bool configured = false;                                                                           \
     if (!configured) {                                                                                        \
@@ -281,7 +295,7 @@ cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, con
       configured = true;                                                                                      \
     }                                                                                                         \
     kern<<<B * tiles, 256, smem, st>>>(g, w, bias, pad_left, gamma, beta, use_layer_norm, out, Tin, Tout, lpad, \
-                                       eps);                                                                  \
+                                       eps, zero_lens);                                                       \
   }
   if (K == 15) PPASR_DW_LAUNCH(15) else if (K == 31) PPASR_DW_LAUNCH(31) else if (K == 7) PPASR_DW_LAUNCH(7) else return cudaErrorInvalidValue;
 #undef PPASR_DW_LAUNCH

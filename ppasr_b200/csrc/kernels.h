@@ -15,9 +15,11 @@ cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const 
                                    const float* bias, __nv_bfloat16* out, int B, int T, int F, int C, int T1, int F1,
                                    int Th, int FH, cudaStream_t st);
 
+// zero_lens (nullable): output rows t >= zero_lens[b] are written as 0 (pad frames of the conv module output)
 cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
                                      const float* gamma, const float* beta, int use_layer_norm, __nv_bfloat16* out,
-                                     int B, int Tin, int Tout, int C, int K, int lpad, float eps, cudaStream_t st);
+                                     int B, int Tin, int Tout, int C, int K, int lpad, float eps, const int* zero_lens,
+                                     cudaStream_t st);
 
 cudaError_t launch_glu_pad(const float* bias_il, float* pad, int C, cudaStream_t st);
 
@@ -41,10 +43,13 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
                                 int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
                                 int* score_cnt, cudaStream_t st);
 
-// Fused feed-forward block (fused_ffn.cu): x += alpha * W2 swish(W1 y + b1) + b2 ; trailing LayerNorm(s)
-cudaError_t launch_fused_ffn(const CUtensorMap& tm_y, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2, int M, int FF,
-                             float alpha, float* x, __nv_bfloat16* y, const float* b1, const float* b2, const float* g1,
-                             const float* bn1, const float* g2, const float* bn2, float eps, cudaStream_t st);
+// Fused feed-forward block (fused_ffn.cu): x += W2s swish(W1 y + b1) + b2s with trailing LayerNorm(s); optional
+// chained pre-GEMM (tm_wp != null): x += mask (Wp z + bp), y = LN(x; gp, bpn) first (tm_a is then the z tile map).
+cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, const CUtensorMap& tm_w1,
+                             const CUtensorMap& tm_w2, int M, int FF, float* x, __nv_bfloat16* y, const float* b1,
+                             const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
+                             float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
+                             cudaStream_t st);
 
 // CTC prefix beam search (beam.cu)
 struct BeamStateHeader {

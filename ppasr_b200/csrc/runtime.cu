@@ -63,8 +63,8 @@ struct LayerW {
   const float *ln_ffm_g, *ln_ffm_b, *ln_mha_g, *ln_mha_b, *ln_conv_g, *ln_conv_b, *ln_ff_g, *ln_ff_b, *ln_fin_g,
       *ln_fin_b;
   // feed-forward (macaron, final): K-major bf16
-  const __nv_bfloat16 *ffm_w1, *ffm_w2, *ff_w1, *ff_w2;
-  const float *ffm_b1, *ffm_b2, *ff_b1, *ff_b2;
+  const __nv_bfloat16 *ffm_w1, *ffm_w2, *ff_w1, *ff_w2, *ffm_w2s, *ff_w2s;  // *_w2s = 0.5 * W2 (macaron scale folded)
+  const float *ffm_b1, *ffm_b2, *ff_b1, *ff_b2, *ffm_b2s, *ff_b2s;
   // attention
   const __nv_bfloat16 *wqkv, *wo;
   const float *bqkv, *bo, *pos_u, *pos_v;
@@ -108,7 +108,7 @@ struct ppasr_b200_ctx {
   // weight tensor maps (B operands)
   CUtensorMap tm_conv2_w, tm_emb_w, tm_ctc_w, tm_pos;
   struct LayerMaps {
-    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2, ffm_w1_128, ff_w1_128;
+    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2, ffm_w1_128, ff_w1_128, ffm_w2s, ff_w2s;
   };
   std::vector<LayerMaps> lmaps;
   Plan plan;
@@ -318,7 +318,7 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
 
   // ---- size the weight slab ----------------------------------------------------------------------
   size_t bytes = 0;
-  bytes += (size_t)L * ((size_t)4 * D * FF + 3 * D * D + D * D + 2 * D * D + D * D) * 2;  // bf16 matrices
+  bytes += (size_t)L * ((size_t)6 * D * FF + 3 * D * D + D * D + 2 * D * D + D * D) * 2;  // bf16 matrices
   bytes += (size_t)D * 9 * D * 2 + (size_t)D * c->Kemb * 2 + (size_t)c->Vpad * D * 2;
   bytes += (size_t)cfg.max_len * L * D * 2 + (size_t)cfg.max_len * D * 2 + (size_t)L * D * D * 2;
   bytes += (size_t)L * (20 * D + 2 * FF + 3 * D + 2 * D + D * K + 64) * 4 + (size_t)(c->Vpad + 4 * D + L * D + 4096) * 4;
@@ -394,6 +394,19 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
     w.ffm_b1 = vecf(p + "feed_forward_macaron.w_1.bias"), w.ffm_b2 = vecf(p + "feed_forward_macaron.w_2.bias");
     w.ff_b1 = vecf(p + "feed_forward.w_1.bias"), w.ff_b2 = vecf(p + "feed_forward.w_2.bias");
     {
+      // ff_scale = 0.5 (encoder.py:331-332) folded into W2 / b2 for the fused kernel (exact: power of two)
+      auto scaled = [&](const std::string& wn, const std::string& bn, const __nv_bfloat16** wd, const float** bd) {
+        std::vector<float> t = transpose_in_out(c->host[wn]);
+        for (auto& v : t) v *= 0.5f;
+        *wd = upload(c, to_bf16(t));
+        std::vector<float> bv = c->host[bn].data;
+        for (auto& v : bv) v *= 0.5f;
+        *bd = upload(c, bv);
+      };
+      scaled(p + "feed_forward_macaron.w_2.weight", p + "feed_forward_macaron.w_2.bias", &w.ffm_w2s, &w.ffm_b2s);
+      scaled(p + "feed_forward.w_2.weight", p + "feed_forward.w_2.bias", &w.ff_w2s, &w.ff_b2s);
+    }
+    {
       std::vector<float> qkv((size_t)3 * D * D), bq((size_t)3 * D);
       const char* nm[3] = {"linear_q", "linear_k", "linear_v"};
       for (int s = 0; s < 3; ++s) {
@@ -463,6 +476,8 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
     bool ok = make_tmap_2d(&m.ffm_w1, w.ffm_w1, D, FF, (uint64_t)D * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.ffm_w2, w.ffm_w2, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.ff_w1, w.ff_w1, D, FF, (uint64_t)D * 2, BN_WIDE, &err) &&
+              make_tmap_2d(&m.ffm_w2s, w.ffm_w2s, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
+              make_tmap_2d(&m.ff_w2s, w.ff_w2s, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.ffm_w1_128, w.ffm_w1, D, FF, (uint64_t)D * 2, 128, &err) &&
               make_tmap_2d(&m.ff_w1_128, w.ff_w1, D, FF, (uint64_t)D * 2, 128, &err) &&
               make_tmap_2d(&m.ff_w2, w.ff_w2, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
@@ -668,8 +683,9 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
     // ---- macaron FFN: x += 0.5 * W2 swish(W1 LN(x)); then y = norm_mha(x)        (encoder.py:380-390)
     if (c->fused_ffn) {
       PROF(PC_FUSED_FFN);
-      PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, m.ffm_w1_128, m.ffm_w2, M, FF, 0.5f, p.x, p.y, w.ffm_b1, w.ffm_b2, w.ln_mha_g,
-                                        w.ln_mha_b, nullptr, nullptr, eps, st));
+      PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, nullptr, m.ffm_w1_128, m.ffm_w2s, M, FF, p.x, p.y, w.ffm_b1, w.ffm_b2s,
+                                        w.ln_mha_g, w.ln_mha_b, nullptr, nullptr, eps, nullptr, nullptr, nullptr, nullptr,
+                                        p.Tp, st));
     } else {
       EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ffm_b1, FF, M, FF};
       { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ffm_w1, M, FF, D, e1, st))); }
@@ -708,7 +724,7 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
         { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st))); }
         const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
         { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
-                                                  cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, st)); }
+                                                  cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, vl, st)); }
       } else {
         // [cnn_cache ; chunk] -> pw1 + GLU -> "valid" depthwise conv; cache <- last K-1 input rows (convolution.py:108-117)
         const int lorder = K - 1;
@@ -716,10 +732,12 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
         EpiGLU<BN_WIDE> eg{p.gcat, w.pw1_b, D, p.Mcat, 2 * D};
         { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_ycat, m.pw1, p.Mcat, 2 * D, D, eg, st))); }
         { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.gcat, w.dw_w, w.dw_b, nullptr, w.cn_g, w.cn_b, cfg.conv_norm == 0,
-                                                  p.z, p.B, p.Tcat, p.Tp, D, K, 0, eps, st)); }
+                                                  p.z, p.B, p.Tcat, p.Tp, D, K, 0, eps, nullptr, st)); }
       }
-      if ((rc = resid_ln(PC_PW2, p.tm_z, m.pw2, D, w.pw2_b, 1.0f, 1, vl, 1, 0, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr)))
-        return rc;
+      if (!c->fused_ffn) {
+        if ((rc = resid_ln(PC_PW2, p.tm_z, m.pw2, D, w.pw2_b, 1.0f, 1, vl, 1, 0, w.ln_ff_g, w.ln_ff_b, nullptr, nullptr)))
+          return rc;
+      }
     }
     // ---- FFN: x += 0.5 * W2 swish(W1 y); x = norm_final(x); y = next block's first LayerNorm (or after_norm)
     //      (encoder.py:419-429, 201-202)
@@ -728,8 +746,9 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
       const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
       if (c->fused_ffn) {
         PROF(PC_FUSED_FFN);
-        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, m.ff_w1_128, m.ff_w2, M, FF, 0.5f, p.x, p.y, w.ff_b1, w.ff_b2, w.ln_fin_g,
-                                          w.ln_fin_b, g2, b2, eps, st));
+        // pointwise_conv2 + residual + norm_ff chained in front (z rows of pad frames are zero, bias masked)
+        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_z, &m.pw2, m.ff_w1_128, m.ff_w2s, M, FF, p.x, p.y, w.ff_b1, w.ff_b2s, w.ln_fin_g,
+                                          w.ln_fin_b, g2, b2, eps, w.pw2_b, w.ln_ff_g, w.ln_ff_b, vl, p.Tp, st));
       } else {
         EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ff_b1, FF, M, FF};
         { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st))); }
@@ -1030,7 +1049,7 @@ int ppasr_b200_op_dwconv(const void* g_bf16, const float* w, const float* bias, 
                          int32_t Tin, int32_t Tout, int32_t C, int32_t K, int32_t lpad, float eps, void* stream) {
   PPASR_REQUIRE(g_bf16 && w && bias && gamma && beta && out_bf16, "null pointer");
   PPASR_CUDA_CHECK(launch_dwconv_norm_swish((const __nv_bfloat16*)g_bf16, w, bias, pad_left, gamma, beta, use_layer_norm,
-                                            (__nv_bfloat16*)out_bf16, B, Tin, Tout, C, K, lpad, eps,
+                                            (__nv_bfloat16*)out_bf16, B, Tin, Tout, C, K, lpad, eps, nullptr,
                                             reinterpret_cast<cudaStream_t>(stream)));
   return PPASR_OK;
 }
