@@ -284,13 +284,20 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     {
       float* slab = reinterpret_cast<float*>(s_h);
       for (int s = 0; s < 4; ++s) {
-        // coalesced: 16 threads per row (16 B each), 16 rows per pass
-        for (int rr = ct >> 4; rr < 128; rr += 16) {
+        // coalesced: 16 threads per row (16 B each), 16 rows per pass; all 8 loads in flight before the stores
+        {
           const int cq = ct & 15;
-          const bool in = (m0 + rr) < p.M;
-          const float4 v = in ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)(m0 + rr) * 256 + s * 64) + cq)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(slab + rr * FFN_SLAB_PITCH + cq * 4) = v;
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (ct >> 4) + 16 * i;
+            v[i] = ((m0 + rr) < p.M)
+                       ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)(m0 + rr) * 256 + s * 64) + cq)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(slab + ((ct >> 4) + 16 * i) * FFN_SLAB_PITCH + cq * 4) = v[i];
         }
         named_bar_sync(1, 256);
         if (half == (s >> 1)) {

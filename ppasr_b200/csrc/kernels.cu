@@ -201,22 +201,40 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
   const int b = blockIdx.x / tiles;
   const int t0 = (blockIdx.x - b * tiles) * TT;
   const int c = threadIdx.x;
-  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + ROWS) and of the weights
-  for (int i = threadIdx.x; i < ROWS * (C / 8); i += C) {
-    const int r = i / (C / 8), seg = i - r * (C / 8);
-    const int ti = t0 - lpad + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (ti >= 0 && ti < Tin) {
-      v = *reinterpret_cast<const uint4*>(g + ((size_t)b * Tin + ti) * C + seg * 8);
-    } else if (ti < 0 && pad_left != nullptr) {
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pad_left + seg * 8));
-      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pad_left + seg * 8) + 1);
-      v = make_uint4(pack_bf16x2(p0.x, p0.y), pack_bf16x2(p0.z, p0.w), pack_bf16x2(p1.x, p1.y),
-                     pack_bf16x2(p1.z, p1.w));
+  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + ROWS) and of the weights; loads are
+  // issued in batches before the shared-memory stores so they overlap
+  {
+    constexpr int NV = (ROWS * (C / 8) + C - 1) / C;
+    uint4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = threadIdx.x + k * C;
+      const int r = i / (C / 8), seg = i - r * (C / 8);
+      const int ti = t0 - lpad + r;
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (r < ROWS) {
+        if (ti >= 0 && ti < Tin) {
+          v[k] = *reinterpret_cast<const uint4*>(g + ((size_t)b * Tin + ti) * C + seg * 8);
+        } else if (ti < 0 && pad_left != nullptr) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(pad_left + seg * 8));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(pad_left + seg * 8) + 1);
+          v[k] = make_uint4(pack_bf16x2(p0.x, p0.y), pack_bf16x2(p0.z, p0.w), pack_bf16x2(p1.x, p1.y),
+                            pack_bf16x2(p1.z, p1.w));
+        }
+      }
     }
-    *reinterpret_cast<uint4*>(sin + (size_t)r * C + seg * 8) = v;
+    float wv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wv[k] = __ldg(w + threadIdx.x + k * C);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = threadIdx.x + k * C;
+      const int r = i / (C / 8), seg = i - r * (C / 8);
+      if (r < ROWS) *reinterpret_cast<uint4*>(sin + (size_t)r * C + seg * 8) = v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) sw[threadIdx.x + k * C] = wv[k];
   }
-  for (int i = threadIdx.x; i < C * K; i += C) sw[i] = __ldg(w + i);
   __syncthreads();
   // depthwise conv: thread = channel, sliding K-wide register window over time (one smem read per output)
   float wk[K];
