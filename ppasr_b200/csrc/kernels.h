@@ -51,6 +51,11 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
                              cudaStream_t st);
 
+// Fused attention out-projection + residual + norm_conv + pointwise_conv1 + GLU (fused_attn_out.cu)
+cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& tm_wo, const CUtensorMap& tm_wpw1, int M,
+                                  float* x, __nv_bfloat16* g, const float* bo, const float* ln_g, const float* ln_b,
+                                  const float* bpw1, const int* lens, int T, float eps, cudaStream_t st);
+
 // CTC prefix beam search (beam.cu)
 struct BeamStateHeader {
   int nb;       // entries in the beam

@@ -127,6 +127,7 @@ struct ppasr_b200_ctx {
   } ss;
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
+  bool fused_attn_out = true;
   bool profiling = false;
   struct ProfRec {
     int cls;
@@ -141,12 +142,12 @@ namespace {
 
 enum ProfClass : int {
   PC_CONV1 = 0, PC_CONV2, PC_EMBED, PC_LAYERNORM, PC_FFN1, PC_FFN2, PC_QKV, PC_ATTENTION, PC_OUTPROJ, PC_PW1_GLU,
-  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_FUSED_FFN, PC_COUNT
+  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_FUSED_FFN, PC_FUSED_ATTN_OUT, PC_COUNT
 };
 const char* const kProfNames[PC_COUNT] = {"conv1_subsample", "conv2_gemm", "embed_gemm", "layernorm", "ffn1_gemm",
                                           "ffn2_gemm", "qkv_gemm", "attention", "outproj_gemm", "pw1_glu_gemm",
                                           "dwconv_norm_swish", "pw2_gemm", "ctc_stats_gemm", "ctc_finalize",
-                                          "ctc_collapse", "ctc_logits_gemm", "softmax", "fused_ffn"};
+                                          "ctc_collapse", "ctc_logits_gemm", "softmax", "fused_ffn", "fused_attn_out"};
 
 struct ProfScope {
   ppasr_b200_ctx* c;
@@ -713,15 +714,24 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
         { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, ss.tm_k[l], c->tm_pos, ss.tm_vt[l], ap, st)); }
       }
       // pad frames of the conv-module input are zeroed (convolution.py:104-106 with the caller's inverted mask)
-      if ((rc = resid_ln(PC_OUTPROJ, p.tm_att, m.wo, D, w.bo, 1.0f, 1, vl, 0, 1, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr)))
+      if (!chunk && c->fused_attn_out) {
+        PROF(PC_FUSED_ATTN_OUT);
+        PPASR_CUDA_CHECK(launch_fused_attn_out(p.tm_att, m.wo, m.pw1, M, p.x, p.g, w.bo, w.ln_conv_g, w.ln_conv_b, w.pw1_b, vl,
+                                               p.Tp, eps, st));
+      } else if ((rc = resid_ln(PC_OUTPROJ, p.tm_att, m.wo, D, w.bo, 1.0f, 1, vl, 0, 1, w.ln_conv_g, w.ln_conv_b, nullptr,
+                                nullptr))) {
         return rc;
+      }
     }
     // ---- conv module: x += mask * pw2 swish(norm(dw(glu(pw1(y))))); then y = norm_ff(x)   (encoder.py:407-421)
     {
       const int K = cfg.conv_kernel;
       if (!chunk) {
-        EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, M, 2 * D};
-        { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st))); }
+        if (!c->fused_attn_out) {
+          EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, M, 2 * D};
+          PROF(PC_PW1_GLU);
+          PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st)));
+        }
         const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
         { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
                                                   cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, vl, st)); }
@@ -995,6 +1005,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   const std::string n(name);
   if (n == "fused_ffn") {
     c->fused_ffn = value != 0;
+    return PPASR_OK;
+  }
+  if (n == "fused_attn_out") {
+    c->fused_attn_out = value != 0;
     return PPASR_OK;
   }
   set_last_error("unknown option: " + n);

@@ -10,7 +10,7 @@ def run(nb, B, T, lens, fused):
     w = init_conformer_weights(cfg)
     feats = synthetic_fbank(B, T)
     for b in range(B): feats[b, lens[b]:] = 0
-    eng = ConformerEngine(cfg, w); eng.set_option("fused_ffn", fused)
+    eng = ConformerEngine(cfg, w); eng.set_option("fused_ffn", fused); eng.set_option("fused_attn_out", fused)
     eng.encode(torch.from_numpy(feats).cuda(), lens)
     lg = eng.ctc_logits().cpu(); torch.cuda.synchronize()
     ref = ConformerOracle(ConformerConf(**cfg.to_dict()), w).get_encoder_out(torch.from_numpy(feats), torch.tensor(lens), return_logits=True)
