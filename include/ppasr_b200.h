@@ -150,6 +150,12 @@ int ppasr_b200_op_dwconv(const void* g_bf16, const float* w, const float* bias, 
                          const float* gamma, const float* beta, int32_t use_layer_norm, void* out_bf16, int32_t B,
                          int32_t Tin, int32_t Tout, int32_t C, int32_t K, int32_t lpad, float eps, void* stream);
 int ppasr_b200_op_softmax(const float* logits, int32_t ldl, float* probs, int32_t M, int32_t V, void* stream);
+/* fused feed-forward block (plain mode of fused_ffn.cu): x += W2s swish(W1 y + b1) + b2s, then LayerNorm(s).
+ * y [M,256] bf16, w1 [FF,256] bf16, w2s [256,FF] bf16 (already scaled by the macaron factor), x fp32 [M,256] in place,
+ * y_out bf16 [M,256]; g2/bn2 NULL = single LayerNorm. */
+int ppasr_b200_op_fused_ffn(const void* y_bf16, const void* w1_bf16, const void* w2s_bf16, float* x, void* y_out,
+                            const float* b1, const float* b2s, const float* g1, const float* bn1, const float* g2,
+                            const float* bn2, int32_t M, int32_t FF, float eps, void* stream);
 /* rel-pos attention on packed q2 [B,H,T1,128], kk [B,H,T2,64], vt [B,H,64,T2p], pos [pos_rows, pos_ld]
  * (all bf16) -> out bf16 [B*T1, H*64]; klens nullable int32 [B]. */
 int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int32_t T2p, const void* pos,

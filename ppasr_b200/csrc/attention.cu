@@ -14,6 +14,7 @@
 //   128 softmax thr: o_reg = o_reg * alpha + O_blk  (online soft-max rescale in registers)
 // Scores never touch HBM. smem: Q 32 KB + (K|P, reused for the probabilities) 32 KB + V^T 16 KB.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace ppasr {
@@ -78,6 +79,8 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_s = tmem_base;        // S: columns [0,128)
   const uint32_t tmem_o = tmem_base + 128;  // O_blk: columns [128,192)
 
@@ -232,9 +235,9 @@ cudaError_t launch_rel_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_
     configured = true;
   }
   dim3 grid((p.T1 + ATT_BM - 1) / ATT_BM, p.H, p.B);
-  rel_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, st>>>(tm_q, tm_k, tm_p, tm_vt, p);
+  cudaError_t le = launch_pdl(rel_attention_kernel, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, st, tm_q, tm_k, tm_p, tm_vt, p);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace ppasr

@@ -11,6 +11,7 @@ void set_last_error(const std::string& msg);
 const char* get_last_error();
 
 int device_sm_count();
+bool pdl_enabled();
 
 // number of kernels launched by this library (all contexts); read by bench.py for "gpu_launches"
 void count_launch();

@@ -11,6 +11,7 @@
 // to HBM -- then the 512-wide pointwise_conv1 runs as two 128x256x16 MMA groups (gate/value rows are
 // interleaved so GLU is thread-local) and g is written with coalesced stores through an smem staging tile.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "row_tile.cuh"
 
@@ -88,6 +89,8 @@ fused_attn_out_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_o = tmem_base + 256;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -320,9 +323,10 @@ cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& 
   }
   AttnOutParams p;
   p.M = M, p.x = x, p.g = g, p.bo = bo, p.ln_g = ln_g, p.ln_b = ln_b, p.bpw1 = bpw1, p.lens = lens, p.T = T, p.eps = eps;
-  fused_attn_out_kernel<<<(M + 127) / 128, AO_THREADS, AO_SMEM_TOTAL, st>>>(tm_att, tm_wo, tm_wpw1, p);
+  cudaError_t le = launch_pdl(fused_attn_out_kernel, dim3((M + 127) / 128), dim3(AO_THREADS), (size_t)AO_SMEM_TOTAL, st, tm_att,
+                              tm_wo, tm_wpw1, p);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace ppasr

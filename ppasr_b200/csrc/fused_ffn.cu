@@ -22,6 +22,7 @@
 //  * Weights stream through a 3 x 32 KB TMA ring (2 MB per CTA per call, L2 resident).
 //  * Epilogue: x/y tiles are staged in the (by then free) smem and written with coalesced 16-byte stores.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "row_tile.cuh"
 
@@ -116,6 +117,8 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_o = tmem_base + 256;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -496,12 +499,13 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
   p.g1 = g1, p.bn1 = bn1, p.g2 = g2, p.bn2 = bn2, p.eps = eps;
   p.bp = bp, p.gp = gp, p.bpn = bpn, p.lens = lens, p.T = T;
   const int grid = (M + 127) / 128;
+  cudaError_t le;
   if (tm_wp != nullptr)
-    fused_ffn_kernel<true><<<grid, FFN_THREADS, FFN_SMEM_TOTAL, st>>>(tm_a, *tm_wp, tm_w1, tm_w2, p);
+    le = launch_pdl(fused_ffn_kernel<true>, dim3(grid), dim3(FFN_THREADS), (size_t)FFN_SMEM_TOTAL, st, tm_a, *tm_wp, tm_w1, tm_w2, p);
   else
-    fused_ffn_kernel<false><<<grid, FFN_THREADS, FFN_SMEM_TOTAL, st>>>(tm_a, tm_w1, tm_w1, tm_w2, p);
+    le = launch_pdl(fused_ffn_kernel<false>, dim3(grid), dim3(FFN_THREADS), (size_t)FFN_SMEM_TOTAL, st, tm_a, tm_w1, tm_w1, tm_w2, p);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace ppasr

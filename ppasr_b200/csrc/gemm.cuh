@@ -15,6 +15,7 @@
 // A is a 3-D tensor [phase(4)][row][256] and k-block kb reads tap kb/kc at row offset
 // (kh>>1)*pitch + (kw>>1) of phase (kh&1)*2 + (kw&1).
 #pragma once
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace ppasr {
@@ -641,6 +642,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();               // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();  // let the next kernel start its own set-up
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -763,9 +766,9 @@ inline cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tma
   const int num_tiles = shape.num_m_tiles * shape.num_n_tiles;
   if (num_tiles <= 0) return cudaSuccess;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(tmap_a, tmap_b, shape, epi);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SM::TOTAL, stream, tmap_a, tmap_b, shape, epi);
   count_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace ppasr

@@ -3,6 +3,7 @@
 // row soft-max, CTC greedy decode. All are HBM-bandwidth bound: coalesced 16-byte accesses,
 // warp-shuffle reductions, no re-reads.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace ppasr {
@@ -193,6 +194,8 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
                                                               __nv_bfloat16* __restrict__ out, int Tin, int Tout,
                                                               int lpad, float eps, const int* __restrict__ zero_lens) {
   extern __shared__ uint8_t dsm[];
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int ROWS = TT + K - 1;
   __nv_bfloat16* sin = reinterpret_cast<__nv_bfloat16*>(dsm);                 // [ROWS][C]
   float* sout = reinterpret_cast<float*>(dsm + (size_t)ROWS * C * 2);         // [TT][C]
@@ -312,8 +315,9 @@ cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, con
       if (e != cudaSuccess) return e;                                                                         \
       configured = true;                                                                                      \
     }                                                                                                         \
-    kern<<<B * tiles, 256, smem, st>>>(g, w, bias, pad_left, gamma, beta, use_layer_norm, out, Tin, Tout, lpad, \
-                                       eps, zero_lens);                                                       \
+    cudaError_t le = launch_pdl(kern, dim3(B * tiles), dim3(256), smem, st, g, w, bias, pad_left, gamma, beta, use_layer_norm, \
+                                out, Tin, Tout, lpad, eps, zero_lens);                                       \
+    if (le != cudaSuccess) return le;                                                                         \
   }
   if (K == 15) PPASR_DW_LAUNCH(15) else if (K == 31) PPASR_DW_LAUNCH(31) else if (K == 7) PPASR_DW_LAUNCH(7) else return cudaErrorInvalidValue;
 #undef PPASR_DW_LAUNCH

@@ -1,0 +1,26 @@
+// Kernel launch helper with programmatic dependent launch (PDL). Every kernel launched through launch_pdl()
+// calls pdl_wait() before it touches memory written by earlier kernels, so overlapping its launch latency,
+// barrier/TMEM set-up and descriptor prefetch with the tail of the previous kernel is safe.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ppasr {
+
+bool pdl_enabled();  // PPASR_B200_PDL=0 disables (plain stream order)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+}  // namespace ppasr

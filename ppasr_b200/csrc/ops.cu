@@ -8,6 +8,7 @@
 #include "tmap.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace ppasr {
@@ -19,6 +20,15 @@ const char* get_last_error() { return g_last_error.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PPASR_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 int device_sm_count() {
   static int sms = 0;
@@ -179,6 +189,25 @@ int ppasr_b200_op_ctc_prune(const float* probs, int32_t rows, int32_t V, float c
   int* cid = cnt + (((size_t)rows + 63) & ~size_t(63));
   float* clp = reinterpret_cast<float*>(cid + (size_t)rows * BEAM_MAX_TOPN);
   PPASR_CUDA_CHECK(launch_ctc_prune(probs, V, rows, cutoff_prob, top_n, cnt, cid, clp, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+// Fused FFN block on raw pointers (plain mode): x += W2s swish(W1 y + b1) + b2s ; y_out = LN(x; g1, bn1) [; double]
+int ppasr_b200_op_fused_ffn(const void* y_bf16, const void* w1_bf16, const void* w2s_bf16, float* x, void* y_out,
+                            const float* b1, const float* b2s, const float* g1, const float* bn1, const float* g2,
+                            const float* bn2, int32_t M, int32_t FF, float eps, void* stream) {
+  PPASR_REQUIRE(y_bf16 && w1_bf16 && w2s_bf16 && x && y_out && b1 && b2s && g1 && bn1, "null pointer");
+  PPASR_REQUIRE(M > 0 && FF > 0 && FF % 128 == 0, "FF must be a positive multiple of 128");
+  std::string err;
+  CUtensorMap ta, t1, t2;
+  if (!make_tmap_2d(&ta, y_bf16, 256, (uint64_t)M, 512, 128, &err) ||
+      !make_tmap_2d(&t1, w1_bf16, 256, (uint64_t)FF, 512, 128, &err) ||
+      !make_tmap_2d(&t2, w2s_bf16, (uint64_t)FF, 256, (uint64_t)FF * 2, 256, &err)) {
+    set_last_error(err);
+    return PPASR_ERR_CUDA;
+  }
+  PPASR_CUDA_CHECK(launch_fused_ffn(ta, nullptr, t1, t2, M, FF, x, (__nv_bfloat16*)y_out, b1, b2s, g1, bn1, g2, bn2, eps,
+                                    nullptr, nullptr, nullptr, nullptr, 1, reinterpret_cast<cudaStream_t>(stream)));
   return PPASR_OK;
 }
 

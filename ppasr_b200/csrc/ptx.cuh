@@ -194,6 +194,12 @@ DEVINL float swish_f(float x) { return x * sigmoid_f(x); }
 DEVINL float sigmoid_precise(float x) { return 1.0f / (1.0f + __expf(-x)); }
 DEVINL float swish_precise(float x) { return x * sigmoid_precise(x); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has
+// completed and its memory is visible, pdl_launch_dependents() lets the successor begin its own prologue.
+DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 DEVINL uint32_t pack_bf16x2(float lo, float hi) {
