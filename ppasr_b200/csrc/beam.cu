@@ -36,56 +36,151 @@ constexpr int BEAM_THREADS = 256;
 // ------------------------------------------------------------------------------------------------
 // (1) pruning scan
 // ------------------------------------------------------------------------------------------------
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) ctc_prune_kernel(const float* __restrict__ probs, int V, int rows,
-                                                               float cutoff_prob, int top_n, int* __restrict__ cnt,
-                                                               int* __restrict__ cid, float* __restrict__ clp) {
-  extern __shared__ float srow[];  // WARPS * Vpad
+// Selection order everywhere: probability descending, index ascending on ties.
+DEVINL bool prune_before(float pa, int ia, float pb, int ib) { return pa > pb || (pa == pb && ia < ib); }
+
+constexpr int PRUNE_CAND_MAX = 256;  // compacted candidates per row; more (mass ties) falls back to full-row rounds
+constexpr int PRUNE_WARPS = 4;
+
+// One warp per frame, no row staging (occupancy, i.e. bytes in flight, is what saturates HBM):
+//   pass 1 streams the row from HBM with 16-byte loads (8 in flight per lane) keeping each lane's two largest values;
+//          the limit-th largest of those 64 values is a lower bound tau of the limit-th largest of the row;
+//   pass 2 re-reads the row (L2 hits: 17 KB touched microseconds earlier) and compacts every element >= tau;
+//   then at most `limit` arg-max rounds over the (typically ~64) candidates, with the cumulative cut-off.
+__global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float* __restrict__ probs, int V, int rows,
+                                                                      float cutoff_prob, int top_n, int* __restrict__ cnt,
+                                                                      int* __restrict__ cid, float* __restrict__ clp) {
+  __shared__ float s_cp[PRUNE_WARPS][PRUNE_CAND_MAX];
+  __shared__ int s_ci[PRUNE_WARPS][PRUNE_CAND_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * WARPS + warp;
+  const int row = blockIdx.x * PRUNE_WARPS + warp;
   if (row >= rows) return;
-  const int Vpad = (V + 3) & ~3;
-  float* s = srow + (size_t)warp * Vpad;
+  float* cp = s_cp[warp];
+  int* ci = s_ci[warp];
   const float* src = probs + (size_t)row * V;
-  // stream the row once (16-byte loads where the 4-byte-aligned row start allows)
+  const bool prune = (cutoff_prob < 1.0f) || (top_n < V);
+  const int limit = min(prune ? min(top_n, V) : V, BEAM_MAXC);
   const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
   const int head = mis ? min(4 - mis, V) : 0;
-  if (lane < head) s[lane] = src[lane];
   const float4* v4 = reinterpret_cast<const float4*>(src + head);
   const int n4 = (V - head) >> 2;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 a = __ldcs(v4 + i);
-    const int j = head + 4 * i;
-    s[j] = a.x, s[j + 1] = a.y, s[j + 2] = a.z, s[j + 3] = a.w;
-  }
   const int tail0 = head + 4 * n4;
-  if (tail0 + lane < V) s[tail0 + lane] = src[tail0 + lane];
+  // ---- pass 1 ----
+  float t1 = -INFINITY, t2 = -INFINITY;
+  auto upd = [&](float x) {
+    t2 = fmaxf(t2, fminf(t1, x));
+    t1 = fmaxf(t1, x);
+  };
+  auto upd4 = [&](const float4& a) { upd(a.x), upd(a.y), upd(a.z), upd(a.w); };
+  if (lane < head) upd(src[lane]);
+  if (tail0 + lane < V) upd(src[tail0 + lane]);
+  int i = lane;
+  for (; i + 224 < n4; i += 256) {
+    const float4 a0 = __ldg(v4 + i), a1 = __ldg(v4 + i + 32), a2 = __ldg(v4 + i + 64), a3 = __ldg(v4 + i + 96);
+    const float4 a4 = __ldg(v4 + i + 128), a5 = __ldg(v4 + i + 160), a6 = __ldg(v4 + i + 192), a7 = __ldg(v4 + i + 224);
+    upd4(a0), upd4(a1), upd4(a2), upd4(a3), upd4(a4), upd4(a5), upd4(a6), upd4(a7);
+  }
+  for (; i < n4; i += 32) upd4(__ldg(v4 + i));
+  // ---- threshold ----
+  float tau = -INFINITY;
+  {
+    float a1 = t1, a2 = t2;
+    for (int k = 0; k < limit; ++k) {
+      const float m = warp_max(fmaxf(a1, a2));
+      tau = m;
+      if (m == -INFINITY) break;
+      const unsigned has = __ballot_sync(0xffffffffu, a1 == m || a2 == m);
+      if (lane == __ffs(has) - 1) {
+        if (a1 == m)
+          a1 = -INFINITY;
+        else
+          a2 = -INFINITY;
+      }
+    }
+  }
+  // ---- pass 2: compact elements >= tau (warp-uniform control flow; lane 0 writes) ----
+  int c = 0;
+  auto emit = [&](float ev, int idx) {  // called with warp-uniform arguments
+    if (ev >= tau && ev > -INFINITY) {
+      if (c < PRUNE_CAND_MAX && lane == 0) {
+        cp[c] = ev;
+        ci[c] = idx;
+      }
+      ++c;
+    }
+  };
+  {
+    const float hv = (lane < head) ? src[lane] : -INFINITY;
+    const float tv = (tail0 + lane < V) ? src[tail0 + lane] : -INFINITY;
+    unsigned hit = __ballot_sync(0xffffffffu, hv >= tau && hv > -INFINITY);
+    while (hit) {
+      const int sl = __ffs(hit) - 1;
+      hit &= hit - 1;
+      emit(__shfl_sync(0xffffffffu, hv, sl), sl);
+    }
+    hit = __ballot_sync(0xffffffffu, tv >= tau && tv > -INFINITY);
+    while (hit) {
+      const int sl = __ffs(hit) - 1;
+      hit &= hit - 1;
+      emit(__shfl_sync(0xffffffffu, tv, sl), tail0 + sl);
+    }
+  }
+  for (int q0 = 0; q0 < n4; q0 += 128) {
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      x[u] = (q < n4) ? __ldg(v4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float mx = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+      unsigned hit = __ballot_sync(0xffffffffu, mx >= tau && mx > -INFINITY);
+      while (hit) {
+        const int sl = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const int base = head + 4 * (q0 + u * 32 + sl);
+        emit(__shfl_sync(0xffffffffu, x[u].x, sl), base);
+        emit(__shfl_sync(0xffffffffu, x[u].y, sl), base + 1);
+        emit(__shfl_sync(0xffffffffu, x[u].z, sl), base + 2);
+        emit(__shfl_sync(0xffffffffu, x[u].w, sl), base + 3);
+      }
+    }
+  }
   __syncwarp();
-  // selection rounds
-  const bool prune = (cutoff_prob < 1.0f) || (top_n < V);
-  const int limit = prune ? min(top_n, V) : V;
-  float last_p = INFINITY;
-  int last_i = -1;
-  double cum = 0.0;
-  int n = 0;
   int* oid = cid + (size_t)row * BEAM_MAXC;
   float* olp = clp + (size_t)row * BEAM_MAXC;
-  while (n < limit && n < BEAM_MAXC) {
+  float last_p = INFINITY;
+  int last_i = -1;
+  float cum = 0.f, cum_c = 0.f;  // Kahan-compensated fp32 running sum (stands in for the reference's double)
+  int n = 0;
+  const bool compact = c <= PRUNE_CAND_MAX;
+  while (n < limit) {
     float bm = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = lane; j < V; j += 32) {
-      const float p = s[j];
-      const bool after = (p < last_p) || (p == last_p && j > last_i);
-      if (after && (p > bm || (p == bm && j < bi))) {
-        bm = p;
-        bi = j;
+    if (compact) {
+      for (int j = lane; j < c; j += 32) {
+        const float pv = cp[j];
+        const int iv = ci[j];
+        if (prune_before(last_p, last_i, pv, iv) && prune_before(pv, iv, bm, bi)) {
+          bm = pv;
+          bi = iv;
+        }
+      }
+    } else {  // mass ties (e.g. uniform rows): rounds over the whole row
+      for (int j = lane; j < V; j += 32) {
+        const float pv = __ldg(src + j);
+        if (prune_before(last_p, last_i, pv, j) && prune_before(pv, j, bm, bi)) {
+          bm = pv;
+          bi = j;
+        }
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float om = __shfl_xor_sync(0xffffffffu, bm, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (om > bm || (om == bm && oi < bi)) {
+      if (prune_before(om, oi, bm, bi)) {
         bm = om;
         bi = oi;
       }
@@ -98,8 +193,11 @@ __global__ void __launch_bounds__(WARPS * 32) ctc_prune_kernel(const float* __re
     last_p = bm;
     last_i = bi;
     ++n;
-    cum += (double)bm;
-    if (cutoff_prob < 1.0f && cum >= (double)cutoff_prob) break;
+    const float yk = bm - cum_c;
+    const float tk = cum + yk;
+    cum_c = (tk - cum) - yk;
+    cum = tk;
+    if (cutoff_prob < 1.0f && cum >= cutoff_prob) break;
   }
   if (lane == 0) cnt[row] = n;
 }
@@ -107,28 +205,8 @@ __global__ void __launch_bounds__(WARPS * 32) ctc_prune_kernel(const float* __re
 cudaError_t launch_ctc_prune(const float* probs, int V, int rows, float cutoff_prob, int top_n, int* cnt, int* cid,
                              float* clp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const size_t per = (size_t)((V + 3) & ~3) * 4;
-  if (per * 4 <= 96 * 1024) {
-    auto k = ctc_prune_kernel<4>;
-    static bool cfg = false;
-    if (!cfg) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      if (e != cudaSuccess) return e;
-      cfg = true;
-    }
-    k<<<(rows + 3) / 4, 128, per * 4, st>>>(probs, V, rows, cutoff_prob, top_n, cnt, cid, clp);
-  } else if (per <= 200 * 1024) {
-    auto k = ctc_prune_kernel<1>;
-    static bool cfg = false;
-    if (!cfg) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return e;
-      cfg = true;
-    }
-    k<<<rows, 32, per, st>>>(probs, V, rows, cutoff_prob, top_n, cnt, cid, clp);
-  } else {
-    return cudaErrorInvalidValue;
-  }
+  ctc_prune_kernel<<<(rows + PRUNE_WARPS - 1) / PRUNE_WARPS, PRUNE_WARPS * 32, 0, st>>>(probs, V, rows, cutoff_prob, top_n, cnt,
+                                                                                 cid, clp);
   count_launch();
   return cudaGetLastError();
 }
