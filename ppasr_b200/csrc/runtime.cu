@@ -128,6 +128,7 @@ struct ppasr_b200_ctx {
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
   bool fused_attn_out = true;
+  bool host_sync = true;  // ctc_* with host outputs synchronise the stream before returning
   bool profiling = false;
   struct ProfRec {
     int cls;
@@ -984,7 +985,7 @@ int ppasr_b200_ctc_greedy(ppasr_b200_ctx* c, int32_t* ids, int32_t* out_lens, fl
   if ((rc = copy_out(scores, p.score, (size_t)p.B * 4, outputs_on_device, st))) return rc;
   if ((rc = copy_out(frame_ids, p.idx, (size_t)p.M * 4, outputs_on_device, st))) return rc;
   if ((rc = copy_out(frame_probs, p.maxp, (size_t)p.M * 4, outputs_on_device, st))) return rc;
-  if (!outputs_on_device) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (!outputs_on_device && c->host_sync) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
   return PPASR_OK;
 }
 
@@ -1005,6 +1006,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   const std::string n(name);
   if (n == "fused_ffn") {
     c->fused_ffn = value != 0;
+    return PPASR_OK;
+  }
+  if (n == "host_sync") {
+    c->host_sync = value != 0;
     return PPASR_OK;
   }
   if (n == "fused_attn_out") {

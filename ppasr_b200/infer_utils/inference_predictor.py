@@ -85,6 +85,7 @@ class InferencePredictor:
                    'cnn_module_norm', 'max_len')
         kw = {k: enc[k] for k in allowed if k in enc}
         self.model_config = ConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        self._weights_ref = weights  # kept for DecodePipeline (extra engines pack their own copy)
         self.engine = ConformerEngine(self.model_config, weights, device=device)
 
     # ---------------------------------------------------------------------------------------------
@@ -109,6 +110,11 @@ class InferencePredictor:
             return ids, ol, scores
         texts = detokenize(ids, ol, vocabulary)
         return list(zip(scores, texts))
+
+    def pipeline(self, depth=2):
+        """Double-buffered throughput mode: `depth` engines on private CUDA streams so the host->device copy of
+        request i+1 overlaps the kernels of request i. See DecodePipeline."""
+        return DecodePipeline(self, depth)
 
     def predict_chunk_deepspeech(self, x_chunk):
         # inference_predictor.py:147-149
@@ -163,3 +169,72 @@ class InferencePredictor:
         self.att_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
         self.cnn_cache = np.zeros([0, 0, 0, 0], dtype=np.float32)
         self.offset = np.array([0], dtype=np.int32)
+
+
+class DecodePipeline:
+    """submit(speech[, lens]) -> ticket ; result(ticket) -> (ids, out_lens, scores).
+
+    Each slot owns an engine (its own packed weights / workspace), a non-blocking CUDA stream and pinned host result
+    buffers. submit() only enqueues work (pinned host features are copied asynchronously inside ppasr_b200_encode);
+    result() synchronises that slot's stream. With depth 2 the PCIe copy of one batch hides behind the compute of the
+    previous one."""
+
+    def __init__(self, predictor, depth=2):
+        import torch
+        self.torch = torch
+        self.pred = predictor
+        self.slots = []
+        for k in range(depth):
+            eng = predictor.engine if k == 0 else ConformerEngine(predictor.model_config, predictor._weights_ref,
+                                                                  device=predictor.engine.device.index)
+            eng.set_option("host_sync", 0)
+            self.slots.append({"eng": eng, "stream": torch.cuda.Stream(device=predictor.engine.device), "bufs": None,
+                               "key": None})
+        self.next = 0
+
+    def submit(self, speech, speech_lengths=None, trim_to_lens=False, blank_id=0, to_host=True):
+        torch = self.torch
+        k = self.next
+        self.next = (self.next + 1) % len(self.slots)
+        slot = self.slots[k]
+        eng = slot["eng"]
+        with torch.cuda.stream(slot["stream"]):
+            eng.encode(speech, speech_lengths, stream=slot["stream"])
+            B, Tp = eng.B, eng.Tp
+            key = (B, Tp, bool(to_host))
+            if slot["bufs"] is None or slot["key"] != key:
+                if to_host:
+                    slot["bufs"] = (torch.empty((B, Tp), dtype=torch.int32).pin_memory(),
+                                    torch.empty((B,), dtype=torch.int32).pin_memory(),
+                                    torch.empty((B,), dtype=torch.float32).pin_memory())
+                else:
+                    dev = eng.device
+                    slot["bufs"] = (torch.empty((B, Tp), dtype=torch.int32, device=dev),
+                                    torch.empty((B,), dtype=torch.int32, device=dev),
+                                    torch.empty((B,), dtype=torch.float32, device=dev))
+                slot["key"] = key
+            ids, ol, sc = slot["bufs"]
+            L.check(eng.lib.ppasr_b200_ctc_greedy(eng._ctx, L.ptr(ids), L.ptr(ol), L.ptr(sc), None, None,
+                                                   0 if to_host else 1, int(trim_to_lens), blank_id,
+                                                   L.stream_ptr(slot["stream"])))
+        return k
+
+    def stream(self, ticket):
+        return self.slots[ticket]["stream"]
+
+    def device_result(self, ticket):
+        """Device tensors (ids, out_lens, scores) of a to_host=False request; valid on that slot's stream."""
+        return self.slots[ticket]["bufs"]
+
+    def result(self, ticket):
+        slot = self.slots[ticket]
+        slot["stream"].synchronize()
+        ids, ol, sc = slot["bufs"]
+        ids, ol, sc = ids.cpu().numpy().copy(), ol.cpu().numpy().copy(), sc.cpu().numpy().copy()
+        scores = [float(s) * 100.0 if n > 0 else 0 for s, n in zip(sc, ol)]
+        return ids, ol, scores
+
+    def close(self):
+        for slot in self.slots[1:]:
+            slot["eng"].close()
+        self.slots[0]["eng"].set_option("host_sync", 1)

@@ -456,3 +456,29 @@ def test_beam_search_full_size_vs_greedy(lib, cuda):
     ids, ol, _, _, _ = greedy_decode_ids(probs)
     for b in range(8):
         assert res[b][0][1] == "".join(vocab[i] for i in ids[b, :ol[b]])
+
+
+def test_decode_pipeline_matches_sync_api(lib, cuda):
+    """Double-buffered public API (two engines / streams) returns exactly what predict_decode returns."""
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+    cfg = ConformerConfig(num_blocks=2, vocab_size=300)
+    w = init_conformer_weights(cfg)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "conformer",
+                              streaming=True, weights=w)
+    batches = [torch.from_numpy(synthetic_fbank(4, 300, seed=s)).pin_memory() for s in (1, 2, 3)]
+    ref = [pred.predict_decode(b.numpy()) for b in batches]
+    pipe = pred.pipeline(depth=2)
+    tickets = []
+    out = []
+    for b in batches:
+        tickets.append(pipe.submit(b))
+        if len(tickets) == 2:
+            out.append(pipe.result(tickets.pop(0)))
+    while tickets:
+        out.append(pipe.result(tickets.pop(0)))
+    pipe.close()
+    for (ids, ol, sc), (rids, rol, rsc) in zip(out, ref):
+        assert np.array_equal(ol, rol) and sc == rsc
+        for b in range(4):
+            assert np.array_equal(ids[b, :ol[b]], rids[b, :rol[b]])
