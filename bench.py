@@ -219,7 +219,7 @@ def main():
     # ---- (b) throughput mode = `value`: two batches in flight (two engines / streams), inputs cycle over a pool of
     #      distinct device-resident batches larger than L2 (16 x 10.2 MB = 163 MB > 126 MB), no explicit flush ----
     pool = [feats_dev] + [torch.from_numpy(synthetic_fbank(B, FRAMES, seed=5000 + 97 * rank + i)).to(dev) for i in range(15)]
-    depth = int(os.environ.get("PPASR_B200_DEPTH", "2"))
+    depth = int(os.environ.get("PPASR_B200_DEPTH", "3"))
     pipe = pred.pipeline(depth=depth)
 
     def finish(ticket):
@@ -270,7 +270,7 @@ def main():
     # ---- e2e through the public API with host buffers (H2D of the features, D2H of ids/lens/scores) ----
     # DecodePipeline = the throughput-mode public API: two engines on two streams, so the pinned H2D copy of batch
     # i+1 overlaps the kernels of batch i. Every step still copies its own inputs in and its own results out.
-    pipe = pred.pipeline(depth=2)
+    pipe = pred.pipeline(depth=depth)
 
     def e2e_finish(ticket):
         ids, ol, scores = pipe.result(ticket)
@@ -282,12 +282,13 @@ def main():
 
     def e2e_run(n):
         texts = None
-        pending = pipe.submit(feats_host)
-        for _ in range(n - 1):
-            nxt = pipe.submit(feats_host)
-            texts = e2e_finish(pending)
-            pending = nxt
-        texts = e2e_finish(pending)
+        pending = []
+        for _ in range(n):
+            pending.append(pipe.submit(feats_host))
+            if len(pending) == depth:
+                texts = e2e_finish(pending.pop(0))
+        while pending:
+            texts = e2e_finish(pending.pop(0))
         return texts
 
     e2e_run(4)
@@ -381,7 +382,7 @@ def main():
             "clocks": sampler.result(),
             "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "InferencePredictor.pipeline(depth=2).submit(host fbank)/result() + host detokenisation"},
+                    "api": f"InferencePredictor.pipeline(depth={depth}).submit(host fbank)/result() + host detokenisation"},
             "gpu_launches": int(launches1 - launches0),
             "roofline": roof, "cpu_baseline": cpu, "kernel_profile": prof_table,
             "sample_text_len": len(texts[0]) if texts else 0,

@@ -44,6 +44,11 @@ int ppasr_b200_abi_version(void);
 /* Number of CUDA kernels this library has launched so far in this process (bench.py "gpu_launches"). */
 int64_t ppasr_b200_launch_count(void);
 
+/* Process-wide: launch kernels with programmatic dependent launch (default 1; env PPASR_B200_PDL=0). PDL shortens the
+ * single-batch critical path (-7 %); with several batches in flight the early-started CTAs only hold SMs, so the
+ * throughput pipeline switches it off. */
+int ppasr_b200_set_pdl(int32_t enable);
+
 /* ---- life cycle ------------------------------------------------------------------------------
  * replaces: InferencePredictor.__init__ loading model.pdmodel/.pdiparams
  *           (infer_utils/inference_predictor.py:12-45). */

@@ -12,6 +12,7 @@ const char* get_last_error();
 
 int device_sm_count();
 bool pdl_enabled();
+void set_pdl_enabled(bool on);
 
 // number of kernels launched by this library (all contexts); read by bench.py for "gpu_launches"
 void count_launch();

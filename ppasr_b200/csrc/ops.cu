@@ -21,14 +21,17 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
-  static int v = -1;
+  int v = g_pdl.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("PPASR_B200_PDL");
     v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
   }
   return v != 0;
 }
+void set_pdl_enabled(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 int device_sm_count() {
   static int sms = 0;
@@ -65,6 +68,11 @@ const char* ppasr_b200_last_error(void) { return get_last_error(); }
 int ppasr_b200_abi_version(void) { return 1; }
 
 int64_t ppasr_b200_launch_count(void) { return (int64_t)launch_count(); }
+
+int ppasr_b200_set_pdl(int32_t enable) {
+  set_pdl_enabled(enable != 0);
+  return PPASR_OK;
+}
 
 // C = epilogue(A[M,K] * W[N,K]^T + bias).  See include/ppasr_b200.h for the epilogue codes.
 int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t w_rows, const float* bias,

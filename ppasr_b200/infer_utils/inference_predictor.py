@@ -191,6 +191,8 @@ class DecodePipeline:
             self.slots.append({"eng": eng, "stream": torch.cuda.Stream(device=predictor.engine.device), "bufs": None,
                                "key": None})
         self.next = 0
+        if depth > 1:
+            predictor.engine.lib.ppasr_b200_set_pdl(0)  # early-started dependent CTAs would only hold SMs
 
     def submit(self, speech, speech_lengths=None, trim_to_lens=False, blank_id=0, to_host=True):
         torch = self.torch
@@ -238,3 +240,4 @@ class DecodePipeline:
         for slot in self.slots[1:]:
             slot["eng"].close()
         self.slots[0]["eng"].set_option("host_sync", 1)
+        self.pred.engine.lib.ppasr_b200_set_pdl(1)
