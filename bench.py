@@ -333,6 +333,7 @@ def main():
             # fused_ffn: W1 + W2 GEMMs (+ the chained pointwise_conv2 in every second launch: averaged)
             "fused_ffn": 2.0 * M * D * FF * 2 + 0.5 * 2.0 * M * D * D,
             "fused_attn_out": 2.0 * M * D * D + 2.0 * M * 2 * D * D,
+            "conv_front": 2.0 * (B * Tp * 19) * D * 9 * D,
         }
         total = sum(v[1] for v in prof.values())
         prof_table = {k: {"launches_per_step": v[0] // reps, "us_per_launch": v[1] / v[0] * 1e3,

@@ -167,8 +167,8 @@ int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int3
                             int32_t pos_rows, int32_t pos_ld, int32_t pos_row0, int32_t pos_col0, void* out,
                             int32_t B, int32_t H, int32_t T1, int32_t T2, const int32_t* klens, void* stream);
 
-/* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels (0 = separate GEMMs, for A/B
- * measurements); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
+/* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels, "fused_conv" (default 0) the
+ * experimental fused conv1+conv2 front end (0 = separate kernels / GEMMs, for A/B measurements); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
  * returning -- 0 leaves the copies in flight (pinned host buffers; the caller synchronises), used by the
  * double-buffered serving pipeline. */
 int ppasr_b200_set_option(ppasr_b200_ctx* ctx, const char* name, int32_t value);

@@ -56,6 +56,11 @@ cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& 
                                   float* x, __nv_bfloat16* g, const float* bo, const float* ln_g, const float* ln_b,
                                   const float* bpw1, const int* lens, int T, float eps, cudaStream_t st);
 
+// Fused CMVN + conv1 + ReLU + conv2 + ReLU (conv_front.cu); tmap_w2 = conv2 weights [256, 9*256] K-major, box {64, 256}
+cudaError_t launch_conv_front(const CUtensorMap& tmap_w2, const float* feats, const float* mean, const float* istd,
+                              const float* w1, const float* b1, const float* b2, __nv_bfloat16* out, int B, int T, int F,
+                              int Th, int FH, int Tout, int Fout, int num_sms, cudaStream_t st);
+
 // CTC prefix beam search (beam.cu)
 struct BeamStateHeader {
   int nb;       // entries in the beam

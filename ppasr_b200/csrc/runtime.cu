@@ -128,6 +128,10 @@ struct ppasr_b200_ctx {
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
   bool fused_attn_out = true;
+  // conv1 computed inside the conv2 GEMM's A producer (conv_front.cu). Bit-identical to the two-kernel path but slower
+  // on B200 (382 us vs 145 + 145 us at C2): the producers' LDS/STS traffic shares the 128 B/clk shared-memory data pipe
+  // with the tensor core's operand reads (ncu: lsu 57 % + tc 20 % of the pipe), so it is opt-in.
+  bool fused_conv = false;
   bool host_sync = true;  // ctc_* with host outputs synchronise the stream before returning
   bool profiling = false;
   struct ProfRec {
@@ -143,12 +147,12 @@ namespace {
 
 enum ProfClass : int {
   PC_CONV1 = 0, PC_CONV2, PC_EMBED, PC_LAYERNORM, PC_FFN1, PC_FFN2, PC_QKV, PC_ATTENTION, PC_OUTPROJ, PC_PW1_GLU,
-  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_FUSED_FFN, PC_FUSED_ATTN_OUT, PC_COUNT
+  PC_DWCONV, PC_PW2, PC_CTC_STATS, PC_CTC_FINALIZE, PC_CTC_COLLAPSE, PC_CTC_LOGITS, PC_SOFTMAX, PC_FUSED_FFN, PC_FUSED_ATTN_OUT, PC_CONV_FRONT, PC_COUNT
 };
 const char* const kProfNames[PC_COUNT] = {"conv1_subsample", "conv2_gemm", "embed_gemm", "layernorm", "ffn1_gemm",
                                           "ffn2_gemm", "qkv_gemm", "attention", "outproj_gemm", "pw1_glu_gemm",
                                           "dwconv_norm_swish", "pw2_gemm", "ctc_stats_gemm", "ctc_finalize",
-                                          "ctc_collapse", "ctc_logits_gemm", "softmax", "fused_ffn", "fused_attn_out"};
+                                          "ctc_collapse", "ctc_logits_gemm", "softmax", "fused_ffn", "fused_attn_out", "conv_front"};
 
 struct ProfScope {
   ppasr_b200_ctx* c;
@@ -652,12 +656,17 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
   const auto& cfg = c->cfg;
   const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, L = cfg.n_layers, M = p.M;
   const float eps = 1e-5f;
-  // CMVN + conv1 + ReLU -> stride-phase images
-  { PROF(PC_CONV1);
-  PPASR_CUDA_CHECK(launch_conv1_subsample(p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.phase, p.B,
-                                          p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st)); }
-  // conv2 + ReLU as 9 shifted GEMM taps -> c2 [M, F2*D]
-  {
+  if (c->fused_conv && D == 256 && c->FH == 20) {  // patch geometry of conv_front.cu assumes feat_dim 80 (pitch 20)
+    // CMVN + conv1 + ReLU + conv2 + ReLU in one kernel (conv_front.cu) -> c2 [M, F2*D]
+    PROF(PC_CONV_FRONT);
+    PPASR_CUDA_CHECK(launch_conv_front(c->tm_conv2_w, p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, c->conv2_b,
+                                       p.c2, p.B, p.T, cfg.feat_dim, p.Th, c->FH, p.Tp, c->F2, c->sms, st));
+  } else {
+    // CMVN + conv1 + ReLU -> stride-phase images
+    { PROF(PC_CONV1);
+    PPASR_CUDA_CHECK(launch_conv1_subsample(p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.phase, p.B,
+                                            p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st)); }
+    // conv2 + ReLU as 9 shifted GEMM taps -> c2 [M, F2*D]
     GemmShape s = make_shape(p.Mr, D, 9 * D, BN_WIDE);
     s.conv_pitch = c->FH;
     s.conv_kc = D / GEMM_BLOCK_K;
@@ -1010,6 +1019,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   }
   if (n == "host_sync") {
     c->host_sync = value != 0;
+    return PPASR_OK;
+  }
+  if (n == "fused_conv") {
+    c->fused_conv = value != 0;
     return PPASR_OK;
   }
   if (n == "fused_attn_out") {

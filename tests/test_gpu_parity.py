@@ -482,3 +482,25 @@ def test_decode_pipeline_matches_sync_api(lib, cuda):
         assert np.array_equal(ol, rol) and sc == rsc
         for b in range(4):
             assert np.array_equal(ids[b, :ol[b]], rids[b, :rol[b]])
+
+
+@pytest.mark.parametrize("B,T,lens", [(3, 523, [523, 333, 260]), (5, 67, [67, 67, 50, 30, 67]), (1, 998, [998])])
+def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
+    """conv_front.cu (conv1 computed inside the conv2 GEMM's A producer; opt-in) == conv1 kernel + conv2 GEMM, bit for bit
+    (same fp32 FMA order, one bf16 rounding of the conv1 output in both)."""
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+    cfg = ConformerConfig(num_blocks=1, vocab_size=300)
+    eng = ConformerEngine(cfg, init_conformer_weights(cfg))
+    feats = synthetic_fbank(B, T)
+    for b in range(B):
+        feats[b, lens[b]:] = 0
+    fd = torch.from_numpy(feats).cuda()
+    outs = []
+    for fused in (0, 1):
+        eng.set_option("fused_conv", fused)
+        eng.encode(fd, lens)
+        outs.append(eng.ctc_logits().float().cpu())
+    torch.cuda.synchronize()
+    eng.close()
+    assert torch.equal(outs[0], outs[1])
