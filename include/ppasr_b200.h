@@ -22,21 +22,25 @@ extern "C" {
 
 typedef struct ppasr_b200_ctx ppasr_b200_ctx;
 
-/* Model hyper-parameters = the inference-relevant keys of configs/conformer.yml (encoder_conf,
- * streaming, preprocess_conf.n_mels) plus the vocabulary size. */
+/* Model hyper-parameters = the inference-relevant keys of configs/conformer.yml / configs/squeezeformer.yml
+ * (encoder_conf, streaming, preprocess_conf.n_mels) plus the vocabulary size. */
 typedef struct ppasr_b200_config {
-  int32_t model_type;      /* 0 = conformer (others: later rounds) */
+  int32_t model_type;      /* 0 = conformer, 1 = squeezeformer */
   int32_t feat_dim;        /* preprocess_conf.n_mels, 80 */
-  int32_t d_model;         /* encoder_conf.output_size, 256 */
+  int32_t d_model;         /* encoder_conf.output_size (squeezeformer: encoder_dim), 256 */
   int32_t n_heads;         /* encoder_conf.attention_heads, 4 (d_model / n_heads must be 64) */
-  int32_t ffn_dim;         /* encoder_conf.linear_units, 2048 */
+  int32_t ffn_dim;         /* encoder_conf.linear_units, 2048 (squeezeformer: encoder_dim * feed_forward_expansion_factor) */
   int32_t n_layers;        /* encoder_conf.num_blocks, 12 */
   int32_t conv_kernel;     /* encoder_conf.cnn_module_kernel, 15 (7, 15 or 31) */
   int32_t causal;          /* `streaming: True` => causal depthwise conv (conformer/model.py:35-39) */
   int32_t conv_norm;       /* 0 = layer_norm (shipped default, conformer/encoder.py:51), 1 = batch_norm */
   int32_t vocab_size;      /* CTC output size V */
   int32_t max_len;         /* positional table length, 5000 (conformer/embedding.py:30) */
-  int32_t reserved[5];
+  /* squeezeformer only (squeezeformer/encoder.py:33-34, model.py:35-41); ignored for model_type 0 */
+  int32_t reduce_idx;          /* block before which the time-reduction layer runs (5), -1 = none */
+  int32_t recover_idx;         /* block before which the sequence is recovered to full length (11), -1 = none */
+  int32_t time_reduce_kernel;  /* 1 = TimeReductionLayerStream (streaming), 5 = TimeReductionLayer1D */
+  int32_t reserved[2];
 } ppasr_b200_config;
 
 const char* ppasr_b200_last_error(void);

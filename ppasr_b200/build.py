@@ -37,7 +37,7 @@ def _newer(src, dst, deps):
 def build(verbose=False, force=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inl"))]
     inc = os.path.join(os.path.dirname(ROOT), "include")
     if os.path.isdir(inc):
         headers += [os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h")]

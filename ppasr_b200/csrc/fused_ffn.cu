@@ -55,6 +55,11 @@ struct FfnParams {
   const float *gp, *bpn;  // LayerNorm between pre-GEMM and FFN
   const int* lens;        // valid frames per utterance (pad rows: pre-GEMM branch contributes 0)
   int T;
+  // post-norm models (Squeezeformer): double mode with y_affine writes x <- LN(x; g1, bn1) and the bf16 output
+  // y = g2 * x + bn2 (adaptive scale / bias of the next module); rows t >= ylens[b] of y are zeroed when ylens != null
+  // (conv-module input, squeezeformer/convolution.py:119-127).
+  int y_affine;
+  const int* ylens;
 };
 
 template <bool PRE>
@@ -438,9 +443,13 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         ffn_add_chunk(s2, v);
       }
-      ffn_exchange(s2, scratch + 256, r, half, 3);
-      mean = s2.mean;
-      rstd = rsqrtf(s2.m2 * (1.0f / 256.0f) + p.eps);
+      if (p.y_affine) {
+        mean = 0.f, rstd = 1.f;
+      } else {
+        ffn_exchange(s2, scratch + 256, r, half, 3);
+        mean = s2.mean;
+        rstd = rsqrtf(s2.m2 * (1.0f / 256.0f) + p.eps);
+      }
     }
     if (half == 0) stats[r] = make_float2(mean, rstd);
     named_bar_sync(1, 256);
@@ -459,10 +468,19 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const float4* src = reinterpret_cast<const float4*>(xs + row * FFN_XS_PITCH);
       float4* dx = reinterpret_cast<float4*>(p.x + (size_t)(m0 + row) * 256);
       uint2* dy = reinterpret_cast<uint2*>(p.y + (size_t)(m0 + row) * 256);
+      bool zero_y = false;
+      if (p.ylens != nullptr) {
+        const int bb = (m0 + row) / p.T;
+        zero_y = (m0 + row - bb * p.T) >= __ldg(p.ylens + bb);
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const float4 v = src[lane + 32 * i];
         dx[lane + 32 * i] = v;
+        if (zero_y) {
+          dy[lane + 32 * i] = make_uint2(0u, 0u);
+          continue;
+        }
         const float y0 = (v.x - ms.x) * ms.y * gv[i].x + bv[i].x;
         const float y1 = (v.y - ms.x) * ms.y * gv[i].y + bv[i].y;
         const float y2 = (v.z - ms.x) * ms.y * gv[i].z + bv[i].z;
@@ -484,7 +502,7 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              const CUtensorMap& tm_w2, int M, int FF, float* x, __nv_bfloat16* y, const float* b1,
                              const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
                              float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
-                             cudaStream_t st) {
+                             cudaStream_t st, int y_affine, const int* ylens) {
   if (FF % 128 != 0 || M <= 0) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
@@ -498,6 +516,7 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
   p.M = M, p.nchunks = FF / 128, p.x = x, p.y = y, p.b1 = b1, p.b2s = b2s;
   p.g1 = g1, p.bn1 = bn1, p.g2 = g2, p.bn2 = bn2, p.eps = eps;
   p.bp = bp, p.gp = gp, p.bpn = bpn, p.lens = lens, p.T = T;
+  p.y_affine = y_affine, p.ylens = ylens;
   const int grid = (M + 127) / 128;
   cudaError_t le;
   if (tm_wp != nullptr)

@@ -194,6 +194,11 @@ struct EpiResidLN {
   const float *g1, *b1, *g2, *b2;
   __nv_bfloat16* y;
   float eps;
+  // post-norm models (Squeezeformer, squeezeformer/encoder.py:468-504): with g2 != null and y_affine the bf16 output is the
+  // element-wise affine y = g2 * x + b2 of the stored fp32 row (the next module's adaptive scale/bias, attention.py:120-123)
+  // instead of a second LayerNorm; no_norm additionally skips LN1 (x = x_new; time-reduction output, encoder.py:213).
+  int y_affine = 0;
+  int no_norm = 0;
 
   struct Stat {
     float n, mean, m2;
@@ -287,7 +292,7 @@ struct EpiResidLN {
         ra[j] = __float_as_uint(v[j]);
       }
       tmem_st_32x32b_x32(taddr + cc, ra);
-      if (in && g2 == nullptr) {
+      if (in && (g2 == nullptr || no_norm)) {
         float4* dst = reinterpret_cast<float4*>(xr + cc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -298,7 +303,7 @@ struct EpiResidLN {
     exchange(st, scratch, r, half);
     float mean = st.mean;
     float rstd = rsqrtf(st.m2 * (1.0f / 256.0f) + eps);
-    if (g2 != nullptr) {
+    if (g2 != nullptr && !no_norm) {
       // pass 2: x <- LN1(x_new) (final residual stream value) -> global + TMEM, statistics of the result
       Stat s2{0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -328,10 +333,13 @@ struct EpiResidLN {
         add_chunk(s2, v);
       }
       tmem_st_wait();
-      exchange(s2, scratch + 2 * GEMM_BLOCK_M, r, half);
-      mean = s2.mean;
-      rstd = rsqrtf(s2.m2 * (1.0f / 256.0f) + eps);
+      if (!y_affine) {
+        exchange(s2, scratch + 2 * GEMM_BLOCK_M, r, half);
+        mean = s2.mean;
+        rstd = rsqrtf(s2.m2 * (1.0f / 256.0f) + eps);
+      }
     }
+    if (g2 != nullptr && y_affine) mean = 0.f, rstd = 1.f;
     // final pass: y = LN(x; gl, bl) as bf16
     const float* gl = g2 ? g2 : g1;
     const float* bl = g2 ? b2 : b1;
@@ -360,6 +368,56 @@ struct EpiResidLN {
         for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
       }
     }
+  }
+};
+
+// Squeezeformer recover step (squeezeformer/encoder.py:216-230): the GEMM rows are the time-reduced frames (b, tr);
+//   v = acc + bias  = time_recover_layer(x_reduced[b, tr])
+//   for t in {2 tr, 2 tr + 1} (t < T):  x[b, t] <- x[b, t] + v  (x holds the activations saved before the reduction)
+//                                       y[b, t]  = ada_scale * x[b, t] + ada_bias   (bf16, next module's input)
+// i.e. repeat_interleave(xs, 2) -> Linear -> [:T] -> + recover_tensor without materialising the repeated tensor.
+template <int BLOCK_N>
+struct EpiRecover {
+  float* x;           // [B*T, N] fp32 (in/out)
+  __nv_bfloat16* y;   // [B*T, N]
+  const float* bias;
+  const float *ys, *yb;  // affine of the bf16 output
+  int M;              // B * Tr reduced rows
+  int N;
+  int Tr, T;
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
+    const bool in = row < M;
+    const int b = in ? row / Tr : 0;
+    const int tr = row - b * Tr;
+    epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
+      const int col = n0 + cc;
+      if (!in || col >= N) return;
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u) {
+        const int t = 2 * tr + u;
+        if (t >= T) break;
+        float* xr = x + ((size_t)b * T + t) * N + col;
+        __nv_bfloat16* yr = y + ((size_t)b * T + t) * N + col;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 xo = *reinterpret_cast<const float4*>(xr + 4 * j);
+          const float4 bv = *reinterpret_cast<const float4*>(sbias + cc + 4 * j);
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(ys + col) + j);
+          const float4 ov = __ldg(reinterpret_cast<const float4*>(yb + col) + j);
+          xo.x += __uint_as_float(r[4 * j + 0]) + bv.x;
+          xo.y += __uint_as_float(r[4 * j + 1]) + bv.y;
+          xo.z += __uint_as_float(r[4 * j + 2]) + bv.z;
+          xo.w += __uint_as_float(r[4 * j + 3]) + bv.w;
+          *reinterpret_cast<float4*>(xr + 4 * j) = xo;
+          pk[2 * j] = pack_bf16x2(fmaf(sv.x, xo.x, ov.x), fmaf(sv.y, xo.y, ov.y));
+          pk[2 * j + 1] = pack_bf16x2(fmaf(sv.z, xo.z, ov.z), fmaf(sv.w, xo.w, ov.w));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(yr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+    });
   }
 };
 

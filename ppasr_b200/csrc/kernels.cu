@@ -649,3 +649,61 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
 }
 
 }  // namespace ppasr
+
+// ---------------------------------------------------------------------------------------------------------------
+// Squeezeformer time-reduction layer, depthwise part (reference: ppasr/model_utils/squeezeformer/time_reduction.py
+// :61-84 TimeReductionLayer1D k=5 s=2 pad=3, :183-206 TimeReductionLayerStream k=1 s=2 pad=0). The input is zeroed at
+// the pad frames first (masked_fill(xs, mask_pad.equal(0), 0)); the pointwise conv that follows is a GEMM.
+// ---------------------------------------------------------------------------------------------------------------
+namespace ppasr {
+
+void count_launch();
+
+__global__ void time_reduce_dw_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                      const int* __restrict__ lens, __nv_bfloat16* __restrict__ out, int T, int Tr, int C, int K,
+                                      int pad) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int tr = blockIdx.x * blockDim.y + threadIdx.y;
+  if (tr >= Tr) return;
+  const int len = lens ? lens[b] : T;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 acc = *reinterpret_cast<const float4*>(bias + c);
+    for (int k = 0; k < K; ++k) {
+      const int t = 2 * tr + k - pad;
+      if (t < 0 || t >= T || t >= len) continue;
+      const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)b * T + t) * C + c);
+      acc.x = fmaf(w[(c + 0) * K + k], v.x, acc.x);
+      acc.y = fmaf(w[(c + 1) * K + k], v.y, acc.y);
+      acc.z = fmaf(w[(c + 2) * K + k], v.z, acc.z);
+      acc.w = fmaf(w[(c + 3) * K + k], v.w, acc.w);
+    }
+    *reinterpret_cast<uint2*>(out + ((size_t)b * Tr + tr) * C + c) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  }
+}
+
+cudaError_t launch_time_reduce_dw(const float* x, const float* w, const float* bias, const int* lens, __nv_bfloat16* out,
+                                  int B, int T, int Tr, int C, int K, int pad, cudaStream_t st) {
+  if (C % 4 != 0 || B <= 0 || Tr <= 0) return cudaErrorInvalidValue;
+  dim3 block(64, 4);
+  dim3 grid((Tr + 3) / 4, B);
+  cudaError_t le = launch_pdl(time_reduce_dw_kernel, grid, block, (size_t)0, st, x, w, bias, lens, out, T, Tr, C, K, pad);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+__global__ void halve_lens_kernel(const int* __restrict__ a, int* __restrict__ o, int B) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) o[i] = (a[i] + 1) / 2;
+}
+
+cudaError_t launch_halve_lens(const int* lens_in, int* lens_out, int B, cudaStream_t st) {
+  cudaError_t le = launch_pdl(halve_lens_kernel, dim3((B + 127) / 128), dim3(128), (size_t)0, st, lens_in, lens_out, B);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+}  // namespace ppasr

@@ -49,7 +49,7 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              const CUtensorMap& tm_w2, int M, int FF, float* x, __nv_bfloat16* y, const float* b1,
                              const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
                              float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
-                             cudaStream_t st);
+                             cudaStream_t st, int y_affine = 0, const int* ylens = nullptr);
 
 // Fused attention out-projection + residual + norm_conv + pointwise_conv1 + GLU (fused_attn_out.cu)
 cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& tm_wo, const CUtensorMap& tm_wpw1, int M,
@@ -60,6 +60,13 @@ cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& 
 cudaError_t launch_conv_front(const CUtensorMap& tmap_w2, const float* feats, const float* mean, const float* istd,
                               const float* w1, const float* b1, const float* b2, __nv_bfloat16* out, int B, int T, int F,
                               int Th, int FH, int Tout, int Fout, int num_sms, cudaStream_t st);
+
+// Squeezeformer time reduction, depthwise part (squeezeformer/time_reduction.py:61-84 conv1d k5 s2 pad3, :183-206 stream
+// k1 s2): out[b, tr, c] = bias[c] + sum_k w[c, k] * xm[b, 2 tr + k - pad, c] with xm = x zeroed at t >= lens[b] -> bf16
+cudaError_t launch_time_reduce_dw(const float* x, const float* w, const float* bias, const int* lens, __nv_bfloat16* out,
+                                  int B, int T, int Tr, int C, int K, int pad, cudaStream_t st);
+// lens_out[b] = (lens_in[b] + 1) / 2
+cudaError_t launch_halve_lens(const int* lens_in, int* lens_out, int B, cudaStream_t st);
 
 // CTC prefix beam search (beam.cu)
 struct BeamStateHeader {

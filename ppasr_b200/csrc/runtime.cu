@@ -80,6 +80,8 @@ struct Plan {  // everything that depends on (B, T)
   int* vlen = nullptr;
   __nv_bfloat16 *phase = nullptr, *c2 = nullptr, *y = nullptr, *h = nullptr, *q2 = nullptr, *kk = nullptr,
                 *vt = nullptr, *att = nullptr, *g = nullptr, *z = nullptr;
+  float *x2 = nullptr;  // Squeezeformer: time-reduced residual stream [B*ceil(Tp/2), D]
+  int* vlen2 = nullptr; // ... and its valid lengths
   float *x = nullptr, *logits = nullptr, *pmax = nullptr, *psum = nullptr, *maxp = nullptr, *score = nullptr,
         *probs = nullptr;
   int *parg = nullptr, *idx = nullptr, *ids = nullptr, *out_len = nullptr;
@@ -111,6 +113,25 @@ struct ppasr_b200_ctx {
     CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2, ffm_w1_128, ff_w1_128, ffm_w2s, ff_w2s;
   };
   std::vector<LayerMaps> lmaps;
+  // ---- Squeezeformer (model_type 1; squeezeformer/encoder.py) ----
+  struct SqLayerW {
+    const float *ln_g[4], *ln_b[4];    // layer_norm1..4
+    const float *ada_s[4], *ada_b[4];  // adaptive scale/bias of: 0 self_attn, 1 ffn1, 2 conv_module, 3 ffn2
+    const __nv_bfloat16 *wqkv, *wo, *w1[2], *w2[2], *pw1, *pw2;
+    const float *bqkv, *bo, *pos_u, *pos_v, *b1[2], *b2[2], *pw1_b, *pw2_b, *dw_w, *dw_b, *cn_g, *cn_b, *glu_pad;
+  };
+  struct SqLayerMaps {
+    CUtensorMap wqkv, wo, w1_128[2], w2[2], pw1, pw2;
+  };
+  struct Sqz {
+    std::vector<SqLayerW> layers;
+    std::vector<SqLayerMaps> maps;
+    const float *preln_g = nullptr, *preln_b = nullptr, *emb_b_scaled = nullptr, *tr_dw_w = nullptr, *tr_dw_b = nullptr,
+                *tr_pw_b = nullptr, *rec_b = nullptr, *ones = nullptr, *zeros = nullptr;
+    const __nv_bfloat16 *tr_pw = nullptr, *rec_w = nullptr;
+    CUtensorMap tm_tr_pw, tm_rec_w, tm_pos2;  // tm_pos2: every second row of the positional table (pos_emb[:, ::2])
+    int reduce_idx = -1, recover_idx = -1, tr_k = 1;
+  } sq;
   Plan plan;
   int sms = 148;
   // ---- streaming state (reference: inference_predictor.py:35-39,215-220; device resident here) ----
@@ -205,6 +226,8 @@ std::vector<float> transpose_in_out(const HostTensor& w, int rows_pad = 0) {
   return o;
 }
 
+int finalize_squeezeformer(ppasr_b200_ctx* c);  // runtime_squeezeformer.inl
+
 template <class T>
 const T* upload(ppasr_b200_ctx* c, const std::vector<T>& v) {
   T* d = c->wslab.take<T>(v.size());
@@ -218,12 +241,18 @@ extern "C" {
 
 int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   PPASR_REQUIRE(cfg && out, "null pointer");
-  PPASR_REQUIRE(cfg->model_type == 0, "only model_type 0 (conformer) is implemented");
+  PPASR_REQUIRE(cfg->model_type == 0 || cfg->model_type == 1, "model_type must be 0 (conformer) or 1 (squeezeformer)");
   PPASR_REQUIRE(cfg->d_model == 256, "d_model must be 256 in this build");
   PPASR_REQUIRE(cfg->n_heads * 64 == cfg->d_model, "head dim must be 64");
   PPASR_REQUIRE(cfg->ffn_dim % 256 == 0 && cfg->ffn_dim > 0, "ffn_dim must be a multiple of 256");
   PPASR_REQUIRE(cfg->conv_kernel == 7 || cfg->conv_kernel == 15 || cfg->conv_kernel == 31, "conv_kernel 7/15/31");
   PPASR_REQUIRE(cfg->feat_dim >= 7 && cfg->vocab_size > 1 && cfg->n_layers > 0 && cfg->max_len > 16, "bad config");
+  if (cfg->model_type == 1) {
+    const int ri = cfg->reduce_idx, ci = cfg->recover_idx;
+    PPASR_REQUIRE((ri < 0 && ci < 0) || (ri >= 0 && ri < ci && ci < cfg->n_layers),
+                  "squeezeformer: need 0 <= reduce_idx < recover_idx < num_blocks (or neither)");
+    PPASR_REQUIRE(cfg->time_reduce_kernel == 1 || cfg->time_reduce_kernel == 5, "time_reduce_kernel must be 1 (stream) or 5 (conv1d)");
+  }
   auto* c = new ppasr_b200_ctx();
   c->cfg = *cfg;
   c->F1 = (cfg->feat_dim - 1) / 2;
@@ -282,6 +311,7 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
     return PPASR_ERR_CUDA;
   }
   c->sms = prop.multiProcessorCount;
+  if (cfg.model_type == 1) return finalize_squeezeformer(c);
 
   std::string missing;
   auto need = [&](const std::string& n) { return find(c, n, &missing); };
@@ -575,6 +605,8 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   acc((size_t)4 * n.Mr * D * 2);
   acc(M * c->Kemb * 2);
   acc(M * D * 4);                                   // x
+  acc(M * D * 2 + 1024);                            // x2 (reduced stream)
+  acc(B * 4);
   acc(M * D * 2 * 4);                               // y, att, g, z
   acc((size_t)n.Mcat * D * 2 * 2);                  // ycat, gcat
   acc(M * FF * 2);                                  // h
@@ -599,6 +631,8 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   n.phase = a.take<__nv_bfloat16>((size_t)4 * n.Mr * D);
   n.c2 = a.take<__nv_bfloat16>(M * c->Kemb);
   n.x = a.take<float>(M * D);
+  n.x2 = a.take<float>((size_t)B * ((n.Tp + 1) / 2) * D);
+  n.vlen2 = a.take<int>(B);
   n.y = a.take<__nv_bfloat16>(M * D);
   n.att = a.take<__nv_bfloat16>(M * D);
   n.g = a.take<__nv_bfloat16>(M * D);
@@ -650,12 +684,12 @@ cudaError_t gemm(ppasr_b200_ctx* c, const CUtensorMap& a, const CUtensorMap& b, 
   return launch_gemm<BN, ST, false>(a, b, s, epi, c->sms, st);
 }
 
-int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
+// CMVN + Conv2d(1->D,k3,s2)+ReLU + Conv2d(D->D,k3,s2)+ReLU -> c2 [M, F2*D] (conformer/subsampling.py:84-87,110-111;
+// squeezeformer/subsampling.py:33-39,59-63 with dw_stride False is the same pair of convolutions)
+int run_subsampling_convs(ppasr_b200_ctx* c, cudaStream_t st) {
   Plan& p = c->plan;
-  auto& ss = c->ss;
   const auto& cfg = c->cfg;
-  const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, L = cfg.n_layers, M = p.M;
-  const float eps = 1e-5f;
+  const int D = cfg.d_model;
   if (c->fused_conv && D == 256 && c->FH == 20) {  // patch geometry of conv_front.cu assumes feat_dim 80 (pitch 20)
     // CMVN + conv1 + ReLU + conv2 + ReLU in one kernel (conv_front.cu) -> c2 [M, F2*D]
     PROF(PC_CONV_FRONT);
@@ -674,6 +708,18 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
     PROF(PC_CONV2);
     PPASR_CUDA_CHECK((launch_gemm<BN_WIDE, ST_WIDE, true>(p.tm_phase, c->tm_conv2_w, s, epi, c->sms, st)));
   }
+  return PPASR_OK;
+}
+
+#include "runtime_squeezeformer.inl"
+
+int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
+  Plan& p = c->plan;
+  auto& ss = c->ss;
+  const auto& cfg = c->cfg;
+  const int D = cfg.d_model, H = cfg.n_heads, FF = cfg.ffn_dim, L = cfg.n_layers, M = p.M;
+  const float eps = 1e-5f;
+  { int rcf = run_subsampling_convs(c, st); if (rcf) return rcf; }
   // Linear(F2*D -> D) then x * sqrt(D) (subsampling.py:113, embedding.py:113), fused with block 0's first LayerNorm
   auto resid_ln = [&](int cls, const CUtensorMap& ta, const CUtensorMap& tb, int K, const float* bias, float alpha,
                       int residual, const int* lens, int mask_resid, int zero_y_pad, const float* g1, const float* b1,
@@ -813,7 +859,7 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
     vlen[b] = (int)v;
   }
   PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-  return run_encoder(c, st, false);
+  return c->cfg.model_type == 1 ? run_encoder_squeezeformer(c, st) : run_encoder(c, st, false);
 }
 
 // ---- streaming ------------------------------------------------------------------------------------
@@ -821,6 +867,10 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
   PPASR_REQUIRE(c && B > 0 && B <= 1024, "bad arguments");
   if (!c->finalized) {
     set_last_error("ppasr_b200_finalize has not been called");
+    return PPASR_ERR_STATE;
+  }
+  if (c->cfg.model_type != 0) {
+    set_last_error("chunk streaming (forward_chunk) is implemented for the conformer only");
     return PPASR_ERR_STATE;
   }
   if (!c->cfg.causal) {

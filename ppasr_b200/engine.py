@@ -15,7 +15,8 @@ class Config(ctypes.Structure):
     _fields_ = [("model_type", ctypes.c_int32), ("feat_dim", ctypes.c_int32), ("d_model", ctypes.c_int32),
                 ("n_heads", ctypes.c_int32), ("ffn_dim", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("conv_kernel", ctypes.c_int32), ("causal", ctypes.c_int32), ("conv_norm", ctypes.c_int32),
-                ("vocab_size", ctypes.c_int32), ("max_len", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5)]
+                ("vocab_size", ctypes.c_int32), ("max_len", ctypes.c_int32), ("reduce_idx", ctypes.c_int32),
+                ("recover_idx", ctypes.c_int32), ("time_reduce_kernel", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2)]
 
 
 def out_frames(T: int) -> int:
@@ -36,9 +37,17 @@ class ConformerEngine:
         torch.cuda.set_device(self.device)
         self.lib = L.load()
         c = Config()
-        c.model_type = 0
+        squeeze = getattr(cfg, "model_type", "conformer") == "squeezeformer"
+        c.model_type = 1 if squeeze else 0
         c.feat_dim = cfg.input_dim
-        c.d_model = cfg.output_size
+        c.d_model = cfg.encoder_dim if squeeze else cfg.output_size
+        c.reduce_idx = c.recover_idx = -1
+        if squeeze:
+            if cfg.output_size != cfg.encoder_dim:
+                raise L.PPASRB200Error("squeezeformer final_proj (output_size != encoder_dim) is not supported")
+            c.reduce_idx = -1 if cfg.reduce_idx is None else int(cfg.reduce_idx)
+            c.recover_idx = -1 if cfg.recover_idx is None else int(cfg.recover_idx)
+            c.time_reduce_kernel = 1 if cfg.time_reduction_layer_type == "stream" else 5
         c.n_heads = cfg.attention_heads
         c.ffn_dim = cfg.linear_units
         c.n_layers = cfg.num_blocks

@@ -19,7 +19,7 @@ import numpy as np
 from .. import _lib as L
 from ..engine import ConformerEngine, out_frames
 from ..parallel import detokenize
-from ..weights import ConformerConfig, load_npz, load_pdparams, read_mean_istd
+from ..weights import ConformerConfig, SqueezeformerConfig, load_npz, load_pdparams, read_mean_istd
 
 
 def _get(obj, key, default=None):
@@ -45,8 +45,8 @@ class InferencePredictor:
                  device=0):
         if not use_gpu:
             raise Exception("ppasr_b200 only runs on a B200 GPU (use_gpu=False is not supported)")
-        if use_model != 'conformer':
-            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 round 1 implements conformer)')
+        if use_model not in ('conformer', 'squeezeformer'):
+            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 implements conformer and squeezeformer)')
         self.configs = configs
         self.use_model = use_model
         self.streaming = streaming
@@ -81,10 +81,17 @@ class InferencePredictor:
                 weights['encoder.global_cmvn.istd'] = istd
         if vocab_size is None:
             vocab_size = int(weights['ctc.ctc_lo.weight'].shape[1])
-        allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
-                   'cnn_module_norm', 'max_len')
-        kw = {k: enc[k] for k in allowed if k in enc}
-        self.model_config = ConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        if use_model == 'squeezeformer':
+            # keys of configs/squeezeformer.yml encoder_conf (squeezeformer/encoder.py:24-53)
+            allowed = ('encoder_dim', 'output_size', 'attention_heads', 'num_blocks', 'reduce_idx', 'recover_idx',
+                       'feed_forward_expansion_factor', 'cnn_module_kernel', 'cnn_norm_type', 'adaptive_scale', 'max_len')
+            kw = {k: enc[k] for k in allowed if k in enc}
+            self.model_config = SqueezeformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        else:
+            allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
+                       'cnn_module_norm', 'max_len')
+            kw = {k: enc[k] for k in allowed if k in enc}
+            self.model_config = ConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
         self._weights_ref = weights  # kept for DecodePipeline (extra engines pack their own copy)
         self.engine = ConformerEngine(self.model_config, weights, device=device)
 

@@ -134,6 +134,136 @@ def init_conformer_weights(cfg: ConformerConfig, seed: int = 1000, ctc_gain: flo
     return w
 
 
+class SqueezeformerConfig:
+    """Inference-relevant keys of configs/squeezeformer.yml (`encoder_conf`, `streaming`, n_mels); model switches per
+    ppasr/model_utils/squeezeformer/model.py:35-41."""
+    model_type = "squeezeformer"
+
+    def __init__(self, input_dim=80, vocab_size=4233, encoder_dim=256, output_size=256, attention_heads=4, num_blocks=12,
+                 reduce_idx=5, recover_idx=11, feed_forward_expansion_factor=8, cnn_module_kernel=31,
+                 cnn_norm_type="layer_norm", adaptive_scale=True, streaming=True, max_len=5000, **_ignored):
+        self.input_dim = int(input_dim)
+        self.vocab_size = int(vocab_size)
+        self.encoder_dim = int(encoder_dim)
+        self.output_size = int(output_size)
+        self.attention_heads = int(attention_heads)
+        self.num_blocks = int(num_blocks)
+        self.reduce_idx = reduce_idx
+        self.recover_idx = recover_idx
+        self.feed_forward_expansion_factor = int(feed_forward_expansion_factor)
+        self.linear_units = self.encoder_dim * self.feed_forward_expansion_factor
+        self.cnn_module_kernel = int(cnn_module_kernel)
+        self.cnn_norm_type = cnn_norm_type
+        self.cnn_module_norm = cnn_norm_type
+        self.adaptive_scale = bool(adaptive_scale)
+        self.streaming = bool(streaming)
+        self.causal = bool(streaming)
+        self.time_reduction_layer_type = "stream" if streaming else "conv1d"
+        self.max_len = int(max_len)
+
+    def to_dict(self):
+        return dict(input_dim=self.input_dim, vocab_size=self.vocab_size, encoder_dim=self.encoder_dim,
+                    output_size=self.output_size, attention_heads=self.attention_heads, num_blocks=self.num_blocks,
+                    reduce_idx=self.reduce_idx, recover_idx=self.recover_idx,
+                    feed_forward_expansion_factor=self.feed_forward_expansion_factor,
+                    cnn_module_kernel=self.cnn_module_kernel, cnn_norm_type=self.cnn_norm_type,
+                    adaptive_scale=self.adaptive_scale, streaming=self.streaming, max_len=self.max_len)
+
+
+def squeezeformer_param_shapes(cfg: SqueezeformerConfig) -> Dict[str, tuple]:
+    """Parameter names/layouts of SqueezeformerModel.encoder + ctc (squeezeformer/encoder.py:129-169,
+    attention.py:24-38, positionwise.py:31-43, convolution.py:36-81, subsampling.py:33-44, time_reduction.py)."""
+    D, FF, K, V, F = cfg.encoder_dim, cfg.linear_units, cfg.cnn_module_kernel, cfg.vocab_size, cfg.input_dim
+    H = cfg.attention_heads
+    f2 = ((F - 1) // 2 - 1) // 2
+    kr = 1 if cfg.time_reduction_layer_type == "stream" else 5
+    s = {
+        "encoder.global_cmvn.mean": (F,), "encoder.global_cmvn.istd": (F,),
+        "encoder.embed.pw_conv.weight": (D, 1, 3, 3), "encoder.embed.pw_conv.bias": (D,),
+        "encoder.embed.dw_conv.weight": (D, D, 3, 3), "encoder.embed.dw_conv.bias": (D,),
+        "encoder.embed.input_proj.0.weight": (D * f2, D), "encoder.embed.input_proj.0.bias": (D,),
+        "encoder.preln.weight": (D,), "encoder.preln.bias": (D,),
+        "encoder.time_reduction_layer.dw_conv.weight": (D, 1, kr), "encoder.time_reduction_layer.dw_conv.bias": (D,),
+        "encoder.time_reduction_layer.pw_conv.weight": (D, D, 1), "encoder.time_reduction_layer.pw_conv.bias": (D,),
+        "encoder.time_recover_layer.weight": (D, D), "encoder.time_recover_layer.bias": (D,),
+        "ctc.ctc_lo.weight": (D, V), "ctc.ctc_lo.bias": (V,),
+    }
+    for i in range(cfg.num_blocks):
+        p = f"encoder.encoders.{i}."
+        for n in ("layer_norm1", "layer_norm2", "layer_norm3", "layer_norm4"):
+            s[p + n + ".weight"] = (D,)
+            s[p + n + ".bias"] = (D,)
+        for n in ("ffn1", "ffn2"):
+            s[p + n + ".w_1.weight"] = (D, FF)
+            s[p + n + ".w_1.bias"] = (FF,)
+            s[p + n + ".w_2.weight"] = (FF, D)
+            s[p + n + ".w_2.bias"] = (D,)
+            s[p + n + ".ada_scale"] = (1, 1, D)
+            s[p + n + ".ada_bias"] = (1, 1, D)
+        for n in ("linear_q", "linear_k", "linear_v", "linear_out", "linear_pos"):
+            s[p + f"self_attn.{n}.weight"] = (D, D)
+            s[p + f"self_attn.{n}.bias"] = (D,)
+        s[p + "self_attn.pos_bias_u"] = (H, D // H)
+        s[p + "self_attn.pos_bias_v"] = (H, D // H)
+        s[p + "self_attn.ada_scale"] = (1, 1, D)
+        s[p + "self_attn.ada_bias"] = (1, 1, D)
+        s[p + "conv_module.ada_scale"] = (1, 1, D)
+        s[p + "conv_module.ada_bias"] = (1, 1, D)
+        s[p + "conv_module.pointwise_conv1.weight"] = (2 * D, D, 1)
+        s[p + "conv_module.pointwise_conv1.bias"] = (2 * D,)
+        s[p + "conv_module.depthwise_conv.weight"] = (D, 1, K)
+        s[p + "conv_module.depthwise_conv.bias"] = (D,)
+        s[p + "conv_module.norm.weight"] = (D,)
+        s[p + "conv_module.norm.bias"] = (D,)
+        if cfg.cnn_norm_type == "batch_norm":
+            s[p + "conv_module.norm._mean"] = (D,)
+            s[p + "conv_module.norm._variance"] = (D,)
+        s[p + "conv_module.pointwise_conv2.weight"] = (D, D, 1)
+        s[p + "conv_module.pointwise_conv2.bias"] = (D,)
+    return s
+
+
+def init_squeezeformer_weights(cfg: SqueezeformerConfig, seed: int = 1000, ctc_gain: float = 8.0,
+                               perturb_norms: bool = True) -> Dict[str, np.ndarray]:
+    """Seeded synthetic parameters; LayerNorm gains/biases and the adaptive scale/bias vectors are perturbed around their
+    reference initial values (1 / 0) so that the parity tests are sensitive to them."""
+    rng = np.random.RandomState(seed)
+    w = {}
+    for name, shape in squeezeformer_param_shapes(cfg).items():
+        leaf = name.split(".")[-1]
+        parent = name.split(".")[-2]
+        if name.endswith("global_cmvn.mean"):
+            a = rng.uniform(-1.0, 1.0, shape) + 10.0
+        elif name.endswith("global_cmvn.istd"):
+            a = rng.uniform(0.2, 0.5, shape)
+        elif leaf == "_mean":
+            a = rng.uniform(-0.1, 0.1, shape)
+        elif leaf == "_variance":
+            a = rng.uniform(0.5, 1.5, shape)
+        elif leaf == "ada_scale":
+            a = rng.uniform(0.8, 1.2, shape) if perturb_norms else np.ones(shape)
+        elif leaf == "ada_bias":
+            a = rng.uniform(-0.1, 0.1, shape) if perturb_norms else np.zeros(shape)
+        elif ("norm" in parent or parent == "preln") and leaf == "weight":
+            a = rng.uniform(0.8, 1.2, shape) if perturb_norms else np.ones(shape)
+        elif ("norm" in parent or parent == "preln") and leaf == "bias":
+            a = rng.uniform(-0.1, 0.1, shape) if perturb_norms else np.zeros(shape)
+        elif leaf in ("pos_bias_u", "pos_bias_v"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            a = rng.uniform(-lim, lim, shape)
+        elif name.startswith("ctc.ctc_lo"):
+            if leaf == "weight":
+                lim = math.sqrt(6.0 / (shape[0] + shape[1])) * ctc_gain
+                a = rng.uniform(-lim, lim, shape)
+            else:
+                a = np.zeros(shape)
+        else:
+            lim = 1.0 / math.sqrt(_fan_in(name, shape))
+            a = rng.uniform(-lim, lim, shape)
+        w[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return w
+
+
 def save_npz(path: str, weights: Dict[str, np.ndarray], cfg: ConformerConfig = None):
     extra = {}
     if cfg is not None:

@@ -216,13 +216,21 @@ def test_greedy_full_size_matches_oracle(lib, cuda):
 # ------------------------------------------------------------------------------------------------
 # whole hot path vs the oracle
 # ------------------------------------------------------------------------------------------------
-def _run_model(cuda, num_blocks, B, T, lens, vocab=4233, streaming=True, norm="layer_norm"):
+def _run_model(cuda, num_blocks, B, T, lens, vocab=4233, streaming=True, norm="layer_norm", model="conformer", **mkw):
     from oracle import decoders_oracle as DO
     from oracle.conformer_oracle import ConformerConf, ConformerOracle
+    from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
     from ppasr_b200.engine import ConformerEngine, out_frames
-    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
-    cfg = ConformerConfig(num_blocks=num_blocks, vocab_size=vocab, streaming=streaming, cnn_module_norm=norm)
-    w = init_conformer_weights(cfg)
+    from ppasr_b200.weights import (ConformerConfig, SqueezeformerConfig, init_conformer_weights,
+                                    init_squeezeformer_weights, synthetic_fbank)
+    if model == "squeezeformer":
+        cfg = SqueezeformerConfig(num_blocks=num_blocks, vocab_size=vocab, streaming=streaming, cnn_norm_type=norm, **mkw)
+        w = init_squeezeformer_weights(cfg)
+        oracle = SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w)
+    else:
+        cfg = ConformerConfig(num_blocks=num_blocks, vocab_size=vocab, streaming=streaming, cnn_module_norm=norm)
+        w = init_conformer_weights(cfg)
+        oracle = ConformerOracle(ConformerConf(**cfg.to_dict()), w)
     feats = synthetic_fbank(B, T)
     for b in range(B):
         feats[b, lens[b]:] = 0
@@ -231,8 +239,7 @@ def _run_model(cuda, num_blocks, B, T, lens, vocab=4233, streaming=True, norm="l
     logits = eng.ctc_logits().cpu()
     probs = eng.ctc_probs().cpu()
     ids, ol, sc, fi, fp = eng.ctc_greedy(to_host=True, with_frames=True)
-    ref_logits = ConformerOracle(ConformerConf(**cfg.to_dict()), w).get_encoder_out(
-        torch.from_numpy(feats), torch.tensor(lens), return_logits=True)
+    ref_logits = oracle.get_encoder_out(torch.from_numpy(feats), torch.tensor(lens), return_logits=True)
     Tp = out_frames(T)
     vl = [min(Tp, (l + 3) // 4) for l in lens]
     scale = ref_logits.abs().max().item()
@@ -270,6 +277,46 @@ def test_model_matches_oracle_small(lib, cuda, kw):
 def test_model_matches_oracle_conformer_12_layers(lib, cuda):
     """conformer.yml sizes (12 blocks, d256, ff2048, V=4233), 4 x 10 s, ragged."""
     _run_model(cuda, 12, 4, 998, [998, 998, 900, 500])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_blocks=1, B=2, T=131, lens=[131, 90], vocab=97, reduce_idx=None, recover_idx=None),
+    dict(num_blocks=3, B=3, T=203, lens=[203, 150, 99], vocab=300, reduce_idx=1, recover_idx=2),          # even T' = 50
+    dict(num_blocks=3, B=3, T=207, lens=[207, 150, 5], vocab=300, reduce_idx=1, recover_idx=2, streaming=False),  # odd T'
+    dict(num_blocks=4, B=2, T=1051, lens=[1051, 700], vocab=300, reduce_idx=1, recover_idx=3),           # T' = 262 > 2 tiles
+    dict(num_blocks=2, B=2, T=300, lens=[300, 200], vocab=300, reduce_idx=None, recover_idx=None, norm="batch_norm",
+         streaming=False),
+])
+def test_squeezeformer_matches_oracle_small(lib, cuda, kw):
+    """squeezeformer/encoder.py:172-236 incl. time reduction ('stream' k1 for streaming, conv1d k5 otherwise) + recover."""
+    _run_model(cuda, model="squeezeformer", **kw)
+
+
+def test_squeezeformer_matches_oracle_12_layers(lib, cuda):
+    """configs/squeezeformer.yml sizes (12 blocks, reduce 5 / recover 11, k31 causal, V=4233), 4 x 10 s, ragged."""
+    _run_model(cuda, 12, 4, 998, [998, 998, 900, 500], model="squeezeformer")
+
+
+def test_squeezeformer_inference_predictor(lib, cuda):
+    """InferencePredictor(use_model='squeezeformer').predict / predict_decode; chunk API raises like the reference does for
+    unsupported models (inference_predictor.py:186)."""
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.weights import SqueezeformerConfig, init_squeezeformer_weights, make_vocab, synthetic_fbank
+    from oracle import decoders_oracle as DO
+    cfg = SqueezeformerConfig(num_blocks=3, vocab_size=200, reduce_idx=1, recover_idx=2)
+    w = init_squeezeformer_weights(cfg)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "squeezeformer",
+                              streaming=True, weights=w)
+    x = synthetic_fbank(2, 260)
+    probs = pred.predict(x, np.array([260, 260]))
+    assert probs.shape == (2, 64, 200) and np.allclose(probs.sum(-1), 1.0, atol=1e-4)
+    vocab = make_vocab(200)
+    got = pred.predict_decode(x, None, vocabulary=vocab)
+    for b in range(2):
+        score, text = DO.greedy_decoder(probs[b], vocab)
+        assert got[b][1] == text and abs(got[b][0] - score) < 1e-3
+    with pytest.raises(Exception):
+        pred.predict_chunk_conformer(x[:1, :67], -1)
 
 
 def test_full_size_properties(lib, cuda):

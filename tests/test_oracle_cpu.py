@@ -182,3 +182,55 @@ def test_pruned_log_probs():
     r = DO.get_pruned_log_probs(p, 1.0, 3)
     assert [i for i, _ in r] == [1, 2, 3]
     assert abs(r[0][1] - math.log(0.6 + DO.NUM_FLT_MIN)) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------
+# Squeezeformer oracle self-consistency (parity unpinned: no Paddle here; see oracle/squeezeformer_oracle.py)
+# ------------------------------------------------------------------------------------------------
+def _squeeze(streaming=True, nb=3, **kw):
+    from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
+    from ppasr_b200.weights import SqueezeformerConfig, init_squeezeformer_weights
+    cfg = SqueezeformerConfig(num_blocks=nb, vocab_size=60, streaming=streaming, **kw)
+    w = init_squeezeformer_weights(cfg)
+    return cfg, w, SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w)
+
+
+@pytest.mark.parametrize("streaming", [True, False])
+def test_squeezeformer_oracle_shapes_and_batch_invariance(streaming):
+    from ppasr_b200.weights import synthetic_fbank
+    cfg, w, o = _squeeze(streaming, reduce_idx=1, recover_idx=2)
+    x = torch.from_numpy(synthetic_fbank(3, 203))
+    lens = torch.tensor([203, 150, 99])
+    y = o.get_encoder_out(x, lens, return_logits=True)
+    assert y.shape == (3, 50, 60)
+    y0 = o.get_encoder_out(x[:1], lens[:1], return_logits=True)
+    assert (y0[0] - y[0]).abs().max() < 1e-3 * y.abs().max()
+    # time-reduction kernel size follows the streaming switch (squeezeformer/model.py:35-41)
+    assert w["encoder.time_reduction_layer.dw_conv.weight"].shape[-1] == (1 if streaming else 5)
+
+
+def test_squeezeformer_oracle_fp64_noise_floor():
+    from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
+    from ppasr_b200.weights import synthetic_fbank
+    cfg, w, o = _squeeze(True, reduce_idx=1, recover_idx=2)
+    o64 = SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w, dtype=torch.float64)
+    x = torch.from_numpy(synthetic_fbank(2, 131))
+    lens = torch.tensor([131, 90])
+    a = o.get_encoder_out(x, lens, return_logits=True)
+    b = o64.get_encoder_out(x, lens, return_logits=True)
+    assert ((a - b.float()).abs().max() / b.abs().max()).item() < 1e-4
+
+
+def test_squeezeformer_oracle_identity_ada_and_no_reduction_is_plain_postnorm():
+    """With ada_scale = 1 / ada_bias = 0 the adaptive-scale code path must be a no-op (positionwise.py:62-63)."""
+    from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
+    from ppasr_b200.weights import synthetic_fbank
+    cfg, w, o = _squeeze(True, nb=2, reduce_idx=None, recover_idx=None)
+    w2 = {k: (np.ones_like(v) if k.endswith("ada_scale") else np.zeros_like(v) if k.endswith("ada_bias") else v)
+          for k, v in w.items()}
+    conf_off = SqueezeformerConf(**{**cfg.to_dict(), "adaptive_scale": False})
+    x = torch.from_numpy(synthetic_fbank(1, 131))
+    lens = torch.tensor([131])
+    a = SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w2).get_encoder_out(x, lens, return_logits=True)
+    b = SqueezeformerOracle(conf_off, w).get_encoder_out(x, lens, return_logits=True)
+    assert torch.equal(a, b)
