@@ -30,6 +30,29 @@ GFLOP_PER_UTT = 23.17  # SURVEY.md §8d algorithmic FLOPs of the conformer path 
 METRIC = "utterances_per_sec"
 
 
+def model_setup(model):
+    """(config, weights, workload name, use_model, algorithmic GFLOP/utt) for --model: conformer = BASELINE configs[1]
+    (the headline metric); squeezeformer = the per-GPU share of configs[3] (256 x 10 s over 8 GPUs = 32 per GPU)."""
+    from ppasr_b200.weights import (ConformerConfig, SqueezeformerConfig, init_conformer_weights,
+                                    init_squeezeformer_weights)
+    if model == "squeezeformer":
+        cfg = SqueezeformerConfig(vocab_size=VOCAB)
+        return (cfg, init_squeezeformer_weights(cfg),
+                "squeezeformer-streaming b32x10s per GPU fbank[32,998,80] ctc_greedy (BASELINE configs[3] shard)",
+                "squeezeformer", 19.0)
+    cfg = ConformerConfig(vocab_size=VOCAB)
+    return (cfg, init_conformer_weights(cfg),
+            "conformer-streaming b32x10s fbank[32,998,80] ctc_greedy (BASELINE configs[1])", "conformer", GFLOP_PER_UTT)
+
+
+def make_oracle(model, cfg, w):
+    if model == "squeezeformer":
+        from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
+        return SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w)
+    from oracle.conformer_oracle import ConformerConf, ConformerOracle
+    return ConformerOracle(ConformerConf(**cfg.to_dict()), w)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -118,13 +141,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.conformer_oracle import ConformerConf, ConformerOracle
-    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab, synthetic_fbank
+    from ppasr_b200.weights import make_vocab, synthetic_fbank
     cores = host_cores()
     torch.set_num_threads(cores)
-    cfg = ConformerConfig(vocab_size=VOCAB)
-    w = init_conformer_weights(cfg)
-    orc = ConformerOracle(ConformerConf(**cfg.to_dict()), w)
+    cfg, w, workload, _, _ = model_setup(args.model)
+    orc = make_oracle(args.model, cfg, w)
     vocab = make_vocab(VOCAB)
     sample_b = 8  # bounded sample of the 32-utterance batch per step
     feats = synthetic_fbank(sample_b, FRAMES)
@@ -141,8 +162,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 * (BATCH_PER_GPU / sample_b), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "conformer-streaming b32x10s fbank[32,998,80] ctc_greedy (BASELINE configs[1])",
-                   "rtf": dt / (sample_b * SECONDS)},
+        "config": {"workload": workload, "rtf": dt / (sample_b * SECONDS)},
         "cpu_baseline": {"value": value, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample_b} of 32 utterances x 10 s per step, PyTorch-CPU fp32 oracle restatement "
                                    "of the reference Paddle graph + reference greedy restatement (Paddle not installable)"},
@@ -158,6 +178,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="conformer", choices=["conformer", "squeezeformer"],
+                    help="conformer = the headline BASELINE metric (default); squeezeformer = configs[3] per-GPU shard")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -167,7 +189,7 @@ def main():
     from ppasr_b200 import _lib as L
     from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
     from ppasr_b200.parallel import all_gather_results, detokenize
-    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab, synthetic_fbank
+    from ppasr_b200.weights import make_vocab, synthetic_fbank
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,11 +201,10 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
-    cfg = ConformerConfig(vocab_size=VOCAB)
-    weights = init_conformer_weights(cfg)
+    cfg, weights, workload, use_model, gflop_per_utt = model_setup(args.model)
     vocab = make_vocab(VOCAB)
     configs = {"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}
-    pred = InferencePredictor(configs, "conformer", streaming=True, weights=weights, device=local_rank)
+    pred = InferencePredictor(configs, use_model, streaming=True, weights=weights, device=local_rank)
     eng = pred.engine
     lib = L.load()
 
@@ -323,6 +344,7 @@ def main():
         eng.profile_enable(False)
         M = B * Tp
         D, FF = cfg.output_size, cfg.linear_units
+        ffn_m = 0.75 if args.model == "squeezeformer" else 1.0  # half of the squeezeformer blocks run at T'/2
         T1 = (FRAMES - 1) // 2
         Th = (T1 + 1) // 2
         flops = {  # algorithmic FLOPs per launch (2*M*N*K)
@@ -331,7 +353,7 @@ def main():
             "conv2_gemm": 2.0 * (B * Tp * 19) * D * 9 * D, "embed_gemm": 2.0 * M * D * 19 * D,
             "ctc_stats_gemm": 2.0 * M * VOCAB * D, "attention": 2.0 * B * 4 * Tp * Tp * (128 + 64),
             # fused_ffn: W1 + W2 GEMMs (+ the chained pointwise_conv2 in every second launch: averaged)
-            "fused_ffn": 2.0 * M * D * FF * 2 + 0.5 * 2.0 * M * D * D,
+            "fused_ffn": (2.0 * M * D * FF * 2) * ffn_m + (0.5 * 2.0 * M * D * D if args.model == "conformer" else 0.0),
             "fused_attn_out": 2.0 * M * D * D + 2.0 * M * 2 * D * D,
             "conv_front": 2.0 * (B * Tp * 19) * D * 9 * D,
         }
@@ -344,14 +366,13 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + " (burst cuBLAS bf16)",
                 "us_per_launch": us, "share_of_step": prof[top][1] / total,
-                "step_tensor_frac_sustained": (GFLOP_PER_UTT * B / ms) / pk["bf16_tflops_sustained"]}
+                "step_tensor_frac_sustained": (gflop_per_utt * B / ms) / pk["bf16_tflops_sustained"]}
 
     # ---- CPU baseline: oracle restatement on the host cores, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.conformer_oracle import ConformerConf, ConformerOracle
         torch.set_num_threads(host_cores())
-        orc = ConformerOracle(ConformerConf(**cfg.to_dict()), weights)
+        orc = make_oracle(args.model, cfg, weights)
         sb = 4
         f = feats_host[:sb].numpy()
         cpu_reference_step(orc, f, [FRAMES] * sb, vocab)
@@ -371,15 +392,14 @@ def main():
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "conformer-streaming b32x10s fbank[32,998,80] per GPU, fused CTC head + ctc_greedy "
-                                   "(BASELINE configs[1])",
+            "config": {"workload": workload + "; per GPU, fused CTC head + ctc_greedy",
                        "global_batch": total_utts, "frames": FRAMES, "out_frames": Tp, "vocab": VOCAB,
                        "parallelism": f"dp{world} (batch sharded, one all-gather of ids)" if world > 1 else "single GPU",
                        "mode": f"throughput: {depth} batches in flight ({depth} engines on {depth} CUDA streams per GPU)",
                        "l2": "inputs larger than L2: 16 distinct device-resident batches (163 MB) cycled; no explicit flush",
                        "single_stream_ms_per_step": single_ms,
                        "single_stream_note": "one batch at a time, 256 MiB memset L2 flush between steps (outside the events)",
-                       "rtf": ms * 1e-3 / (B * SECONDS), "gflop_per_step_per_gpu": GFLOP_PER_UTT * B},
+                       "rtf": ms * 1e-3 / (B * SECONDS), "gflop_per_step_per_gpu": gflop_per_utt * B},
             "clocks": sampler.result(),
             "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

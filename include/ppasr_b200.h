@@ -25,14 +25,15 @@ typedef struct ppasr_b200_ctx ppasr_b200_ctx;
 /* Model hyper-parameters = the inference-relevant keys of configs/conformer.yml / configs/squeezeformer.yml
  * (encoder_conf, streaming, preprocess_conf.n_mels) plus the vocabulary size. */
 typedef struct ppasr_b200_config {
-  int32_t model_type;      /* 0 = conformer, 1 = squeezeformer */
+  int32_t model_type;      /* 0 = conformer, 1 = squeezeformer, 2 = deepspeech2 */
   int32_t feat_dim;        /* preprocess_conf.n_mels, 80 */
-  int32_t d_model;         /* encoder_conf.output_size (squeezeformer: encoder_dim), 256 */
+  int32_t d_model;         /* encoder_conf.output_size (squeezeformer: encoder_dim), 256; deepspeech2: rnn_size (<= 1024) */
   int32_t n_heads;         /* encoder_conf.attention_heads, 4 (d_model / n_heads must be 64) */
   int32_t ffn_dim;         /* encoder_conf.linear_units, 2048 (squeezeformer: encoder_dim * feed_forward_expansion_factor) */
-  int32_t n_layers;        /* encoder_conf.num_blocks, 12 */
+  int32_t n_layers;        /* encoder_conf.num_blocks, 12; deepspeech2: num_rnn_layers, 5 */
   int32_t conv_kernel;     /* encoder_conf.cnn_module_kernel, 15 (7, 15 or 31) */
-  int32_t causal;          /* `streaming: True` => causal depthwise conv (conformer/model.py:35-39) */
+  int32_t causal;          /* `streaming: True` => causal depthwise conv (conformer/model.py:35-39); deepspeech2: forward-only
+                            * RNN instead of bidirectional (deepspeech2/model.py:40) */
   int32_t conv_norm;       /* 0 = layer_norm (shipped default, conformer/encoder.py:51), 1 = batch_norm */
   int32_t vocab_size;      /* CTC output size V */
   int32_t max_len;         /* positional table length, 5000 (conformer/embedding.py:30) */
@@ -40,7 +41,8 @@ typedef struct ppasr_b200_config {
   int32_t reduce_idx;          /* block before which the time-reduction layer runs (5), -1 = none */
   int32_t recover_idx;         /* block before which the sequence is recovered to full length (11), -1 = none */
   int32_t time_reduce_kernel;  /* 1 = TimeReductionLayerStream (streaming), 5 = TimeReductionLayer1D */
-  int32_t reserved[2];
+  int32_t use_gru;             /* deepspeech2 only: encoder_conf.use_gru (GRU instead of LSTM, deepspeech2/encoder.py:41-53) */
+  int32_t reserved[1];
 } ppasr_b200_config;
 
 const char* ppasr_b200_last_error(void);
@@ -111,6 +113,11 @@ int ppasr_b200_ctc_greedy(ppasr_b200_ctx* ctx, int32_t* ids, int32_t* out_lens, 
 int ppasr_b200_stream_reset(ppasr_b200_ctx* ctx, int32_t B);
 int ppasr_b200_encode_chunk(ppasr_b200_ctx* ctx, const float* feats, int32_t feats_on_device, int32_t B, int32_t t,
                             int32_t required_cache_size, void* stream);
+/* DeepSpeech2 streaming states after the last encode_chunk: h, c fp32 [num_rnn_layers * num_directions, B, rnn_size]
+ * (either may be NULL). replaces: self.output_state_h / self.output_state_c copy_to_cpu
+ * (infer_utils/inference_predictor.py:176-180). */
+int ppasr_b200_ds2_states(ppasr_b200_ctx* ctx, float* h, float* c, int32_t on_device, void* stream);
+
 /* offset = encoder frames produced so far (== self.offset of the reference), cache_t = cached keys. */
 int ppasr_b200_stream_info(ppasr_b200_ctx* ctx, int32_t* offset, int32_t* cache_t);
 /* fp32 copies of stream 0's caches in the reference layouts: att_cache [L, H, cache_t, 128] (k | v),

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "ppasr_b200_stream_reset": (c_int, [P, I]),
     "ppasr_b200_encode_chunk": (c_int, [P, P, I, I, I, I, P]),
     "ppasr_b200_stream_info": (c_int, [P, P, P]),
+    "ppasr_b200_ds2_states": (c_int, [P, P, P, I, P]),
     "ppasr_b200_stream_export": (c_int, [P, P, P, I, P]),
     "ppasr_b200_beam_state_bytes": (c_int64, [I, I, I]),
     "ppasr_b200_beam_workspace_bytes": (c_int64, [I, I]),

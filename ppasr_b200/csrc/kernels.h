@@ -68,6 +68,17 @@ cudaError_t launch_time_reduce_dw(const float* x, const float* w, const float* b
 // lens_out[b] = (lens_in[b] + 1) / 2
 cudaError_t launch_halve_lens(const int* lens_in, int* lens_out, int B, cudaStream_t st);
 
+// DeepSpeech2 (ds2.cu): fused CMVN + 2 x (Conv2d k3 s2 + ReLU) with 32 channels; recurrent half of one LSTM / GRU layer
+// (persistent weight-stationary cooperative kernel, both directions concurrently); LayerNorm over wide rows
+cudaError_t launch_ds2_conv(const float* feats, const float* mean, const float* istd, const float* w1, const float* b1,
+                            const float* w2t, const float* b2, __nv_bfloat16* out, int B, int T, int F, int Tp, int Kpad,
+                            cudaStream_t st);
+cudaError_t launch_rnn_layer(const float* xg, const __nv_bfloat16* whh, const float* bhh, const int* lens, const float* h_init,
+                             const float* c_init, float* h_final, float* c_final, float* out, float* hbuf, unsigned* bar,
+                             int B, int T, int H, int nd, int gru, int num_sms, cudaStream_t st);
+cudaError_t launch_row_layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int M, int N, float eps,
+                                 cudaStream_t st);
+
 // CTC prefix beam search (beam.cu)
 struct BeamStateHeader {
   int nb;       // entries in the beam

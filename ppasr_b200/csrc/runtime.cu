@@ -132,6 +132,24 @@ struct ppasr_b200_ctx {
     CUtensorMap tm_tr_pw, tm_rec_w, tm_pos2;  // tm_pos2: every second row of the positional table (pos_emb[:, ::2])
     int reduce_idx = -1, recover_idx = -1, tr_k = 1;
   } sq;
+  // ---- DeepSpeech2 (model_type 2; deepspeech2/encoder.py) ----
+  struct Ds2LayerW {
+    const __nv_bfloat16 *wih = nullptr, *whh = nullptr;  // [nd*G*H, Kin_pad], [nd][G*H][H]
+    const float *bih = nullptr, *bhh = nullptr, *ln_g = nullptr, *ln_b = nullptr;
+    CUtensorMap tm_wih;
+  };
+  struct Ds2 {
+    std::vector<Ds2LayerW> layers;
+    const float* conv2_wt = nullptr;  // [cin*9 + k][cout]
+    int nd = 2, gru = 0, kin0 = 0, kin0_pad = 0;
+    float *xg = nullptr, *rnn_out = nullptr, *hbuf = nullptr;
+    unsigned* bar = nullptr;
+    CUtensorMap tm_y0;
+    // streaming states [L*nd, B, H] (inference_predictor.py:157-164), device resident
+    float *h_state = nullptr, *c_state = nullptr;
+    int state_B = 0;
+  } ds;
+  int ctc_k = 0;  // input features of the CTC projection (0 = d_model)
   Plan plan;
   int sms = 148;
   // ---- streaming state (reference: inference_predictor.py:35-39,215-220; device resident here) ----
@@ -227,6 +245,7 @@ std::vector<float> transpose_in_out(const HostTensor& w, int rows_pad = 0) {
 }
 
 int finalize_squeezeformer(ppasr_b200_ctx* c);  // runtime_squeezeformer.inl
+int finalize_ds2(ppasr_b200_ctx* c);            // runtime_ds2.inl
 
 template <class T>
 const T* upload(ppasr_b200_ctx* c, const std::vector<T>& v) {
@@ -241,12 +260,18 @@ extern "C" {
 
 int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   PPASR_REQUIRE(cfg && out, "null pointer");
-  PPASR_REQUIRE(cfg->model_type == 0 || cfg->model_type == 1, "model_type must be 0 (conformer) or 1 (squeezeformer)");
-  PPASR_REQUIRE(cfg->d_model == 256, "d_model must be 256 in this build");
-  PPASR_REQUIRE(cfg->n_heads * 64 == cfg->d_model, "head dim must be 64");
-  PPASR_REQUIRE(cfg->ffn_dim % 256 == 0 && cfg->ffn_dim > 0, "ffn_dim must be a multiple of 256");
-  PPASR_REQUIRE(cfg->conv_kernel == 7 || cfg->conv_kernel == 15 || cfg->conv_kernel == 31, "conv_kernel 7/15/31");
-  PPASR_REQUIRE(cfg->feat_dim >= 7 && cfg->vocab_size > 1 && cfg->n_layers > 0 && cfg->max_len > 16, "bad config");
+  PPASR_REQUIRE(cfg->model_type >= 0 && cfg->model_type <= 2, "model_type must be 0 (conformer), 1 (squeezeformer) or 2 (deepspeech2)");
+  PPASR_REQUIRE(cfg->feat_dim >= 7 && cfg->vocab_size > 1 && cfg->n_layers > 0, "bad config");
+  if (cfg->model_type == 2) {
+    PPASR_REQUIRE(cfg->d_model >= 64 && cfg->d_model <= 1024 && cfg->d_model % 64 == 0,
+                  "deepspeech2: rnn_size must be a multiple of 64 and <= 1024 in this build (W_hh slices live in shared memory)");
+  } else {
+    PPASR_REQUIRE(cfg->d_model == 256, "d_model must be 256 in this build");
+    PPASR_REQUIRE(cfg->n_heads * 64 == cfg->d_model, "head dim must be 64");
+    PPASR_REQUIRE(cfg->ffn_dim % 256 == 0 && cfg->ffn_dim > 0, "ffn_dim must be a multiple of 256");
+    PPASR_REQUIRE(cfg->conv_kernel == 7 || cfg->conv_kernel == 15 || cfg->conv_kernel == 31, "conv_kernel 7/15/31");
+    PPASR_REQUIRE(cfg->max_len > 16, "bad config");
+  }
   if (cfg->model_type == 1) {
     const int ri = cfg->reduce_idx, ci = cfg->recover_idx;
     PPASR_REQUIRE((ri < 0 && ci < 0) || (ri >= 0 && ri < ci && ci < cfg->n_layers),
@@ -259,7 +284,7 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   c->F2 = (c->F1 - 1) / 2;
   c->FH = (c->F1 + 1) / 2;
   c->Kemb = c->F2 * cfg->d_model;
-  if (c->Kemb % GEMM_BLOCK_K != 0) {
+  if (cfg->model_type != 2 && c->Kemb % GEMM_BLOCK_K != 0) {
     delete c;
     set_last_error("subsampled feature size * d_model must be a multiple of 64");
     return PPASR_ERR_INVALID;
@@ -278,6 +303,8 @@ int ppasr_b200_destroy(ppasr_b200_ctx* ctx) {
   if (ctx->ss.kk) cudaFree(ctx->ss.kk);
   if (ctx->ss.vt) cudaFree(ctx->ss.vt);
   if (ctx->ss.cnn) cudaFree(ctx->ss.cnn);
+  if (ctx->ds.h_state) cudaFree(ctx->ds.h_state);
+  if (ctx->ds.c_state) cudaFree(ctx->ds.c_state);
   delete ctx;
   return PPASR_OK;
 }
@@ -312,6 +339,7 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
   }
   c->sms = prop.multiProcessorCount;
   if (cfg.model_type == 1) return finalize_squeezeformer(c);
+  if (cfg.model_type == 2) return finalize_ds2(c);
 
   std::string missing;
   auto need = [&](const std::string& n) { return find(c, n, &missing); };
@@ -712,6 +740,7 @@ int run_subsampling_convs(ppasr_b200_ctx* c, cudaStream_t st) {
 }
 
 #include "runtime_squeezeformer.inl"
+#include "runtime_ds2.inl"
 
 int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
   Plan& p = c->plan;
@@ -844,21 +873,24 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
     return PPASR_ERR_STATE;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc = build_plan(c, B, T);
+  const bool ds2 = c->cfg.model_type == 2;
+  int rc = ds2 ? build_plan_ds2(c, B, T) : build_plan(c, B, T);
   if (rc != PPASR_OK) return rc;
   Plan& p = c->plan;
   PPASR_CUDA_CHECK(cudaMemcpyAsync(p.feats, feats, (size_t)B * T * c->cfg.feat_dim * sizeof(float),
                                    feats_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-  // valid subsampled frames: mask[:, :, :-2:2][:, :, :-2:2] keeps frame j iff 4*j < len (subsampling.py:115)
+  // valid subsampled frames: mask[:, :, :-2:2][:, :, :-2:2] keeps frame j iff 4*j < len (subsampling.py:115);
+  // deepspeech2 uses x_len = ((len - 1) // 2 - 1) // 2 as the RNN sequence_length (deepspeech2/conv.py:20)
   std::vector<int> vlen(B);
   for (int b = 0; b < B; ++b) {
     const int64_t len = lens_host ? lens_host[b] : T;
-    int64_t v = (len + 3) / 4;
+    int64_t v = ds2 ? ((len - 1) / 2 - 1) / 2 : (len + 3) / 4;
     if (v > p.Tp) v = p.Tp;
     if (v < 0) v = 0;
     vlen[b] = (int)v;
   }
   PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  if (ds2) return run_encoder_ds2(c, st, false);
   return c->cfg.model_type == 1 ? run_encoder_squeezeformer(c, st) : run_encoder(c, st, false);
 }
 
@@ -869,8 +901,25 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
     set_last_error("ppasr_b200_finalize has not been called");
     return PPASR_ERR_STATE;
   }
+  if (c->cfg.model_type == 2) {
+    // zero LSTM / GRU states [L*nd, B, H] (inference_predictor.py:157-164)
+    auto& ds = c->ds;
+    const size_t n = (size_t)c->cfg.n_layers * ds.nd * B * c->cfg.d_model;
+    if (ds.state_B != B || !ds.h_state) {
+      PPASR_CUDA_CHECK(cudaDeviceSynchronize());
+      if (ds.h_state) cudaFree(ds.h_state);
+      if (ds.c_state) cudaFree(ds.c_state);
+      ds.h_state = ds.c_state = nullptr;
+      PPASR_CUDA_CHECK(cudaMalloc(&ds.h_state, n * 4));
+      PPASR_CUDA_CHECK(cudaMalloc(&ds.c_state, n * 4));
+      ds.state_B = B;
+    }
+    PPASR_CUDA_CHECK(cudaMemset(ds.h_state, 0, n * 4));
+    PPASR_CUDA_CHECK(cudaMemset(ds.c_state, 0, n * 4));
+    return PPASR_OK;
+  }
   if (c->cfg.model_type != 0) {
-    set_last_error("chunk streaming (forward_chunk) is implemented for the conformer only");
+    set_last_error("chunk streaming (forward_chunk) is implemented for the conformer and deepspeech2 only");
     return PPASR_ERR_STATE;
   }
   if (!c->cfg.causal) {
@@ -906,6 +955,22 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
 int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_device, int32_t B, int32_t t,
                             int32_t required_cache_size, void* stream) {
   PPASR_REQUIRE(c && feats && B > 0 && t > 0, "bad arguments");
+  if (c->cfg.model_type == 2) {
+    // predict_chunk_deepspeech (inference_predictor.py:147-182): every row of the chunk is valid; states carry over
+    if (c->ds.state_B != B || !c->ds.h_state) {
+      int rc0 = ppasr_b200_stream_reset(c, B);
+      if (rc0) return rc0;
+    }
+    cudaStream_t st2 = reinterpret_cast<cudaStream_t>(stream);
+    int rc2 = build_plan_ds2(c, B, t);
+    if (rc2 != PPASR_OK) return rc2;
+    Plan& p2 = c->plan;
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(p2.feats, feats, (size_t)B * t * c->cfg.feat_dim * sizeof(float),
+                                     feats_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st2));
+    std::vector<int> vlen(B, p2.Tp);
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(p2.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st2));
+    return run_encoder_ds2(c, st2, true);
+  }
   auto& ss = c->ss;
   if (ss.B != B || !ss.kk) {
     int rc = ppasr_b200_stream_reset(c, B);
@@ -950,6 +1015,18 @@ int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats
   return PPASR_OK;
 }
 
+int ppasr_b200_ds2_states(ppasr_b200_ctx* c, float* h, float* cc, int32_t on_device, void* stream) {
+  PPASR_REQUIRE(c && c->cfg.model_type == 2, "deepspeech2 context required");
+  PPASR_REQUIRE(c->ds.h_state, "no stream state (call stream_reset / encode_chunk first)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)c->cfg.n_layers * c->ds.nd * c->ds.state_B * c->cfg.d_model * 4;
+  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (h) PPASR_CUDA_CHECK(cudaMemcpyAsync(h, c->ds.h_state, n, k, st));
+  if (cc) PPASR_CUDA_CHECK(cudaMemcpyAsync(cc, c->ds.c_state, n, k, st));
+  if (!on_device) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
+  return PPASR_OK;
+}
+
 int ppasr_b200_stream_info(ppasr_b200_ctx* c, int32_t* offset, int32_t* cache_t) {
   PPASR_REQUIRE(c, "null ctx");
   if (offset) *offset = c->ss.offset;
@@ -990,7 +1067,7 @@ static int run_ctc_logits(ppasr_b200_ctx* c, cudaStream_t st) {
   Plan& p = c->plan;
   EpiLogitsF32<BN_NARROW> e{p.logits, c->ctc_b, c->Vld, p.M, c->cfg.vocab_size};
   PROF(PC_CTC_LOGITS);
-  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, c->cfg.vocab_size, c->cfg.d_model, e, st)));
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, c->cfg.vocab_size, c->ctc_k ? c->ctc_k : c->cfg.d_model, e, st)));
   return PPASR_OK;
 }
 
@@ -1032,7 +1109,7 @@ int ppasr_b200_ctc_greedy(ppasr_b200_ctx* c, int32_t* ids, int32_t* out_lens, fl
   const int V = c->cfg.vocab_size;
   EpiCtcStats<BN_NARROW> e{p.pmax, p.parg, p.psum, c->ctc_b, p.M, V, c->ctc_parts};
   { PROF(PC_CTC_STATS);
-  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, V, c->cfg.d_model, e, st))); }
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, V, c->ctc_k ? c->ctc_k : c->cfg.d_model, e, st))); }
   { PROF(PC_CTC_FINALIZE);
   PPASR_CUDA_CHECK(launch_ctc_stats_finalize(p.pmax, p.parg, p.psum, c->ctc_parts, p.M, p.idx, p.maxp, st)); }
   PROF(PC_CTC_COLLAPSE);

@@ -16,7 +16,7 @@ class Config(ctypes.Structure):
                 ("n_heads", ctypes.c_int32), ("ffn_dim", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("conv_kernel", ctypes.c_int32), ("causal", ctypes.c_int32), ("conv_norm", ctypes.c_int32),
                 ("vocab_size", ctypes.c_int32), ("max_len", ctypes.c_int32), ("reduce_idx", ctypes.c_int32),
-                ("recover_idx", ctypes.c_int32), ("time_reduce_kernel", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2)]
+                ("recover_idx", ctypes.c_int32), ("time_reduce_kernel", ctypes.c_int32), ("use_gru", ctypes.c_int32), ("reserved", ctypes.c_int32 * 1)]
 
 
 def out_frames(T: int) -> int:
@@ -37,11 +37,23 @@ class ConformerEngine:
         torch.cuda.set_device(self.device)
         self.lib = L.load()
         c = Config()
-        squeeze = getattr(cfg, "model_type", "conformer") == "squeezeformer"
+        kind = getattr(cfg, "model_type", "conformer")
+        squeeze = kind == "squeezeformer"
+        c.reduce_idx = c.recover_idx = -1
+        if kind == "deepspeech2":
+            c.model_type = 2
+            c.feat_dim = cfg.input_dim
+            c.d_model = cfg.rnn_size
+            c.n_layers = cfg.num_rnn_layers
+            c.causal = int(cfg.streaming)
+            c.use_gru = int(cfg.use_gru)
+            c.vocab_size = cfg.vocab_size
+            c.max_len = 5000
+            self._create(c, weights)
+            return
         c.model_type = 1 if squeeze else 0
         c.feat_dim = cfg.input_dim
         c.d_model = cfg.encoder_dim if squeeze else cfg.output_size
-        c.reduce_idx = c.recover_idx = -1
         if squeeze:
             if cfg.output_size != cfg.encoder_dim:
                 raise L.PPASRB200Error("squeezeformer final_proj (output_size != encoder_dim) is not supported")
@@ -56,6 +68,9 @@ class ConformerEngine:
         c.conv_norm = 0 if cfg.cnn_module_norm == "layer_norm" else 1
         c.vocab_size = cfg.vocab_size
         c.max_len = cfg.max_len
+        self._create(c, weights)
+
+    def _create(self, c, weights):
         self._ctx = ctypes.c_void_p()
         L.check(self.lib.ppasr_b200_create(ctypes.byref(c), ctypes.byref(self._ctx)))
         for name, arr in weights.items():
@@ -98,6 +113,16 @@ class ConformerEngine:
         L.check(self.lib.ppasr_b200_encode(self._ctx, ptr, on_dev, lens_p, B, T, L.stream_ptr(stream)))
         self.B, self.Tp = B, out_frames(T)
         return self
+
+    def ds2_states(self):
+        """DeepSpeech2: (h, c) numpy [num_rnn_layers * num_directions, B, rnn_size] after the last encode_chunk."""
+        cfg = self.cfg
+        n = cfg.num_rnn_layers * cfg.num_directions
+        h = np.empty((n, self.B, cfg.rnn_size), dtype=np.float32)
+        c = np.empty_like(h)
+        L.check(self.lib.ppasr_b200_ds2_states(self._ctx, h.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p),
+                                               0, None))
+        return h, c
 
     # ---- chunk streaming -------------------------------------------------------------------------
     def stream_reset(self, B=1):

@@ -19,7 +19,7 @@ import numpy as np
 from .. import _lib as L
 from ..engine import ConformerEngine, out_frames
 from ..parallel import detokenize
-from ..weights import ConformerConfig, SqueezeformerConfig, load_npz, load_pdparams, read_mean_istd
+from ..weights import ConformerConfig, DeepSpeech2Config, SqueezeformerConfig, load_npz, load_pdparams, read_mean_istd
 
 
 def _get(obj, key, default=None):
@@ -45,8 +45,8 @@ class InferencePredictor:
                  device=0):
         if not use_gpu:
             raise Exception("ppasr_b200 only runs on a B200 GPU (use_gpu=False is not supported)")
-        if use_model not in ('conformer', 'squeezeformer'):
-            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 implements conformer and squeezeformer)')
+        if use_model not in ('conformer', 'squeezeformer', 'deepspeech2'):
+            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 implements conformer, squeezeformer and deepspeech2)')
         self.configs = configs
         self.use_model = use_model
         self.streaming = streaming
@@ -80,8 +80,13 @@ class InferencePredictor:
                 weights['encoder.global_cmvn.mean'] = mean
                 weights['encoder.global_cmvn.istd'] = istd
         if vocab_size is None:
-            vocab_size = int(weights['ctc.ctc_lo.weight'].shape[1])
-        if use_model == 'squeezeformer':
+            key = 'decoder.ctc_lo.weight' if use_model == 'deepspeech2' else 'ctc.ctc_lo.weight'
+            vocab_size = int(weights[key].shape[1])
+        if use_model == 'deepspeech2':
+            # configs/deepspeech2.yml encoder_conf (deepspeech2/encoder.py:8-16); streaming => forward-only RNN (model.py:40)
+            kw = {k: enc[k] for k in ('num_rnn_layers', 'rnn_size', 'use_gru') if k in enc}
+            self.model_config = DeepSpeech2Config(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        elif use_model == 'squeezeformer':
             # keys of configs/squeezeformer.yml encoder_conf (squeezeformer/encoder.py:24-53)
             allowed = ('encoder_dim', 'output_size', 'attention_heads', 'num_blocks', 'reduce_idx', 'recover_idx',
                        'feed_forward_expansion_factor', 'cnn_module_kernel', 'cnn_norm_type', 'adaptive_scale', 'max_len')
@@ -124,8 +129,20 @@ class InferencePredictor:
         return DecodePipeline(self, depth)
 
     def predict_chunk_deepspeech(self, x_chunk):
-        # inference_predictor.py:147-149
-        raise Exception(f'当前模型不支持该方法，当前模型为：{self.use_model}')
+        """inference_predictor.py:147-182: x_chunk f32 [B, t, n_mels] -> (probs f32 [B, t', V], lens i64 [B]). The LSTM /
+        GRU states (zero at the start of a stream, :157-164) stay on the device; `output_state_h` / `output_state_c`
+        mirror them as NumPy [num_rnn_layers, B, rnn_size] after every call like the reference attributes."""
+        if not (self.use_model == 'deepspeech2' and self.streaming):
+            raise Exception(f'当前模型不支持该方法，当前模型为：{self.use_model}')
+        x_chunk = np.ascontiguousarray(x_chunk, dtype=np.float32)
+        if self.output_state_h is None or self._stream_batch != x_chunk.shape[0]:
+            self.engine.stream_reset(x_chunk.shape[0])
+            self._stream_active, self._stream_batch = True, x_chunk.shape[0]
+        self.engine.encode_chunk(x_chunk)
+        output_chunk_probs = self.engine.ctc_probs(to_host=True)
+        self.output_state_h, self.output_state_c = self.engine.ds2_states()
+        output_lens = np.full([x_chunk.shape[0]], output_chunk_probs.shape[1], dtype=np.int64)
+        return output_chunk_probs, output_lens
 
     def predict_chunk_conformer(self, x_chunk, required_cache_size):
         """inference_predictor.py:184-212: x_chunk f32 [1, <=67, n_mels] -> probs f32 [1, chunk, V]; advances

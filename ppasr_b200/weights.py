@@ -264,6 +264,83 @@ def init_squeezeformer_weights(cfg: SqueezeformerConfig, seed: int = 1000, ctc_g
     return w
 
 
+class DeepSpeech2Config:
+    """configs/deepspeech2.yml `encoder_conf` + the streaming switch (deepspeech2/model.py:40: 'forward' LSTM when streaming,
+    'bidirect' otherwise)."""
+    model_type = "deepspeech2"
+
+    def __init__(self, input_dim=80, vocab_size=4233, num_rnn_layers=5, rnn_size=1024, use_gru=False, streaming=False,
+                 **_ignored):
+        self.input_dim = int(input_dim)
+        self.vocab_size = int(vocab_size)
+        self.num_rnn_layers = int(num_rnn_layers)
+        self.rnn_size = int(rnn_size)
+        self.use_gru = bool(use_gru)
+        self.streaming = bool(streaming)
+        self.num_directions = 1 if streaming else 2
+
+    def to_dict(self):
+        return dict(input_dim=self.input_dim, vocab_size=self.vocab_size, num_rnn_layers=self.num_rnn_layers,
+                    rnn_size=self.rnn_size, use_gru=self.use_gru, streaming=self.streaming)
+
+
+def deepspeech2_param_shapes(cfg: DeepSpeech2Config) -> Dict[str, tuple]:
+    """deepspeech2/conv.py:8-12, encoder.py:29-55, model.py:36-44 (the CTC module is named `decoder`); RNN parameters use
+    paddle.nn.LSTM/GRU's flat names weight_ih_l0 / weight_hh_l0 / bias_ih_l0 / bias_hh_l0 (+ `_reverse`)."""
+    F, V, H = cfg.input_dim, cfg.vocab_size, cfg.rnn_size
+    f2 = ((F - 1) // 2 - 1) // 2
+    G = 3 if cfg.use_gru else 4
+    nd = cfg.num_directions
+    s = {
+        "encoder.global_cmvn.mean": (F,), "encoder.global_cmvn.istd": (F,),
+        "encoder.conv.conv.0.weight": (32, 1, 3, 3), "encoder.conv.conv.0.bias": (32,),
+        "encoder.conv.conv.2.weight": (32, 32, 3, 3), "encoder.conv.conv.2.bias": (32,),
+        "decoder.ctc_lo.weight": (H * nd, V), "decoder.ctc_lo.bias": (V,),
+    }
+    for i in range(cfg.num_rnn_layers):
+        isz = 32 * f2 if i == 0 else H * nd
+        for suf in ([""] if nd == 1 else ["", "_reverse"]):
+            s[f"encoder.rnn.{i}.weight_ih_l0{suf}"] = (G * H, isz)
+            s[f"encoder.rnn.{i}.weight_hh_l0{suf}"] = (G * H, H)
+            s[f"encoder.rnn.{i}.bias_ih_l0{suf}"] = (G * H,)
+            s[f"encoder.rnn.{i}.bias_hh_l0{suf}"] = (G * H,)
+        s[f"encoder.layernorm_list.{i}.weight"] = (H * nd,)
+        s[f"encoder.layernorm_list.{i}.bias"] = (H * nd,)
+    return s
+
+
+def init_deepspeech2_weights(cfg: DeepSpeech2Config, seed: int = 1000, ctc_gain: float = 8.0,
+                             perturb_norms: bool = True) -> Dict[str, np.ndarray]:
+    """Seeded synthetic parameters: RNN weights/biases U(+-1/sqrt(H)) (paddle.nn.LSTM default), conv Kaiming-uniform."""
+    rng = np.random.RandomState(seed)
+    w = {}
+    H = cfg.rnn_size
+    for name, shape in deepspeech2_param_shapes(cfg).items():
+        leaf = name.split(".")[-1]
+        if name.endswith("global_cmvn.mean"):
+            a = rng.uniform(-1.0, 1.0, shape) + 10.0
+        elif name.endswith("global_cmvn.istd"):
+            a = rng.uniform(0.2, 0.5, shape)
+        elif "layernorm_list" in name and leaf == "weight":
+            a = rng.uniform(0.8, 1.2, shape) if perturb_norms else np.ones(shape)
+        elif "layernorm_list" in name and leaf == "bias":
+            a = rng.uniform(-0.1, 0.1, shape) if perturb_norms else np.zeros(shape)
+        elif ".rnn." in name:
+            lim = 1.0 / math.sqrt(H)
+            a = rng.uniform(-lim, lim, shape)
+        elif name.startswith("decoder.ctc_lo"):
+            if leaf == "weight":
+                lim = math.sqrt(6.0 / (shape[0] + shape[1])) * ctc_gain
+                a = rng.uniform(-lim, lim, shape)
+            else:
+                a = np.zeros(shape)
+        else:
+            lim = 1.0 / math.sqrt(_fan_in(name, shape))
+            a = rng.uniform(-lim, lim, shape)
+        w[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return w
+
+
 def save_npz(path: str, weights: Dict[str, np.ndarray], cfg: ConformerConfig = None):
     extra = {}
     if cfg is not None:

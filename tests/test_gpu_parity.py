@@ -551,3 +551,73 @@ def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
     torch.cuda.synchronize()
     eng.close()
     assert torch.equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# DeepSpeech2 (deepspeech2/encoder.py:61-104): conv -> {bi-}LSTM / GRU + LayerNorm x N -> CTC
+# ------------------------------------------------------------------------------------------------
+def _run_ds2(cuda, nl, H, B, T, lens, streaming=False, gru=False, vocab=300):
+    from oracle.deepspeech2_oracle import DeepSpeech2Conf, DeepSpeech2Oracle
+    from oracle import decoders_oracle as DO
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200.weights import DeepSpeech2Config, init_deepspeech2_weights, synthetic_fbank
+    cfg = DeepSpeech2Config(num_rnn_layers=nl, rnn_size=H, vocab_size=vocab, streaming=streaming, use_gru=gru)
+    w = init_deepspeech2_weights(cfg)
+    feats = synthetic_fbank(B, T)
+    for b in range(B):
+        feats[b, lens[b]:] = 0
+    eng = ConformerEngine(cfg, w)
+    eng.encode(torch.from_numpy(feats).to(cuda), lens)
+    logits = eng.ctc_logits().float().cpu()
+    probs = eng.ctc_probs().cpu().numpy()
+    ids, ol, sc = eng.ctc_greedy(to_host=True)
+    ref = DeepSpeech2Oracle(DeepSpeech2Conf(**cfg.to_dict()), w).get_encoder_out(
+        torch.from_numpy(feats), torch.tensor(lens), return_logits=True)
+    rel = ((logits - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 1e-2, f"logits rel err {rel}"
+    for b in range(B):  # fused head == reference greedy on the materialised posterior (bit-exact ids)
+        _, coll, _ = DO.greedy_ids(probs[b])
+        assert ids[b, :ol[b]].tolist() == coll
+    eng.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nl=1, H=128, B=2, T=131, lens=[131, 90]),                       # bidirectional LSTM, ragged
+    dict(nl=2, H=256, B=3, T=203, lens=[203, 150, 99], streaming=True),  # forward LSTM
+    dict(nl=2, H=256, B=3, T=203, lens=[203, 150, 99], gru=True),        # bidirectional GRU
+    dict(nl=2, H=128, B=11, T=131, lens=[131] * 5 + [100] * 6),          # batch > one shared-memory tile of 8
+    dict(nl=1, H=64, B=1, T=7, lens=[7]),                                # one output frame
+])
+def test_deepspeech2_matches_oracle_small(lib, cuda, kw):
+    _run_ds2(cuda, **kw)
+
+
+def test_deepspeech2_matches_oracle_full_size(lib, cuda):
+    """configs/deepspeech2.yml (5 x bi-LSTM 1024, V=4233) on BASELINE configs[0]: one 5 s utterance."""
+    _run_ds2(cuda, 5, 1024, 1, 498, [498], vocab=4233)
+
+
+def test_deepspeech2_chunk_streaming(lib, cuda):
+    """predict_chunk_deepspeech (inference_predictor.py:147-182): chunk-by-chunk with carried states == the oracle's
+    get_encoder_out_chunk chain; returned state arrays have the reference shape."""
+    from oracle.deepspeech2_oracle import DeepSpeech2Conf, DeepSpeech2Oracle
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.weights import DeepSpeech2Config, init_deepspeech2_weights, synthetic_fbank
+    cfg = DeepSpeech2Config(num_rnn_layers=2, rnn_size=256, vocab_size=120, streaming=True)
+    w = init_deepspeech2_weights(cfg)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "deepspeech2",
+                              streaming=True, weights=w)
+    o = DeepSpeech2Oracle(DeepSpeech2Conf(**cfg.to_dict()), w)
+    x = synthetic_fbank(2, 67 + 64 * 2)
+    h = c = None
+    for s in range(0, x.shape[1] - 66, 64):
+        ch = x[:, s:s + 67]
+        probs, lens = pred.predict_chunk_deepspeech(ch)
+        ref, rl, h, c = o.get_encoder_out_chunk(torch.from_numpy(ch), torch.tensor([67, 67]), h, c)
+        assert probs.shape == tuple(ref.shape) and lens.tolist() == rl.tolist()
+        assert np.abs(probs - ref.numpy()).max() < 2e-2
+        assert pred.output_state_h.shape == (2, 2, 256)
+        assert np.abs(pred.output_state_h - h.numpy()).max() < 2e-2 and np.abs(pred.output_state_c - c.numpy()).max() < 5e-2
+    pred.reset_stream()
+    with pytest.raises(Exception):
+        pred.predict_chunk_conformer(x[:1, :67], -1)

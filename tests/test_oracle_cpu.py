@@ -234,3 +234,53 @@ def test_squeezeformer_oracle_identity_ada_and_no_reduction_is_plain_postnorm():
     a = SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w2).get_encoder_out(x, lens, return_logits=True)
     b = SqueezeformerOracle(conf_off, w).get_encoder_out(x, lens, return_logits=True)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# DeepSpeech2 oracle: the restated paddle.nn.LSTM / GRU equations == torch.nn.LSTM / GRU on packed sequences
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("streaming,gru", [(False, False), (True, False), (False, True)])
+def test_deepspeech2_oracle_rnn_matches_torch_nn(streaming, gru):
+    from oracle.deepspeech2_oracle import DeepSpeech2Conf, DeepSpeech2Oracle
+    from ppasr_b200.weights import DeepSpeech2Config, init_deepspeech2_weights
+    cfg = DeepSpeech2Config(num_rnn_layers=1, rnn_size=64, vocab_size=30, streaming=streaming, use_gru=gru)
+    w = init_deepspeech2_weights(cfg)
+    o = DeepSpeech2Oracle(DeepSpeech2Conf(**cfg.to_dict()), w)
+    x = torch.from_numpy(synthetic_fbank(3, 131))
+    lens = torch.tensor([131, 100, 60])
+    xs = (x - o.w["encoder.global_cmvn.mean"]) * o.w["encoder.global_cmvn.istd"]
+    c1, l1 = o.conv(xs, lens)
+    assert c1.shape == (3, 32, 32 * 19) and l1.tolist() == [32, 24, 14]
+    nd = cfg.num_directions
+    mod = (torch.nn.GRU if gru else torch.nn.LSTM)(c1.shape[-1], 64, batch_first=True, bidirectional=nd == 2)
+    sd = {}
+    for suf in ([""] if nd == 1 else ["", "_reverse"]):
+        for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            sd[f"{n}_l0{suf}"] = o.w[f"encoder.rnn.0.{n}_l0{suf}"]
+    mod.load_state_dict(sd)
+    pk = torch.nn.utils.rnn.pack_padded_sequence(c1, l1, batch_first=True, enforce_sorted=False)
+    with torch.no_grad():
+        out, st = mod(pk)
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=c1.shape[1])
+    outs, hs = [], []
+    for d in range(nd):
+        oo, hh, _ = o.run_direction("encoder.rnn.0", "_reverse" if d else "", c1, l1, None, None, d == 1)
+        outs.append(oo)
+        hs.append(hh)
+    assert (torch.cat(outs, -1) - out).abs().max() < 1e-5
+    h_n = st if gru else st[0]
+    assert (torch.stack(hs, 0) - h_n).abs().max() < 1e-5
+
+
+def test_deepspeech2_oracle_chunked_equals_offline_forward():
+    """Forward (streaming) model: feeding the subsampled sequence in two chunks with carried states == one pass."""
+    from oracle.deepspeech2_oracle import DeepSpeech2Conf, DeepSpeech2Oracle
+    from ppasr_b200.weights import DeepSpeech2Config, init_deepspeech2_weights
+    cfg = DeepSpeech2Config(num_rnn_layers=2, rnn_size=64, vocab_size=30, streaming=True)
+    w = init_deepspeech2_weights(cfg)
+    o = DeepSpeech2Oracle(DeepSpeech2Conf(**cfg.to_dict()), w)
+    x = torch.from_numpy(synthetic_fbank(1, 67 + 64))
+    full = o.get_encoder_out(x, torch.tensor([131]), return_logits=True)
+    a, _, h, c = o.get_encoder_out_chunk(x[:, :67], torch.tensor([67]), None, None, return_logits=True)
+    b, _, _, _ = o.get_encoder_out_chunk(x[:, 64:131], torch.tensor([67]), h, c, return_logits=True)
+    assert (torch.cat([a, b], 1) - full).abs().max() < 1e-4
