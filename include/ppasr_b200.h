@@ -25,7 +25,7 @@ typedef struct ppasr_b200_ctx ppasr_b200_ctx;
 /* Model hyper-parameters = the inference-relevant keys of configs/conformer.yml / configs/squeezeformer.yml
  * (encoder_conf, streaming, preprocess_conf.n_mels) plus the vocabulary size. */
 typedef struct ppasr_b200_config {
-  int32_t model_type;      /* 0 = conformer, 1 = squeezeformer, 2 = deepspeech2 */
+  int32_t model_type;      /* 0 = conformer, 1 = squeezeformer, 2 = deepspeech2, 3 = efficient_conformer */
   int32_t feat_dim;        /* preprocess_conf.n_mels, 80 */
   int32_t d_model;         /* encoder_conf.output_size (squeezeformer: encoder_dim), 256; deepspeech2: rnn_size (<= 1024) */
   int32_t n_heads;         /* encoder_conf.attention_heads, 4 (d_model / n_heads must be 64) */
@@ -42,6 +42,12 @@ typedef struct ppasr_b200_config {
   int32_t recover_idx;         /* block before which the sequence is recovered to full length (11), -1 = none */
   int32_t time_reduce_kernel;  /* 1 = TimeReductionLayerStream (streaming), 5 = TimeReductionLayer1D */
   int32_t use_gru;             /* deepspeech2 only: encoder_conf.use_gru (GRU instead of LSTM, deepspeech2/encoder.py:41-53) */
+  /* efficient_conformer only (efficient_conformer/encoder.py:49-54; the constructor defaults 3 / 0..3 / 3 / True apply to
+   * the shipped config because its `efficient_conf` block is swallowed by **kwargs) */
+  int32_t stride_layer_idx;    /* block whose depthwise conv has stride 2 (3), -1 = none */
+  int32_t group_layer_mask;    /* bit l set: block l uses GroupedRelPositionMultiHeadedAttention (0b1111) */
+  int32_t group_size;          /* 3 */
+  int32_t stride_kernel;       /* 1: depthwise kernel 15 -> 7 after the stride block */
   int32_t reserved[1];
 } ppasr_b200_config;
 
@@ -77,7 +83,8 @@ int ppasr_b200_finalize(ppasr_b200_ctx* ctx);
  * (NULL = all T). Leaves the encoder output in the context for the ctc_* calls below. */
 int ppasr_b200_encode(ppasr_b200_ctx* ctx, const float* feats, int32_t feats_on_device, const int64_t* lens_host,
                       int32_t B, int32_t T, void* stream);
-/* T' = ((T-1)/2 - 1)/2 : output frames for T input frames (conformer/subsampling.py:96-115). */
+/* T' = ((T-1)/2 - 1)/2 : output frames for T input frames (conformer/subsampling.py:96-115); efficient_conformer with a
+ * stride block: ceil(T'/2) (efficient_conformer/encoder.py:255-260). */
 int ppasr_b200_out_frames(const ppasr_b200_ctx* ctx, int32_t T);
 
 /* replaces: CTCLoss.softmax (model_utils/loss/ctc.py:62-70) + copy_to_cpu

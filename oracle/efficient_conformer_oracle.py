@@ -1,0 +1,158 @@
+"""CPU oracle for the Efficient-Conformer hot path (TEST INFRASTRUCTURE ONLY -- see oracle/conformer_oracle.py header).
+
+PyTorch-CPU restatement of ppasr/model_utils/efficient_conformer/ (paths relative to /root/reference, yeyupiaoling/PPASR
+@ c8bb3b96): Conv2dSubsampling4 -> 12 pre-norm macaron blocks (conformer/encoder.py:346-431) where
+  * blocks in group_layer_idx use GroupedRelPositionMultiHeadedAttention (attention.py:40-79,128-193: q/k/v/p padded to
+    a multiple of group_size frames and re-viewed as T/3 tokens of 4 x 192 features, scale 1/sqrt(192), mask [::3, ::3],
+    linear_pos WITH bias),
+  * block stride_layer_idx is a StrideConformerEncoderLayer (encoder.py:455-548): its depthwise conv has stride 2 and the
+    residual goes through AvgPool1D(k2, s2, ceil_mode) (encoder.py:171-172,523-526); afterwards masks / pos_emb are
+    strided (encoder.py:255-260) and the conv kernel shrinks 15 -> 7 (encoder.py:123-128),
+-> after_norm -> CTC. `efficient_conf` in configs/efficient_conformer.yml is swallowed by **kwargs (encoder.py:55), so the
+constructor defaults (stride_layer_idx 3, stride 2, group_layer_idx 0..3, group_size 3, stride_kernel True) apply.
+
+PARITY STATUS: **unpinned** (no Paddle here, no reference tests); self-consistency checks in tests/test_oracle_cpu.py.
+"""
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle.conformer_oracle import (ConformerConf, ConformerOracle, add_optional_chunk_mask, layer_norm, linear,
+                                     make_non_pad_mask, swish)
+
+
+class EfficientConformerConf(ConformerConf):
+    def __init__(self, stride_layer_idx=3, stride=2, group_layer_idx=(0, 1, 2, 3), group_size=3, stride_kernel=True, **kw):
+        super().__init__(**kw)
+        self.stride_layer_idx = stride_layer_idx
+        self.stride = stride
+        self.group_layer_idx = tuple(group_layer_idx)
+        self.group_size = group_size
+        self.stride_kernel = stride_kernel
+        # encoder.py:123-128
+        k0 = self.cnn_module_kernel
+        self.cnn_module_kernels = [k0, (k0 // stride) if stride_kernel else k0]
+
+
+class EfficientConformerOracle(ConformerOracle):
+    def layer_kernel(self, i):
+        conf = self.conf
+        return conf.cnn_module_kernels[1 if (conf.stride_layer_idx is not None and i > conf.stride_layer_idx) else 0]
+
+    # -- efficient_conformer/attention.py:128-193 (+ pad4group :40-79, forward_attention :81-126) -----------------
+    def grouped_mha(self, prefix, x, mask, pos_emb):
+        w = self.w
+        H = self.conf.attention_heads
+        D = self.conf.output_size
+        dk = D // H
+        gs = self.conf.group_size
+        B = x.shape[0]
+        q = linear(x, w[prefix + ".linear_q.weight"], w[prefix + ".linear_q.bias"])
+        k = linear(x, w[prefix + ".linear_k.weight"], w[prefix + ".linear_k.bias"])
+        v = linear(x, w[prefix + ".linear_v.weight"], w[prefix + ".linear_v.bias"])
+        p = linear(pos_emb, w[prefix + ".linear_pos.weight"], w[prefix + ".linear_pos.bias"])  # (1, T2, D)
+        T = q.shape[1]
+        pad = (gs - T % gs) % gs
+        # (B,T,D) == (B,T,H,dk) flattened: padding frames and re-viewing as (B, T/gs, H, dk*gs) is a plain reshape
+        qg = F.pad(q, (0, 0, 0, pad)).reshape(B, -1, H, dk * gs).transpose(1, 2)
+        kg = F.pad(k, (0, 0, 0, pad)).reshape(B, -1, H, dk * gs).transpose(1, 2)
+        vg = F.pad(v, (0, 0, 0, pad)).reshape(B, -1, H, dk * gs).transpose(1, 2)
+        padp = (gs - p.shape[1] % gs) % gs
+        pg = F.pad(p, (0, 0, 0, padp)).reshape(p.shape[0], -1, H, dk * gs).transpose(1, 2)
+        if mask is not None and mask.shape[2] > 0:
+            mask = mask[:, ::gs, ::gs]
+        q_u = qg + w[prefix + ".pos_bias_u"].unsqueeze(1)  # (B,H,Tg,192) + (H,1,192)
+        q_v = qg + w[prefix + ".pos_bias_v"].unsqueeze(1)
+        scores = (q_u @ kg.transpose(-2, -1) + q_v @ pg.transpose(-2, -1)) / math.sqrt(dk * gs)
+        if mask is not None and mask.shape[2] > 0:
+            m = mask.unsqueeze(1).eq(0)[:, :, :, :scores.shape[-1]]
+            scores = scores.masked_fill(m, -float("inf"))
+            attn = torch.softmax(scores, dim=-1).masked_fill(m, 0.0)
+        else:
+            attn = torch.softmax(scores, dim=-1)
+        o = (attn @ vg).transpose(1, 2).reshape(B, -1, D)
+        o = o[:, :o.shape[1] - pad]
+        return linear(o, w[prefix + ".linear_out.weight"], w[prefix + ".linear_out.bias"])
+
+    # plain rel-pos MHA of the later blocks: conformer attention (linear_pos without bias, conformer/attention.py:192)
+    # -- efficient_conformer/convolution.py:80-138 ---------------------------------------------------------------------
+    def eff_conv_module(self, prefix, x, mask_pad, K, stride):
+        w = self.w
+        conf = self.conf
+        lorder = K - 1 if conf.causal else 0
+        x = x.transpose(1, 2)
+        x = x.masked_fill(~mask_pad, 0.0)
+        if lorder > 0:
+            x = F.pad(x, (lorder, 0), "constant", 0.0)
+        x = F.conv1d(x, w[prefix + ".pointwise_conv1.weight"], w[prefix + ".pointwise_conv1.bias"])
+        x = F.glu(x, dim=1)
+        pad = 0 if conf.causal else (K - 1) // 2
+        x = F.conv1d(x, w[prefix + ".depthwise_conv.weight"], w[prefix + ".depthwise_conv.bias"], stride=stride, padding=pad,
+                     groups=x.shape[1])
+        if conf.cnn_module_norm == "layer_norm":
+            x = layer_norm(x.transpose(1, 2), w[prefix + ".norm.weight"], w[prefix + ".norm.bias"]).transpose(1, 2)
+        else:
+            x = F.batch_norm(x, w[prefix + ".norm._mean"], w[prefix + ".norm._variance"], w[prefix + ".norm.weight"],
+                             w[prefix + ".norm.bias"], training=False, eps=1e-5)
+        x = swish(x)
+        x = F.conv1d(x, w[prefix + ".pointwise_conv2.weight"], w[prefix + ".pointwise_conv2.bias"])
+        if mask_pad.shape[2] != x.shape[2]:
+            mask_pad = mask_pad[:, :, ::stride]
+        x = x.masked_fill(~mask_pad, 0.0)
+        return x.transpose(1, 2)
+
+    # -- conformer/encoder.py:346-431 and efficient_conformer/encoder.py:455-548 ----------------------------------------
+    def eff_layer(self, i, x, mask, pos_emb, mask_pad):
+        w = self.w
+        conf = self.conf
+        p = f"encoder.encoders.{i}"
+
+        def ln(name, t):
+            return layer_norm(t, w[f"{p}.{name}.weight"], w[f"{p}.{name}.bias"])
+
+        x = x + 0.5 * self.ffn(p + ".feed_forward_macaron", ln("norm_ff_macaron", x))
+        if i in conf.group_layer_idx:
+            x = x + self.grouped_mha(p + ".self_attn", ln("norm_mha", x), mask, pos_emb)
+        else:
+            x = x + self.rel_mha(p + ".self_attn", ln("norm_mha", x), mask, pos_emb, None)[0]
+        strided = conf.stride_layer_idx is not None and i == conf.stride_layer_idx
+        residual = x
+        xc = self.eff_conv_module(p + ".conv_module", ln("norm_conv", x), mask_pad, self.layer_kernel(i),
+                                  conf.stride if strided else 1)
+        if strided:  # AvgPool1D(kernel 2, stride 2, ceil_mode=True, exclusive) on the residual
+            residual = F.avg_pool1d(residual.transpose(1, 2), conf.stride, conf.stride, 0, ceil_mode=True,
+                                    count_include_pad=False).transpose(1, 2)
+        x = residual + xc
+        x = x + 0.5 * self.ffn(p + ".feed_forward", ln("norm_ff", x))
+        return ln("norm_final", x)
+
+    # -- efficient_conformer/encoder.py:212-264 ------------------------------------------------------------------------------
+    def encoder_forward(self, xs, xs_lens, decoding_chunk_size=-1, num_decoding_left_chunks=-1):
+        conf = self.conf
+        xs = xs.to(self.dtype)
+        T = xs.shape[1]
+        masks = make_non_pad_mask(xs_lens)
+        if masks.shape[1] < T:
+            masks = F.pad(masks, (0, T - masks.shape[1]), value=False)
+        masks = masks.unsqueeze(1)
+        xs = self.global_cmvn(xs)
+        xs, pos_emb, masks = self.embed(xs, masks, offset=0)
+        mask_pad = masks
+        chunk_masks = add_optional_chunk_mask(xs, masks, conf.use_dynamic_chunk, decoding_chunk_size, 0,
+                                              num_decoding_left_chunks)
+        for i in range(conf.num_blocks):
+            xs = self.eff_layer(i, xs, chunk_masks, pos_emb, mask_pad)
+            if conf.stride_layer_idx is not None and i == conf.stride_layer_idx:
+                s = conf.stride
+                masks = masks[:, :, ::s]
+                chunk_masks = chunk_masks[:, ::s, ::s]
+                mask_pad = masks
+                pos_emb = pos_emb[:, ::s, :]
+        xs = layer_norm(xs, self.w["encoder.after_norm.weight"], self.w["encoder.after_norm.bias"])
+        return xs, masks
+
+    def encoder_forward_chunk(self, *a, **k):
+        raise NotImplementedError("Efficient-Conformer forward_chunk (encoder.py:266-394) is not restated yet")

@@ -523,6 +523,85 @@ struct EpiQKV {
   }
 };
 
+// Fused QKV projection epilogue for GroupedRelPositionMultiHeadedAttention (reference:
+// ppasr/model_utils/efficient_conformer/attention.py:40-79,128-193; group size 3, H heads of 64).
+// pad4group views the zero-padded (B, Tpad, H*64) q / k / v tensors as (B, Tpad/3, H, 192): with
+//   i = (t % 3) * 256 + column,  g = t / 3,  h' = i / 192,  d' = i % 192
+//   q2g[b,h',g, d'] = q + pos_bias_u[h'][d'],  q2g[b,h',g,192+d'] = q + pos_bias_v[h'][d']     (bf16)
+//   kkg[b,h',g, d'] = k ;  vtg[b,h',d',g] = v (transposed: K-major B operand of P.V)
+// The thread that owns the last frame of an utterance also writes the zero-padded frames t = T .. 3*Tg-1
+// (q = 0 -> bias only, k = v = 0).
+template <int BLOCK_N>
+struct EpiQKVGrouped {
+  __nv_bfloat16* q2g;   // [B*H*Tg, 384]
+  __nv_bfloat16* kkg;   // [B*H*Tg, 192]
+  __nv_bfloat16* vtg;   // [B*H*192, Tgp]
+  const float* bias;    // [3D]
+  const float* bias_u;  // [H*192]
+  const float* bias_v;  // [H*192]
+  int M, T, H, Tg, Tgp;
+  DEVINL void put(int b, int t, int which, int c0, const float (&v)[32]) const {
+    const int i0 = (t % 3) * 256 + c0;
+    const int g = t / 3;
+    const int hp = i0 / 192;
+    const int dp = i0 - hp * 192;
+    const size_t bh = (size_t)b * H + hp;
+    if (which == 0) {
+      __nv_bfloat16* dst = q2g + (bh * Tg + g) * 384 + dp;
+      uint32_t pu[16], pv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 u = __ldg(reinterpret_cast<const float2*>(bias_u + hp * 192 + dp) + j);
+        const float2 w = __ldg(reinterpret_cast<const float2*>(bias_v + hp * 192 + dp) + j);
+        pu[j] = pack_bf16x2(v[2 * j] + u.x, v[2 * j + 1] + u.y);
+        pv[j] = pack_bf16x2(v[2 * j] + w.x, v[2 * j + 1] + w.y);
+      }
+      uint4* du = reinterpret_cast<uint4*>(dst);
+      uint4* dv = reinterpret_cast<uint4*>(dst + 192);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        du[j] = make_uint4(pu[4 * j], pu[4 * j + 1], pu[4 * j + 2], pu[4 * j + 3]);
+        dv[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+      }
+    } else if (which == 1) {
+      __nv_bfloat16* dst = kkg + (bh * Tg + g) * 192 + dp;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      uint4* dk = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dk[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    } else {
+      __nv_bfloat16* dst = vtg + (bh * 192 + dp) * Tgp + g;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[(size_t)j * Tgp] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
+    const int D = H * 64;
+    int b = 0, t = 0;
+    if (row < M) {
+      b = row / T;
+      t = row - b * T;
+    }
+    epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
+      const int col = n0 + cc;
+      if (row >= M || col >= 3 * D) return;
+      const int which = col / D;
+      const int c0 = col - which * D;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sbias[cc + j];
+      put(b, t, which, c0, v);
+      if (t == T - 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int tp = T; tp < 3 * Tg; ++tp) put(b, tp, which, c0, v);
+      }
+    });
+  }
+};
+
 // Second subsampling conv: rows are the padded raster R = (b*Th + t')*pitch + f'; valid rows are
 // written compactly as out[((b*Tout + t')*Fout + f'), n] = relu(acc + bias[n]) in bf16.
 template <int BLOCK_N>

@@ -120,4 +120,22 @@ struct AttnParams {
 cudaError_t launch_rel_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_p,
                                  const CUtensorMap& tm_vt, const AttnParams& p, cudaStream_t st);
 
+
+// Grouped rel-pos attention of the Efficient Conformer (grouped_attention.cu)
+struct GroupedAttnParams {
+  int B, H;
+  int T;    // frames per utterance
+  int Tg;   // groups per utterance = ceil(T / 3) (queries == keys)
+  const int* klens;     // per-utterance valid frame count (nullable)
+  __nv_bfloat16* out;   // [B*T, 256]
+};
+cudaError_t launch_grouped_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_p,
+                                     const CUtensorMap& tm_vt, const GroupedAttnParams& p, cudaStream_t st);
+cudaError_t launch_grouped_pos(const __nv_bfloat16* tab, int ldtab, int col0, int T, int Tpad, __nv_bfloat16* out,
+                               cudaStream_t st);
+cudaError_t launch_dwconv_stride(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
+                                 const float* ng, const float* nb, int layer_norm, __nv_bfloat16* z, int B, int T, int Tout,
+                                 int C, int K, int lpad, int stride, float eps, const int* zero_lens, cudaStream_t st);
+cudaError_t launch_avgpool2(const float* x, float* out, int B, int T, int Tout, int C, cudaStream_t st);
+
 }  // namespace ppasr

@@ -65,7 +65,7 @@ extern "C" {
 
 const char* ppasr_b200_last_error(void) { return get_last_error(); }
 
-int ppasr_b200_abi_version(void) { return 1; }
+int ppasr_b200_abi_version(void) { return 2; }
 
 int64_t ppasr_b200_launch_count(void) { return (int64_t)launch_count(); }
 

@@ -80,7 +80,14 @@ struct Plan {  // everything that depends on (B, T)
   int* vlen = nullptr;
   __nv_bfloat16 *phase = nullptr, *c2 = nullptr, *y = nullptr, *h = nullptr, *q2 = nullptr, *kk = nullptr,
                 *vt = nullptr, *att = nullptr, *g = nullptr, *z = nullptr;
-  float *x2 = nullptr;  // Squeezeformer: time-reduced residual stream [B*ceil(Tp/2), D]
+  // view of the encoder output the CTC head reads (== M / Tp / vlen unless the model changes the frame rate)
+  int Mc = 0, Tc = 0;
+  int* vc = nullptr;
+  // Efficient Conformer grouped attention operands
+  int Tg = 0, Tgp = 0;
+  __nv_bfloat16 *q2g = nullptr, *kkg = nullptr, *vtg = nullptr, *pg = nullptr;
+  CUtensorMap tm_qg, tm_kg, tm_vtg, tm_pg[4];
+  float *x2 = nullptr;  // Squeezeformer / Efficient Conformer: half-rate residual stream [B*ceil(Tp/2), D]
   int* vlen2 = nullptr; // ... and its valid lengths
   float *x = nullptr, *logits = nullptr, *pmax = nullptr, *psum = nullptr, *maxp = nullptr, *score = nullptr,
         *probs = nullptr;
@@ -150,6 +157,11 @@ struct ppasr_b200_ctx {
     int state_B = 0;
   } ds;
   int ctc_k = 0;  // input features of the CTC projection (0 = d_model)
+  // ---- Efficient Conformer (model_type 3; efficient_conformer/encoder.py) ----
+  int eff_stride_idx = -1;      // block with the strided depthwise conv (-1: none)
+  unsigned eff_group_mask = 0;  // bit l: block l uses grouped attention
+  std::vector<int> layer_k;     // depthwise kernel size per block
+  CUtensorMap tm_pos2;          // every second row of the positional table (pos_emb[:, ::2])
   Plan plan;
   int sms = 148;
   // ---- streaming state (reference: inference_predictor.py:35-39,215-220; device resident here) ----
@@ -260,7 +272,8 @@ extern "C" {
 
 int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   PPASR_REQUIRE(cfg && out, "null pointer");
-  PPASR_REQUIRE(cfg->model_type >= 0 && cfg->model_type <= 2, "model_type must be 0 (conformer), 1 (squeezeformer) or 2 (deepspeech2)");
+  PPASR_REQUIRE(cfg->model_type >= 0 && cfg->model_type <= 3,
+                "model_type must be 0 (conformer), 1 (squeezeformer), 2 (deepspeech2) or 3 (efficient_conformer)");
   PPASR_REQUIRE(cfg->feat_dim >= 7 && cfg->vocab_size > 1 && cfg->n_layers > 0, "bad config");
   if (cfg->model_type == 2) {
     PPASR_REQUIRE(cfg->d_model >= 64 && cfg->d_model <= 1024 && cfg->d_model % 64 == 0,
@@ -278,8 +291,28 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
                   "squeezeformer: need 0 <= reduce_idx < recover_idx < num_blocks (or neither)");
     PPASR_REQUIRE(cfg->time_reduce_kernel == 1 || cfg->time_reduce_kernel == 5, "time_reduce_kernel must be 1 (stream) or 5 (conv1d)");
   }
+  if (cfg->model_type == 3) {
+    PPASR_REQUIRE(cfg->group_size == 3, "efficient_conformer: group_size must be 3");
+    PPASR_REQUIRE(cfg->stride_layer_idx >= -1 && cfg->stride_layer_idx < cfg->n_layers, "bad stride_layer_idx");
+    PPASR_REQUIRE(cfg->n_layers <= 32, "at most 32 blocks");
+    for (int l = 0; l < cfg->n_layers; ++l)
+      if ((cfg->group_layer_mask >> l) & 1)
+        PPASR_REQUIRE(cfg->stride_layer_idx < 0 || l <= cfg->stride_layer_idx,
+                      "efficient_conformer: grouped attention is supported in blocks up to the stride block");
+    int ng = 0;
+    for (int l = 0; l < cfg->n_layers; ++l) ng += (cfg->group_layer_mask >> l) & 1;
+    PPASR_REQUIRE(ng <= 4, "at most 4 grouped-attention blocks");
+    PPASR_REQUIRE(cfg->conv_kernel == 15 || !cfg->stride_kernel, "stride_kernel needs cnn_module_kernel 15 (15 -> 7)");
+  }
   auto* c = new ppasr_b200_ctx();
   c->cfg = *cfg;
+  c->layer_k.assign(cfg->n_layers, cfg->conv_kernel);
+  if (cfg->model_type == 3) {
+    c->eff_stride_idx = cfg->stride_layer_idx;
+    c->eff_group_mask = (unsigned)cfg->group_layer_mask;
+    if (cfg->stride_layer_idx >= 0 && cfg->stride_kernel)
+      for (int l = cfg->stride_layer_idx + 1; l < cfg->n_layers; ++l) c->layer_k[l] = cfg->conv_kernel / 2;
+  }
   c->F1 = (cfg->feat_dim - 1) / 2;
   c->F2 = (c->F1 - 1) / 2;
   c->FH = (c->F1 + 1) / 2;
@@ -327,7 +360,8 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
   PPASR_REQUIRE(c, "null ctx");
   if (c->finalized) return PPASR_OK;
   const auto& cfg = c->cfg;
-  const int D = cfg.d_model, L = cfg.n_layers, FF = cfg.ffn_dim, K = cfg.conv_kernel, V = cfg.vocab_size;
+  const int D = cfg.d_model, L = cfg.n_layers, FF = cfg.ffn_dim, V = cfg.vocab_size;
+  const int Kmax = cfg.conv_kernel;
   int dev = 0;
   PPASR_CUDA_CHECK(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -363,6 +397,7 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
       names.push_back(p + "self_attn." + s + ".bias");
     }
     names.push_back(p + "self_attn.linear_pos.weight");
+    if ((c->eff_group_mask >> l) & 1) names.push_back(p + "self_attn.linear_pos.bias");  // efficient_conformer/attention.py:31
     names.push_back(p + "self_attn.pos_bias_u");
     names.push_back(p + "self_attn.pos_bias_v");
     for (const char* s : {"pointwise_conv1", "depthwise_conv", "pointwise_conv2", "norm"}) {
@@ -385,7 +420,7 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
   bytes += (size_t)L * ((size_t)6 * D * FF + 3 * D * D + D * D + 2 * D * D + D * D) * 2;  // bf16 matrices
   bytes += (size_t)D * 9 * D * 2 + (size_t)D * c->Kemb * 2 + (size_t)c->Vpad * D * 2;
   bytes += (size_t)cfg.max_len * L * D * 2 + (size_t)cfg.max_len * D * 2 + (size_t)L * D * D * 2;
-  bytes += (size_t)L * (20 * D + 2 * FF + 3 * D + 2 * D + D * K + 64) * 4 + (size_t)(c->Vpad + 4 * D + L * D + 4096) * 4;
+  bytes += (size_t)L * (20 * D + 2 * FF + 3 * D + 2 * D + D * Kmax + 64 + 8 * 192) * 4 + (size_t)(c->Vpad + 4 * D + 2 * L * D + 4096) * 4;
   bytes += 4u << 20;  // alignment slack
   PPASR_CUDA_CHECK(c->wslab.reserve(bytes));
   c->wslab.used = 0;
@@ -442,10 +477,15 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
   // ---- encoder layers -------------------------------------------------------------------------
   c->layers.resize(L);
   c->lmaps.resize(L);
-  std::vector<float> wpos_all((size_t)L * D * D);
+  std::vector<float> wpos_all((size_t)L * D * D), bpos_all((size_t)L * D, 0.f);
   for (int l = 0; l < L; ++l) {
     const std::string p = "encoder.encoders." + std::to_string(l) + ".";
     LayerW& w = c->layers[l];
+    const int K = c->layer_k[l];
+    const bool grouped = (c->eff_group_mask >> l) & 1;
+    PPASR_REQUIRE(c->host[p + "self_attn.pos_bias_u"].numel() == (int64_t)cfg.n_heads * (grouped ? 192 : 64) &&
+                      c->host[p + "self_attn.pos_bias_v"].numel() == (int64_t)cfg.n_heads * (grouped ? 192 : 64),
+                  "pos_bias_u / pos_bias_v shape");
     w.ln_ffm_g = vecf(p + "norm_ff_macaron.weight"), w.ln_ffm_b = vecf(p + "norm_ff_macaron.bias");
     w.ln_mha_g = vecf(p + "norm_mha.weight"), w.ln_mha_b = vecf(p + "norm_mha.bias");
     w.ln_conv_g = vecf(p + "norm_conv.weight"), w.ln_conv_b = vecf(p + "norm_conv.bias");
@@ -488,6 +528,8 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
     {
       auto t = transpose_in_out(c->host[p + "self_attn.linear_pos.weight"]);
       std::memcpy(wpos_all.data() + (size_t)l * D * D, t.data(), sizeof(float) * D * D);
+      if (grouped)
+        std::memcpy(bpos_all.data() + (size_t)l * D, c->host[p + "self_attn.linear_pos.bias"].data.data(), sizeof(float) * D);
     }
     {
       // pointwise_conv1.weight [2D, D, 1]: rows [0,D) = "a", [D,2D) = gate -> interleave (2c, 2c+1)
@@ -579,12 +621,14 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
     CUtensorMap ta, tb;
     if (!make_tmap_2d(&ta, pe_d, D, ML, (uint64_t)D * 2, GEMM_BLOCK_M, &err) ||
         !make_tmap_2d(&tb, wpos_d, D, (uint64_t)L * D, (uint64_t)D * 2, BN_WIDE, &err) ||
-        !make_tmap_2d(&c->tm_pos, tab, (uint64_t)L * D, ML, (uint64_t)L * D * 2, 128, &err)) {
+        !make_tmap_2d(&c->tm_pos, tab, (uint64_t)L * D, ML, (uint64_t)L * D * 2, 128, &err) ||
+        !make_tmap_2d(&c->tm_pos2, tab, (uint64_t)L * D, ML / 2, (uint64_t)2 * L * D * 2, 128, &err)) {
       set_last_error(err);
       return PPASR_ERR_CUDA;
     }
     GemmShape s = make_shape(ML, L * D, D, BN_WIDE);
-    EpiStoreBF16<BN_WIDE, ACT_NONE> epi{tab, c->zero_bias, L * D, ML, L * D};
+    const float* bpos_d = upload(c, bpos_all);  // zero except for grouped blocks (their linear_pos has a bias)
+    EpiStoreBF16<BN_WIDE, ACT_NONE> epi{tab, bpos_d, L * D, ML, L * D};
     PPASR_CUDA_CHECK((launch_gemm<BN_WIDE, ST_WIDE, false>(ta, tb, s, epi, c->sms, 0)));
     c->pos_tab = tab;
   }
@@ -598,9 +642,11 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
   return PPASR_OK;
 }
 
-int ppasr_b200_out_frames(const ppasr_b200_ctx*, int32_t T) {
+int ppasr_b200_out_frames(const ppasr_b200_ctx* c, int32_t T) {
   if (T < 7) return 0;
-  return ((T - 1) / 2 - 1) / 2;
+  const int tp = ((T - 1) / 2 - 1) / 2;
+  if (c && c->cfg.model_type == 3 && c->eff_stride_idx >= 0) return (tp + 1) / 2;
+  return tp;
 }
 
 }  // extern "C"
@@ -634,6 +680,13 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   acc(M * c->Kemb * 2);
   acc(M * D * 4);                                   // x
   acc(M * D * 2 + 1024);                            // x2 (reduced stream)
+  if (cfg.model_type == 3) {
+    const size_t tg = (n.Tp + 2) / 3, tgp = (tg + 63) / 64 * 64;
+    acc((size_t)B * H * tg * 384 * 2 + 4096);
+    acc((size_t)B * H * tg * 192 * 2 + 4096);
+    acc((size_t)B * H * 192 * tgp * 2 + 4096);
+    acc((size_t)4 * tg * 768 * 2 + 4096);
+  }
   acc(B * 4);
   acc(M * D * 2 * 4);                               // y, att, g, z
   acc((size_t)n.Mcat * D * 2 * 2);                  // ycat, gcat
@@ -661,6 +714,14 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
   n.x = a.take<float>(M * D);
   n.x2 = a.take<float>((size_t)B * ((n.Tp + 1) / 2) * D);
   n.vlen2 = a.take<int>(B);
+  if (cfg.model_type == 3) {
+    n.Tg = (n.Tp + 2) / 3;
+    n.Tgp = (n.Tg + 63) / 64 * 64;
+    n.q2g = a.take<__nv_bfloat16>((size_t)B * H * n.Tg * 384);
+    n.kkg = a.take<__nv_bfloat16>((size_t)B * H * n.Tg * 192);
+    n.vtg = a.take<__nv_bfloat16>((size_t)B * H * 192 * n.Tgp);
+    n.pg = a.take<__nv_bfloat16>((size_t)4 * n.Tg * 768);
+  }
   n.y = a.take<__nv_bfloat16>(M * D);
   n.att = a.take<__nv_bfloat16>(M * D);
   n.g = a.take<__nv_bfloat16>(M * D);
@@ -697,9 +758,22 @@ int build_plan(ppasr_b200_ctx* c, int B, int T) {
             make_tmap_2d(&n.tm_q, n.q2, 128, (uint64_t)B * H * n.Tp, 256, 128, &err) &&
             make_tmap_2d(&n.tm_k, n.kk, 64, (uint64_t)B * H * n.Tp, 128, 128, &err) &&
             make_tmap_2d(&n.tm_vt, n.vt, n.Tp, (uint64_t)B * H * 64, (uint64_t)n.Tkp * 2, 64, &err);
+  if (ok && cfg.model_type == 3) {
+    ok = make_tmap_2d(&n.tm_qg, n.q2g, 384, (uint64_t)B * H * n.Tg, 384 * 2, 128, &err) &&
+         make_tmap_2d(&n.tm_kg, n.kkg, 192, (uint64_t)B * H * n.Tg, 192 * 2, 64, &err) &&
+         make_tmap_2d(&n.tm_vtg, n.vtg, n.Tg, (uint64_t)B * H * 192, (uint64_t)n.Tgp * 2, 192, &err);
+    for (int i = 0; ok && i < 4; ++i)
+      ok = make_tmap_2d(&n.tm_pg[i], n.pg + (size_t)i * n.Tg * 768, 768, n.Tg, 768 * 2, 64, &err);
+  }
   if (!ok) {
     set_last_error(err);
     return PPASR_ERR_CUDA;
+  }
+  n.Mc = n.M, n.Tc = n.Tp, n.vc = n.vlen;
+  if (cfg.model_type == 3 && c->eff_stride_idx >= 0) {
+    n.Tc = (n.Tp + 1) / 2;
+    n.Mc = B * n.Tc;
+    n.vc = n.vlen2;
   }
   p = n;
   return PPASR_OK;
@@ -741,6 +815,7 @@ int run_subsampling_convs(ppasr_b200_ctx* c, cudaStream_t st) {
 
 #include "runtime_squeezeformer.inl"
 #include "runtime_ds2.inl"
+#include "runtime_effconf.inl"
 
 int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
   Plan& p = c->plan;
@@ -891,6 +966,7 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
   }
   PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
   if (ds2) return run_encoder_ds2(c, st, false);
+  if (c->cfg.model_type == 3) return run_encoder_effconf(c, st);
   return c->cfg.model_type == 1 ? run_encoder_squeezeformer(c, st) : run_encoder(c, st, false);
 }
 
@@ -1065,36 +1141,36 @@ int ppasr_b200_stream_export(ppasr_b200_ctx* c, float* att_cache, float* cnn_cac
 
 static int run_ctc_logits(ppasr_b200_ctx* c, cudaStream_t st) {
   Plan& p = c->plan;
-  EpiLogitsF32<BN_NARROW> e{p.logits, c->ctc_b, c->Vld, p.M, c->cfg.vocab_size};
+  EpiLogitsF32<BN_NARROW> e{p.logits, c->ctc_b, c->Vld, p.Mc, c->cfg.vocab_size};
   PROF(PC_CTC_LOGITS);
-  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, c->cfg.vocab_size, c->ctc_k ? c->ctc_k : c->cfg.d_model, e, st)));
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.Mc, c->cfg.vocab_size, c->ctc_k ? c->ctc_k : c->cfg.d_model, e, st)));
   return PPASR_OK;
 }
 
 int ppasr_b200_ctc_logits(ppasr_b200_ctx* c, float* logits, int32_t on_device, void* stream) {
-  PPASR_REQUIRE(c && logits && c->plan.M > 0, "encode first");
+  PPASR_REQUIRE(c && logits && c->plan.Mc > 0, "encode first");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = run_ctc_logits(c, st);
   if (rc) return rc;
   Plan& p = c->plan;
   PPASR_CUDA_CHECK(cudaMemcpy2DAsync(logits, (size_t)c->cfg.vocab_size * 4, p.logits, (size_t)c->Vld * 4,
-                                     (size_t)c->cfg.vocab_size * 4, p.M,
+                                     (size_t)c->cfg.vocab_size * 4, p.Mc,
                                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   if (!on_device) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
   return PPASR_OK;
 }
 
 int ppasr_b200_ctc_probs(ppasr_b200_ctx* c, float* probs, int32_t probs_on_device, void* stream) {
-  PPASR_REQUIRE(c && probs && c->plan.M > 0, "encode first");
+  PPASR_REQUIRE(c && probs && c->plan.Mc > 0, "encode first");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = run_ctc_logits(c, st);
   if (rc) return rc;
   Plan& p = c->plan;
   float* dst = probs_on_device ? probs : p.probs;
   { PROF(PC_SOFTMAX);
-  PPASR_CUDA_CHECK(launch_softmax_rows(p.logits, c->Vld, dst, p.M, c->cfg.vocab_size, st)); }
+  PPASR_CUDA_CHECK(launch_softmax_rows(p.logits, c->Vld, dst, p.Mc, c->cfg.vocab_size, st)); }
   if (!probs_on_device) {
-    PPASR_CUDA_CHECK(cudaMemcpyAsync(probs, p.probs, (size_t)p.M * c->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, st));
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(probs, p.probs, (size_t)p.Mc * c->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, st));
     PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   return PPASR_OK;
@@ -1103,24 +1179,24 @@ int ppasr_b200_ctc_probs(ppasr_b200_ctx* c, float* probs, int32_t probs_on_devic
 int ppasr_b200_ctc_greedy(ppasr_b200_ctx* c, int32_t* ids, int32_t* out_lens, float* scores, int32_t* frame_ids,
                           float* frame_probs, int32_t outputs_on_device, int32_t trim_to_lens, int32_t blank_id,
                           void* stream) {
-  PPASR_REQUIRE(c && c->plan.M > 0, "encode first");
+  PPASR_REQUIRE(c && c->plan.Mc > 0, "encode first");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   Plan& p = c->plan;
   const int V = c->cfg.vocab_size;
-  EpiCtcStats<BN_NARROW> e{p.pmax, p.parg, p.psum, c->ctc_b, p.M, V, c->ctc_parts};
+  EpiCtcStats<BN_NARROW> e{p.pmax, p.parg, p.psum, c->ctc_b, p.Mc, V, c->ctc_parts};
   { PROF(PC_CTC_STATS);
-  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.M, V, c->ctc_k ? c->ctc_k : c->cfg.d_model, e, st))); }
+  PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, c->tm_ctc_w, p.Mc, V, c->ctc_k ? c->ctc_k : c->cfg.d_model, e, st))); }
   { PROF(PC_CTC_FINALIZE);
-  PPASR_CUDA_CHECK(launch_ctc_stats_finalize(p.pmax, p.parg, p.psum, c->ctc_parts, p.M, p.idx, p.maxp, st)); }
+  PPASR_CUDA_CHECK(launch_ctc_stats_finalize(p.pmax, p.parg, p.psum, c->ctc_parts, p.Mc, p.idx, p.maxp, st)); }
   PROF(PC_CTC_COLLAPSE);
-  PPASR_CUDA_CHECK(launch_ctc_collapse(p.idx, p.maxp, p.B, p.Tp, trim_to_lens ? p.vlen : nullptr, blank_id, p.ids, p.Tp,
+  PPASR_CUDA_CHECK(launch_ctc_collapse(p.idx, p.maxp, p.B, p.Tc, trim_to_lens ? p.vc : nullptr, blank_id, p.ids, p.Tc,
                                        p.out_len, p.score, nullptr, nullptr, st));
   int rc;
-  if ((rc = copy_out(ids, p.ids, (size_t)p.M * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(ids, p.ids, (size_t)p.Mc * 4, outputs_on_device, st))) return rc;
   if ((rc = copy_out(out_lens, p.out_len, (size_t)p.B * 4, outputs_on_device, st))) return rc;
   if ((rc = copy_out(scores, p.score, (size_t)p.B * 4, outputs_on_device, st))) return rc;
-  if ((rc = copy_out(frame_ids, p.idx, (size_t)p.M * 4, outputs_on_device, st))) return rc;
-  if ((rc = copy_out(frame_probs, p.maxp, (size_t)p.M * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(frame_ids, p.idx, (size_t)p.Mc * 4, outputs_on_device, st))) return rc;
+  if ((rc = copy_out(frame_probs, p.maxp, (size_t)p.Mc * 4, outputs_on_device, st))) return rc;
   if (!outputs_on_device && c->host_sync) PPASR_CUDA_CHECK(cudaStreamSynchronize(st));
   return PPASR_OK;
 }

@@ -168,6 +168,7 @@ int build_plan_ds2(ppasr_b200_ctx* c, int B, int T) {
     set_last_error(err);
     return PPASR_ERR_CUDA;
   }
+  n.Mc = n.M, n.Tc = n.Tp, n.vc = n.vlen;
   p = n;
   return PPASR_OK;
 }

@@ -16,7 +16,9 @@ class Config(ctypes.Structure):
                 ("n_heads", ctypes.c_int32), ("ffn_dim", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("conv_kernel", ctypes.c_int32), ("causal", ctypes.c_int32), ("conv_norm", ctypes.c_int32),
                 ("vocab_size", ctypes.c_int32), ("max_len", ctypes.c_int32), ("reduce_idx", ctypes.c_int32),
-                ("recover_idx", ctypes.c_int32), ("time_reduce_kernel", ctypes.c_int32), ("use_gru", ctypes.c_int32), ("reserved", ctypes.c_int32 * 1)]
+                ("recover_idx", ctypes.c_int32), ("time_reduce_kernel", ctypes.c_int32), ("use_gru", ctypes.c_int32), ("stride_layer_idx", ctypes.c_int32),
+                ("group_layer_mask", ctypes.c_int32), ("group_size", ctypes.c_int32), ("stride_kernel", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 1)]
 
 
 def out_frames(T: int) -> int:
@@ -51,7 +53,13 @@ class ConformerEngine:
             c.max_len = 5000
             self._create(c, weights)
             return
-        c.model_type = 1 if squeeze else 0
+        c.model_type = 1 if squeeze else (3 if kind == "efficient_conformer" else 0)
+        c.stride_layer_idx = -1
+        if kind == "efficient_conformer":
+            c.stride_layer_idx = -1 if cfg.stride_layer_idx is None else int(cfg.stride_layer_idx)
+            c.group_layer_mask = sum(1 << int(i) for i in cfg.group_layer_idx)
+            c.group_size = cfg.group_size
+            c.stride_kernel = int(cfg.stride_kernel)
         c.feat_dim = cfg.input_dim
         c.d_model = cfg.encoder_dim if squeeze else cfg.output_size
         if squeeze:
@@ -111,7 +119,7 @@ class ConformerEngine:
             lens = np.ascontiguousarray(np.asarray(lens), dtype=np.int64)
             lens_p = ctypes.c_void_p(lens.ctypes.data)
         L.check(self.lib.ppasr_b200_encode(self._ctx, ptr, on_dev, lens_p, B, T, L.stream_ptr(stream)))
-        self.B, self.Tp = B, out_frames(T)
+        self.B, self.Tp = B, int(self.lib.ppasr_b200_out_frames(self._ctx, T))
         return self
 
     def ds2_states(self):
@@ -141,7 +149,7 @@ class ConformerEngine:
             ptr, on_dev = ctypes.c_void_p(feats.data_ptr()), int(feats.is_cuda)
         L.check(self.lib.ppasr_b200_encode_chunk(self._ctx, ptr, on_dev, B, T, int(required_cache_size),
                                                  L.stream_ptr(stream)))
-        self.B, self.Tp = B, out_frames(T)
+        self.B, self.Tp = B, int(self.lib.ppasr_b200_out_frames(self._ctx, T))
         return self
 
     def stream_info(self):

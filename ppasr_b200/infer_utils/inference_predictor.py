@@ -19,7 +19,7 @@ import numpy as np
 from .. import _lib as L
 from ..engine import ConformerEngine, out_frames
 from ..parallel import detokenize
-from ..weights import ConformerConfig, DeepSpeech2Config, SqueezeformerConfig, load_npz, load_pdparams, read_mean_istd
+from ..weights import ConformerConfig, DeepSpeech2Config, EfficientConformerConfig, SqueezeformerConfig, load_npz, load_pdparams, read_mean_istd
 
 
 def _get(obj, key, default=None):
@@ -45,8 +45,8 @@ class InferencePredictor:
                  device=0):
         if not use_gpu:
             raise Exception("ppasr_b200 only runs on a B200 GPU (use_gpu=False is not supported)")
-        if use_model not in ('conformer', 'squeezeformer', 'deepspeech2'):
-            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 implements conformer, squeezeformer and deepspeech2)')
+        if use_model not in ('conformer', 'squeezeformer', 'deepspeech2', 'efficient_conformer'):
+            raise Exception(f'当前模型不支持该方法，当前模型为：{use_model} (ppasr_b200 implements conformer, squeezeformer, efficient_conformer and deepspeech2)')
         self.configs = configs
         self.use_model = use_model
         self.streaming = streaming
@@ -82,7 +82,13 @@ class InferencePredictor:
         if vocab_size is None:
             key = 'decoder.ctc_lo.weight' if use_model == 'deepspeech2' else 'ctc.ctc_lo.weight'
             vocab_size = int(weights[key].shape[1])
-        if use_model == 'deepspeech2':
+        if use_model == 'efficient_conformer':
+            allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
+                       'cnn_module_norm', 'max_len', 'stride_layer_idx', 'stride', 'group_layer_idx', 'group_size',
+                       'stride_kernel')
+            kw = {k: enc[k] for k in allowed if k in enc}
+            self.model_config = EfficientConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        elif use_model == 'deepspeech2':
             # configs/deepspeech2.yml encoder_conf (deepspeech2/encoder.py:8-16); streaming => forward-only RNN (model.py:40)
             kw = {k: enc[k] for k in ('num_rnn_layers', 'rnn_size', 'use_gru') if k in enc}
             self.model_config = DeepSpeech2Config(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)

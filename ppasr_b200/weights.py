@@ -134,6 +134,85 @@ def init_conformer_weights(cfg: ConformerConfig, seed: int = 1000, ctc_gain: flo
     return w
 
 
+class EfficientConformerConfig(ConformerConfig):
+    """configs/efficient_conformer.yml `encoder_conf`; the nested `efficient_conf` block is swallowed by **kwargs in the
+    reference constructor (efficient_conformer/encoder.py:55), so its defaults apply unless given at the top level."""
+    model_type = "efficient_conformer"
+
+    def __init__(self, stride_layer_idx=3, stride=2, group_layer_idx=(0, 1, 2, 3), group_size=3, stride_kernel=True,
+                 efficient_conf=None, **kw):
+        super().__init__(**kw)
+        if isinstance(stride_layer_idx, (list, tuple)):
+            assert len(stride_layer_idx) == 1, "one stride layer is supported"
+            stride_layer_idx = stride_layer_idx[0]
+        if isinstance(stride, (list, tuple)):
+            stride = stride[0]
+        assert stride == 2 and group_size == 3, "stride 2 / group size 3 (the reference defaults) are supported"
+        self.stride_layer_idx = None if stride_layer_idx is None else int(stride_layer_idx)
+        self.stride = int(stride)
+        self.group_layer_idx = tuple(int(i) for i in group_layer_idx)
+        self.group_size = int(group_size)
+        self.stride_kernel = bool(stride_kernel)
+
+    def to_dict(self):
+        d = super().to_dict()
+        d.update(stride_layer_idx=self.stride_layer_idx, stride=self.stride, group_layer_idx=list(self.group_layer_idx),
+                 group_size=self.group_size, stride_kernel=self.stride_kernel)
+        return d
+
+    def layer_kernel(self, i):
+        k = self.cnn_module_kernel
+        if self.stride_layer_idx is None or i <= self.stride_layer_idx:
+            return k
+        return k // self.stride if self.stride_kernel else k
+
+
+def efficient_conformer_param_shapes(cfg: EfficientConformerConfig) -> Dict[str, tuple]:
+    s = conformer_param_shapes(cfg)
+    D, H = cfg.output_size, cfg.attention_heads
+    for i in range(cfg.num_blocks):
+        p = f"encoder.encoders.{i}."
+        s[p + "conv_module.depthwise_conv.weight"] = (D, 1, cfg.layer_kernel(i))
+        if i in cfg.group_layer_idx:  # efficient_conformer/attention.py:31-38
+            s[p + "self_attn.linear_pos.bias"] = (D,)
+            s[p + "self_attn.pos_bias_u"] = (H, D // H * cfg.group_size)
+            s[p + "self_attn.pos_bias_v"] = (H, D // H * cfg.group_size)
+    return s
+
+
+def init_efficient_conformer_weights(cfg: EfficientConformerConfig, seed: int = 1000, ctc_gain: float = 8.0,
+                                     perturb_norms: bool = True) -> Dict[str, np.ndarray]:
+    rng = np.random.RandomState(seed)
+    w = {}
+    for name, shape in efficient_conformer_param_shapes(cfg).items():
+        if name.endswith("global_cmvn.mean"):
+            a = rng.uniform(-1.0, 1.0, shape) + 10.0
+        elif name.endswith("global_cmvn.istd"):
+            a = rng.uniform(0.2, 0.5, shape)
+        elif ".norm" in name and name.endswith("_mean"):
+            a = rng.uniform(-0.1, 0.1, shape)
+        elif ".norm" in name and name.endswith("_variance"):
+            a = rng.uniform(0.5, 1.5, shape)
+        elif ("norm" in name.split(".")[-2]) and name.endswith(".weight"):
+            a = rng.uniform(0.8, 1.2, shape) if perturb_norms else np.ones(shape)
+        elif ("norm" in name.split(".")[-2]) and name.endswith(".bias"):
+            a = rng.uniform(-0.1, 0.1, shape) if perturb_norms else np.zeros(shape)
+        elif name.endswith("pos_bias_u") or name.endswith("pos_bias_v"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            a = rng.uniform(-lim, lim, shape)
+        elif name.startswith("ctc.ctc_lo"):
+            if name.endswith("weight"):
+                lim = math.sqrt(6.0 / (shape[0] + shape[1])) * ctc_gain
+                a = rng.uniform(-lim, lim, shape)
+            else:
+                a = np.zeros(shape)
+        else:
+            lim = 1.0 / math.sqrt(_fan_in(name, shape))
+            a = rng.uniform(-lim, lim, shape)
+        w[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return w
+
+
 class SqueezeformerConfig:
     """Inference-relevant keys of configs/squeezeformer.yml (`encoder_conf`, `streaming`, n_mels); model switches per
     ppasr/model_utils/squeezeformer/model.py:35-41."""

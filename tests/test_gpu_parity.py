@@ -223,7 +223,13 @@ def _run_model(cuda, num_blocks, B, T, lens, vocab=4233, streaming=True, norm="l
     from ppasr_b200.engine import ConformerEngine, out_frames
     from ppasr_b200.weights import (ConformerConfig, SqueezeformerConfig, init_conformer_weights,
                                     init_squeezeformer_weights, synthetic_fbank)
-    if model == "squeezeformer":
+    if model == "efficient_conformer":
+        from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
+        from ppasr_b200.weights import EfficientConformerConfig, init_efficient_conformer_weights
+        cfg = EfficientConformerConfig(num_blocks=num_blocks, vocab_size=vocab, streaming=streaming, cnn_module_norm=norm, **mkw)
+        w = init_efficient_conformer_weights(cfg)
+        oracle = EfficientConformerOracle(EfficientConformerConf(**cfg.to_dict()), w)
+    elif model == "squeezeformer":
         cfg = SqueezeformerConfig(num_blocks=num_blocks, vocab_size=vocab, streaming=streaming, cnn_norm_type=norm, **mkw)
         w = init_squeezeformer_weights(cfg)
         oracle = SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w)
@@ -242,6 +248,10 @@ def _run_model(cuda, num_blocks, B, T, lens, vocab=4233, streaming=True, norm="l
     ref_logits = oracle.get_encoder_out(torch.from_numpy(feats), torch.tensor(lens), return_logits=True)
     Tp = out_frames(T)
     vl = [min(Tp, (l + 3) // 4) for l in lens]
+    if model == "efficient_conformer" and cfg.stride_layer_idx is not None:
+        Tp = (Tp + 1) // 2                      # efficient_conformer/encoder.py:255-260
+        vl = [(v + 1) // 2 for v in vl]
+    assert tuple(logits.shape) == tuple(ref_logits.shape) == (B, Tp, vocab)
     scale = ref_logits.abs().max().item()
     worst = max((logits[b, :vl[b]] - ref_logits[b, :vl[b]]).abs().max().item() for b in range(B) if vl[b] > 0) / scale
     assert worst < 1e-2, f"logits rel err {worst}"
@@ -317,6 +327,27 @@ def test_squeezeformer_inference_predictor(lib, cuda):
         assert got[b][1] == text and abs(got[b][0] - score) < 1e-3
     with pytest.raises(Exception):
         pred.predict_chunk_conformer(x[:1, :67], -1)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_blocks=1, B=2, T=131, lens=[131, 90], vocab=97, group_layer_idx=(0,), stride_layer_idx=None),  # T'=32 -> pad 1
+    dict(num_blocks=1, B=2, T=135, lens=[135, 90], vocab=97, group_layer_idx=(), stride_layer_idx=0),       # odd T'=33
+    dict(num_blocks=2, B=3, T=203, lens=[203, 150, 99], vocab=300, group_layer_idx=(0, 1), stride_layer_idx=1),
+    dict(num_blocks=2, B=3, T=207, lens=[207, 150, 5], vocab=300, group_layer_idx=(0, 1), stride_layer_idx=1,
+         streaming=False),
+    dict(num_blocks=3, B=2, T=1051, lens=[1051, 700], vocab=300, group_layer_idx=(0, 1), stride_layer_idx=1),  # 88 groups
+    dict(num_blocks=2, B=2, T=300, lens=[300, 200], vocab=300, group_layer_idx=(0,), stride_layer_idx=0,
+         streaming=False, norm="batch_norm"),
+])
+def test_efficient_conformer_matches_oracle_small(lib, cuda, kw):
+    """efficient_conformer/encoder.py:212-264: grouped attention (attention.py:128-193), stride block with AvgPool residual
+    (encoder.py:455-548), kernel 15 -> 7, output at ceil(T'/2)."""
+    _run_model(cuda, model="efficient_conformer", **kw)
+
+
+def test_efficient_conformer_matches_oracle_12_layers(lib, cuda):
+    """configs/efficient_conformer.yml sizes (12 blocks, grouped 0-3, stride block 3, V=4233), 4 x 5 s, ragged."""
+    _run_model(cuda, 12, 4, 498, [498, 498, 400, 250], model="efficient_conformer")
 
 
 def test_full_size_properties(lib, cuda):

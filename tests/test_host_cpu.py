@@ -30,12 +30,19 @@ def test_library_exports_every_header_symbol(lib):
         if s in ("ppasr_b200_last_error", "ppasr_b200_abi_version"):
             continue
         assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype in ppasr_b200/_lib.py"
-    assert lib.ppasr_b200_abi_version() == 1
+    assert lib.ppasr_b200_abi_version() == 2
 
 
 def test_config_struct_matches_header():
+    import re
     from ppasr_b200.engine import Config
-    assert ctypes.sizeof(Config) == 16 * 4
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "ppasr_b200.h")).read()
+    body = hdr[hdr.index("typedef struct ppasr_b200_config {"):hdr.index("} ppasr_b200_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"int32_t\s+(\w+)(\[(\d+)\])?;", body)
+    n_ints = sum(int(n[2]) if n[2] else 1 for n in names)
+    assert ctypes.sizeof(Config) == 4 * n_ints
+    assert [n[0] for n in names] == [f[0] for f in Config._fields_]
 
 
 def test_create_validates_and_finalize_reports_missing(lib):
@@ -45,7 +52,7 @@ def test_create_validates_and_finalize_reports_missing(lib):
                conv_norm=0, vocab_size=100, max_len=5000)
     ctx = ctypes.c_void_p()
     assert lib.ppasr_b200_create(ctypes.byref(c), ctypes.byref(ctx)) == 0
-    bad = Config(model_type=3, feat_dim=80, d_model=256, n_heads=4, ffn_dim=2048, n_layers=1, conv_kernel=15,
+    bad = Config(model_type=9, feat_dim=80, d_model=256, n_heads=4, ffn_dim=2048, n_layers=1, conv_kernel=15,
                  vocab_size=100, max_len=5000)
     ctx2 = ctypes.c_void_p()
     assert lib.ppasr_b200_create(ctypes.byref(bad), ctypes.byref(ctx2)) != 0

@@ -284,3 +284,42 @@ def test_deepspeech2_oracle_chunked_equals_offline_forward():
     a, _, h, c = o.get_encoder_out_chunk(x[:, :67], torch.tensor([67]), None, None, return_logits=True)
     b, _, _, _ = o.get_encoder_out_chunk(x[:, 64:131], torch.tensor([67]), h, c, return_logits=True)
     assert (torch.cat([a, b], 1) - full).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# Efficient-Conformer oracle self-consistency (parity unpinned; oracle/efficient_conformer_oracle.py)
+# ------------------------------------------------------------------------------------------------
+def test_efficient_conformer_oracle_shapes_and_batch_invariance():
+    from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
+    from ppasr_b200.weights import EfficientConformerConfig, init_efficient_conformer_weights
+    cfg = EfficientConformerConfig(num_blocks=5, vocab_size=60)
+    w = init_efficient_conformer_weights(cfg)
+    assert w["encoder.encoders.3.conv_module.depthwise_conv.weight"].shape[-1] == 15
+    assert w["encoder.encoders.4.conv_module.depthwise_conv.weight"].shape[-1] == 7      # encoder.py:123-128
+    assert w["encoder.encoders.0.self_attn.pos_bias_u"].shape == (4, 192)                # attention.py:35-38
+    assert w["encoder.encoders.4.self_attn.pos_bias_u"].shape == (4, 64)
+    o = EfficientConformerOracle(EfficientConformerConf(**cfg.to_dict()), w)
+    x = torch.from_numpy(synthetic_fbank(3, 207))
+    lens = torch.tensor([207, 150, 99])
+    y = o.get_encoder_out(x, lens, return_logits=True)
+    assert y.shape == (3, 26, 60)  # T' = 51 -> ceil(51 / 2)
+    y0 = o.get_encoder_out(x[:1], lens[:1], return_logits=True)
+    assert (y0[0] - y[0]).abs().max() < 1e-3 * y.abs().max()
+
+
+def test_efficient_conformer_grouped_attention_group1_equals_plain():
+    """With group_size 1 the grouped attention must reduce to the plain rel-pos attention plus the linear_pos bias."""
+    from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
+    from ppasr_b200.weights import EfficientConformerConfig, init_efficient_conformer_weights
+    cfg = EfficientConformerConfig(num_blocks=1, vocab_size=30, group_layer_idx=(), stride_layer_idx=None)
+    w = init_efficient_conformer_weights(cfg)
+    w["encoder.encoders.0.self_attn.linear_pos.bias"] = np.zeros(256, dtype=np.float32)
+    conf = EfficientConformerConf(**cfg.to_dict())
+    o = EfficientConformerOracle(conf, w)
+    x = torch.randn(2, 20, 256)
+    pos = o.position_encoding(0, 20)
+    mask = torch.ones(2, 20, 20, dtype=torch.bool)
+    a = o.rel_mha("encoder.encoders.0.self_attn", x, mask, pos, None)[0]
+    conf.group_size = 1
+    b = o.grouped_mha("encoder.encoders.0.self_attn", x, mask, pos)
+    assert (a - b).abs().max() < 1e-5
