@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
   const float4* v4 = reinterpret_cast<const float4*>(src + head);
   const int n4 = (V - head) >> 2;
   const int tail0 = head + 4 * n4;
-  // ---- pass 1 ----
+  int* oid = cid + (size_t)row * BEAM_MAXC;
+  float* olp = clp + (size_t)row * BEAM_MAXC;
+  // ---- pass 1: stream the row once keeping each lane's two largest values (2 FMNMX per element) ----
   float t1 = -INFINITY, t2 = -INFINITY;
   auto upd = [&](float x) {
     t2 = fmaxf(t2, fminf(t1, x));
@@ -81,14 +83,19 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
     upd4(a0), upd4(a1), upd4(a2), upd4(a3), upd4(a4), upd4(a5), upd4(a6), upd4(a7);
   }
   for (; i < n4; i += 32) upd4(__ldg(v4 + i));
-  // ---- threshold ----
+  // ---- threshold: walk the 64 per-lane maxima in descending order. They are row elements, so the k-th of them is a lower
+  //      bound of the k-th largest of the row and their running sum a lower bound of the true cumulative mass: as soon as it
+  //      reaches cutoff_prob (or k = limit) everything that can be selected is >= tau = the value just taken.
   float tau = -INFINITY;
   {
     float a1 = t1, a2 = t2;
+    float cumx = 0.f;
     for (int k = 0; k < limit; ++k) {
       const float m = warp_max(fmaxf(a1, a2));
       tau = m;
       if (m == -INFINITY) break;
+      cumx += m;
+      if (cutoff_prob < 1.0f && cumx >= cutoff_prob * 1.0001f) break;  // margin: fp32 sum vs the Kahan sum used below
       const unsigned has = __ballot_sync(0xffffffffu, a1 == m || a2 == m);
       if (lane == __ffs(has) - 1) {
         if (a1 == m)
@@ -97,6 +104,7 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
           a2 = -INFINITY;
       }
     }
+    if (!prune) tau = -INFINITY;
   }
   // ---- pass 2: compact elements >= tau (warp-uniform control flow; lane 0 writes) ----
   int c = 0;
@@ -148,8 +156,6 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
     }
   }
   __syncwarp();
-  int* oid = cid + (size_t)row * BEAM_MAXC;
-  float* olp = clp + (size_t)row * BEAM_MAXC;
   float last_p = INFINITY;
   int last_i = -1;
   float cum = 0.f, cum_c = 0.f;  // Kahan-compensated fp32 running sum (stands in for the reference's double)
