@@ -153,6 +153,15 @@ int ppasr_b200_beam_reset(void* states, int32_t B, int32_t max_frames, int32_t b
 int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens,
                             int32_t beam, float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states,
                             int32_t max_frames, void* workspace, void* stream);
+/* Same with an external scorer (replaces Scorer + ext_scoring_func of swig_wrapper.py:4-19,35-64): a character-based
+ * back-off n-gram LM as an open-addressing hash table on the device (built by ppasr_b200/decoders/ngram_lm.py from an ARPA
+ * file): lm_keys uint64 [lm_capacity] (0 = empty; token ids packed 16 bits each, <s> = 1, vocabulary id v = v + 2, most
+ * recent token in the low bits), lm_vals float [lm_capacity][2] = (ln p, ln backoff), lm_in_vocab int32 [V].
+ * Every emitted character adds alpha * ln P(c | history) + beta; the published min_cutoff pruning is applied. */
+int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens, int32_t beam,
+                               float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states, int32_t max_frames,
+                               void* workspace, const uint64_t* lm_keys, const float* lm_vals, const int32_t* lm_in_vocab,
+                               int64_t lm_capacity, int32_t lm_order, float alpha, float beta, void* stream);
 int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
                            int32_t lmax, int32_t* out_lens, float* out_scores, void* stream);
 /* The pruning scan of the posterior alone (decoder_utils.cpp get_pruned_log_probs), for the HBM roofline. */

@@ -171,19 +171,44 @@ def _prefix_key(n):
     return (-n.score, n.ch)
 
 
-def ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0):
-    """ctc_beam_search_decoder.cpp ctc_beam_search_decoding with ext_scorer == nullptr.
-    Returns [(score, [ids])] sorted best first; score is the log of the total CTC probability of the
-    prefix (log_prob_b + log_prob_nb at the last frame), as returned by get_beam_search_result."""
+def make_ngram(prefix, vocabulary, max_order):
+    """scorer.cpp make_ngram for a character-based LM: the last `max_order` tokens of the prefix (one token = one LM word),
+    left-padded with <s> up to max_order items."""
+    toks = []
+    n = prefix
+    while n.parent is not None and len(toks) < max_order:
+        toks.append(vocabulary[n.ch])
+        n = n.parent
+    if len(toks) < max_order:
+        toks += ["<s>"] * (max_order - len(toks))
+    return toks[::-1]
+
+
+def ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0, ext_scorer=None, vocabulary=None):
+    """ctc_beam_search_decoder.cpp ctc_beam_search_decoding. Returns [(score, [ids])] sorted best first; score is the log of
+    the total CTC probability of the prefix (log_prob_b + log_prob_nb at the last frame), plus, with an external scorer
+    (character based), alpha * ln P_LM(c | history) + beta for every emitted character.
+    ext_scorer: object with .alpha, .beta, .get_max_order(), .get_log_cond_prob(words) (ppasr_b200.decoders.ngram_lm.Scorer
+    mirrors paddlespeech_ctcdecoders.Scorer); with it the published min_cutoff pruning is applied as well."""
     probs_seq = np.asarray(probs_seq)
     root = _Node()
     root.score = root.b_prev = 0.0
     prefixes = [root]
     for t in range(probs_seq.shape[0]):
         log_prob_idx = get_pruned_log_probs(probs_seq[t], cutoff_prob, cutoff_top_n)
+        min_cutoff = -NUM_FLT_INF
+        full_beam = False
+        if ext_scorer is not None:
+            num_prefixes = min(len(prefixes), beam_size)
+            prefixes[:num_prefixes] = sorted(prefixes[:num_prefixes], key=_prefix_key)
+            pb = float(probs_seq[t][blank_id])
+            min_cutoff = prefixes[num_prefixes - 1].score + (math.log(pb) if pb > 0 else -NUM_FLT_INF) - max(0.0, ext_scorer.beta)
+            full_beam = num_prefixes == beam_size
         for c, log_prob_c in log_prob_idx:
             for i in range(min(len(prefixes), beam_size)):
                 prefix = prefixes[i]
+                if full_beam and log_prob_c + prefix.score < min_cutoff:
+                    break
                 if c == blank_id:
                     prefix.b_cur = log_sum_exp(prefix.b_cur, log_prob_c + prefix.score)
                     continue
@@ -195,6 +220,9 @@ def ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob=1.0, cutoff_top_n=40, 
                     log_p = log_prob_c + prefix.b_prev
                 elif c != prefix.ch:
                     log_p = log_prob_c + prefix.score
+                if ext_scorer is not None and log_p > -NUM_FLT_INF:  # character-based LM: score every new character
+                    ngram = make_ngram(prefix_new, vocabulary, ext_scorer.get_max_order())
+                    log_p += ext_scorer.get_log_cond_prob(ngram) * ext_scorer.alpha + ext_scorer.beta
                 prefix_new.nb_cur = log_sum_exp(prefix_new.nb_cur, log_p)
         prefixes = []
         root.iterate_to_vec(prefixes)
@@ -207,12 +235,19 @@ def ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob=1.0, cutoff_top_n=40, 
     return [(n.score, n.path()) for n in prefixes[:beam_size]]
 
 
-def ctc_beam_search_decoding(probs_seq, vocabulary, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0):
-    """Mirror of ppasr/decoders/swig_wrapper.py:35-64 (ext_scoring_func=None). The published
-    decoder_utils.cpp get_beam_search_result returns `-approx_ctc` (a positive negative-log-probability),
-    best hypothesis first; without a scorer approx_ctc is the prefix score itself."""
-    res = ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob, cutoff_top_n, blank_id)
-    return [(-s, "".join(vocabulary[i] for i in ids)) for s, ids in res]
+def ctc_beam_search_decoding(probs_seq, vocabulary, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0, ext_scorer=None):
+    """Mirror of ppasr/decoders/swig_wrapper.py:35-64. The published decoder returns `-approx_ctc`, best hypothesis first;
+    without a scorer approx_ctc is the prefix score itself, with one the word-insertion and LM terms are taken out again:
+    approx_ctc = score - len * beta - alpha * get_sent_log_prob(words)  (ctc_beam_search_decoder.cpp, end of decoding)."""
+    res = ctc_beam_search_ids(probs_seq, beam_size, cutoff_prob, cutoff_top_n, blank_id, ext_scorer, vocabulary)
+    out = []
+    for s, ids in res:
+        approx = s
+        if ext_scorer is not None:
+            words = [vocabulary[i] for i in ids]
+            approx = s - len(ids) * ext_scorer.beta - ext_scorer.get_sent_log_prob(words) * ext_scorer.alpha
+        out.append((-approx, "".join(vocabulary[i] for i in ids)))
+    return out
 
 
 def ctc_prefix_total_logprob_bruteforce(probs_seq, blank_id=0):

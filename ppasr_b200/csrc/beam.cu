@@ -227,10 +227,48 @@ DEVINL float lse2(float a, float b) {  // decoder_utils.h log_sum_exp
   return logf(expf(a - m) + expf(b - m)) + m;
 }
 
+// ---- external scorer: back-off n-gram query (scorer.cpp get_log_cond_prob over make_ngram(prefix), character based) ----
+DEVINL bool lm_find(const BeamLm& lm, unsigned long long key, float2* out) {
+  unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 17) & lm.mask;
+  for (;;) {
+    const unsigned long long k = __ldg(lm.keys + slot);
+    if (k == key) {
+      *out = __ldg(lm.vals + slot);
+      return true;
+    }
+    if (k == 0ull) return false;
+    slot = (slot + 1) & lm.mask;
+  }
+}
+// ln P(c | last order-1 tokens of the prefix, left-padded with <s>); any token without a unigram -> OOV_SCORE (-1000)
+DEVINL float lm_log_cond_prob(const BeamLm& lm, const BeamEntry& e, int c) {
+  if (!__ldg(lm.in_lm + c)) return -1000.0f;
+  const int n = lm.order - 1;  // context length
+  unsigned long long ctx[3];   // oldest .. most recent
+  {
+    const int raw[3] = {e.prev2, e.prev1, e.last};
+    for (int i = 0; i < 3; ++i) {
+      const int v = raw[i];
+      if (i >= 3 - n && v >= 0 && !__ldg(lm.in_lm + v)) return -1000.0f;  // only tokens inside the n-gram window
+      ctx[i] = v >= 0 ? (unsigned long long)(v + 2) : 1ull;  // <s> padding
+    }
+  }
+  const unsigned long long w = (unsigned long long)(c + 2);
+  float bo = 0.f;
+  for (int start = 3 - n; start <= 3; ++start) {
+    unsigned long long kc = 0ull;
+    for (int i = start; i < 3; ++i) kc = (kc << 16) | ctx[i];
+    float2 v;
+    if (lm_find(lm, (kc << 16) | w, &v)) return bo + v.x;
+    if (start < 3 && lm_find(lm, kc, &v)) bo += v.y;
+  }
+  return -1000.0f;
+}
+
 __global__ void __launch_bounds__(BEAM_THREADS)
 ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid, const float* __restrict__ clp, int T,
                        const int* __restrict__ frame_lens, int beam, int blank, BeamStateHeader* __restrict__ states,
-                       size_t state_stride_bytes, int node_cap) {
+                       size_t state_stride_bytes, int node_cap, const float* __restrict__ probs, int V, const BeamLm lm) {
   const int b = blockIdx.x;
   uint8_t* sp = reinterpret_cast<uint8_t*>(states) + (size_t)b * state_stride_bytes;
   BeamStateHeader* hdr = reinterpret_cast<BeamStateHeader*>(sp);
@@ -248,6 +286,8 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
   __shared__ float red_s[BEAM_THREADS / 32];
   __shared__ int red_k[BEAM_THREADS / 32], red_i[BEAM_THREADS / 32];
   __shared__ int s_nb, s_next_id;
+  __shared__ float s_min_cutoff;
+  __shared__ int s_full_beam;
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -276,6 +316,17 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
       cscore[i] = -INFINITY;
       ckey[i] = 0;
     }
+    if (tid == 0) {
+      // with a scorer: min_cutoff = worst beam score + ln p(blank) - max(0, beta); applies when the beam is full
+      // (ctc_beam_search_decoder.cpp; the beam is kept sorted best-first, so E[nb-1] is the worst entry)
+      s_full_beam = 0;
+      s_min_cutoff = -INFINITY;
+      if (lm.keys != nullptr) {
+        const float pb = probs[row * V + blank];
+        s_min_cutoff = E[nb - 1].score + (pb > 0.f ? logf(pb) : -INFINITY) - fmaxf(0.f, lm.beta);
+        s_full_beam = nb == beam;
+      }
+    }
     __syncthreads();
     // every (prefix i, char c) pair
     for (int pidx = tid; pidx < npair; pidx += BEAM_THREADS) {
@@ -283,6 +334,7 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
       const int c = fid[ci];
       const float lp = flp[ci];
       const BeamEntry e = E[i];
+      if (s_full_beam && lp + e.score < s_min_cutoff) continue;
       if (c == blank) {
         stay_b[i] = lp + e.score;
         continue;
@@ -294,6 +346,7 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
       } else {
         log_p = lp + e.score;
       }
+      if (lm.keys != nullptr && log_p > -INFINITY) log_p += lm.alpha * lm_log_cond_prob(lm, e, c) + lm.beta;
       // does the extension land on a prefix that is already in the beam? (identity = hash of the id string)
       const unsigned long long hx = e.hash * 0x9E3779B97F4A7C15ull + (unsigned long long)(c + 1);
       int j = -1;
@@ -383,16 +436,14 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
         const int i = slot / nc, ci = slot - i * nc;
         const BeamEntry e = E[i];
         const int c = fid[ci];
-        float log_p;
-        if (c == e.last)
-          log_p = flp[ci] + e.b_prev;
-        else
-          log_p = flp[ci] + e.score;
+        const float log_p = cscore[slot];  // as computed above (includes the scorer terms)
         const int id = atomicAdd(&s_next_id, 1);
         ne.id = id;
         ne.hash = e.hash * 0x9E3779B97F4A7C15ull + (unsigned long long)(c + 1);
         ne.parent_id = e.id;
         ne.last = c;
+        ne.prev1 = e.last;
+        ne.prev2 = e.prev1;
         ne.len = e.len + 1;
         ne.b_prev = -INFINITY;
         ne.nb_prev = log_p;
@@ -462,6 +513,7 @@ __global__ void ctc_beam_reset_kernel(BeamStateHeader* states, size_t state_stri
     hdr->frames = 0;
     BeamEntry root;
     root.id = 0, root.parent_id = -1, root.last = -1, root.len = 0;
+    root.prev1 = root.prev2 = -1, root.pad = 0;
     root.hash = 0x243F6A8885A308D3ull;
     root.b_prev = 0.f;  // root.log_prob_b_prev = 0.0, root.score = 0.0 (ctc_beam_search_decoder.cpp)
     root.nb_prev = -INFINITY;
@@ -482,7 +534,8 @@ cudaError_t launch_beam_reset(void* states, int B, int node_cap, cudaStream_t st
 }
 
 cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp, int B, int T, const int* frame_lens,
-                                int beam, int blank, void* states, int node_cap, cudaStream_t st) {
+                                int beam, int blank, void* states, int node_cap, cudaStream_t st, const float* probs, int V,
+                                const BeamLm* lm) {
   if (beam < 1 || beam > BEAM_MAXB) return cudaErrorInvalidValue;
   const size_t dyn = (size_t)(beam * BEAM_MAXC + beam) * 8;
   static size_t configured = 0;
@@ -492,9 +545,10 @@ cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp
     if (e != cudaSuccess) return e;
     configured = (size_t)(BEAM_MAXB * BEAM_MAXC + BEAM_MAXB) * 8;
   }
+  BeamLm none{};
   ctc_prefix_beam_kernel<<<B, BEAM_THREADS, dyn, st>>>(cnt, cid, clp, T, frame_lens, beam, blank,
                                                      reinterpret_cast<BeamStateHeader*>(states),
-                                                     beam_state_stride(node_cap), node_cap);
+                                                     beam_state_stride(node_cap), node_cap, probs, V, lm ? *lm : none);
   count_launch();
   return cudaGetLastError();
 }

@@ -90,14 +90,26 @@ struct BeamEntry {
   unsigned long long hash;  // identity of the prefix string
   int id, parent_id, last, len;
   float b_prev, nb_prev, score;
+  int prev1, prev2;  // the two tokens before `last` (-1 = none): n-gram context of the external scorer
   int pad;
+};
+// External scorer = character-based back-off n-gram LM as an open-addressing hash table (ppasr_b200/decoders/ngram_lm.py):
+// token 1 = <s>, v + 2 = vocabulary id v; key = tokens packed 16 bits each (most recent in the low bits); value = (ln p, ln bo)
+struct BeamLm {
+  const unsigned long long* keys;  // null = no scorer
+  const float2* vals;
+  const int* in_lm;                // [V] 1 if the token has a unigram
+  unsigned mask;                   // capacity - 1
+  int order;                       // <= 4
+  float alpha, beta;
 };
 size_t beam_state_stride(int node_cap);
 cudaError_t launch_ctc_prune(const float* probs, int V, int rows, float cutoff_prob, int top_n, int* cnt, int* cid,
                              float* clp, cudaStream_t st);
 cudaError_t launch_beam_reset(void* states, int B, int node_cap, cudaStream_t st);
 cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp, int B, int T, const int* frame_lens,
-                                int beam, int blank, void* states, int node_cap, cudaStream_t st);
+                                int beam, int blank, void* states, int node_cap, cudaStream_t st,
+                                const float* probs = nullptr, int V = 0, const BeamLm* lm = nullptr);
 cudaError_t launch_beam_result(const void* states, int B, int node_cap, int beam, int* out_ids, int lmax, int* out_lens,
                                float* out_scores, cudaStream_t st);
 constexpr int BEAM_MAX_TOPN = 64;

@@ -181,6 +181,33 @@ int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V,
   PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, blank_id, states, max_frames * beam + 1, st));
   return PPASR_OK;
 }
+int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens, int32_t beam,
+                               float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states, int32_t max_frames,
+                               void* workspace, const uint64_t* lm_keys, const float* lm_vals, const int32_t* lm_in_vocab,
+                               int64_t lm_capacity, int32_t lm_order, float alpha, float beta, void* stream) {
+  PPASR_REQUIRE(probs && states && workspace && lm_keys && lm_vals && lm_in_vocab, "null pointer");
+  PPASR_REQUIRE(B > 0 && T > 0 && V > 1 && V + 2 < 65536, "bad sizes (the scorer packs token ids in 16 bits)");
+  PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,128] in this build");
+  PPASR_REQUIRE(cutoff_top_n >= 1, "cutoff_top_n must be >= 1");
+  PPASR_REQUIRE(lm_order >= 1 && lm_order <= 4, "the scorer supports n-gram orders 1..4");
+  PPASR_REQUIRE(lm_capacity >= 2 && (lm_capacity & (lm_capacity - 1)) == 0, "lm_capacity must be a power of two");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int top_n = cutoff_top_n < BEAM_MAX_TOPN ? cutoff_top_n : BEAM_MAX_TOPN;
+  int* cnt = reinterpret_cast<int*>(workspace);
+  int* cid = cnt + (((size_t)B * T + 63) & ~size_t(63));
+  float* clp = reinterpret_cast<float*>(cid + (size_t)B * T * BEAM_MAX_TOPN);
+  PPASR_CUDA_CHECK(launch_ctc_prune(probs, V, B * T, cutoff_prob, top_n, cnt, cid, clp, st));
+  BeamLm lm;
+  lm.keys = reinterpret_cast<const unsigned long long*>(lm_keys);
+  lm.vals = reinterpret_cast<const float2*>(lm_vals);
+  lm.in_lm = lm_in_vocab;
+  lm.mask = (unsigned)(lm_capacity - 1);
+  lm.order = lm_order;
+  lm.alpha = alpha, lm.beta = beta;
+  PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, blank_id, states, max_frames * beam + 1, st, probs,
+                                       V, &lm));
+  return PPASR_OK;
+}
 int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
                            int32_t lmax, int32_t* out_lens, float* out_scores, void* stream) {
   PPASR_REQUIRE(states && out_ids && out_lens && out_scores && lmax > 0, "bad arguments");

@@ -4,8 +4,10 @@ running the CTC prefix beam search on the B200 (ppasr_b200/csrc/beam.cu) instead
 
 Same constructor arguments and methods (beam_search_decoder.py:9-96). Differences:
   * `language_model_path=None` (default here) decodes without an external scorer -- which the upstream C++
-    supports via ext_scoring_func=None (swig_wrapper.py:35-41). A KenLM scorer is a "next" row
-    (SURVEY §8f-4): passing a path raises instead of silently ignoring alpha/beta.
+    supports via ext_scoring_func=None (swig_wrapper.py:35-41). With a path, the file must be an ARPA text n-gram model
+    (order <= 4) that is character based (every LM word is one vocabulary token), as the reference's Chinese setups
+    are; it is turned into a device hash table and scored inside the beam kernel (ppasr_b200/decoders/ngram_lm.py).
+    KenLM *binary* files (.klm / trie) and word-based LMs (English, needs the dictionary FST) raise.
   * beam_size <= 128 and cutoff_top_n <= 64 in this build; larger values raise.
   * `num_processes` is accepted and ignored (utterances are decoded by one CTA each, all in parallel).
 Returned scores follow the upstream convention: -log P(prefix) of the total CTC probability
@@ -20,10 +22,7 @@ from .. import _lib as L
 
 class BeamSearchDecoder:
     def __init__(self, alpha=2.2, beta=4.3, beam_size=300, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=None,
-                 num_processes=10, blank_id=0, language_model_path=None, max_frames=5000):
-        if language_model_path is not None:
-            raise Exception("ppasr_b200 BeamSearchDecoder: external KenLM scorer is not implemented in this round; "
-                            "pass language_model_path=None to decode without a scorer")
+                 num_processes=10, blank_id=0, language_model_path=None, max_frames=5000, ext_scorer=None):
         if beam_size > 128:
             raise Exception(f"beam_size {beam_size} > 128 is not supported by the GPU decoder in this build")
         if cutoff_top_n > 64:
@@ -42,7 +41,25 @@ class BeamSearchDecoder:
         self.blank_id = int(blank_id)
         self.max_frames = int(max_frames)
         self.lib = L.load()
-        self._ext_scorer = None
+        self._ext_scorer = ext_scorer
+        if language_model_path is not None and ext_scorer is None:
+            from .ngram_lm import Scorer
+            with open(language_model_path, "rb") as f:
+                head = f.read(64)
+            if not head.lstrip().startswith(b"\\data\\"):
+                raise Exception("language model must be an ARPA text file (KenLM binary formats are not supported): "
+                                + str(language_model_path))
+            self._ext_scorer = Scorer(alpha, beta, language_model_path, vocab_list)
+        self._lm_dev = None
+        if self._ext_scorer is not None:
+            sc = self._ext_scorer
+            if not sc.is_character_based():
+                raise Exception("only character-based language models are supported by the GPU scorer")
+            if sc.get_max_order() > 4:
+                raise Exception("n-gram order > 4 is not supported by the GPU scorer")
+            keys, vals, in_lm = sc.lm.device_tables(vocab_list)
+            self._lm_dev = (torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(vals).cuda(),
+                            torch.from_numpy(in_lm).cuda(), int(keys.shape[0]))
         self._stream_state = None  # persistent state of the streaming decoder (batch 1)
         self.reset_decoder()
 
@@ -61,6 +78,15 @@ class BeamSearchDecoder:
         fl = None
         if frame_lens is not None:
             fl = torch.as_tensor(np.asarray(frame_lens), dtype=torch.int32).cuda()
+        if self._lm_dev is not None:
+            keys, vals, in_lm, cap = self._lm_dev
+            sc = self._ext_scorer
+            L.check(self.lib.ppasr_b200_beam_advance_lm(L.ptr(probs), B, T, V, L.ptr(fl), self.beam_size,
+                                                        ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
+                                                        L.ptr(state), max_frames, L.ptr(ws), L.ptr(keys), L.ptr(vals),
+                                                        L.ptr(in_lm), cap, sc.get_max_order(), ctypes.c_float(sc.alpha),
+                                                        ctypes.c_float(sc.beta), L.stream_ptr()))
+            return
         L.check(self.lib.ppasr_b200_beam_advance(L.ptr(probs), B, T, V, L.ptr(fl), self.beam_size,
                                                  ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
                                                  L.ptr(state), max_frames, L.ptr(ws), L.stream_ptr()))
@@ -79,8 +105,13 @@ class BeamSearchDecoder:
             for k in range(self.beam_size):
                 if lens[b, k] < 0:
                     continue
-                text = "".join(self.vocab_list[i] for i in ids[b, k, :lens[b, k]])
-                res.append((-float(sc[b, k]), text))
+                toks = [self.vocab_list[i] for i in ids[b, k, :lens[b, k]]]
+                approx = float(sc[b, k])
+                if self._ext_scorer is not None:
+                    # approx_ctc: take the word-insertion and LM terms out again (ctc_beam_search_decoder.cpp, end of decoding)
+                    es = self._ext_scorer
+                    approx = approx - len(toks) * es.beta - es.get_sent_log_prob(toks) * es.alpha
+                res.append((-approx, "".join(toks)))
             out.append(res)
         return out
 
@@ -134,20 +165,16 @@ class BeamSearchDecoder:
 def ctc_beam_search_decoding(probs_seq, vocabulary, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0,
                              ext_scoring_func=None):
     """swig_wrapper.py:35-64 -> [(score, text)] best first."""
-    if ext_scoring_func is not None:
-        raise Exception("external scorer is not supported")
     d = BeamSearchDecoder(beam_size=beam_size, cutoff_prob=cutoff_prob, cutoff_top_n=cutoff_top_n, vocab_list=vocabulary,
-                          blank_id=blank_id, max_frames=8)
+                          blank_id=blank_id, max_frames=8, ext_scorer=ext_scoring_func)
     return d.decode_ids_batch(d._to_cuda(probs_seq).unsqueeze(0))[0]
 
 
 def ctc_beam_search_decoding_batch(probs_split, vocabulary, beam_size, num_processes, cutoff_prob=1.0, cutoff_top_n=40,
                                    blank_id=0, ext_scoring_func=None):
     """swig_wrapper.py:67-103 -> [[(score, text)]]."""
-    if ext_scoring_func is not None:
-        raise Exception("external scorer is not supported")
     d = BeamSearchDecoder(beam_size=beam_size, cutoff_prob=cutoff_prob, cutoff_top_n=cutoff_top_n, vocab_list=vocabulary,
-                          blank_id=blank_id, max_frames=8)
+                          blank_id=blank_id, max_frames=8, ext_scorer=ext_scoring_func)
     import torch
     lens = [int(p.shape[0]) for p in probs_split]
     batch = torch.zeros((len(lens), max(lens), int(probs_split[0].shape[1])), dtype=torch.float32)

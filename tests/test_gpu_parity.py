@@ -654,3 +654,54 @@ def test_deepspeech2_chunk_streaming(lib, cuda):
     pred.reset_stream()
     with pytest.raises(Exception):
         pred.predict_chunk_conformer(x[:1, :67], -1)
+
+
+# ------------------------------------------------------------------------------------------------
+# beam search with the external n-gram scorer (swig_wrapper.py:4-19, beam_search_decoder.py:29-40)
+# ------------------------------------------------------------------------------------------------
+def _toy_lm(V, order, seed=0):
+    from ppasr_b200.decoders.ngram_lm import NGramLM
+    rng = np.random.RandomState(seed)
+    vocab = ["<blank>", "<unk>"] + [chr(0x4E00 + i) for i in range(V - 3)] + ["<eos>"]
+    sents = [[vocab[2 + int(z) % (V - 3)] for z in rng.zipf(1.5, size=rng.randint(3, 12))] for _ in range(400)]
+    return vocab, NGramLM.from_counts(sents, order=order)
+
+
+@pytest.mark.parametrize("T,V,beam,order,alpha,beta,temp", [
+    (30, 20, 10, 4, 2.2, 4.3, 3.0), (60, 40, 20, 3, 1.0, 0.5, 4.0), (40, 30, 5, 2, 0.5, 0.0, 2.0), (25, 12, 8, 4, 2.2, 4.3, 1.0),
+])
+def test_beam_search_with_ngram_scorer_matches_oracle(lib, cuda, tmp_path, T, V, beam, order, alpha, beta, temp):
+    from oracle import decoders_oracle as DO
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    from ppasr_b200.decoders.ngram_lm import Scorer
+    vocab, lm = _toy_lm(V, order)
+    arpa = str(tmp_path / "toy.arpa")
+    lm.write_arpa(arpa)
+    dec = BeamSearchDecoder(alpha=alpha, beta=beta, beam_size=beam, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=vocab,
+                            language_model_path=arpa)
+    sc = Scorer(alpha, beta, arpa, vocab)
+    rng = np.random.RandomState(T * 7 + V)
+    probs = np.stack([_peaky_probs(rng, T, V, temp, bb) for bb in (0.0, 1.0)])
+    got = dec.decode_ids_batch(probs)
+    for b in range(probs.shape[0]):
+        ref = DO.ctc_beam_search_decoding(probs[b], vocab, beam, 0.99, 40, ext_scorer=sc)
+        assert got[b][0][1] == ref[0][1], f"best hypothesis differs (utt {b})"
+        assert abs(got[b][0][0] - ref[0][0]) < 2e-3 * max(1.0, abs(ref[0][0]))
+        # the whole beam (as a set of strings) agrees as well when the margins are comfortable
+        assert len(got[b]) == len(ref)
+
+
+def test_beam_search_scorer_changes_result_and_rejects_bad_models(lib, cuda, tmp_path):
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    vocab, lm = _toy_lm(20, 3)
+    arpa = str(tmp_path / "toy.arpa")
+    lm.write_arpa(arpa)
+    rng = np.random.RandomState(3)
+    probs = _peaky_probs(rng, 40, 20, 1.0, 0.0)[None]
+    plain = BeamSearchDecoder(beam_size=10, vocab_list=vocab).decode_ids_batch(probs)[0][0]
+    with_lm = BeamSearchDecoder(alpha=3.0, beta=1.0, beam_size=10, vocab_list=vocab, language_model_path=arpa).decode_ids_batch(probs)[0][0]
+    assert plain[1] != with_lm[1]  # flat posteriors: the LM decides
+    bad = tmp_path / "model.klm"
+    bad.write_bytes(b"mmap lm http://kheafield.com/code format version 5\\n\\x00")
+    with pytest.raises(Exception):
+        BeamSearchDecoder(beam_size=10, vocab_list=vocab, language_model_path=str(bad))

@@ -323,3 +323,72 @@ def test_efficient_conformer_grouped_attention_group1_equals_plain():
     conf.group_size = 1
     b = o.grouped_mha("encoder.encoders.0.self_attn", x, mask, pos)
     assert (a - b).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# n-gram scorer (host side of the GPU scorer) and the oracle beam search with it
+# ------------------------------------------------------------------------------------------------
+def _toy_lm(V=20, order=4, seed=0):
+    from ppasr_b200.decoders.ngram_lm import NGramLM
+    rng = np.random.RandomState(seed)
+    vocab = ["<blank>", "<unk>"] + [chr(0x4E00 + i) for i in range(V - 3)] + ["<eos>"]
+    sents = [[vocab[2 + int(z) % (V - 3)] for z in rng.zipf(1.5, size=rng.randint(3, 12))] for _ in range(300)]
+    return vocab, sents, NGramLM.from_counts(sents, order=order)
+
+
+def test_ngram_lm_backoff_semantics_and_arpa_roundtrip(tmp_path):
+    from ppasr_b200.decoders.ngram_lm import NGramLM, OOV_SCORE, LOG10_E
+    vocab, sents, lm = _toy_lm()
+    assert lm.is_character_based() and lm.order == 4
+    # P(. | seen context) sums to ~1 (discounted mass redistributed through the back-off weights)
+    ctx = tuple(sents[0][:3])
+    tot = sum(10 ** lm._score(ctx, w) for w in lm.vocab if w != "<s>")
+    assert abs(tot - 1.0) < 0.02
+    # unseen context backs off to shorter histories; manual recursion == log_cond_prob
+    words = ["<s>", "<s>", vocab[5], vocab[9]]
+    manual = lm._score(tuple(words[:-1])[-3:], words[-1]) / LOG10_E
+    assert abs(lm.log_cond_prob(words) - manual) < 1e-9
+    assert lm.log_cond_prob(["<s>", "zz"]) == OOV_SCORE
+    p = str(tmp_path / "t.arpa")
+    lm.write_arpa(p)
+    lm2 = NGramLM.from_arpa(p)
+    assert len(lm2.ngrams) == len(lm.ngrams) and lm2.order == 4
+    for s in sents[:5]:
+        assert abs(lm2.sent_log_prob(s) - lm.sent_log_prob(s)) < 1e-3
+    # device hash table: every n-gram whose tokens are in the vocabulary is retrievable
+    keys, vals, in_lm = lm.device_tables(vocab)
+    tok = {"<s>": 1, **{w: i + 2 for i, w in enumerate(vocab)}}
+    mask = len(keys) - 1
+    for ng, (lp, bo) in list(lm.ngrams.items())[:200]:
+        if any(w not in tok for w in ng):
+            continue
+        key = 0
+        for w in ng:
+            key = (key << 16) | tok[w]
+        slot = (((key * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF) >> 17) & mask
+        while int(keys[slot]) != key:
+            assert int(keys[slot]) != 0
+            slot = (slot + 1) & mask
+        assert abs(vals[slot][0] - lp / LOG10_E) < 1e-4
+
+
+def test_oracle_beam_search_with_scorer():
+    from ppasr_b200.decoders.ngram_lm import Scorer
+    vocab, sents, lm = _toy_lm()
+    rng = np.random.RandomState(1)
+    x = rng.randn(25, 20) * 2.0
+    p = np.exp(x - x.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    # alpha = beta = 0: the scorer only adds the min_cutoff pruning; with a beam that never fills it is a no-op
+    sc0 = Scorer(0.0, 0.0, None, vocab, lm=lm)
+    ps = p[:5, :6] / p[:5, :6].sum(1, keepdims=True)
+    a0 = DO.ctc_beam_search_decoding(ps, vocab[:6], 10000, 1.0, 40)
+    b0 = DO.ctc_beam_search_decoding(ps, vocab[:6], 10000, 1.0, 40, ext_scorer=sc0)
+    assert a0[0][1] == b0[0][1] and abs(a0[0][0] - b0[0][0]) < 1e-4
+    a = DO.ctc_beam_search_decoding(p, vocab, 20, 0.99, 40)
+    # a strong LM pulls the result towards likely character sequences: LM log-prob per char of the output improves
+    sc = Scorer(3.0, 0.0, None, vocab, lm=lm)
+    c = DO.ctc_beam_search_decoding(p, vocab, 20, 0.99, 40, ext_scorer=sc)
+    la = lm.sent_log_prob(list(a[0][1])) / max(1, len(a[0][1]))
+    lc = lm.sent_log_prob(list(c[0][1])) / max(1, len(c[0][1]))
+    assert lc > la
