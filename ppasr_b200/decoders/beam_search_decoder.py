@@ -91,7 +91,7 @@ class BeamSearchDecoder:
                                                  ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
                                                  L.ptr(state), max_frames, L.ptr(ws), L.stream_ptr()))
 
-    def _results(self, state, B, max_frames, lmax):
+    def _results(self, state, B, max_frames, lmax, nbest=None):
         torch = self.torch
         ids = torch.zeros((B, self.beam_size, lmax), dtype=torch.int32, device="cuda")
         lens = torch.zeros((B, self.beam_size), dtype=torch.int32, device="cuda")
@@ -102,7 +102,7 @@ class BeamSearchDecoder:
         out = []
         for b in range(B):
             res = []
-            for k in range(self.beam_size):
+            for k in range(self.beam_size if nbest is None else min(nbest, self.beam_size)):
                 if lens[b, k] < 0:
                     continue
                 toks = [self.vocab_list[i] for i in ids[b, k, :lens[b, k]]]
@@ -120,19 +120,19 @@ class BeamSearchDecoder:
         t = probs if isinstance(probs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(probs, dtype=np.float32))
         return t.to(device="cuda", dtype=torch.float32).contiguous()
 
-    def decode_ids_batch(self, probs, frame_lens=None):
-        """probs [B,T,V] -> per utterance list of (score, text), best first (all beam entries)."""
+    def decode_ids_batch(self, probs, frame_lens=None, nbest=None):
+        """probs [B,T,V] -> per utterance list of (score, text), best first (all beam entries, or the first `nbest`)."""
         p = self._to_cuda(probs)
         B, T, V = p.shape
         st = self._alloc_state(B, T)
         self._advance(st, p, frame_lens, T)
-        return self._results(st, B, T, T)
+        return self._results(st, B, T, T, nbest)
 
     # ---- reference API --------------------------------------------------------------------------
     def decode_beam_search_offline(self, probs_split):
         """beam_search_decoder.py:45-56 -> (score, text) of the best hypothesis."""
         p = self._to_cuda(probs_split)
-        return self.decode_ids_batch(p.unsqueeze(0))[0][0]
+        return self.decode_ids_batch(p.unsqueeze(0), nbest=1)[0][0]
 
     def decode_batch_beam_search_offline(self, probs_split):
         """beam_search_decoder.py:59-73 -> [text]; probs_split: list of [T_i,V] arrays or a [B,T,V] tensor."""
@@ -143,9 +143,9 @@ class BeamSearchDecoder:
             batch = torch.zeros((len(lens), max(lens), V), dtype=torch.float32)
             for i, p in enumerate(probs_split):
                 batch[i, :lens[i]] = torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p.cpu())
-            res = self.decode_ids_batch(batch, lens)
+            res = self.decode_ids_batch(batch, lens, nbest=1)
         else:
-            res = self.decode_ids_batch(probs_split)
+            res = self.decode_ids_batch(probs_split, nbest=1)
         return [r[0][1] for r in res]
 
     def decode_chunk(self, probs, logits_lens):
@@ -155,7 +155,7 @@ class BeamSearchDecoder:
             p = p.unsqueeze(0)
         lens = np.asarray(logits_lens).astype(np.int32)
         self._advance(self._stream_state, p[:1], lens[:1], self.max_frames)
-        return self._results(self._stream_state, 1, self.max_frames, self.max_frames)[0][0]
+        return self._results(self._stream_state, 1, self.max_frames, self.max_frames, nbest=1)[0][0]
 
     def reset_decoder(self):
         """beam_search_decoder.py:93-96."""
