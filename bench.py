@@ -365,8 +365,11 @@ def main():
         top = max((k for k in prof if k in flops), key=lambda k: prof[k][1])
         us = prof[top][1] / prof[top][0] * 1e3
         ach = flops[top] / (us * 1e-6) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # kernel (profiles/r1_final_ncu_fused_ffn.txt: 14.35 MB read + 0 written, the outputs still sit in L2)
+        ncu_traffic = {"fused_ffn": 14.35e6}
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + " (burst cuBLAS bf16)",
+                "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic.get(top), "peak_source": pk["src"] + " (burst cuBLAS bf16)",
                 "us_per_launch": us, "share_of_step": prof[top][1] / total,
                 "step_tensor_frac_sustained": (gflop_per_utt * B / ms) / pk["bf16_tflops_sustained"]}
 
