@@ -194,6 +194,17 @@ int ppasr_b200_op_attention(const void* q2, const void* kk, const void* vt, int3
                             int32_t pos_rows, int32_t pos_ld, int32_t pos_row0, int32_t pos_col0, void* out,
                             int32_t B, int32_t H, int32_t T1, int32_t T2, const int32_t* klens, void* stream);
 
+/* ---- front end (the step before the hot path) ----------------------------------------
+ * replaces: AudioFeaturizer.featurize for feature_method 'fbank' (data_utils/featurizer/audio_featurizer.py:37-69,120-138):
+ * optional -20 dB RMS normalisation (data_utils/audio.py:287-304), int16 scaling (audio.py:549-574), Kaldi fbank with
+ * 25 ms / 10 ms frames, dither 0, n_mels bins. audio: fp32 in [-1, 1], device memory, [B, stride] with N valid samples per
+ * row (n_samples: optional device int32 [B] per-utterance counts <= N). out: device fp32 [B, Tmax, n_mels], frames beyond an
+ * utterance's own count are zero. gain_ws: device float [B] scratch (needed when db_normalize != 0). */
+int ppasr_b200_fbank_frames(int32_t n_samples);
+int ppasr_b200_fbank(const float* audio, int32_t B, int64_t stride, int32_t N, const int32_t* n_samples, int32_t n_mels,
+                     int32_t sample_rate, int32_t db_normalize, float target_db, float* gain_ws, float* out, int32_t Tmax,
+                     void* stream);
+
 /* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels, "fused_conv" (default 0) the
  * experimental fused conv1+conv2 front end (0 = separate kernels / GEMMs, for A/B measurements); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
  * returning -- 0 leaves the copies in flight (pinned host buffers; the caller synchronises), used by the

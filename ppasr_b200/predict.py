@@ -106,6 +106,24 @@ class PPASRPredictor:
         audio_feature = self._audio_featurizer.featurize(audio_data, sample_rate)
         return self.predict_features(audio_feature, use_pun=use_pun, is_itn=is_itn)
 
+    def predict_batch(self, audio_batch, n_samples=None):
+        """Extension: a batch of 16 kHz waveforms float32 [B, N] -> [{'text', 'score'}], everything from the fbank
+        front end (csrc/fbank.cu) to the greedy decode on the GPU; only the decoded ids come back to the host."""
+        from .featurizer import GpuFbank
+        from .parallel import detokenize
+        if self.decoder != 'ctc_greedy':
+            raise Exception("predict_batch implements the ctc_greedy decoder")
+        if getattr(self, '_gpu_fbank', None) is None:
+            pre = _get(self.configs, 'preprocess_conf', {}) or {}
+            pre = dict(pre) if isinstance(pre, dict) else vars(pre)
+            self._gpu_fbank = GpuFbank(n_mels=pre.get('n_mels', 80), sample_rate=pre.get('sample_rate', 16000),
+                                       use_dB_normalization=pre.get('use_dB_normalization', True),
+                                       target_dB=pre.get('target_dB', -20))
+        feats, counts = self._gpu_fbank.featurize_batch(audio_batch, n_samples)
+        res = self.predictor.predict_decode(feats, np.asarray(counts, dtype=np.int64), vocabulary=self.vocab_list,
+                                            trim_to_lens=n_samples is not None)
+        return [{'text': t, 'score': s} for s, t in res]
+
     def predict_features(self, audio_feature, use_pun=False, is_itn=False):
         """Same as predict() from the featurizer output on ([T, n_mels] fp32)."""
         input_data = np.array(audio_feature).astype(np.float32)[np.newaxis, :]

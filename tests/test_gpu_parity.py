@@ -705,3 +705,52 @@ def test_beam_search_scorer_changes_result_and_rejects_bad_models(lib, cuda, tmp
     bad.write_bytes(b"mmap lm http://kheafield.com/code format version 5\\n\\x00")
     with pytest.raises(Exception):
         BeamSearchDecoder(beam_size=10, vocab_list=vocab, language_model_path=str(bad))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU fbank front end (csrc/fbank.cu) vs the oracle restatement of AudioFeaturizer.featurize
+# ------------------------------------------------------------------------------------------------
+def _wave(seconds, seed, amp=0.2):
+    rng = np.random.RandomState(seed)
+    t = np.arange(int(16000 * seconds)) / 16000.0
+    x = 0.1 * rng.randn(t.size) + 0.3 * np.sin(2 * np.pi * (200 + 300 * seed) * t) * (1 + 0.5 * np.sin(2 * np.pi * 4 * t))
+    return (x * amp).astype(np.float32)
+
+
+@pytest.mark.parametrize("db", [True, False])
+def test_gpu_fbank_matches_oracle(lib, cuda, db):
+    from oracle import fbank_oracle as FO
+    from ppasr_b200.featurizer import GpuFbank
+    fb = GpuFbank(use_dB_normalization=db)
+    waves = [_wave(2.0, 0), _wave(2.0, 1, 0.01), _wave(2.0, 2, 0.9)]
+    lens = [32000, 20000, 399]
+    batch = np.stack(waves)
+    for b in range(3):
+        batch[b, lens[b]:] = 0
+    out, counts = fb.featurize_batch(batch, lens)
+    out = out.cpu().numpy()
+    assert out.shape == (3, 198, 80) and counts == [198, 123, 0]
+    for b in range(3):
+        ref = FO.featurize(batch[b, :lens[b]], use_db_normalization=db) if lens[b] >= 400 else np.zeros((0, 80), np.float32)
+        got = out[b, :counts[b]]
+        # fp32 FFT orderings differ (pocketfft vs radix-2): compare energies relatively, logs absolutely
+        if counts[b]:
+            assert np.abs(got - ref).max() < 5e-3, np.abs(got - ref).max()
+        assert np.all(out[b, counts[b]:] == 0)
+    assert fb.featurize(waves[0]).shape == (198, 80)
+
+
+def test_predict_batch_from_waveforms(lib, cuda):
+    """Waveform batch -> text entirely on the GPU == fbank on the host (reference path) -> predict."""
+    from ppasr_b200.predict import PPASRPredictor
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab
+    cfg = ConformerConfig(num_blocks=2, vocab_size=200)
+    vocab = make_vocab(200)
+    p = PPASRPredictor({"use_model": "conformer", "streaming": True, "decoder": "ctc_greedy", "encoder_conf": cfg.to_dict(),
+                        "preprocess_conf": {"feature_method": "fbank", "n_mels": 80}}, vocab_list=vocab,
+                       weights=init_conformer_weights(cfg))
+    waves = np.stack([_wave(3.0, 0), _wave(3.0, 1)])
+    got = p.predict_batch(waves)
+    for b in range(2):
+        ref = p.predict(waves[b])
+        assert got[b]['text'] == ref['text'] and abs(got[b]['score'] - ref['score']) < 0.5

@@ -392,3 +392,31 @@ def test_oracle_beam_search_with_scorer():
     la = lm.sent_log_prob(list(a[0][1])) / max(1, len(a[0][1]))
     lc = lm.sent_log_prob(list(c[0][1])) / max(1, len(c[0][1]))
     assert lc > la
+
+
+# ------------------------------------------------------------------------------------------------
+# fbank front end oracle == torchaudio's Kaldi port (the reference uses paddleaudio's port of the same code)
+# ------------------------------------------------------------------------------------------------
+def _test_wave(seconds=1.3, seed=0, amp=0.2):
+    rng = np.random.RandomState(seed)
+    t = np.arange(int(16000 * seconds)) / 16000.0
+    x = 0.1 * rng.randn(t.size) + 0.3 * np.sin(2 * np.pi * 440 * t) * (1 + 0.5 * np.sin(2 * np.pi * 4 * t))
+    return (x * amp).astype(np.float32)
+
+
+def test_fbank_oracle_matches_torchaudio_kaldi():
+    import torchaudio
+    from oracle import fbank_oracle as FO
+    for seed, amp in ((0, 0.2), (1, 0.01), (2, 0.9)):
+        x = _test_wave(seed=seed, amp=amp)
+        xs = FO.to_int16_scale(FO.db_normalize(x))
+        a = FO.kaldi_fbank(xs)
+        b = torchaudio.compliance.kaldi.fbank(torch.from_numpy(xs)[None], num_mel_bins=80, frame_length=25, frame_shift=10,
+                                              dither=0.0, sample_frequency=16000.0).numpy()
+        assert a.shape == b.shape == (1 + (x.size - 400) // 160, 80)
+        assert np.abs(a - b).max() < 2e-3
+    assert FO.kaldi_fbank(np.zeros(399, dtype=np.float32)).shape == (0, 80)
+    # AudioFeaturizer of the product (host path) is the same computation
+    from ppasr_b200.predict import AudioFeaturizer
+    x = _test_wave(seed=3)
+    assert np.abs(AudioFeaturizer().featurize(x) - FO.featurize(x)).max() < 2e-3
