@@ -183,5 +183,67 @@ class SqueezeformerOracle(ConformerOracle):
             xs, _, _ = self.layer(i, xs, chunk_masks, pos_emb, mask_pad)
         return xs, masks
 
+    # -- squeezeformer/encoder.py:246-258 ------------------------------------------------------------------------
+    def calculate_downsampling_factor(self, i):
+        conf = self.conf
+        if conf.reduce_idx is None:
+            return 1
+        reduce_exp = 1 if i >= conf.reduce_idx else 0
+        recover_exp = 1 if (conf.recover_idx is not None and i >= conf.recover_idx) else 0
+        return int(2 ** (reduce_exp - recover_exp))
+
+    # -- squeezeformer/encoder.py:260-383 ------------------------------------------------------------------------
     def encoder_forward_chunk(self, xs, offset, required_cache_size, att_cache, cnn_cache):
-        raise NotImplementedError("Squeezeformer forward_chunk (encoder.py:260-383) is not restated yet")
+        """att_cache (L, H, t, 2 dk) stored at the FULL frame rate for every block (the half-rate blocks write each key twice,
+        encoder.py:368, and read every second one, :351); cnn_cache (L, 1, D, lorder)."""
+        conf = self.conf
+        assert xs.shape[0] == 1
+        xs = self.global_cmvn(xs.to(self.dtype))
+        tmp_masks = torch.ones(1, 1, xs.shape[1], dtype=torch.bool)
+        xs, pos_emb, _ = self.embed(xs, tmp_masks, offset=offset)
+        cache_t1 = att_cache.shape[2] if att_cache.dim() == 4 else 0
+        chunk_size = xs.shape[1]
+        attention_key_size = cache_t1 + chunk_size
+        pos_emb = self.position_encoding(offset=offset - cache_t1, size=attention_key_size)
+        if required_cache_size < 0:
+            next_cache_start = 0
+        elif required_cache_size == 0:
+            next_cache_start = attention_key_size
+        else:
+            next_cache_start = max(attention_key_size - required_cache_size, 0)
+        r_att, r_cnn = [], []
+        mask_pad = torch.ones(1, 1, xs.shape[1], dtype=torch.bool)
+        att_mask = torch.ones(0, 0, 0, dtype=torch.bool)
+        recover = None
+        max_att_len = 0
+        xs = layer_norm(xs, self.w["encoder.preln.weight"], self.w["encoder.preln.bias"])
+        for i in range(conf.num_blocks):
+            if conf.reduce_idx is not None and i == conf.reduce_idx:
+                recover = (xs, att_mask, pos_emb, mask_pad)
+                xs, _m, mask_pad = self.time_reduction(xs, torch.ones(1, xs.shape[1], xs.shape[1], dtype=torch.bool), mask_pad)
+                pos_emb = pos_emb[:, ::2, :]
+            if conf.recover_idx is not None and i == conf.recover_idx and recover is not None:
+                rec_x, att_mask, rec_pos, rec_pad = recover
+                xs = torch.repeat_interleave(xs, 2, dim=1)
+                xs = linear(xs, self.w["encoder.time_recover_layer.weight"], self.w["encoder.time_recover_layer.bias"])
+                xs = rec_x + xs[:, :rec_x.shape[1], :]
+                pos_emb, mask_pad = rec_pos, rec_pad
+            factor = self.calculate_downsampling_factor(i)
+            ac = None
+            if att_cache.numel() > 0:
+                ac = att_cache[i:i + 1][:, :, ::factor, :][:, :, :pos_emb.shape[1] - xs.shape[1], :]
+            cc = cnn_cache[i] if cnn_cache.numel() > 0 else None
+            xs, new_att, new_cnn = self.layer(i, xs, None, pos_emb, None, ac, cc)
+            cached_att = new_att[:, :, next_cache_start // factor:, :]
+            cached_att = torch.repeat_interleave(cached_att, factor, dim=2)
+            if i == 0:
+                max_att_len = cached_att.shape[2]
+            r_att.append(cached_att[:, :, :max_att_len, :])
+            r_cnn.append(new_cnn.unsqueeze(0))
+        return xs, torch.cat(r_att, dim=0), torch.cat(r_cnn, dim=0)
+
+    @torch.no_grad()
+    def get_encoder_out_chunk(self, speech, offset, required_cache_size, att_cache, cnn_cache, return_logits=False):
+        xs, att_cache, cnn_cache = self.encoder_forward_chunk(speech, offset, required_cache_size, att_cache, cnn_cache)
+        out = self.ctc_logits(xs) if return_logits else self.ctc_softmax(xs)
+        return out, att_cache, cnn_cache

@@ -994,8 +994,8 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
     PPASR_CUDA_CHECK(cudaMemset(ds.c_state, 0, n * 4));
     return PPASR_OK;
   }
-  if (c->cfg.model_type != 0) {
-    set_last_error("chunk streaming (forward_chunk) is implemented for the conformer and deepspeech2 only");
+  if (c->cfg.model_type != 0 && c->cfg.model_type != 1) {
+    set_last_error("chunk streaming (forward_chunk) is implemented for conformer, squeezeformer and deepspeech2");
     return PPASR_ERR_STATE;
   }
   if (!c->cfg.causal) {
@@ -1071,15 +1071,23 @@ int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats
   // per-layer cache maps with extent = keys valid after this chunk (TMA zero-fills beyond)
   std::string err;
   const int kend_new = ss.kend + p.Tp;
+  const bool sqz = cfg.model_type == 1;
+  if (sqz && c->sq.reduce_idx >= 0) {
+    // the half-rate blocks address their caches / positions at half rate (runtime_squeezeformer.inl)
+    PPASR_REQUIRE(p.Tp % 2 == 0 && ss.kend % 2 == 0 && ss.kstart % 2 == 0 && ss.offset % 2 == 0 &&
+                      (required_cache_size < 0 || required_cache_size % 2 == 0),
+                  "squeezeformer chunk streaming needs an even number of output frames per chunk and an even required_cache_size");
+  }
   for (int l = 0; l < L; ++l) {
     const size_t lk = (size_t)l * B * H * ss.Tcap * 64;
+    const int rate = (sqz && c->sq.reduce_idx >= 0 && l >= c->sq.reduce_idx && l < c->sq.recover_idx) ? 2 : 1;
     if (!make_tmap_2d(&ss.tm_k[l], ss.kk + lk, 64, (uint64_t)B * H * ss.Tcap, 128, 128, &err) ||
-        !make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, kend_new, (uint64_t)B * H * 64, (uint64_t)ss.Tcap * 2, 64, &err)) {
+        !make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, kend_new / rate, (uint64_t)B * H * 64, (uint64_t)ss.Tcap * 2, 64, &err)) {
       set_last_error(err);
       return PPASR_ERR_CUDA;
     }
   }
-  rc = run_encoder(c, st, true);
+  rc = sqz ? run_encoder_squeezeformer(c, st, true) : run_encoder(c, st, true);
   if (rc) return rc;
   // cache bookkeeping (encoder.py:255-260,272): keep everything (<0), nothing (0) or the last `required` keys
   ss.kend = kend_new;
@@ -1112,6 +1120,7 @@ int ppasr_b200_stream_info(ppasr_b200_ctx* c, int32_t* offset, int32_t* cache_t)
 
 int ppasr_b200_stream_export(ppasr_b200_ctx* c, float* att_cache, float* cnn_cache, int32_t on_device, void* stream) {
   PPASR_REQUIRE(c && c->ss.kk, "no stream state");
+  PPASR_REQUIRE(c->cfg.model_type == 0, "cache export in the reference layout is implemented for the conformer only");
   auto& ss = c->ss;
   const auto& cfg = c->cfg;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

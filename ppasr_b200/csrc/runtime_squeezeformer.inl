@@ -285,7 +285,7 @@ int finalize_squeezeformer(ppasr_b200_ctx* c) {
   return PPASR_OK;
 }
 
-int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st) {
+int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st, bool chunk = false) {
   Plan& p = c->plan;
   const auto& cfg = c->cfg;
   auto& sq = c->sq;
@@ -294,9 +294,15 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st) {
   int rc = run_subsampling_convs(c, st);
   if (rc) return rc;
   // current resolution of the residual stream
+  // chunk mode (forward_chunk, encoder.py:260-383): no padding masks; K/V and the conv-module inputs of earlier chunks come
+  // from the device-resident caches in c->ss. The half-rate blocks keep their cache at half rate (the reference stores every
+  // key twice and reads every second one, encoder.py:351,368): positions / lengths are halved for them, which needs even
+  // chunk and cache sizes (checked by the caller).
+  auto& ss = c->ss;
   float* xc = p.x;
   int Tc = p.Tp, Mc = p.M;
-  const int* vl = p.vlen;
+  int rate = 1;  // 2 inside the time-reduced section
+  const int* vl = chunk ? nullptr : p.vlen;
   const CUtensorMap* tmpos = &c->tm_pos;
   const int Tr = (p.Tp + 1) / 2, Mr = p.B * Tr;
 
@@ -326,11 +332,11 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st) {
     const auto& m = sq.maps[l];
     if (l == sq.reduce_idx) {
       // ---- time reduction (encoder.py:211-214): masked depthwise stride-2 conv -> pointwise conv; masks / pos_emb [::2]
-      PPASR_CUDA_CHECK(launch_halve_lens(p.vlen, p.vlen2, p.B, st));
+      if (!chunk) PPASR_CUDA_CHECK(launch_halve_lens(p.vlen, p.vlen2, p.B, st));
       { PROF(PC_DWCONV);
-        PPASR_CUDA_CHECK(launch_time_reduce_dw(p.x, sq.tr_dw_w, sq.tr_dw_b, p.vlen, p.z, p.B, p.Tp, Tr, D, sq.tr_k,
+        PPASR_CUDA_CHECK(launch_time_reduce_dw(p.x, sq.tr_dw_w, sq.tr_dw_b, vl, p.z, p.B, p.Tp, Tr, D, sq.tr_k,
                                                sq.tr_k > 2 ? sq.tr_k - 2 : 0, st)); }
-      xc = p.x2, Tc = Tr, Mc = Mr, vl = p.vlen2, tmpos = &sq.tm_pos2;
+      xc = p.x2, Tc = Tr, Mc = Mr, vl = chunk ? nullptr : p.vlen2, tmpos = &sq.tm_pos2, rate = 2;
       ys = w.ada_s[0], yb = w.ada_b[0];
       if ((rc = post_ln(PC_PW2, p.tm_z, sq.tm_tr_pw, D, sq.tr_pw_b, 1.0f, 0, nullptr, 0, sq.ones, sq.zeros, ys, yb, 1))) return rc;
     }
@@ -338,16 +344,28 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st) {
       // ---- recover (encoder.py:216-230): x_full += Linear(repeat_interleave(x_reduced, 2))[:T']; y = ada_mha(l)(x_full)
       EpiRecover<BN_WIDE> e{p.x, p.y, sq.rec_b, w.ada_s[0], w.ada_b[0], Mr, D, Tr, p.Tp};
       { PROF(PC_OUTPROJ); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, sq.tm_rec_w, Mr, D, D, e, st))); }
-      xc = p.x, Tc = p.Tp, Mc = p.M, vl = p.vlen, tmpos = &c->tm_pos;
+      xc = p.x, Tc = p.Tp, Mc = p.M, vl = chunk ? nullptr : p.vlen, tmpos = &c->tm_pos, rate = 1;
     }
     // ---- MHA: x = LN1(x + Wo attn(ada x)); y = ada_ffn1(x)                 (encoder.py:468-478)
     {
       AttnParams ap{};
       ap.B = p.B, ap.H = H, ap.T1 = Tc, ap.D = D, ap.pos_col0 = l * D, ap.out = p.att, ap.q_rows_per_bh = Tc;
-      EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, Mc, Tc, H, Tc, p.Tkp, 0};
-      { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, Mc, 3 * D, D, e, st))); }
-      ap.T2 = Tc, ap.k_rows_per_bh = Tc, ap.k_row0 = 0, ap.pos_row0 = 0, ap.klens = vl;
-      { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, *tmpos, p.tm_vt, ap, st)); }
+      if (!chunk) {
+        EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, Mc, Tc, H, Tc, p.Tkp, 0};
+        { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, Mc, 3 * D, D, e, st))); }
+        ap.T2 = Tc, ap.k_rows_per_bh = Tc, ap.k_row0 = 0, ap.pos_row0 = 0, ap.klens = vl;
+        { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, *tmpos, p.tm_vt, ap, st)); }
+      } else {
+        // this chunk's K/V are appended to the block's cache at its own rate; keys kstart .. kend + chunk are attended with
+        // positions offset - cache_t .. (attention.py:127-134, encoder.py:302,351)
+        const size_t lk = (size_t)l * ss.B * H * ss.Tcap * 64;
+        const int kend = ss.kend / rate, kstart = ss.kstart / rate, cache_t = kend - kstart;
+        EpiQKV<BN_NARROW> e{p.q2, ss.kk + lk, ss.vt + lk, w.bqkv, w.pos_u, w.pos_v, Mc, Tc, H, ss.Tcap, ss.Tcap, kend};
+        { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, Mc, 3 * D, D, e, st))); }
+        ap.T2 = cache_t + Tc, ap.k_rows_per_bh = ss.Tcap, ap.k_row0 = kstart, ap.pos_row0 = (ss.offset - (ss.kend - ss.kstart)) / rate;
+        ap.klens = nullptr;
+        { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, ss.tm_k[l], *tmpos, ss.tm_vt[l], ap, st)); }
+      }
       feed(l, 1, &ys, &yb);
       if ((rc = post_ln(PC_OUTPROJ, p.tm_att, m.wo, D, w.bo, 1.0f, 1, nullptr, 0, w.ln_g[0], w.ln_b[0], ys, yb, 0))) return rc;
     }
@@ -360,12 +378,23 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st) {
     }
     // ---- conv module: x = LN3(x + mask * pw2 swish(norm(dw(glu(pw1 y))))); y = ada_ffn2(x)   (encoder.py:489-496)
     {
-      EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, Mc, 2 * D};
-      { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, Mc, 2 * D, D, eg, st))); }
-      const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
-      { PROF(PC_DWCONV);
-        PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
-                                                  cfg.conv_norm == 0, p.z, p.B, Tc, Tc, D, K, lpad, eps, vl, st)); }
+      if (!chunk) {
+        EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, Mc, 2 * D};
+        { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, Mc, 2 * D, D, eg, st))); }
+        const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
+        { PROF(PC_DWCONV);
+          PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
+                                                    cfg.conv_norm == 0, p.z, p.B, Tc, Tc, D, K, lpad, eps, vl, st)); }
+      } else {
+        // [cnn_cache ; chunk] -> pw1 + GLU -> "valid" depthwise conv; cache <- last K-1 input rows (convolution.py:129-138)
+        const int lorder = K - 1, Tcat = Tc + lorder, Mcat = p.B * Tcat;
+        PPASR_CUDA_CHECK(launch_conv_cache_concat(ss.cnn + (size_t)l * ss.B * lorder * D, p.y, p.ycat, p.B, Tc, lorder, D, st));
+        EpiGLU<BN_WIDE> eg{p.gcat, w.pw1_b, D, Mcat, 2 * D};
+        { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_ycat, m.pw1, Mcat, 2 * D, D, eg, st))); }
+        { PROF(PC_DWCONV);
+          PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.gcat, w.dw_w, w.dw_b, nullptr, w.cn_g, w.cn_b, cfg.conv_norm == 0, p.z, p.B,
+                                                    Tcat, Tc, D, K, 0, eps, nullptr, st)); }
+      }
       feed(l, 3, &ys, &yb);
       if ((rc = post_ln(PC_PW2, p.tm_z, m.pw2, D, w.pw2_b, 1.0f, 1, vl, 1, w.ln_g[2], w.ln_b[2], ys, yb, 0))) return rc;
     }

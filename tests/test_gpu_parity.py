@@ -754,3 +754,32 @@ def test_predict_batch_from_waveforms(lib, cuda):
     for b in range(2):
         ref = p.predict(waves[b])
         assert got[b]['text'] == ref['text'] and abs(got[b]['score'] - ref['score']) < 0.5
+
+
+@pytest.mark.parametrize("nb,reduce_idx,recover_idx,required", [(4, 1, 3, -1), (4, 1, 3, 32), (3, None, None, -1), (12, 5, 11, -1)])
+def test_squeezeformer_chunk_streaming_matches_oracle(lib, cuda, nb, reduce_idx, recover_idx, required):
+    """squeezeformer/encoder.py:260-383 forward_chunk: 67-frame windows with stride 64, device-resident caches (the half-rate
+    blocks keep theirs at half rate); compared chunk by chunk on the logits with the oracle's forward_chunk chain (which equals
+    the chunk-masked offline forward, tests/test_oracle_cpu.py)."""
+    from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.weights import SqueezeformerConfig, init_squeezeformer_weights, synthetic_fbank
+    cfg = SqueezeformerConfig(num_blocks=nb, vocab_size=120, reduce_idx=reduce_idx, recover_idx=recover_idx)
+    w = init_squeezeformer_weights(cfg)
+    orc = SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "squeezeformer",
+                              streaming=True, weights=w)
+    feats = synthetic_fbank(1, 67 + 64 * 3)
+    att = torch.zeros(0, 0, 0, 0)
+    cnn = torch.zeros(0, 0, 0, 0)
+    off = 0
+    for s in range(0, feats.shape[1] - 66, 64):
+        ch = feats[:, s:s + 67]
+        ref, att, cnn = orc.get_encoder_out_chunk(torch.from_numpy(ch), off, required, att, cnn, return_logits=True)
+        off += ref.shape[1]
+        probs = pred.predict_chunk_conformer(ch, required)
+        assert probs.shape == tuple(ref.shape) and np.allclose(probs.sum(-1), 1.0, atol=1e-4)
+        lg = pred.engine.ctc_logits().float().cpu()
+        assert ((lg - ref).abs().max() / ref.abs().max()).item() < 1e-2, s
+        assert int(pred.offset[0]) == off
+    pred.reset_stream()

@@ -420,3 +420,23 @@ def test_fbank_oracle_matches_torchaudio_kaldi():
     from ppasr_b200.predict import AudioFeaturizer
     x = _test_wave(seed=3)
     assert np.abs(AudioFeaturizer().featurize(x) - FO.featurize(x)).max() < 2e-3
+
+
+def test_squeezeformer_oracle_chunked_equals_chunk_masked_offline():
+    """forward_chunk over 67-frame windows == offline forward with decoding_chunk_size=16 (only true if the cache rate rules of
+    the time-reduced blocks, the positional offsets and the causal conv caches are wired as in the reference)."""
+    cfg, w, o = _squeeze(True, nb=4, reduce_idx=1, recover_idx=3)
+    from ppasr_b200.weights import synthetic_fbank
+    x = torch.from_numpy(synthetic_fbank(1, 67 + 64 * 2))
+    att = torch.zeros(0, 0, 0, 0)
+    cnn = torch.zeros(0, 0, 0, 0)
+    off, outs = 0, []
+    for s in range(0, x.shape[1] - 66, 64):
+        y, att, cnn = o.get_encoder_out_chunk(x[:, s:s + 67], off, -1, att, cnn, return_logits=True)
+        off += y.shape[1]
+        outs.append(y)
+    chunked = torch.cat(outs, 1)
+    enc, _ = o.encoder_forward(x, torch.tensor([x.shape[1]]), decoding_chunk_size=16, num_decoding_left_chunks=-1)
+    full = o.ctc_logits(enc)
+    assert (chunked - full[:, :chunked.shape[1]]).abs().max() < 1e-3 * full.abs().max()
+    assert att.shape == (4, 4, 48, 128) and cnn.shape == (4, 1, 256, 30)
