@@ -60,6 +60,10 @@ struct FfnParams {
   // (conv-module input, squeezeformer/convolution.py:119-127).
   int y_affine;
   const int* ylens;
+  // post-norm chained mode (pre_ys != null): the LayerNorm after the pre-GEMM is the block's own post-norm, i.e. the
+  // residual itself becomes x <- LN(x + Wp z + bp; gp, bpn) (written back into TMEM O) and the FFN input is its adaptive
+  // affine pre_ys * x + pre_yb (squeezeformer/encoder.py:468-487: MHA -> layer_norm1 -> ffn1, conv -> layer_norm3 -> ffn2)
+  const float *pre_ys, *pre_yb;
 };
 
 template <bool PRE>
@@ -329,13 +333,21 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int j = 0; j < 8; ++j) {
           const float4 gg = __ldg(reinterpret_cast<const float4*>(p.gp + cc) + j);
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bpn + cc) + j);
-          const float y0 = (__uint_as_float(ro[4 * j + 0]) - mean) * rstd * gg.x + bb.x;
-          const float y1 = (__uint_as_float(ro[4 * j + 1]) - mean) * rstd * gg.y + bb.y;
-          const float y2 = (__uint_as_float(ro[4 * j + 2]) - mean) * rstd * gg.z + bb.z;
-          const float y3 = (__uint_as_float(ro[4 * j + 3]) - mean) * rstd * gg.w + bb.w;
+          float y0 = (__uint_as_float(ro[4 * j + 0]) - mean) * rstd * gg.x + bb.x;
+          float y1 = (__uint_as_float(ro[4 * j + 1]) - mean) * rstd * gg.y + bb.y;
+          float y2 = (__uint_as_float(ro[4 * j + 2]) - mean) * rstd * gg.z + bb.z;
+          float y3 = (__uint_as_float(ro[4 * j + 3]) - mean) * rstd * gg.w + bb.w;
+          if (p.pre_ys != nullptr) {
+            ro[4 * j + 0] = __float_as_uint(y0), ro[4 * j + 1] = __float_as_uint(y1);
+            ro[4 * j + 2] = __float_as_uint(y2), ro[4 * j + 3] = __float_as_uint(y3);
+            const float4 as = __ldg(reinterpret_cast<const float4*>(p.pre_ys + cc) + j);
+            const float4 ab = __ldg(reinterpret_cast<const float4*>(p.pre_yb + cc) + j);
+            y0 = fmaf(as.x, y0, ab.x), y1 = fmaf(as.y, y1, ab.y), y2 = fmaf(as.z, y2, ab.z), y3 = fmaf(as.w, y3, ab.w);
+          }
           pk[2 * j] = pack_bf16x2(y0, y1);
           pk[2 * j + 1] = pack_bf16x2(y2, y3);
         }
+        if (p.pre_ys != nullptr) tmem_st_32x32b_x32(tmem_o + lane_base + cc, ro);  // the normalised row is the new residual
         // columns cc .. cc+31 live in k-block cc/64, 16-byte chunks (cc%64)/8 .. +3
         uint8_t* atile = s_a + (cc >> 6) * FFN_TILE + r * 128;
         const int ch0 = (cc & 63) >> 3;
@@ -344,6 +356,7 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           *reinterpret_cast<uint4*>(atile + (((ch0 + q4) ^ (r & 7)) << 4)) =
               make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
       }
+      if (p.pre_ys != nullptr) tmem_st_wait();
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
@@ -502,7 +515,7 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              const CUtensorMap& tm_w2, int M, int FF, float* x, __nv_bfloat16* y, const float* b1,
                              const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
                              float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
-                             cudaStream_t st, int y_affine, const int* ylens) {
+                             cudaStream_t st, int y_affine, const int* ylens, const float* pre_ys, const float* pre_yb) {
   if (FF % 128 != 0 || M <= 0) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
@@ -516,7 +529,7 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
   p.M = M, p.nchunks = FF / 128, p.x = x, p.y = y, p.b1 = b1, p.b2s = b2s;
   p.g1 = g1, p.bn1 = bn1, p.g2 = g2, p.bn2 = bn2, p.eps = eps;
   p.bp = bp, p.gp = gp, p.bpn = bpn, p.lens = lens, p.T = T;
-  p.y_affine = y_affine, p.ylens = ylens;
+  p.y_affine = y_affine, p.ylens = ylens, p.pre_ys = pre_ys, p.pre_yb = pre_yb;
   const int grid = (M + 127) / 128;
   cudaError_t le;
   if (tm_wp != nullptr)

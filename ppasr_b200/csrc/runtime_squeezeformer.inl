@@ -366,15 +366,24 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st, bool chunk = f
         ap.klens = nullptr;
         { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, ss.tm_k[l], *tmpos, ss.tm_vt[l], ap, st)); }
       }
-      feed(l, 1, &ys, &yb);
-      if ((rc = post_ln(PC_OUTPROJ, p.tm_att, m.wo, D, w.bo, 1.0f, 1, nullptr, 0, w.ln_g[0], w.ln_b[0], ys, yb, 0))) return rc;
+      if (!c->fused_ffn) {
+        feed(l, 1, &ys, &yb);
+        if ((rc = post_ln(PC_OUTPROJ, p.tm_att, m.wo, D, w.bo, 1.0f, 1, nullptr, 0, w.ln_g[0], w.ln_b[0], ys, yb, 0))) return rc;
+      }
     }
     // ---- FFN1: x = LN2(x + W2 swish(W1 y)); y = ada_conv(x), pad frames zeroed  (encoder.py:480-487, convolution.py:119-127)
+    //      fused: the attention out-projection + residual + layer_norm1 run in the kernel's chained pre-GEMM slot
     {
       feed(l, 2, &ys, &yb);
       PROF(PC_FUSED_FFN);
-      PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, nullptr, m.w1_128[0], m.w2[0], Mc, FF, xc, p.y, w.b1[0], w.b2[0], w.ln_g[1],
-                                        w.ln_b[1], ys, yb, eps, nullptr, nullptr, nullptr, nullptr, Tc, st, 1, vl));
+      if (c->fused_ffn) {
+        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_att, &m.wo, m.w1_128[0], m.w2[0], Mc, FF, xc, p.y, w.b1[0], w.b2[0], w.ln_g[1],
+                                          w.ln_b[1], ys, yb, eps, w.bo, w.ln_g[0], w.ln_b[0], nullptr, Tc, st, 1, vl,
+                                          w.ada_s[1], w.ada_b[1]));
+      } else {
+        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, nullptr, m.w1_128[0], m.w2[0], Mc, FF, xc, p.y, w.b1[0], w.b2[0], w.ln_g[1],
+                                          w.ln_b[1], ys, yb, eps, nullptr, nullptr, nullptr, nullptr, Tc, st, 1, vl));
+      }
     }
     // ---- conv module: x = LN3(x + mask * pw2 swish(norm(dw(glu(pw1 y))))); y = ada_ffn2(x)   (encoder.py:489-496)
     {
@@ -395,15 +404,24 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st, bool chunk = f
           PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.gcat, w.dw_w, w.dw_b, nullptr, w.cn_g, w.cn_b, cfg.conv_norm == 0, p.z, p.B,
                                                     Tcat, Tc, D, K, 0, eps, nullptr, st)); }
       }
-      feed(l, 3, &ys, &yb);
-      if ((rc = post_ln(PC_PW2, p.tm_z, m.pw2, D, w.pw2_b, 1.0f, 1, vl, 1, w.ln_g[2], w.ln_b[2], ys, yb, 0))) return rc;
+      if (!c->fused_ffn) {
+        feed(l, 3, &ys, &yb);
+        if ((rc = post_ln(PC_PW2, p.tm_z, m.pw2, D, w.pw2_b, 1.0f, 1, vl, 1, w.ln_g[2], w.ln_b[2], ys, yb, 0))) return rc;
+      }
     }
     // ---- FFN2: x = LN4(x + W2 swish(W1 y)); y = input of whatever comes next       (encoder.py:498-506)
     {
       feed(l, 4, &ys, &yb);
       PROF(PC_FUSED_FFN);
-      PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, nullptr, m.w1_128[1], m.w2[1], Mc, FF, xc, p.y, w.b1[1], w.b2[1], w.ln_g[3],
-                                        w.ln_b[3], ys, yb, eps, nullptr, nullptr, nullptr, nullptr, Tc, st, 1, nullptr));
+      if (c->fused_ffn) {
+        // pointwise_conv2 (pad rows masked) + residual + layer_norm3 in the chained pre-GEMM slot
+        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_z, &m.pw2, m.w1_128[1], m.w2[1], Mc, FF, xc, p.y, w.b1[1], w.b2[1], w.ln_g[3],
+                                          w.ln_b[3], ys, yb, eps, w.pw2_b, w.ln_g[2], w.ln_b[2], vl, Tc, st, 1, nullptr,
+                                          w.ada_s[3], w.ada_b[3]));
+      } else {
+        PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, nullptr, m.w1_128[1], m.w2[1], Mc, FF, xc, p.y, w.b1[1], w.b2[1], w.ln_g[3],
+                                          w.ln_b[3], ys, yb, eps, nullptr, nullptr, nullptr, nullptr, Tc, st, 1, nullptr));
+      }
     }
   }
   return PPASR_OK;

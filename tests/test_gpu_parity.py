@@ -308,8 +308,7 @@ def test_squeezeformer_matches_oracle_12_layers(lib, cuda):
 
 
 def test_squeezeformer_inference_predictor(lib, cuda):
-    """InferencePredictor(use_model='squeezeformer').predict / predict_decode; chunk API raises like the reference does for
-    unsupported models (inference_predictor.py:186)."""
+    """InferencePredictor(use_model='squeezeformer').predict / predict_decode (the chunk API has its own test)."""
     from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
     from ppasr_b200.weights import SqueezeformerConfig, init_squeezeformer_weights, make_vocab, synthetic_fbank
     from oracle import decoders_oracle as DO
