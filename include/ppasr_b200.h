@@ -205,7 +205,8 @@ int ppasr_b200_fbank(const float* audio, int32_t B, int64_t stride, int32_t N, c
                      int32_t sample_rate, int32_t db_normalize, float target_db, float* gain_ws, float* out, int32_t Tmax,
                      void* stream);
 
-/* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels, "fused_conv" (default 0) the
+/* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels, "fused_dwconv" (default 0; causal
+ * models) computes the conv module's depthwise stage in the chained FFN kernel's prologue (measured slower, kept for A/B), "fused_conv" (default 0) the
  * experimental fused conv1+conv2 front end (0 = separate kernels / GEMMs, for A/B measurements); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
  * returning -- 0 leaves the copies in flight (pinned host buffers; the caller synchronises), used by the
  * double-buffered serving pipeline. */

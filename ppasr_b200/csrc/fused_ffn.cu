@@ -64,7 +64,112 @@ struct FfnParams {
   // residual itself becomes x <- LN(x + Wp z + bp; gp, bpn) (written back into TMEM O) and the FFN input is its adaptive
   // affine pre_ys * x + pre_yb (squeezeformer/encoder.py:468-487: MHA -> layer_norm1 -> ffn1, conv -> layer_norm3 -> ffn2)
   const float *pre_ys, *pre_yb;
+  // chained mode with the depthwise conv in front (dw_g != null): the A operand z of the pre-GEMM is not loaded but computed
+  // by the compute warps, z = swish(norm(depthwise_conv(g))) with causal left padding (convolution.py:108-133), rows t >=
+  // lens[b] zeroed -- the conv module's depthwise stage never leaves the SM either.
+  const __nv_bfloat16* dw_g;  // [M, 256] GLU output
+  const float *dw_w, *dw_b;   // [256, K], [256]
+  const float* dw_pad;        // [256] value of a left-padding frame (GLU(bias)); causal only
+  const float *dw_ng, *dw_nb; // norm gamma / beta (LayerNorm) or folded BatchNorm scale / shift
+  int dw_K, dw_ln;
 };
+
+// depthwise conv (+ norm + swish) of one 128-row tile straight into the swizzled A tiles. thread = channel for the
+// convolution (K-wide register ring over time, restarted every 16 rows and at utterance starts), warp = row for the norm.
+template <int K>
+DEVINL void dwconv_a_tiles(const FfnParams& p, int m0, int ct, int ew, int lane, uint8_t* s_a, uint8_t* scratch) {
+  // scratch (the idle H region, 64 KB): staged bf16 input rows [64 + K - 1][256], then the fp32 conv output of one
+  // 16-row sub-tile [16][256]
+  __nv_bfloat16* sin = reinterpret_cast<__nv_bfloat16*>(scratch);
+  float* sout = reinterpret_cast<float*>(scratch + (size_t)(64 + K - 1) * 512);
+  const int c = ct;
+  float wk[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wk[j] = __ldg(p.dw_w + c * K + j);
+  const float bs = __ldg(p.dw_b + c);
+  const float padv = __bfloat162float(__float2bfloat16_rn(__ldg(p.dw_pad + c)));
+  const float sc = p.dw_ln ? 1.f : __ldg(p.dw_ng + c);
+  const float sh = p.dw_ln ? 0.f : __ldg(p.dw_nb + c);
+  const int T = p.T;
+#pragma unroll 1
+  for (int hf = 0; hf < 2; ++hf) {
+    // ---- stage rows [m0 + 64 hf - (K-1), m0 + 64 hf + 64) with coalesced 16-byte loads (all in flight together) ----
+    const int gr0 = m0 + hf * 64 - (K - 1);
+    constexpr int NCHUNK = (64 + K - 1) * 32;
+    for (int i = ct; i < NCHUNK; i += 256) {
+      const int rr = i >> 5, seg = i & 31;
+      const int gr = gr0 + rr;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (gr >= 0 && gr < p.M) v = *reinterpret_cast<const uint4*>(p.dw_g + (size_t)gr * 256 + seg * 8);
+      *reinterpret_cast<uint4*>(sin + (size_t)rr * 256 + seg * 8) = v;
+    }
+    named_bar_sync(1, 256);
+#pragma unroll 1
+    for (int sub = 0; sub < 4; ++sub) {
+      const int l0 = sub * 16;            // first local row of the sub-tile inside this half
+      const int R0 = m0 + hf * 64 + l0;
+      int b = R0 / T, t = R0 - b * T;
+      float win[K];
+#pragma unroll
+      for (int j = 0; j < K - 1; ++j)     // history: frames t-(K-1)+j, left padding before the utterance start
+        win[j] = (t - (K - 1) + j >= 0) ? __bfloat162float(sin[(size_t)(l0 + j) * 256 + c]) : padv;
+#pragma unroll
+      for (int tb = 0; tb < 16; tb += K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          const int r = tb + u;
+          if (r < 16) {
+            if (t == 0 && r > 0) {  // a new utterance starts inside the sub-tile: its history is left padding
+#pragma unroll
+              for (int j = 0; j < K; ++j) win[j] = padv;
+            }
+            win[(u + K - 1) % K] = __bfloat162float(sin[(size_t)(l0 + r + K - 1) * 256 + c]);
+            float acc = bs;
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc = fmaf(wk[j], win[(u + j) % K], acc);
+            sout[r * 256 + c] = acc * sc + sh;
+            if (++t == T) t = 0, ++b;
+          }
+        }
+      }
+      named_bar_sync(1, 256);
+      // norm + swish, warp = row, lane = 8 channels = one 16-byte chunk of the A tile
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int r = ew + 8 * q;
+        const int R = R0 + r;
+        float v[8];
+        const float4 a0 = *reinterpret_cast<const float4*>(sout + r * 256 + lane * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(sout + r * 256 + lane * 8 + 4);
+        v[0] = a0.x, v[1] = a0.y, v[2] = a0.z, v[3] = a0.w, v[4] = a1.x, v[5] = a1.y, v[6] = a1.z, v[7] = a1.w;
+        if (p.dw_ln) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s += v[i];
+          const float mean = warp_sum(s) * (1.0f / 256.0f);
+          float qq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) qq += (v[i] - mean) * (v[i] - mean);
+          const float rstd = rsqrtf(warp_sum(qq) * (1.0f / 256.0f) + p.eps);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * __ldg(p.dw_ng + lane * 8 + i) + __ldg(p.dw_nb + lane * 8 + i);
+        }
+        bool zero = R >= p.M;
+        if (!zero && p.lens != nullptr) {
+          const int bb = R / T;
+          zero = (R - bb * T) >= __ldg(p.lens + bb);
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[i] = zero ? 0u : pack_bf16x2(swish_precise(v[2 * i]), swish_precise(v[2 * i + 1]));
+        const int row = hf * 64 + l0 + r;
+        uint8_t* atile = s_a + (lane >> 3) * FFN_TILE + row * 128;
+        *reinterpret_cast<uint4*>(atile + (((lane & 7) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      named_bar_sync(1, 256);
+    }
+  }
+}
 
 template <bool PRE>
 __global__ void __launch_bounds__(FFN_THREADS, 1)
@@ -102,7 +207,7 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (PRE) tma_prefetch_desc(&tm_wp);
   }
   if (warp_idx == 1 && elect_one()) {
-    mbar_init(a_full, 1);
+    mbar_init(a_full, (PRE && p.dw_g != nullptr) ? 256 : 1);
     for (int i = 0; i < FFN_RING; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
@@ -132,8 +237,10 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
     if (elect_one()) {
-      mbar_arrive_expect_tx(a_full, 4 * FFN_TILE);
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * FFN_TILE, &tm_a, a_full, kb * 64, m0);
+      if (!(PRE && p.dw_g != nullptr)) {
+        mbar_arrive_expect_tx(a_full, 4 * FFN_TILE);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * FFN_TILE, &tm_a, a_full, kb * 64, m0);
+      }
       int slot = 0;
       uint32_t phase = 0;
       auto load_rows256 = [&](const CUtensorMap* tm, int k0) {  // one big slot: [256 rows x 64 K]
@@ -257,6 +364,14 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (PRE && p.lens != nullptr && row_g < p.M) {
       const int b = row_g / p.T;
       pad = (row_g - b * p.T) >= __ldg(p.lens + b);
+    }
+    if (PRE && p.dw_g != nullptr) {
+      // ---- z = swish(norm(dwconv(g))) -> A tiles of the pre-GEMM (H region = fp32 scratch of one 16-row sub-tile) ----
+      if (p.dw_K == 15) dwconv_a_tiles<15>(p, m0, ct, ew, lane, s_a, s_h);
+      else if (p.dw_K == 31) dwconv_a_tiles<31>(p, m0, ct, ew, lane, s_a, s_h);
+      else dwconv_a_tiles<7>(p, m0, ct, ew, lane, s_a, s_h);
+      fence_proxy_async_smem();
+      mbar_arrive(a_full);
     }
     // ---- residual tile -> TMEM O, 64 columns at a time through a coalesced smem slab (the H region is idle) ----
     {
@@ -515,7 +630,8 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              const CUtensorMap& tm_w2, int M, int FF, float* x, __nv_bfloat16* y, const float* b1,
                              const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
                              float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
-                             cudaStream_t st, int y_affine, const int* ylens, const float* pre_ys, const float* pre_yb) {
+                             cudaStream_t st, int y_affine, const int* ylens, const float* pre_ys, const float* pre_yb,
+                             const FfnDw* dw) {
   if (FF % 128 != 0 || M <= 0) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
@@ -530,6 +646,12 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
   p.g1 = g1, p.bn1 = bn1, p.g2 = g2, p.bn2 = bn2, p.eps = eps;
   p.bp = bp, p.gp = gp, p.bpn = bpn, p.lens = lens, p.T = T;
   p.y_affine = y_affine, p.ylens = ylens, p.pre_ys = pre_ys, p.pre_yb = pre_yb;
+  p.dw_g = nullptr, p.dw_w = p.dw_b = p.dw_pad = p.dw_ng = p.dw_nb = nullptr, p.dw_K = 0, p.dw_ln = 0;
+  if (dw != nullptr && tm_wp != nullptr) {
+    if (dw->K != 7 && dw->K != 15 && dw->K != 31) return cudaErrorInvalidValue;
+    p.dw_g = dw->g, p.dw_w = dw->w, p.dw_b = dw->bias, p.dw_pad = dw->pad_left, p.dw_ng = dw->ng, p.dw_nb = dw->nb;
+    p.dw_K = dw->K, p.dw_ln = dw->layer_norm;
+  }
   const int grid = (M + 127) / 128;
   cudaError_t le;
   if (tm_wp != nullptr)

@@ -43,6 +43,13 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
                                 int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
                                 int* score_cnt, cudaStream_t st);
 
+// depthwise-conv stage folded into the chained fused FFN kernel (causal conv module only)
+struct FfnDw {
+  const __nv_bfloat16* g;  // [M, 256] GLU output
+  const float *w, *bias, *pad_left, *ng, *nb;
+  int K, layer_norm;
+};
+
 // Fused feed-forward block (fused_ffn.cu): x += W2s swish(W1 y + b1) + b2s with trailing LayerNorm(s); optional
 // chained pre-GEMM (tm_wp != null): x += mask (Wp z + bp), y = LN(x; gp, bpn) first (tm_a is then the z tile map).
 cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, const CUtensorMap& tm_w1,
@@ -50,7 +57,7 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              const float* b2s, const float* g1, const float* bn1, const float* g2, const float* bn2,
                              float eps, const float* bp, const float* gp, const float* bpn, const int* lens, int T,
                              cudaStream_t st, int y_affine = 0, const int* ylens = nullptr, const float* pre_ys = nullptr,
-                             const float* pre_yb = nullptr);
+                             const float* pre_yb = nullptr, const FfnDw* dw = nullptr);
 
 // Fused attention out-projection + residual + norm_conv + pointwise_conv1 + GLU (fused_attn_out.cu)
 cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& tm_wo, const CUtensorMap& tm_wpw1, int M,

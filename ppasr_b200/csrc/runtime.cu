@@ -7,6 +7,7 @@
 //   -> ConformerEncoder.forward (ppasr/model_utils/conformer/encoder.py:164-206)
 //   -> CTCLoss.softmax (ppasr/model_utils/loss/ctc.py:62-70) -> greedy_decoder (ppasr/decoders/ctc_greedy_decoder.py)
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -179,6 +180,10 @@ struct ppasr_b200_ctx {
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
   bool fused_attn_out = true;
+  // causal models: depthwise conv + norm + swish computed in the chained FFN kernel's prologue. Bit-identical to the
+  // stand-alone kernel but slower (2.53 vs 2.20 ms single stream, 1.45 vs 1.36 ms in throughput mode at C2): the
+  // prologue (~27 us on 62 CTAs, before any MMA can start) costs more SM time than the 13 us grid-wide kernel. Opt-in.
+  bool fused_dwconv = false;
   // conv1 computed inside the conv2 GEMM's A producer (conv_front.cu). Bit-identical to the two-kernel path but slower
   // on B200 (382 us vs 145 + 145 us at C2): the producers' LDS/STS traffic shares the 128 B/clk shared-memory data pipe
   // with the tensor core's operand reads (ncu: lsu 57 % + tc 20 % of the pipe), so it is opt-in.
@@ -307,6 +312,7 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   auto* c = new ppasr_b200_ctx();
   c->cfg = *cfg;
   c->layer_k.assign(cfg->n_layers, cfg->conv_kernel);
+  if (const char* e = std::getenv("PPASR_B200_FUSED_DWCONV")) c->fused_dwconv = std::atoi(e) != 0;  // A/B switch for bench runs
   if (cfg->model_type == 3) {
     c->eff_stride_idx = cfg->stride_layer_idx;
     c->eff_group_mask = (unsigned)cfg->group_layer_mask;
@@ -893,8 +899,11 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
           PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, M, 2 * D, D, eg, st)));
         }
         const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
-        { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
-                                                  cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, vl, st)); }
+        if (!(cfg.causal && c->fused_ffn && c->fused_dwconv)) {
+          PROF(PC_DWCONV);
+          PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
+                                                    cfg.conv_norm == 0, p.z, p.B, p.Tp, p.Tp, D, K, lpad, eps, vl, st));
+        }
       } else {
         // [cnn_cache ; chunk] -> pw1 + GLU -> "valid" depthwise conv; cache <- last K-1 input rows (convolution.py:108-117)
         const int lorder = K - 1;
@@ -916,9 +925,13 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
       const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
       if (c->fused_ffn) {
         PROF(PC_FUSED_FFN);
-        // pointwise_conv2 + residual + norm_ff chained in front (z rows of pad frames are zero, bias masked)
+        // pointwise_conv2 + residual + norm_ff chained in front (z rows of pad frames are zero, bias masked); for causal
+        // models the depthwise conv + norm + swish that produces z runs in the same kernel's prologue
+        FfnDw dw{p.g, w.dw_w, w.dw_b, w.glu_pad, w.cn_g, w.cn_b, cfg.conv_kernel, cfg.conv_norm == 0};
+        const bool fdw = !chunk && cfg.causal && c->fused_dwconv;
         PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_z, &m.pw2, m.ff_w1_128, m.ff_w2s, M, FF, p.x, p.y, w.ff_b1, w.ff_b2s, w.ln_fin_g,
-                                          w.ln_fin_b, g2, b2, eps, w.pw2_b, w.ln_ff_g, w.ln_ff_b, vl, p.Tp, st));
+                                          w.ln_fin_b, g2, b2, eps, w.pw2_b, w.ln_ff_g, w.ln_ff_b, vl, p.Tp, st, 0, nullptr, nullptr,
+                                          nullptr, fdw ? &dw : nullptr));
       } else {
         EpiStoreBF16<BN_WIDE, ACT_SWISH> e1{p.h, w.ff_b1, FF, M, FF};
         { PROF(PC_FFN1); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.ff_w1, M, FF, D, e1, st))); }
@@ -1231,6 +1244,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   }
   if (n == "host_sync") {
     c->host_sync = value != 0;
+    return PPASR_OK;
+  }
+  if (n == "fused_dwconv") {
+    c->fused_dwconv = value != 0;
     return PPASR_OK;
   }
   if (n == "fused_conv") {

@@ -62,7 +62,10 @@ int run_encoder_effconf(ppasr_b200_ctx* c, cudaStream_t st) {
     }
     // ---- depthwise conv + norm + swish -> z (half rate in the stride block)
     const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
-    if (!strided) {
+    const bool fdw = !strided && cfg.causal && c->fused_dwconv;
+    if (fdw) {
+      // computed in the prologue of the chained FFN kernel below
+    } else if (!strided) {
       PROF(PC_DWCONV);
       PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
                                                 cfg.conv_norm == 0, p.z, p.B, Tc, Tc, D, K, lpad, eps, vl, st));
@@ -81,8 +84,10 @@ int run_encoder_effconf(ppasr_b200_ctx* c, cudaStream_t st) {
       const float* g2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_g : c->after_g;
       const float* b2 = (l + 1 < L) ? c->layers[l + 1].ln_ffm_b : c->after_b;
       PROF(PC_FUSED_FFN);
+      FfnDw dw{p.g, w.dw_w, w.dw_b, w.glu_pad, w.cn_g, w.cn_b, K, cfg.conv_norm == 0};
       PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_z, &m.pw2, m.ff_w1_128, m.ff_w2s, Mc, FF, xc, p.y, w.ff_b1, w.ff_b2s, w.ln_fin_g,
-                                        w.ln_fin_b, g2, b2, eps, w.pw2_b, w.ln_ff_g, w.ln_ff_b, vl, Tc, st));
+                                        w.ln_fin_b, g2, b2, eps, w.pw2_b, w.ln_ff_g, w.ln_ff_b, vl, Tc, st, 0, nullptr, nullptr,
+                                        nullptr, fdw ? &dw : nullptr));
     }
   }
   return PPASR_OK;

@@ -391,9 +391,11 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st, bool chunk = f
         EpiGLU<BN_WIDE> eg{p.g, w.pw1_b, D, Mc, 2 * D};
         { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.pw1, Mc, 2 * D, D, eg, st))); }
         const int lpad = cfg.causal ? K - 1 : (K - 1) / 2;
-        { PROF(PC_DWCONV);
+        if (!(cfg.causal && c->fused_ffn && c->fused_dwconv)) {
+          PROF(PC_DWCONV);
           PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.g, w.dw_w, w.dw_b, cfg.causal ? w.glu_pad : nullptr, w.cn_g, w.cn_b,
-                                                    cfg.conv_norm == 0, p.z, p.B, Tc, Tc, D, K, lpad, eps, vl, st)); }
+                                                    cfg.conv_norm == 0, p.z, p.B, Tc, Tc, D, K, lpad, eps, vl, st));
+        }
       } else {
         // [cnn_cache ; chunk] -> pw1 + GLU -> "valid" depthwise conv; cache <- last K-1 input rows (convolution.py:129-138)
         const int lorder = K - 1, Tcat = Tc + lorder, Mcat = p.B * Tcat;
@@ -415,9 +417,11 @@ int run_encoder_squeezeformer(ppasr_b200_ctx* c, cudaStream_t st, bool chunk = f
       PROF(PC_FUSED_FFN);
       if (c->fused_ffn) {
         // pointwise_conv2 (pad rows masked) + residual + layer_norm3 in the chained pre-GEMM slot
+        FfnDw dw{p.g, w.dw_w, w.dw_b, w.glu_pad, w.cn_g, w.cn_b, K, cfg.conv_norm == 0};
+        const bool fdw = !chunk && cfg.causal && c->fused_dwconv;
         PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_z, &m.pw2, m.w1_128[1], m.w2[1], Mc, FF, xc, p.y, w.b1[1], w.b2[1], w.ln_g[3],
                                           w.ln_b[3], ys, yb, eps, w.pw2_b, w.ln_g[2], w.ln_b[2], vl, Tc, st, 1, nullptr,
-                                          w.ada_s[3], w.ada_b[3]));
+                                          w.ada_s[3], w.ada_b[3], fdw ? &dw : nullptr));
       } else {
         PPASR_CUDA_CHECK(launch_fused_ffn(p.tm_y, nullptr, m.w1_128[1], m.w2[1], Mc, FF, xc, p.y, w.b1[1], w.b2[1], w.ln_g[3],
                                           w.ln_b[3], ys, yb, eps, nullptr, nullptr, nullptr, nullptr, Tc, st, 1, nullptr));

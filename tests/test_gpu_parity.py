@@ -782,3 +782,32 @@ def test_squeezeformer_chunk_streaming_matches_oracle(lib, cuda, nb, reduce_idx,
         assert ((lg - ref).abs().max() / ref.abs().max()).item() < 1e-2, s
         assert int(pred.offset[0]) == off
     pred.reset_stream()
+
+
+@pytest.mark.parametrize("model", ["conformer", "squeezeformer"])
+def test_fused_dwconv_bit_identical(lib, cuda, model):
+    """The depthwise conv + norm + swish stage computed inside the chained FFN kernel (option fused_dwconv, default) equals the
+    stand-alone dwconv kernel bit for bit (same FMA order, same bf16 roundings), incl. utterance boundaries inside a row tile
+    and padded frames."""
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200 import weights as W
+    if model == "conformer":
+        cfg = W.ConformerConfig(num_blocks=2, vocab_size=300)
+        w = W.init_conformer_weights(cfg)
+    else:
+        cfg = W.SqueezeformerConfig(num_blocks=3, vocab_size=300, reduce_idx=1, recover_idx=2)
+        w = W.init_squeezeformer_weights(cfg)
+    eng = ConformerEngine(cfg, w)
+    B, T, lens = 5, 363, [363, 200, 363, 90, 300]   # T' = 90: row tiles of 128 straddle utterances
+    feats = W.synthetic_fbank(B, T)
+    for b in range(B):
+        feats[b, lens[b]:] = 0
+    fd = torch.from_numpy(feats).cuda()
+    outs = []
+    for fused in (0, 1):
+        eng.set_option("fused_dwconv", fused)
+        eng.encode(fd, lens)
+        outs.append(eng.ctc_logits().float().cpu())
+    torch.cuda.synchronize()
+    eng.close()
+    assert torch.equal(outs[0], outs[1])
