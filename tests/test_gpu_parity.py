@@ -809,3 +809,40 @@ def test_fused_dwconv_bit_identical(lib, cuda, model):
     torch.cuda.synchronize()
     eng.close()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("use_model", ["deepspeech2", "squeezeformer"])
+def test_predict_stream_other_models(lib, cuda, use_model):
+    """PPASRPredictor.predict_stream_features dispatches to predict_chunk_deepspeech / predict_chunk_conformer by model
+    (predict.py:302-311); feeding arbitrary slices equals feeding the reference's 67/64 windows by hand."""
+    from oracle import decoders_oracle as DO
+    from oracle.conformer_oracle import stream_windows
+    from ppasr_b200.predict import PPASRPredictor
+    from ppasr_b200 import weights as W
+    if use_model == "deepspeech2":
+        cfg = W.DeepSpeech2Config(num_rnn_layers=2, rnn_size=256, vocab_size=150, streaming=True)
+        w = W.init_deepspeech2_weights(cfg)
+    else:
+        cfg = W.SqueezeformerConfig(num_blocks=3, vocab_size=150, reduce_idx=1, recover_idx=2)
+        w = W.init_squeezeformer_weights(cfg)
+    vocab = W.make_vocab(150)
+    p = PPASRPredictor({"use_model": use_model, "streaming": True, "decoder": "ctc_greedy", "encoder_conf": cfg.to_dict(),
+                        "preprocess_conf": {"feature_method": "fbank", "n_mels": 80}}, vocab_list=vocab, weights=w)
+    T = 67 + 64 * 3
+    feats = W.synthetic_fbank(1, T)
+    res, pos = None, 0
+    for n in (40, 90, 100, 29):
+        r = p.predict_stream_features(feats[:, pos:pos + n], is_end=(pos + n >= T))
+        pos += n
+        res = r if r is not None else res
+    assert pos == T and res is not None
+    p.reset_stream()
+    chunks = []
+    for (s, e) in stream_windows(T, is_end=True):
+        if use_model == "deepspeech2":
+            chunks.append(p.predictor.predict_chunk_deepspeech(feats[:, s:e])[0][0])
+        else:
+            chunks.append(p.predictor.predict_chunk_conformer(feats[:, s:e], -16)[0])
+    score, text = DO.greedy_decoder(np.concatenate(chunks, 0), vocab)
+    assert res["text"] == text and abs(res["score"] - score) < 1e-3
+    p.reset_stream()
