@@ -1087,15 +1087,16 @@ int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats
   const bool sqz = cfg.model_type == 1;
   if (sqz && c->sq.reduce_idx >= 0) {
     // the half-rate blocks address their caches / positions at half rate (runtime_squeezeformer.inl)
-    PPASR_REQUIRE(p.Tp % 2 == 0 && ss.kend % 2 == 0 && ss.kstart % 2 == 0 && ss.offset % 2 == 0 &&
+    // (an odd number of frames is fine for the LAST chunk of a stream: the state it leaves behind is not used again)
+    PPASR_REQUIRE(ss.kend % 2 == 0 && ss.kstart % 2 == 0 && ss.offset % 2 == 0 &&
                       (required_cache_size < 0 || required_cache_size % 2 == 0),
-                  "squeezeformer chunk streaming needs an even number of output frames per chunk and an even required_cache_size");
+                  "squeezeformer chunk streaming needs even chunk sizes (all but the last chunk) and an even required_cache_size");
   }
   for (int l = 0; l < L; ++l) {
     const size_t lk = (size_t)l * B * H * ss.Tcap * 64;
     const int rate = (sqz && c->sq.reduce_idx >= 0 && l >= c->sq.reduce_idx && l < c->sq.recover_idx) ? 2 : 1;
     if (!make_tmap_2d(&ss.tm_k[l], ss.kk + lk, 64, (uint64_t)B * H * ss.Tcap, 128, 128, &err) ||
-        !make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, kend_new / rate, (uint64_t)B * H * 64, (uint64_t)ss.Tcap * 2, 64, &err)) {
+        !make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, (kend_new + rate - 1) / rate, (uint64_t)B * H * 64, (uint64_t)ss.Tcap * 2, 64, &err)) {
       set_last_error(err);
       return PPASR_ERR_CUDA;
     }
