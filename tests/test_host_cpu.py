@@ -149,3 +149,17 @@ def test_gloo_world2_all_gather(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and "RANK_OK" in out, out
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/ppasr_b200.h compiles as C99 and a C program links against the library."""
+    import subprocess
+    root = os.path.join(os.path.dirname(__file__), "..")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.abspath(os.path.join(root, "ppasr_b200", "lib"))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "examples", "c_abi_demo.c"), "-L" + libdir, "-lppasr_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "out_frames(998) = 248" in out.stdout and "fbank_frames(160000) = 998" in out.stdout
