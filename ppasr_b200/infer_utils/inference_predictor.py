@@ -19,7 +19,7 @@ import numpy as np
 from .. import _lib as L
 from ..engine import ConformerEngine, out_frames
 from ..parallel import detokenize
-from ..weights import ConformerConfig, DeepSpeech2Config, EfficientConformerConfig, SqueezeformerConfig, load_npz, load_pdparams, read_mean_istd
+from ..weights import ConformerConfig, DeepSpeech2Config, EfficientConformerConfig, SqueezeformerConfig, load_npz, load_pdiparams, load_pdparams, read_mean_istd
 
 
 def _get(obj, key, default=None):
@@ -71,6 +71,9 @@ class InferencePredictor:
                 weights, _ = load_npz(npz)
             elif os.path.exists(pdp):
                 weights = load_pdparams(pdp)
+            elif os.path.exists(os.path.join(model_dir, 'model.pdiparams')):
+                # the reference's own exported inference model (inference_predictor.py:41-45)
+                weights = load_pdiparams(os.path.join(model_dir, 'model.pdiparams'))
             else:
                 # same failure mode as inference_predictor.py:43-44
                 raise Exception("模型文件不存在，请检查%s和%s是否存在！" % (npz, pdp))

@@ -453,6 +453,132 @@ def load_pdparams(path: str) -> Dict[str, np.ndarray]:
     return out
 
 
+# ---- exported inference model: model.pdiparams (+ model.pdiparams.info), written by paddle.jit.save (ppasr/trainer.py:675-681)
+# and read by the reference through paddle.inference (infer_utils/inference_predictor.py:41-45). Format restated from the
+# Paddle 2.5 sources (paddle/fluid/framework/lod_tensor.cc SerializeToStream, tensor_util.cc TensorToStream, save_combine_op):
+# tensors concatenated in the order of the sorted program variable names; per tensor
+#   uint32 lod-tensor version (0) | uint64 number of LoD levels | per level: uint64 byte size + data
+#   uint32 tensor version (0) | int32 size of the TensorDesc protobuf | TensorDesc { 1: data_type (varint), 2: dims (int64) }
+#   raw little-endian data.
+# `model.pdiparams.info` is a pickle {program variable name: {'structured_name': 'encoder.embed.conv.0.weight', ...}} that maps the
+# auto-generated variable names back to the state-dict names. UNVERIFIED against a real file (no Paddle in this sandbox);
+# `save_pdiparams` writes the same layout so the reader is at least round-trip tested.
+_PD_DTYPES = {0: np.bool_, 1: np.int16, 2: np.int32, 3: np.int64, 4: np.float16, 5: np.float32, 6: np.float64, 20: np.uint8,
+              21: np.int8}
+
+
+def _read_varint(buf, pos):
+    val, shift = 0, 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        val |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return val, pos
+        shift += 7
+
+
+def _parse_tensor_desc(buf):
+    pos, dtype, dims = 0, None, []
+    while pos < len(buf):
+        key, pos = _read_varint(buf, pos)
+        field, wire = key >> 3, key & 7
+        if wire == 0:
+            v, pos = _read_varint(buf, pos)
+            if v >= 1 << 63:
+                v -= 1 << 64
+            if field == 1:
+                dtype = v
+            elif field == 2:
+                dims.append(v)
+        elif wire == 2:  # packed repeated int64
+            n, pos = _read_varint(buf, pos)
+            end = pos + n
+            while pos < end:
+                v, pos = _read_varint(buf, pos)
+                if field == 2:
+                    dims.append(v - (1 << 64) if v >= 1 << 63 else v)
+        else:
+            raise ValueError("unexpected wire type in TensorDesc")
+    return dtype, dims
+
+
+def load_pdiparams(path: str, info_path: str = None) -> Dict[str, np.ndarray]:
+    """Reads `model.pdiparams`; names come from `model.pdiparams.info` (structured names) when present, else tensors are
+    returned as 'param_%d' in file order."""
+    import struct
+    data = open(path, "rb").read()
+    pos, tensors = 0, []
+    while pos < len(data):
+        (ver,) = struct.unpack_from("<I", data, pos)
+        pos += 4
+        if ver != 0:
+            raise ValueError(f"unsupported LoDTensor version {ver} at byte {pos - 4}")
+        (nlod,) = struct.unpack_from("<Q", data, pos)
+        pos += 8
+        for _ in range(nlod):
+            (nbytes,) = struct.unpack_from("<Q", data, pos)
+            pos += 8 + nbytes
+        (tver,) = struct.unpack_from("<I", data, pos)
+        pos += 4
+        if tver != 0:
+            raise ValueError(f"unsupported Tensor version {tver}")
+        (dsz,) = struct.unpack_from("<i", data, pos)
+        pos += 4
+        dtype, dims = _parse_tensor_desc(data[pos:pos + dsz])
+        pos += dsz
+        if dtype not in _PD_DTYPES:
+            raise ValueError(f"unsupported Paddle dtype enum {dtype}")
+        npdt = np.dtype(_PD_DTYPES[dtype])
+        n = int(np.prod(dims)) if dims else 1
+        arr = np.frombuffer(data, dtype=npdt, count=n, offset=pos).reshape(dims)
+        pos += n * npdt.itemsize
+        tensors.append(arr)
+    if info_path is None and os.path.exists(path + ".info"):
+        info_path = path + ".info"
+    names = None
+    if info_path is not None:
+        with open(info_path, "rb") as f:
+            info = pickle.load(f, encoding="latin1")
+        keys = sorted(k for k in info if isinstance(info[k], dict))
+        if len(keys) == len(tensors):
+            names = [info[k].get("structured_name", k) for k in keys]
+    if names is None:
+        names = [f"param_{i}" for i in range(len(tensors))]
+    return {n: np.asarray(t, dtype=np.float32) if t.dtype.kind == "f" else np.asarray(t) for n, t in zip(names, tensors)}
+
+
+def save_pdiparams(path: str, weights: Dict[str, np.ndarray], write_info: bool = True):
+    """Writes the layout `load_pdiparams` reads (variable names = 'param_%05d' in the order of the structured names)."""
+    import struct
+
+    def varint(v):
+        if v < 0:
+            v += 1 << 64
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+
+    rev = {np.dtype(v): k for k, v in _PD_DTYPES.items()}
+    info = {}
+    with open(path, "wb") as f:
+        for i, (name, arr) in enumerate(weights.items()):
+            arr = np.ascontiguousarray(arr)
+            desc = b"\x08" + varint(rev[arr.dtype]) + b"".join(b"\x10" + varint(int(d)) for d in arr.shape)
+            f.write(struct.pack("<IQ", 0, 0))
+            f.write(struct.pack("<Ii", 0, len(desc)))
+            f.write(desc)
+            f.write(arr.tobytes())
+            info[f"param_{i:05d}"] = {"structured_name": name, "stop_gradient": False, "trainable": True}
+    if write_info:
+        with open(path + ".info", "wb") as f:
+            pickle.dump(info, f, protocol=2)
+
+
 def make_vocab(vocab_size: int):
     """Synthetic vocabulary in the reference's order (ppasr/trainer.py:479-487): <blank>, <unk>, chars, <eos>."""
     chars = [chr(0x4E00 + i) for i in range(vocab_size - 3)]
