@@ -120,6 +120,17 @@ int ppasr_b200_ctc_greedy(ppasr_b200_ctx* ctx, int32_t* ids, int32_t* out_lens, 
 int ppasr_b200_stream_reset(ppasr_b200_ctx* ctx, int32_t B);
 int ppasr_b200_encode_chunk(ppasr_b200_ctx* ctx, const float* feats, int32_t feats_on_device, int32_t B, int32_t t,
                             int32_t required_cache_size, void* stream);
+/* ---- ragged streaming sessions (conformer): many independent streams, each with its own position and caches, stepped
+ * together in one batch -- the engine side of a continuous-batching scheduler for predict_stream traffic (the reference
+ * serves one stream per process: predict.py:232-337, infer_server.py:103-156).
+ * sessions_init allocates `max_sessions` cache slots; sessions_reset(slot) starts a new stream in a slot; sessions_step
+ * runs one chunk [n, t, feat_dim] for the n distinct slots listed in `slots` (host int32 [n]); afterwards the ctc_* calls
+ * return the n chunk results in that order. required_cache_size as in encode_chunk. */
+int ppasr_b200_sessions_init(ppasr_b200_ctx* ctx, int32_t max_sessions);
+int ppasr_b200_sessions_reset(ppasr_b200_ctx* ctx, int32_t slot);
+int ppasr_b200_sessions_step(ppasr_b200_ctx* ctx, const float* feats, int32_t feats_on_device, const int32_t* slots, int32_t n,
+                             int32_t t, int32_t required_cache_size, void* stream);
+
 /* DeepSpeech2 streaming states after the last encode_chunk: h, c fp32 [num_rnn_layers * num_directions, B, rnn_size]
  * (either may be NULL). replaces: self.output_state_h / self.output_state_c copy_to_cpu
  * (infer_utils/inference_predictor.py:176-180). */

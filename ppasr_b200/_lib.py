@@ -64,6 +64,9 @@ PROTOTYPES = {
     "ppasr_b200_stream_reset": (c_int, [P, I]),
     "ppasr_b200_encode_chunk": (c_int, [P, P, I, I, I, I, P]),
     "ppasr_b200_stream_info": (c_int, [P, P, P]),
+    "ppasr_b200_sessions_init": (c_int, [P, I]),
+    "ppasr_b200_sessions_reset": (c_int, [P, I]),
+    "ppasr_b200_sessions_step": (c_int, [P, P, I, P, I, I, I, P]),
     "ppasr_b200_fbank_frames": (c_int, [I]),
     "ppasr_b200_fbank": (c_int, [P, I, c_int64, I, P, I, I, I, c_float, P, P, I, P]),
     "ppasr_b200_ds2_states": (c_int, [P, P, P, I, P]),

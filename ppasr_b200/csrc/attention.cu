@@ -54,6 +54,9 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int bh = b * p.H + h;
+  const int kbh = (p.slots ? __ldg(p.slots + b) : b) * p.H + h;  // (slot, head) of the cached K / V rows
+  const int k_row0 = p.k_row0s ? __ldg(p.k_row0s + b) : p.k_row0;
+  const int pos_row0 = p.pos_row0s ? __ldg(p.pos_row0s + b) : p.pos_row0;
   const int row0 = q_tile * ATT_BM;
   const int klen = p.klens ? min(p.T2, __ldg(p.klens + b)) : p.T2;
   const int nblk = (p.T2 + ATT_BN - 1) / ATT_BN;
@@ -98,10 +101,10 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           mbar_wait(bar_o_full, (j - 1) & 1);  // PV(j-1) finished: probabilities + V^T smem are free
         }
         mbar_arrive_expect_tx(bar_kv_full, 3 * ATT_TILE_BYTES);
-        tma_load_2d(s_kp, &tm_k, bar_kv_full, 0, bh * p.k_rows_per_bh + p.k_row0 + k0);
-        tma_load_2d(s_kp + ATT_TILE_BYTES, &tm_p, bar_kv_full, p.pos_col0 + h * 64, p.pos_row0 + k0);
-        tma_load_2d(s_v, &tm_vt, bar_kv_full, p.k_row0 + k0, bh * 64);
-        tma_load_2d(s_v + ATT_TILE_BYTES / 2, &tm_vt, bar_kv_full, p.k_row0 + k0 + 64, bh * 64);
+        tma_load_2d(s_kp, &tm_k, bar_kv_full, 0, kbh * p.k_rows_per_bh + k_row0 + k0);
+        tma_load_2d(s_kp + ATT_TILE_BYTES, &tm_p, bar_kv_full, p.pos_col0 + h * 64, pos_row0 + k0);
+        tma_load_2d(s_v, &tm_vt, bar_kv_full, k_row0 + k0, kbh * 64);
+        tma_load_2d(s_v + ATT_TILE_BYTES / 2, &tm_vt, bar_kv_full, k_row0 + k0 + 64, kbh * 64);
         if (j == 0) mbar_wait(bar_q_full, 0);
         mbar_wait(bar_kv_full, j & 1);
         tc_fence_after();

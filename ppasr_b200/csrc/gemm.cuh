@@ -472,6 +472,10 @@ struct EpiQKV {
   int Tk;               // rows per (b,h) in kk
   int Tkp;              // padded key pitch of vt
   int kofs;             // first key position written
+  // ragged streaming sessions (ppasr_b200_sessions_step): utterance b of the batch lives in cache slot slots[b] and appends
+  // its keys at position kofs_b[b]; null = lock-step streams (slot b, position kofs)
+  const int* kofs_b = nullptr;
+  const int* slots = nullptr;
   DEVINL void tile(uint32_t taddr, int row, int n0, int, int half, const float* sbias, float4*) const {
     const int D = H * 64;
     int b = 0, t = 0;
@@ -479,6 +483,8 @@ struct EpiQKV {
       b = row / T;
       t = row - b * T;
     }
+    const int kb = slots ? __ldg(slots + b) : b;               // cache slot of the K / V rows
+    const int kofs = kofs_b ? __ldg(kofs_b + b) : this->kofs;  // shadows the member on purpose
     epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
       const int col = n0 + cc;
       if (row >= M || col >= 3 * D) return;
@@ -507,7 +513,7 @@ struct EpiQKV {
           dv[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
         }
       } else if (which == 1) {
-        __nv_bfloat16* dst = kk + ((size_t)(b * H + h) * Tk + kofs + t) * 64 + d0;
+        __nv_bfloat16* dst = kk + ((size_t)(kb * H + h) * Tk + kofs + t) * 64 + d0;
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -515,7 +521,7 @@ struct EpiQKV {
 #pragma unroll
         for (int j = 0; j < 4; ++j) dk[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
       } else {
-        __nv_bfloat16* dst = vt + ((size_t)(b * H + h) * 64 + d0) * Tkp + kofs + t;
+        __nv_bfloat16* dst = vt + ((size_t)(kb * H + h) * 64 + d0) * Tkp + kofs + t;
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[(size_t)j * Tkp] = __float2bfloat16_rn(v[j]);
       }

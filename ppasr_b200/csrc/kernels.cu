@@ -341,11 +341,12 @@ cudaError_t launch_glu_pad(const float* bias_il, float* pad, int C, cudaStream_t
 // Streaming conv cache: one block per stream. ycat[b] = [cache[b] ; y[b]] ; cache[b] <- tail(ycat[b], lorder)
 // ------------------------------------------------------------------------------------------------
 __global__ void conv_cache_concat_kernel(__nv_bfloat16* __restrict__ cache, const __nv_bfloat16* __restrict__ y,
-                                         __nv_bfloat16* __restrict__ ycat, int T, int lorder, int C) {
+                                         __nv_bfloat16* __restrict__ ycat, int T, int lorder, int C,
+                                         const int* __restrict__ slots) {
   extern __shared__ uint4 s_old[];  // lorder * C / 8
   const int b = blockIdx.x;
   const int vec = C / 8;
-  uint4* cb = reinterpret_cast<uint4*>(cache + (size_t)b * lorder * C);
+  uint4* cb = reinterpret_cast<uint4*>(cache + (size_t)(slots ? slots[b] : b) * lorder * C);
   const uint4* yb = reinterpret_cast<const uint4*>(y + (size_t)b * T * C);
   uint4* ob = reinterpret_cast<uint4*>(ycat + (size_t)b * (lorder + T) * C);
   for (int i = threadIdx.x; i < lorder * vec; i += blockDim.x) s_old[i] = cb[i];
@@ -359,9 +360,9 @@ __global__ void conv_cache_concat_kernel(__nv_bfloat16* __restrict__ cache, cons
   }
 }
 cudaError_t launch_conv_cache_concat(__nv_bfloat16* cache, const __nv_bfloat16* y, __nv_bfloat16* ycat, int B, int T,
-                                     int lorder, int C, cudaStream_t st) {
+                                     int lorder, int C, cudaStream_t st, const int* slots) {
   if (B <= 0) return cudaSuccess;
-  conv_cache_concat_kernel<<<B, 256, (size_t)lorder * C * 2, st>>>(cache, y, ycat, T, lorder, C);
+  conv_cache_concat_kernel<<<B, 256, (size_t)lorder * C * 2, st>>>(cache, y, ycat, T, lorder, C, slots);
   count_launch();
   return cudaGetLastError();
 }

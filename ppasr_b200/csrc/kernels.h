@@ -33,7 +33,7 @@ cudaError_t launch_ctc_stats_finalize(const float* pmax, const int* parg, const 
 // Streaming conv-module cache (reference: conformer/convolution.py:108-117): ycat[b] = [cache[b] ; y[b]],
 // then cache[b] <- last `lorder` rows of ycat[b]. cache: bf16 [B, lorder, C]; y: [B, T, C]; ycat: [B, lorder+T, C].
 cudaError_t launch_conv_cache_concat(__nv_bfloat16* cache, const __nv_bfloat16* y, __nv_bfloat16* ycat, int B, int T,
-                                     int lorder, int C, cudaStream_t st);
+                                     int lorder, int C, cudaStream_t st, const int* slots = nullptr);
 // fp32 export of the device-resident caches in the reference's layouts.
 cudaError_t launch_export_att_cache(const __nv_bfloat16* kk, const __nv_bfloat16* vt, float* out, int H, int Tcap,
                                     int Tcapp, int k0, int t, cudaStream_t st);
@@ -135,6 +135,10 @@ struct AttnParams {
   int pos_col0;  // first column (layer * D) of this layer's slice in the positional table
   int D;         // H * 64
   const int* klens;  // per-utterance valid key count (nullable = all T2 valid)
+  // ragged streaming sessions: per-utterance cache slot, first key row and first positional row (nullable = scalars above)
+  const int* slots;
+  const int* k_row0s;
+  const int* pos_row0s;
   __nv_bfloat16* out;  // [B*T1, D]
 };
 cudaError_t launch_rel_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_p,

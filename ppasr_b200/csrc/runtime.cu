@@ -176,6 +176,11 @@ struct ppasr_b200_ctx {
     __nv_bfloat16* vt = nullptr;   // [L][B,H,64,Tcap]
     __nv_bfloat16* cnn = nullptr;  // [L][B,lorder,D]
     std::vector<CUtensorMap> tm_k, tm_vt;  // per layer, rebuilt every chunk (extent = kend)
+    // ragged sessions (ppasr_b200_sessions_*): every cache slot is an independent stream with its own positions
+    bool ragged = false;                        // set for the duration of a sessions_step
+    std::vector<int> s_kstart, s_kend, s_offset;  // per slot (host)
+    int* d_step = nullptr;                      // device [5][B]: slots, kofs, k_row0, pos_row0, klen of the current step
+    int step_T2 = 0;
   } ss;
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
@@ -342,6 +347,7 @@ int ppasr_b200_destroy(ppasr_b200_ctx* ctx) {
   if (ctx->ss.kk) cudaFree(ctx->ss.kk);
   if (ctx->ss.vt) cudaFree(ctx->ss.vt);
   if (ctx->ss.cnn) cudaFree(ctx->ss.cnn);
+  if (ctx->ss.d_step) cudaFree(ctx->ss.d_step);
   if (ctx->ds.h_state) cudaFree(ctx->ds.h_state);
   if (ctx->ds.c_state) cudaFree(ctx->ds.c_state);
   delete ctx;
@@ -873,10 +879,15 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
         // keys kstart .. kend+chunk are attended, positions offset-cache_t .. (encoder.py:253)
         const size_t lk = (size_t)l * ss.B * H * ss.Tcap * 64;
         EpiQKV<BN_NARROW> e{p.q2, ss.kk + lk, ss.vt + lk, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, ss.Tcap, ss.Tcap, ss.kend};
+        if (ss.ragged) e.slots = ss.d_step, e.kofs_b = ss.d_step + p.B;
         { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st))); }
         const int cache_t = ss.kend - ss.kstart;
         ap.T2 = cache_t + p.Tp, ap.k_rows_per_bh = ss.Tcap, ap.k_row0 = ss.kstart, ap.pos_row0 = ss.offset - cache_t;
         ap.klens = nullptr;
+        if (ss.ragged) {  // per-session cache slot / key range / positions
+          ap.T2 = ss.step_T2;
+          ap.slots = ss.d_step, ap.k_row0s = ss.d_step + 2 * p.B, ap.pos_row0s = ss.d_step + 3 * p.B, ap.klens = ss.d_step + 4 * p.B;
+        }
         { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, ss.tm_k[l], c->tm_pos, ss.tm_vt[l], ap, st)); }
       }
       // pad frames of the conv-module input are zeroed (convolution.py:104-106 with the caller's inverted mask)
@@ -907,7 +918,8 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
       } else {
         // [cnn_cache ; chunk] -> pw1 + GLU -> "valid" depthwise conv; cache <- last K-1 input rows (convolution.py:108-117)
         const int lorder = K - 1;
-        PPASR_CUDA_CHECK(launch_conv_cache_concat(ss.cnn + (size_t)l * ss.B * lorder * D, p.y, p.ycat, p.B, p.Tp, lorder, D, st));
+        PPASR_CUDA_CHECK(launch_conv_cache_concat(ss.cnn + (size_t)l * ss.B * lorder * D, p.y, p.ycat, p.B, p.Tp, lorder, D, st,
+                                                  ss.ragged ? ss.d_step : nullptr));
         EpiGLU<BN_WIDE> eg{p.gcat, w.pw1_b, D, p.Mcat, 2 * D};
         { PROF(PC_PW1_GLU); PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_ycat, m.pw1, p.Mcat, 2 * D, D, eg, st))); }
         { PROF(PC_DWCONV); PPASR_CUDA_CHECK(launch_dwconv_norm_swish(p.gcat, w.dw_w, w.dw_b, nullptr, w.cn_g, w.cn_b, cfg.conv_norm == 0,
@@ -1110,6 +1122,95 @@ int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats
     ss.kstart = ss.kend;
   else if (required_cache_size > 0 && ss.kend - ss.kstart > required_cache_size)
     ss.kstart = ss.kend - required_cache_size;
+  return PPASR_OK;
+}
+
+// ---- ragged streaming sessions (many independent streams stepped in one batch) --------------------
+int ppasr_b200_sessions_init(ppasr_b200_ctx* c, int32_t max_sessions) {
+  PPASR_REQUIRE(c && max_sessions > 0 && max_sessions <= 1024, "bad arguments");
+  PPASR_REQUIRE(c->cfg.model_type == 0, "sessions are implemented for the conformer");
+  int rc = ppasr_b200_stream_reset(c, max_sessions);  // caches for max_sessions slots, zeroed
+  if (rc) return rc;
+  auto& ss = c->ss;
+  ss.s_kstart.assign(max_sessions, 0);
+  ss.s_kend.assign(max_sessions, 0);
+  ss.s_offset.assign(max_sessions, 0);
+  if (ss.d_step) cudaFree(ss.d_step);
+  ss.d_step = nullptr;
+  PPASR_CUDA_CHECK(cudaMalloc(&ss.d_step, sizeof(int) * 5 * max_sessions));
+  return PPASR_OK;
+}
+
+int ppasr_b200_sessions_reset(ppasr_b200_ctx* c, int32_t slot) {
+  PPASR_REQUIRE(c && c->ss.d_step && slot >= 0 && slot < c->ss.B, "bad slot (call sessions_init first)");
+  auto& ss = c->ss;
+  const auto& cfg = c->cfg;
+  const int lorder = cfg.conv_kernel - 1, D = cfg.d_model;
+  ss.s_kstart[slot] = ss.s_kend[slot] = ss.s_offset[slot] = 0;
+  for (int l = 0; l < cfg.n_layers; ++l)  // empty conv cache == zero left padding of the first chunk
+    PPASR_CUDA_CHECK(cudaMemset(ss.cnn + ((size_t)l * ss.B + slot) * lorder * D, 0, (size_t)lorder * D * 2));
+  return PPASR_OK;
+}
+
+int ppasr_b200_sessions_step(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_device, const int32_t* slots, int32_t n,
+                             int32_t t, int32_t required_cache_size, void* stream) {
+  PPASR_REQUIRE(c && feats && slots && n > 0 && t > 0, "bad arguments");
+  auto& ss = c->ss;
+  PPASR_REQUIRE(ss.d_step && n <= ss.B, "call ppasr_b200_sessions_init with enough slots first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = build_plan(c, n, t);
+  if (rc != PPASR_OK) return rc;
+  Plan& p = c->plan;
+  const auto& cfg = c->cfg;
+  const int H = cfg.n_heads, L = cfg.n_layers, S = ss.B;
+  std::vector<int> step(5 * n);
+  int T2max = 0;
+  for (int b = 0; b < n; ++b) {
+    const int s = slots[b];
+    PPASR_REQUIRE(s >= 0 && s < S, "slot out of range");
+    for (int q = 0; q < b; ++q) PPASR_REQUIRE(slots[q] != s, "a slot may appear only once per step");
+    if (ss.s_kend[s] + p.Tp > ss.Tcap || ss.s_offset[s] + p.Tp >= cfg.max_len) {
+      set_last_error("session longer than the positional table (max_len); reset it");
+      return PPASR_ERR_STATE;
+    }
+    const int cache_t = ss.s_kend[s] - ss.s_kstart[s];
+    step[b] = s;
+    step[n + b] = ss.s_kend[s];
+    step[2 * n + b] = ss.s_kstart[s];
+    step[3 * n + b] = ss.s_offset[s] - cache_t;
+    step[4 * n + b] = cache_t + p.Tp;
+    T2max = std::max(T2max, cache_t + p.Tp);
+  }
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(p.feats, feats, (size_t)n * t * cfg.feat_dim * sizeof(float),
+                                   feats_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(ss.d_step, step.data(), sizeof(int) * 5 * n, cudaMemcpyHostToDevice, st));
+  {
+    std::vector<int> vlen(n, p.Tp);
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  }
+  std::string err;
+  for (int l = 0; l < L; ++l) {  // whole-capacity maps: validity comes from the per-session key counts
+    const size_t lk = (size_t)l * S * H * ss.Tcap * 64;
+    if (!make_tmap_2d(&ss.tm_k[l], ss.kk + lk, 64, (uint64_t)S * H * ss.Tcap, 128, 128, &err) ||
+        !make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, ss.Tcap, (uint64_t)S * H * 64, (uint64_t)ss.Tcap * 2, 64, &err)) {
+      set_last_error(err);
+      return PPASR_ERR_CUDA;
+    }
+  }
+  ss.ragged = true;
+  ss.step_T2 = T2max;
+  rc = run_encoder(c, st, true);
+  ss.ragged = false;
+  if (rc) return rc;
+  for (int b = 0; b < n; ++b) {  // cache bookkeeping per session (encoder.py:255-260,272)
+    const int s = slots[b];
+    ss.s_kend[s] += p.Tp;
+    ss.s_offset[s] += p.Tp;
+    if (required_cache_size == 0)
+      ss.s_kstart[s] = ss.s_kend[s];
+    else if (required_cache_size > 0 && ss.s_kend[s] - ss.s_kstart[s] > required_cache_size)
+      ss.s_kstart[s] = ss.s_kend[s] - required_cache_size;
+  }
   return PPASR_OK;
 }
 

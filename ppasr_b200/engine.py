@@ -122,6 +122,31 @@ class ConformerEngine:
         self.B, self.Tp = B, int(self.lib.ppasr_b200_out_frames(self._ctx, T))
         return self
 
+    # ---- ragged sessions (continuous batching of independent streams) -----------------------------------------------
+    def sessions_init(self, max_sessions):
+        L.check(self.lib.ppasr_b200_sessions_init(self._ctx, int(max_sessions)))
+
+    def sessions_reset(self, slot):
+        L.check(self.lib.ppasr_b200_sessions_reset(self._ctx, int(slot)))
+
+    def sessions_step(self, feats, slots, required_cache_size=-1, stream=None):
+        """feats float32 [n, t, F] (host NumPy or CUDA tensor), slots: the n distinct cache slots these chunks belong to."""
+        torch = self.torch
+        slots = np.ascontiguousarray(np.asarray(slots), dtype=np.int32)
+        if isinstance(feats, np.ndarray):
+            feats = np.ascontiguousarray(feats, dtype=np.float32)
+            n, T, _ = feats.shape
+            ptr, on_dev = ctypes.c_void_p(feats.ctypes.data), 0
+        else:
+            feats = feats.contiguous()
+            n, T, _ = feats.shape
+            ptr, on_dev = ctypes.c_void_p(feats.data_ptr()), int(feats.is_cuda)
+        assert slots.shape == (n,)
+        L.check(self.lib.ppasr_b200_sessions_step(self._ctx, ptr, on_dev, ctypes.c_void_p(slots.ctypes.data), n, T,
+                                                  int(required_cache_size), L.stream_ptr(stream)))
+        self.B, self.Tp = n, int(self.lib.ppasr_b200_out_frames(self._ctx, T))
+        return self
+
     def ds2_states(self):
         """DeepSpeech2: (h, c) numpy [num_rnn_layers * num_directions, B, rnn_size] after the last encode_chunk."""
         cfg = self.cfg
