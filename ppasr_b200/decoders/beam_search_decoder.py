@@ -91,7 +91,7 @@ class BeamSearchDecoder:
                                                  ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
                                                  L.ptr(state), max_frames, L.ptr(ws), L.stream_ptr()))
 
-    def _results(self, state, B, max_frames, lmax, nbest=None):
+    def _results(self, state, B, max_frames, lmax, nbest=None, approx=True):
         torch = self.torch
         ids = torch.zeros((B, self.beam_size, lmax), dtype=torch.int32, device="cuda")
         lens = torch.zeros((B, self.beam_size), dtype=torch.int32, device="cuda")
@@ -107,7 +107,7 @@ class BeamSearchDecoder:
                     continue
                 toks = [self.vocab_list[i] for i in ids[b, k, :lens[b, k]]]
                 approx = float(sc[b, k])
-                if self._ext_scorer is not None:
+                if self._ext_scorer is not None and approx:
                     # approx_ctc: take the word-insertion and LM terms out again (ctc_beam_search_decoder.cpp, end of decoding)
                     es = self._ext_scorer
                     approx = approx - len(toks) * es.beta - es.get_sent_log_prob(toks) * es.alpha
@@ -120,13 +120,14 @@ class BeamSearchDecoder:
         t = probs if isinstance(probs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(probs, dtype=np.float32))
         return t.to(device="cuda", dtype=torch.float32).contiguous()
 
-    def decode_ids_batch(self, probs, frame_lens=None, nbest=None):
-        """probs [B,T,V] -> per utterance list of (score, text), best first (all beam entries, or the first `nbest`)."""
+    def decode_ids_batch(self, probs, frame_lens=None, nbest=None, approx=True):
+        """probs [B,T,V] -> per utterance list of (score, text), best first (all beam entries, or the first `nbest`).
+        approx=False skips the host-side approx_ctc rescoring of the returned scores (texts and their order are unaffected)."""
         p = self._to_cuda(probs)
         B, T, V = p.shape
         st = self._alloc_state(B, T)
         self._advance(st, p, frame_lens, T)
-        return self._results(st, B, T, T, nbest)
+        return self._results(st, B, T, T, nbest, approx)
 
     # ---- reference API --------------------------------------------------------------------------
     def decode_beam_search_offline(self, probs_split):
@@ -143,9 +144,9 @@ class BeamSearchDecoder:
             batch = torch.zeros((len(lens), max(lens), V), dtype=torch.float32)
             for i, p in enumerate(probs_split):
                 batch[i, :lens[i]] = torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p.cpu())
-            res = self.decode_ids_batch(batch, lens, nbest=1)
+            res = self.decode_ids_batch(batch, lens, nbest=1, approx=False)  # texts only
         else:
-            res = self.decode_ids_batch(probs_split, nbest=1)
+            res = self.decode_ids_batch(probs_split, nbest=1, approx=False)
         return [r[0][1] for r in res]
 
     def decode_chunk(self, probs, logits_lens):

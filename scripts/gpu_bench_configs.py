@@ -52,7 +52,7 @@ lm = NGramLM.from_counts(sents, order=4)
 dec = BeamSearchDecoder(alpha=2.2, beta=4.3, beam_size=20, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=vocab,
                         ext_scorer=Scorer(2.2, 4.3, None, vocab, lm=lm))
 def c5():
-    eng.encode(fd); p = eng.ctc_probs(); return dec.decode_ids_batch(p, nbest=1)
+    eng.encode(fd); p = eng.ctc_probs(); return dec.decode_batch_beam_search_offline(p)   # texts, like the reference's evaluate
 ms_enc = timed(lambda: (eng.encode(fd), eng.ctc_probs()), reps=10)
 ms_all = timed(c5, reps=3, warm=1)
 out["C5 shard efficient_conformer b64x5s beam20 + 4-gram LM (offline forward)"] = {
@@ -65,5 +65,27 @@ eng = ConformerEngine(cfg, W.init_deepspeech2_weights(cfg))
 fd = torch.from_numpy(W.synthetic_fbank(1, 498)).cuda()
 ms = timed(lambda: (eng.encode(fd), eng.ctc_greedy(to_host=False)), reps=10)
 out["C1 deepspeech2 non-streaming 1x5s greedy"] = {"ms_per_utt": ms, "rtf": ms * 1e-3 / 5}
+eng.close(); del eng, fd
+# ---- 8f: GPU fbank front end and ragged streaming sessions
+from ppasr_b200.featurizer import GpuFbank
+from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+fb = GpuFbank()
+audio = torch.randn(32, 160000, device="cuda") * 0.05
+ms = timed(lambda: fb.featurize_batch(audio), reps=20)
+out["8f fbank 32x10s waveforms -> [32,998,80] (dB norm + int16 + Kaldi fbank)"] = {
+    "ms": ms, "audio_seconds_per_s": 320 / ms * 1e3, "bytes_in_out_GBps": (32 * 160000 * 4 * 2 + 32 * 998 * 80 * 4) / ms / 1e6}
+cfg = W.ConformerConfig(vocab_size=V)
+pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "conformer", streaming=True,
+                          weights=W.init_conformer_weights(cfg))
+S = 64
+pred.engine.sessions_init(S)
+chunk = torch.from_numpy(W.synthetic_fbank(S, 67)).cuda()
+slots = list(range(S))
+def sess_step():
+    pred.engine.sessions_step(chunk, slots, -1); pred.engine.ctc_greedy(to_host=False)
+for _ in range(10): sess_step()   # 10 chunks of history (160 cached keys)
+ms = timed(sess_step, reps=20, warm=0)
+out["8f ragged streaming sessions: 64 conformer streams, one 67-frame chunk each (0.64 s of audio per stream)"] = {
+    "ms_per_step": ms, "real_time_streams_per_gpu": 64 * 0.64 / (ms * 1e-3)}
 for k, v in out.items(): print(k, {a: (round(b, 5) if isinstance(b, float) else b) for a, b in v.items()}, flush=True)
 json.dump(out, open('gpurun_out/configs_r1.json', 'w'), indent=1)
