@@ -197,8 +197,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # keeps the version banner off stdout (one JSON line)
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner to stdout at the VERSION and WARN levels: send its log to stderr so that stdout
+        # carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -296,18 +297,21 @@ def main():
     pipe = pred.pipeline(depth=depth)
 
     def e2e_finish(ticket):
-        ids, ol, scores = pipe.result(ticket)
         if world > 1:
-            g = all_gather_results(torch.from_numpy(ids).to(dev), torch.from_numpy(ol).to(dev),
-                                   torch.tensor(scores, dtype=torch.float32, device=dev), total_utts, lmax)
-            ids, ol = g[0].cpu().numpy(), g[1].cpu().numpy()
+            # results stay on the device until the single all-gather, then ONE D2H of the gathered records
+            ids, ol, sc = pipe.device_result(ticket)
+            with torch.cuda.stream(pipe.stream(ticket)):
+                g = all_gather_results(ids, ol, sc, total_utts, lmax)
+                ids, ol = g[0].cpu().numpy(), g[1].cpu().numpy()
+        else:
+            ids, ol, scores = pipe.result(ticket)
         return detokenize(ids, ol, vocab)
 
     def e2e_run(n):
         texts = None
         pending = []
         for _ in range(n):
-            pending.append(pipe.submit(feats_host))
+            pending.append(pipe.submit(feats_host, to_host=(world == 1)))
             if len(pending) == depth:
                 texts = e2e_finish(pending.pop(0))
         while pending:

@@ -50,5 +50,13 @@ def detokenize(ids, out_lens, vocabulary):
     """Host-side string assembly (ppasr/decoders/ctc_greedy_decoder.py:27-31)."""
     ids = np.asarray(ids)
     out_lens = np.asarray(out_lens)
-    return ["".join(vocabulary[int(i)] for i in ids[b, :int(out_lens[b])]).replace("<space>", " ")
-            for b in range(ids.shape[0])]
+    key = id(vocabulary)
+    tab = _VOCAB_ARRAYS.get(key)
+    if tab is None or len(tab) != len(vocabulary):
+        tab = np.asarray(vocabulary, dtype=object)  # one object-array gather per utterance instead of a Python loop per token
+        _VOCAB_ARRAYS.clear()
+        _VOCAB_ARRAYS[key] = tab
+    return ["".join(tab[ids[b, :int(out_lens[b])]].tolist()).replace("<space>", " ") for b in range(ids.shape[0])]
+
+
+_VOCAB_ARRAYS = {}
