@@ -52,7 +52,7 @@ def detokenize(ids, out_lens, vocabulary):
     out_lens = np.asarray(out_lens)
     key = id(vocabulary)
     tab = _VOCAB_ARRAYS.get(key)
-    if tab is None or len(tab) != len(vocabulary):
+    if tab is None or len(tab) != len(vocabulary) or tab[0] != vocabulary[0] or tab[-1] != vocabulary[-1]:
         tab = np.asarray(vocabulary, dtype=object)  # one object-array gather per utterance instead of a Python loop per token
         _VOCAB_ARRAYS.clear()
         _VOCAB_ARRAYS[key] = tab

@@ -180,3 +180,17 @@ def test_pdiparams_roundtrip(tmp_path):
     os.remove(p + ".info")
     r2 = load_pdiparams(p)
     assert list(r2)[0] == "param_0" and len(r2) == len(w)
+
+
+def test_detokenize_matches_reference_join():
+    """parallel.detokenize (vectorised) == ''.join(vocabulary[i] ...).replace('<space>', ' ') of ctc_greedy_decoder.py:27-31."""
+    from ppasr_b200.parallel import detokenize
+    rng = np.random.RandomState(0)
+    vocab = ["<blank>", "<unk>", "<space>"] + [chr(0x4E00 + i) for i in range(50)] + ["ab", "<eos>"]
+    ids = rng.randint(0, len(vocab), size=(7, 33)).astype(np.int32)
+    lens = np.array([33, 0, 5, 17, 1, 32, 9], dtype=np.int32)
+    ref = ["".join(vocab[int(i)] for i in ids[b, :lens[b]]).replace("<space>", " ") for b in range(7)]
+    assert detokenize(ids, lens, vocab) == ref
+    vocab2 = list(reversed(vocab))  # a different vocabulary object must not hit the cached table of the first one
+    ref2 = ["".join(vocab2[int(i)] for i in ids[b, :lens[b]]).replace("<space>", " ") for b in range(7)]
+    assert detokenize(ids, lens, vocab2) == ref2
