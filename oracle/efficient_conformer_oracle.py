@@ -154,5 +154,131 @@ class EfficientConformerOracle(ConformerOracle):
         xs = layer_norm(xs, self.w["encoder.after_norm.weight"], self.w["encoder.after_norm.bias"])
         return xs, masks
 
-    def encoder_forward_chunk(self, *a, **k):
-        raise NotImplementedError("Efficient-Conformer forward_chunk (encoder.py:266-394) is not restated yet")
+    # -- efficient_conformer/encoder.py:205-210 -------------------------------------------------------------------------
+    def calculate_downsampling_factor(self, i):
+        conf = self.conf
+        return conf.stride if (conf.stride_layer_idx is not None and i > conf.stride_layer_idx) else 1
+
+    # grouped attention with a K/V cache (attention.py:153-160): the cache is concatenated BEFORE pad4group, so the groups of
+    # the keys are re-formed from the first cached frame for every chunk
+    def grouped_mha_chunk(self, prefix, x, pos_emb, cache):
+        w = self.w
+        H, D = self.conf.attention_heads, self.conf.output_size
+        dk, gs = D // H, self.conf.group_size
+        B = x.shape[0]
+        q = linear(x, w[prefix + ".linear_q.weight"], w[prefix + ".linear_q.bias"]).reshape(B, -1, H, dk).transpose(1, 2)
+        k = linear(x, w[prefix + ".linear_k.weight"], w[prefix + ".linear_k.bias"]).reshape(B, -1, H, dk).transpose(1, 2)
+        v = linear(x, w[prefix + ".linear_v.weight"], w[prefix + ".linear_v.bias"]).reshape(B, -1, H, dk).transpose(1, 2)
+        p = linear(pos_emb, w[prefix + ".linear_pos.weight"], w[prefix + ".linear_pos.bias"])
+        if cache is not None and cache.numel() > 0:
+            kc, vc = torch.split(cache, cache.shape[-1] // 2, dim=-1)
+            k = torch.cat([kc, k], dim=2)
+            v = torch.cat([vc, v], dim=2)
+        new_cache = torch.cat((k, v), dim=-1)
+
+        def group(t):  # (B,H,T,dk) -> pad T to a multiple of gs -> (B,H,T/gs,dk*gs) through the (B,T,H*dk) view
+            T = t.shape[2]
+            pad = (gs - T % gs) % gs
+            t = F.pad(t, (0, 0, 0, pad))
+            return t.transpose(1, 2).reshape(B, -1, H, dk * gs).transpose(1, 2), pad
+
+        qg, pad_q = group(q)
+        kg, _ = group(k)
+        vg, _ = group(v)
+        padp = (gs - p.shape[1] % gs) % gs
+        pg = F.pad(p, (0, 0, 0, padp)).reshape(p.shape[0], -1, H, dk * gs).transpose(1, 2)
+        q_u = qg + w[prefix + ".pos_bias_u"].unsqueeze(1)
+        q_v = qg + w[prefix + ".pos_bias_v"].unsqueeze(1)
+        scores = (q_u @ kg.transpose(-2, -1) + q_v @ pg.transpose(-2, -1)) / math.sqrt(dk * gs)
+        attn = torch.softmax(scores, dim=-1)  # fake (0,0,0) mask in forward_chunk
+        o = (attn @ vg).transpose(1, 2).reshape(B, -1, D)
+        o = o[:, :o.shape[1] - pad_q]
+        return linear(o, w[prefix + ".linear_out.weight"], w[prefix + ".linear_out.bias"]), new_cache
+
+    # efficient_conformer/convolution.py:80-138 with a cache (cache[:, :, -lorder:], :108)
+    def eff_conv_module_chunk(self, prefix, x, cache, K, stride):
+        w = self.w
+        conf = self.conf
+        lorder = K - 1
+        x = x.transpose(1, 2)
+        if cache is None or cache.numel() == 0:
+            x = F.pad(x, (lorder, 0), "constant", 0.0)
+        else:
+            x = torch.cat((cache[:, :, -lorder:], x), dim=2)
+        new_cache = x[:, :, -lorder:]
+        x = F.conv1d(x, w[prefix + ".pointwise_conv1.weight"], w[prefix + ".pointwise_conv1.bias"])
+        x = F.glu(x, dim=1)
+        x = F.conv1d(x, w[prefix + ".depthwise_conv.weight"], w[prefix + ".depthwise_conv.bias"], stride=stride, groups=x.shape[1])
+        if conf.cnn_module_norm == "layer_norm":
+            x = layer_norm(x.transpose(1, 2), w[prefix + ".norm.weight"], w[prefix + ".norm.bias"]).transpose(1, 2)
+        else:
+            x = F.batch_norm(x, w[prefix + ".norm._mean"], w[prefix + ".norm._variance"], w[prefix + ".norm.weight"],
+                             w[prefix + ".norm.bias"], training=False, eps=1e-5)
+        x = swish(x)
+        x = F.conv1d(x, w[prefix + ".pointwise_conv2.weight"], w[prefix + ".pointwise_conv2.bias"])
+        return x.transpose(1, 2), new_cache
+
+    # -- efficient_conformer/encoder.py:266-394 (streaming model only: causal conv) ----------------------------------------
+    @torch.no_grad()
+    def encoder_forward_chunk(self, xs, offset, required_cache_size, att_cache, cnn_cache):
+        """att_cache (L, H, t, 2 dk) at the full frame rate (half-rate blocks repeat every key, :368, and read every second
+        one, :351); cnn_cache (L, 1, D, cnn_module_kernel - 1), left-padded with zeros for the kernel-7 blocks (:370-372).
+        `offset` counts OUTPUT frames (8 per 16-frame chunk) and is scaled back to the full rate first (:304)."""
+        conf = self.conf
+        w = self.w
+        assert xs.shape[0] == 1 and conf.causal
+        has_stride = conf.stride_layer_idx is not None
+        offset = offset * (conf.stride if has_stride else 1)
+        xs = self.global_cmvn(xs.to(self.dtype))
+        tmp_masks = torch.ones(1, 1, xs.shape[1], dtype=torch.bool)
+        xs, pos_emb, _ = self.embed(xs, tmp_masks, offset=offset)
+        cache_t1 = att_cache.shape[2] if att_cache.dim() == 4 else 0
+        attention_key_size = cache_t1 + xs.shape[1]
+        pos_emb = self.position_encoding(offset=offset - cache_t1, size=attention_key_size)
+        if required_cache_size < 0:
+            next_cache_start = 0
+        elif required_cache_size == 0:
+            next_cache_start = attention_key_size
+        else:
+            next_cache_start = max(attention_key_size - required_cache_size, 0)
+        r_att, r_cnn = [], []
+        kmax = conf.cnn_module_kernel
+        for i in range(conf.num_blocks):
+            p = f"encoder.encoders.{i}"
+            factor = self.calculate_downsampling_factor(i)
+            ac = att_cache[i:i + 1, :, ::factor, :] if att_cache.numel() > 0 else None
+            cc = cnn_cache[i] if cnn_cache.numel() > 0 else None
+
+            def ln(name, t):
+                return layer_norm(t, w[f"{p}.{name}.weight"], w[f"{p}.{name}.bias"])
+
+            xs = xs + 0.5 * self.ffn(p + ".feed_forward_macaron", ln("norm_ff_macaron", xs))
+            if i in conf.group_layer_idx:
+                x_att, new_att = self.grouped_mha_chunk(p + ".self_attn", ln("norm_mha", xs), pos_emb, ac)
+            else:
+                x_att, new_att = self.rel_mha(p + ".self_attn", ln("norm_mha", xs), None, pos_emb, ac)
+            xs = xs + x_att
+            strided = has_stride and i == conf.stride_layer_idx
+            residual = xs
+            xc, new_cnn = self.eff_conv_module_chunk(p + ".conv_module", ln("norm_conv", xs), cc, self.layer_kernel(i),
+                                                     conf.stride if strided else 1)
+            if strided:
+                residual = F.avg_pool1d(residual.transpose(1, 2), conf.stride, conf.stride, 0, ceil_mode=True,
+                                        count_include_pad=False).transpose(1, 2)
+                pos_emb = pos_emb[:, ::conf.stride, :]
+            xs = residual + xc
+            xs = xs + 0.5 * self.ffn(p + ".feed_forward", ln("norm_ff", xs))
+            xs = ln("norm_final", xs)
+            new_att = new_att[:, :, next_cache_start // factor:, :]
+            new_att = torch.repeat_interleave(new_att, factor, dim=2)
+            new_cnn = F.pad(new_cnn.unsqueeze(0), (kmax - 1 - new_cnn.shape[2], 0))
+            r_att.append(new_att)
+            r_cnn.append(new_cnn)
+        xs = layer_norm(xs, w["encoder.after_norm.weight"], w["encoder.after_norm.bias"])
+        return xs, torch.cat(r_att, dim=0), torch.cat(r_cnn, dim=0)
+
+    @torch.no_grad()
+    def get_encoder_out_chunk(self, speech, offset, required_cache_size, att_cache, cnn_cache, return_logits=False):
+        xs, att_cache, cnn_cache = self.encoder_forward_chunk(speech, offset, required_cache_size, att_cache, cnn_cache)
+        out = self.ctc_logits(xs) if return_logits else self.ctc_softmax(xs)
+        return out, att_cache, cnn_cache

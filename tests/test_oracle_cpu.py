@@ -440,3 +440,34 @@ def test_squeezeformer_oracle_chunked_equals_chunk_masked_offline():
     full = o.ctc_logits(enc)
     assert (chunked - full[:, :chunked.shape[1]]).abs().max() < 1e-3 * full.abs().max()
     assert att.shape == (4, 4, 48, 128) and cnn.shape == (4, 1, 256, 30)
+
+
+def test_efficient_conformer_oracle_chunk_path():
+    """forward_chunk restatement (efficient_conformer/encoder.py:266-394). Without grouped attention the chunked run equals the
+    chunk-masked offline forward (stride block, kernel 15 -> 7, half-rate cache rules and positions are consistent); WITH the
+    grouped attention of the shipped config it does not -- the reference re-forms the key groups from the first cached frame
+    for every chunk (attention.py:153-160) and strides the chunk mask by 3 offline (:63-64), so its own streaming and offline
+    paths disagree. Both facts are pinned here so a GPU implementation knows what it has to reproduce."""
+    from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
+    from ppasr_b200.weights import EfficientConformerConfig, init_efficient_conformer_weights
+    x = torch.from_numpy(synthetic_fbank(1, 67 + 64 * 2))
+    gaps = {}
+    for name, groups in (("plain", ()), ("grouped", (0, 1))):
+        cfg = EfficientConformerConfig(num_blocks=3, vocab_size=40, group_layer_idx=groups, stride_layer_idx=1)
+        w = init_efficient_conformer_weights(cfg)
+        o = EfficientConformerOracle(EfficientConformerConf(**cfg.to_dict()), w)
+        att = torch.zeros(0, 0, 0, 0)
+        cnn = torch.zeros(0, 0, 0, 0)
+        off, outs = 0, []
+        for s in range(0, x.shape[1] - 66, 64):
+            y, att, cnn = o.get_encoder_out_chunk(x[:, s:s + 67], off, -1, att, cnn, return_logits=True)
+            assert y.shape[1] == 8  # 16 full-rate frames -> 8 output frames per chunk
+            off += y.shape[1]
+            outs.append(y)
+        assert att.shape == (3, 4, 48, 128) and cnn.shape == (3, 1, 256, 14)
+        chunked = torch.cat(outs, 1)
+        enc, _ = o.encoder_forward(x, torch.tensor([x.shape[1]]), decoding_chunk_size=16, num_decoding_left_chunks=-1)
+        full = o.ctc_logits(enc)
+        gaps[name] = ((chunked - full[:, :chunked.shape[1]]).abs().max() / full.abs().max()).item()
+    assert gaps["plain"] < 1e-4
+    assert gaps["grouped"] > 1e-3
