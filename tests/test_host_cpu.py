@@ -194,3 +194,76 @@ def test_detokenize_matches_reference_join():
     vocab2 = list(reversed(vocab))  # a different vocabulary object must not hit the cached table of the first one
     ref2 = ["".join(vocab2[int(i)] for i in ids[b, :lens[b]]).replace("<space>", " ") for b in range(7)]
     assert detokenize(ids, lens, vocab2) == ref2
+
+
+def test_stream_scheduler_window_logic_cpu(monkeypatch):
+    """StreamScheduler host logic with a fake engine (and the oracle's chunk decoder: the product one needs the GPU): each session is cut into exactly the reference's windows (67 frames,
+    stride 64, short tail at is_end: predict.py:277-300 == oracle stream_windows), sessions are batched by window length,
+    slots are unique inside a step and recycled on close."""
+    from oracle.conformer_oracle import stream_windows
+    from ppasr_b200.infer_utils import stream_scheduler as SS
+
+    class FakeEngine:
+        def __init__(self):
+            self.calls = []
+
+        def sessions_init(self, n):
+            self.n = n
+
+        def sessions_reset(self, slot):
+            pass
+
+        def sessions_step(self, batch, slots, required):
+            assert len(set(slots)) == len(slots)
+            self.calls.append((batch.copy(), list(slots)))
+            self.last = batch
+
+        def ctc_probs(self, to_host=True):
+            B, t, _ = self.last.shape
+            Tp = ((t - 1) // 2 - 1) // 2
+            p = np.zeros((B, Tp, 5), dtype=np.float32)
+            p[:, :, 0] = 1.0
+            return p
+
+    class FakePred:
+        use_model, streaming = "conformer", True
+
+        class model_config:
+            input_dim = 4
+
+        def __init__(self):
+            self.engine = FakeEngine()
+
+    from oracle import decoders_oracle as DO
+    monkeypatch.setattr(SS, "greedy_decoder_chunk", DO.greedy_decoder_chunk)
+    pred = FakePred()
+    sch = SS.StreamScheduler(pred, ["<blank>", "a", "b", "c", "d"], max_sessions=3)
+    lens = {0: 67 + 64 * 2 + 20, 1: 67 + 5, 2: 30}
+    feats = {k: np.arange(n * 4, dtype=np.float32).reshape(n, 4) + 1000 * k for k, n in lens.items()}
+    sids = {k: sch.open() for k in lens}
+    seen = {k: [] for k in lens}
+    pos = {k: 0 for k in lens}
+    for rnd in range(40):
+        for k in lens:
+            n = min(45, lens[k] - pos[k])
+            if n > 0:
+                sch.feed(sids[k], feats[k][pos[k]:pos[k] + n], is_end=(pos[k] + n >= lens[k]))
+                pos[k] += n
+        before = len(pred.engine.calls)
+        sch.step()
+        for batch, slots in pred.engine.calls[before:]:
+            for b, slot in enumerate(slots):
+                k = [kk for kk in lens if sch._sessions[sids[kk]].slot == slot][0]
+                seen[k].append(batch[b])
+        if all(pos[k] >= lens[k] for k in lens) and not sch.pending():
+            break
+    for k, n in lens.items():
+        wins = stream_windows(n, is_end=True)
+        assert len(seen[k]) == len(wins), (k, len(seen[k]), wins)
+        for w, (s, e) in zip(seen[k], wins):
+            assert np.array_equal(w, feats[k][s:e])
+    for k in lens:
+        sch.close(sids[k])
+    assert sorted(sch._free) == [0, 1, 2]
+    with pytest.raises(Exception):
+        SS.StreamScheduler(type("P", (), {"use_model": "deepspeech2", "streaming": True})(), [], 1)
