@@ -8,25 +8,38 @@ NumPy restatement of AudioFeaturizer.featurize for feature_method='fbank'
      (paddleaudio >= 1.0.1, requirements.txt:14; not installable here), a port of Kaldi's compute-fbank-feats with the
      defaults: snip_edges, remove_dc_offset, preemphasis 0.97, povey window, FFT size 512, power spectrum, mel filters from
      20 Hz to Nyquist on the scale 1127 ln(1 + f/700), log(max(e, FLT_EPSILON)).
-PARITY: pinned against torchaudio.compliance.kaldi.fbank (the same Kaldi port, importable here) in tests/test_oracle_cpu.py.
+PARITY: steps 1-2 are PINNED bit-for-bit against the reference's own AudioSegment code (tests/golden/audio_golden.npz, made by
+tests/golden/make_audio_golden.py); step 3 is pinned against torchaudio.compliance.kaldi.fbank (the same Kaldi port,
+importable here) in tests/test_oracle_cpu.py.
 """
 import numpy as np
 
 EPS = np.float32(1.1920928955078125e-07)
 
 
-def db_normalize(samples, target_db=-20.0, max_gain_db=300.0):
-    samples = np.asarray(samples, dtype=np.float32)
-    mean_square = np.mean(samples.astype(np.float64) ** 2)
-    rms_db = 10 * np.log10(max(mean_square, 1e-20))
+def db_normalize(samples, target_db=-20, max_gain_db=300.0):
+    """AudioSegment.normalize / rms_db / gain_db (audio.py:287-304,519-529,256-264), expression by expression: the mean square
+    and the gain are float32 quantities (NumPy >= 2 promotion rules), an all-zero segment has rms_db = 0."""
+    samples = np.asarray(samples, dtype=np.float32).copy()
+    mean_square = np.mean(samples ** 2)
+    if mean_square == 0:
+        mean_square = 1
+    rms_db = 10 * np.log10(mean_square)
     gain = target_db - rms_db
     if gain > max_gain_db:
         raise ValueError("gain exceeds max_gain_db")
-    return samples * np.float32(10.0 ** (gain / 20.0))
+    samples *= 10. ** (min(max_gain_db, target_db - rms_db) / 20.)
+    return samples
 
 
 def to_int16_scale(samples):
-    return np.clip(np.asarray(samples, dtype=np.float32) * np.float32(32768.0), -32768, 32767).astype(np.int16).astype(np.float32)
+    """AudioSegment.to('int16') (audio.py:244-254,549-574): scale by 2^15, clip to the int16 range, truncate; returned as
+    float32 (what the fbank routine is fed with, audio_featurizer.py:128)."""
+    out = np.asarray(samples, dtype=np.float32).copy()
+    out *= (2 ** 15 / 1.)
+    out[out > 32767] = 32767
+    out[out < -32768] = -32768
+    return out.astype(np.int16).astype(np.float32)
 
 
 def mel_banks(n_mels, nfft=512, sr=16000, low=20.0):

@@ -50,7 +50,7 @@ __global__ void fbank_gain_kernel(const float* __restrict__ audio, long long str
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     const double ms = n > 0 ? t / n : 0.0;
-    const double rms_db = 10.0 * log10(fmax(ms, 1e-20));
+    const double rms_db = 10.0 * log10(ms == 0.0 ? 1.0 : ms);  // audio.py:526-529: an all-zero segment counts as 0 dB
     gain[b] = (float)pow(10.0, ((double)target_db - rms_db) / 20.0);
   }
 }

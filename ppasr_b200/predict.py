@@ -31,8 +31,10 @@ class AudioFeaturizer:
 
     @staticmethod
     def _rms_db(samples):
-        mean_square = np.mean(samples.astype(np.float64) ** 2)
-        return 10 * np.log10(max(mean_square, 1e-20))  # audio.py rms_db
+        mean_square = np.mean(samples ** 2)  # audio.py:519-529 (float32 like the reference; silence -> 0 dB)
+        if mean_square == 0:
+            mean_square = 1
+        return 10 * np.log10(mean_square)
 
     def featurize(self, samples, sample_rate=16000):
         """samples: float32 in [-1, 1]. Returns fbank [T, n_mels] float32."""

@@ -471,3 +471,25 @@ def test_efficient_conformer_oracle_chunk_path():
         gaps[name] = ((chunked - full[:, :chunked.shape[1]]).abs().max() / full.abs().max()).item()
     assert gaps["plain"] < 1e-4
     assert gaps["grouped"] > 1e-3
+
+
+def test_audio_normalisation_oracle_matches_reference_golden():
+    """db_normalize / to_int16_scale of oracle/fbank_oracle.py against outputs of the reference's own AudioSegment.normalize /
+    to('int16') (tests/golden/make_audio_golden.py). Bit-exact under NumPy >= 2 (the golden was made with its promotion rules:
+    the gain is a float32 quantity); one int16 LSB otherwise."""
+    from oracle import fbank_oracle as FO
+    g = np.load(os.path.join(GOLD, "audio_golden.npz"))
+    exact = int(np.__version__.split(".")[0]) >= 2
+    for k in ("quiet", "loud_clipping", "tone", "int16_input", "silence"):
+        x = g[k + "/float32"]
+        n = FO.db_normalize(x)
+        i16 = FO.to_int16_scale(n)
+        if exact:
+            assert np.array_equal(n, g[k + "/normalized"]), k
+            assert np.array_equal(i16, g[k + "/int16"].astype(np.float32)), k
+        else:
+            assert np.abs(i16 - g[k + "/int16"].astype(np.float32)).max() <= 1, k
+    # the product's host featurizer applies the same normalisation (then torchaudio's Kaldi port)
+    from ppasr_b200.predict import AudioFeaturizer
+    x = g["tone/float32"]
+    assert np.abs(AudioFeaturizer().featurize(x) - FO.kaldi_fbank(g["tone/int16"].astype(np.float32))).max() < 2e-3
