@@ -267,3 +267,14 @@ def test_stream_scheduler_window_logic_cpu(monkeypatch):
     assert sorted(sch._free) == [0, 1, 2]
     with pytest.raises(Exception):
         SS.StreamScheduler(type("P", (), {"use_model": "deepspeech2", "streaming": True})(), [], 1)
+
+
+def test_read_vocab_file_matches_reference_golden(tmp_path):
+    """weights.read_vocab_file == TextFeaturizer.vocab_list of the reference run on the same file
+    (tests/golden/make_vocab_golden.py; text_featurizer.py:52-59)."""
+    import json
+    from ppasr_b200.weights import read_vocab_file
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vocab_golden.json"), encoding="utf-8"))
+    p = tmp_path / "vocabulary.txt"
+    p.write_text(g["file"], encoding="utf-8")
+    assert read_vocab_file(str(p)) == g["vocab_list"] and len(g["vocab_list"]) == g["vocab_size"]
