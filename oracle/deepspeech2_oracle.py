@@ -11,8 +11,12 @@ published cell equations (python/paddle/nn/layer/rnn.py LSTMCell / GRUCell) are 
     GRU   x_g = W_ih x + b_ih, h_g = W_hh h + b_hh, chunks (r, z, c):  r = sig(x_r + h_r); z = sig(x_z + h_z);
           c = tanh(x_c + r * h_c);  h' = (h - c) * z + c
 and the sequence_length rule of paddle.nn.RNN: steps t >= len keep the state and emit zeros; the reverse direction walks
-t = len-1 .. 0. PARITY STATUS: **unpinned** (no Paddle, no reference tests); checked against torch.nn.LSTM/GRU with packed
-sequences (identical published equations and gate order) in tests/test_oracle_cpu.py.
+t = len-1 .. 0. PARITY STATUS: the WIRING (conv reshape, subsampled lengths, per-layer state-box split/concat, LayerNorm
+placement, CTC head) is pinned against the reference's own CRNNEncoder run on tests/golden/paddle_shim
+(tests/golden/encoder_golden_deepspeech2_*.npz: LSTM/GRU x offline-bidirectional/streaming-forward, chunk chains with
+their final state boxes; tests/test_encoder_golden_cpu.py, 5e-5). The CELL arithmetic of paddle.nn.LSTM/GRU stays unpinned
+(third-party, not installable): the shim and tests/test_oracle_cpu.py both use torch.nn.LSTM/GRU with packed sequences,
+which implement the same published equations and gate order.
 """
 from typing import Dict, Optional
 

@@ -11,7 +11,12 @@ PyTorch-CPU restatement of ppasr/model_utils/efficient_conformer/ (paths relativ
 -> after_norm -> CTC. `efficient_conf` in configs/efficient_conformer.yml is swallowed by **kwargs (encoder.py:55), so the
 constructor defaults (stride_layer_idx 3, stride 2, group_layer_idx 0..3, group_size 3, stride_kernel True) apply.
 
-PARITY STATUS: **unpinned** (no Paddle here, no reference tests); self-consistency checks in tests/test_oracle_cpu.py.
+PARITY STATUS: **pinned against the reference's own model code** run on tests/golden/paddle_shim (see the Conformer oracle
+header): tests/golden/encoder_golden_efficient_conformer_{offline,stream}.npz come from the unmodified
+EfficientConformerEncoder (grouped attention in blocks 0-1, stride block 1, batch_norm / layer_norm conv norm);
+tests/test_encoder_golden_cpu.py checks offline logits (padded frames included) and the forward_chunk chain with its caches
+to 5e-5 (observed 1e-5). The reference's StrideConformerEncoderLayer also owns an unused `concat_linear` parameter
+(encoder.py:453, read only when concat_after=True): it appears in .pdparams files and is ignored by name here.
 """
 import math
 from typing import Dict

@@ -6,8 +6,11 @@ PyTorch-CPU restatement of the reference inference math of ppasr/model_utils/squ
 time-reduction layer before block `reduce_idx` and the recover step before block `recover_idx` -> CTC projection
 -> softmax. No final norm, no final_proj when output_size == encoder_dim (encoder.py:167-169).
 
-PARITY STATUS: **unpinned** (same reasons as the Conformer oracle: Paddle is not installable here and the reference
-ships no tests). Pinned only by self-consistency properties (tests/test_oracle_cpu.py) and an fp64 re-run.
+PARITY STATUS: **pinned against the reference's own model code** run on tests/golden/paddle_shim (see the Conformer oracle
+header): tests/golden/encoder_golden_squeezeformer_{stream,offline}.npz come from the unmodified SqueezeformerEncoder
+(stream = TimeReductionLayerStream + causal + dynamic chunk, offline = TimeReductionLayer1D), and
+tests/test_encoder_golden_cpu.py checks offline logits (padded frames included), a forward_chunk chain and its final
+caches to 5e-5 (observed 1.1e-5). Plus self-consistency properties (tests/test_oracle_cpu.py) and an fp64 re-run.
 """
 import math
 from typing import Dict

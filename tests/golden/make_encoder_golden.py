@@ -1,0 +1,251 @@
+"""Generate tests/golden/encoder_golden_<model>.npz by running the reference's OWN, unmodified model code.
+
+PaddlePaddle is not installable here, so the reference classes are imported from /root/reference with `paddle` provided by
+tests/golden/paddle_shim (a torch-CPU stand-in implementing exactly the Paddle calls those files make, see its README).
+Weights: the seeded synthetic initialisers of ppasr_b200/weights.py (reference parameter names), small dimensions so the
+fixtures stay a few hundred KB. Recorded per model: the offline `get_encoder_out` CTC probabilities (+ logits) for a ragged
+batch, and a `get_encoder_out_chunk` chain (67-frame windows, stride 64, as predict.py:232-337 drives it) for one utterance.
+
+Run (in the build container only; /root/reference is not on the GPU box):
+    python tests/golden/make_encoder_golden.py [conformer squeezeformer efficient_conformer deepspeech2]
+tests/test_oracle_cpu.py::test_encoder_oracle_vs_reference_code then checks oracle/*_oracle.py against these files.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+sys.dont_write_bytecode = True  # /root/reference is read-only
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "paddle_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, REPO)
+
+import paddle  # noqa: E402  (the shim)
+import torch  # noqa: E402
+
+from ppasr_b200 import weights as W  # noqa: E402
+
+
+def load_into(layer, weights, prefix, unused=()):
+    """`unused`: substrings of parameters the reference constructs but never reads at inference (left at zero)."""
+    own = layer.state_dict()
+    sub = {k[len(prefix):]: v for k, v in weights.items() if k.startswith(prefix)}
+    for k in [k for k in own if any(u in k for u in unused)]:
+        own.pop(k)
+    missing = [k for k in own if k not in sub]
+    extra = [k for k in sub if k not in own]
+    assert not missing and not extra, ("state mismatch", prefix, missing[:6], extra[:6])
+    with torch.no_grad():
+        for k, v in own.items():
+            assert tuple(v.shape) == tuple(sub[k].shape), (k, v.shape, sub[k].shape)
+            v.copy_(torch.from_numpy(sub[k]))
+
+
+def stream_windows(num_frames, window=67, stride=64):
+    """predict.py:281-297 with is_end on the last call: offsets of the decoding windows over the whole feature matrix."""
+    out = []
+    for cur in range(0, num_frames - 7 + 1, stride):
+        out.append((cur, min(cur + window, num_frames)))
+    return out
+
+
+def t(x, dtype=None):
+    return paddle.to_tensor(np.ascontiguousarray(x), dtype=dtype)
+
+
+def logits_of(ctc, hs):
+    return ctc.ctc_lo(hs)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def build_conformer(cfg, weights, streaming):
+    from ppasr.model_utils.conformer.encoder import ConformerEncoder
+    from ppasr.model_utils.loss.ctc import CTCLoss
+    from ppasr.model_utils.utils.cmvn import GlobalCMVN
+    cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
+    enc = ConformerEncoder(input_size=cfg.input_dim, global_cmvn=cmvn, use_dynamic_chunk=streaming, causal=streaming,
+                           output_size=cfg.output_size, attention_heads=cfg.attention_heads, linear_units=cfg.linear_units,
+                           num_blocks=cfg.num_blocks, cnn_module_kernel=cfg.cnn_module_kernel,
+                           cnn_module_norm=cfg.cnn_module_norm, max_len=cfg.max_len)
+    ctc = CTCLoss(cfg.vocab_size, enc.output_size())
+    return enc, ctc
+
+
+def run_former(enc, ctc, feats, lens, chunk_feats):
+    """model.py:148-184 get_encoder_out / get_encoder_out_chunk, called on the reference encoder + CTC head."""
+    enc.eval(), ctc.eval()
+    out = {}
+    with torch.no_grad():
+        hs, _ = enc(t(feats), t(lens, "int64"), decoding_chunk_size=-1, num_decoding_left_chunks=-1)
+        out["offline_logits"] = logits_of(ctc, hs).numpy()
+        out["offline_probs"] = ctc.softmax(hs).numpy()
+        if chunk_feats is not None:
+            att = paddle.zeros([0, 0, 0, 0])
+            cnn = paddle.zeros([0, 0, 0, 0])
+            offset = 0
+            logits = []
+            for (a, b) in stream_windows(chunk_feats.shape[0]):
+                xs, att, cnn = enc.forward_chunk(xs=t(chunk_feats[None, a:b]), offset=offset, required_cache_size=-16,
+                                                 att_cache=att, cnn_cache=cnn)
+                offset += int(xs.shape[1])
+                logits.append(logits_of(ctc, xs).numpy()[0])
+            out["chunk_logits"] = np.concatenate(logits, 0)
+            out["chunk_att_cache"] = att.numpy()
+            out["chunk_cnn_cache"] = cnn.numpy()
+    return out
+
+
+def make_conformer(path, streaming=True, norm="layer_norm", seed=1000):
+    cfg = W.ConformerConfig(input_dim=80, vocab_size=40, output_size=64, attention_heads=4, linear_units=128, num_blocks=3,
+                            cnn_module_kernel=15, streaming=streaming, cnn_module_norm=norm, max_len=600)
+    weights = W.init_conformer_weights(cfg, seed=seed)
+    enc, ctc = build_conformer(cfg, weights, streaming)
+    load_into(enc, weights, "encoder.")
+    load_into(ctc, weights, "ctc.")
+    rng = np.random.RandomState(seed + 1)
+    lens = np.array([131, 96, 57], dtype=np.int64)
+    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
+    for b, n in enumerate(lens):
+        feats[b, n:] = 0
+    chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0] if streaming else None
+    out = run_former(enc, ctc, feats, lens, chunk_feats)
+    np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
+                        chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
+    return out
+
+
+def make_squeezeformer(path, streaming=True, seed=1000):
+    from ppasr.model_utils.loss.ctc import CTCLoss
+    from ppasr.model_utils.squeezeformer.encoder import SqueezeformerEncoder
+    from ppasr.model_utils.utils.cmvn import GlobalCMVN
+    cfg = W.SqueezeformerConfig(input_dim=80, vocab_size=40, encoder_dim=64, output_size=64, attention_heads=4, num_blocks=4,
+                                reduce_idx=1, recover_idx=3, feed_forward_expansion_factor=2, cnn_module_kernel=15,
+                                streaming=streaming, max_len=600)
+    weights = W.init_squeezeformer_weights(cfg, seed=seed)
+    cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
+    # squeezeformer/model.py:35-50
+    enc = SqueezeformerEncoder(input_size=cfg.input_dim, global_cmvn=cmvn,
+                               time_reduction_layer_type="stream" if streaming else "conv1d", use_dynamic_chunk=streaming,
+                               causal=streaming, encoder_dim=cfg.encoder_dim, output_size=cfg.output_size,
+                               attention_heads=cfg.attention_heads, num_blocks=cfg.num_blocks, reduce_idx=cfg.reduce_idx,
+                               recover_idx=cfg.recover_idx, feed_forward_expansion_factor=cfg.feed_forward_expansion_factor,
+                               cnn_module_kernel=cfg.cnn_module_kernel, cnn_norm_type=cfg.cnn_norm_type,
+                               adaptive_scale=cfg.adaptive_scale)
+    ctc = CTCLoss(cfg.vocab_size, enc.output_size())
+    load_into(enc, weights, "encoder.")
+    load_into(ctc, weights, "ctc.")
+    lens = np.array([131, 96, 57], dtype=np.int64)
+    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
+    for b, n in enumerate(lens):
+        feats[b, n:] = 0
+    chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0] if streaming else None
+    out = run_former(enc, ctc, feats, lens, chunk_feats)
+    np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
+                        chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
+    return out
+
+
+def make_efficient_conformer(path, streaming=False, seed=1000, norm="batch_norm"):
+    from ppasr.model_utils.efficient_conformer.encoder import EfficientConformerEncoder
+    from ppasr.model_utils.loss.ctc import CTCLoss
+    from ppasr.model_utils.utils.cmvn import GlobalCMVN
+    cfg = W.EfficientConformerConfig(input_dim=80, vocab_size=40, output_size=64, attention_heads=4, linear_units=128,
+                                     num_blocks=4, cnn_module_kernel=15, streaming=streaming, cnn_module_norm=norm,
+                                     max_len=600, stride_layer_idx=1, group_layer_idx=(0, 1), group_size=3)
+    weights = W.init_efficient_conformer_weights(cfg, seed=seed)
+    cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
+    # efficient_conformer/model.py:34-47
+    enc = EfficientConformerEncoder(input_size=cfg.input_dim, global_cmvn=cmvn, use_dynamic_chunk=streaming, causal=streaming,
+                                    output_size=cfg.output_size, attention_heads=cfg.attention_heads,
+                                    linear_units=cfg.linear_units, num_blocks=cfg.num_blocks,
+                                    cnn_module_kernel=cfg.cnn_module_kernel, cnn_module_norm=cfg.cnn_module_norm,
+                                    stride_layer_idx=cfg.stride_layer_idx, stride=cfg.stride,
+                                    group_layer_idx=list(cfg.group_layer_idx), group_size=cfg.group_size,
+                                    stride_kernel=cfg.stride_kernel)
+    ctc = CTCLoss(cfg.vocab_size, enc.output_size())
+    # StrideConformerEncoderLayer always builds concat_linear (efficient_conformer/encoder.py:453) but only reads it when
+    # concat_after=True (:504-506), which no shipped config sets
+    load_into(enc, weights, "encoder.", unused=("concat_linear",))
+    load_into(ctc, weights, "ctc.")
+    lens = np.array([131, 96, 57], dtype=np.int64)
+    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
+    for b, n in enumerate(lens):
+        feats[b, n:] = 0
+    chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0] if streaming else None
+    out = run_former(enc, ctc, feats, lens, chunk_feats)
+    np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
+                        chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
+    return out
+
+
+def make_deepspeech2(path, streaming, use_gru, seed=1000):
+    """deepspeech2/model.py:24-72: CRNNEncoder + CTC head `decoder`; offline get_encoder_out for a ragged batch and, for the
+    streaming (forward-RNN) model, a get_encoder_out_chunk chain carrying the state boxes. The recurrent cells themselves are
+    torch.nn.LSTM/GRU inside the shim (same gate order and equations as paddle.nn.LSTM/GRU), so this pins the wiring
+    (conv reshape, lengths, state-box split/concat, LayerNorm placement), not the cell arithmetic."""
+    from ppasr.model_utils.deepspeech2.encoder import CRNNEncoder
+    from ppasr.model_utils.loss.ctc import CTCLoss
+    from ppasr.model_utils.utils.cmvn import GlobalCMVN
+    cfg = W.DeepSpeech2Config(input_dim=80, vocab_size=40, num_rnn_layers=3, rnn_size=64, use_gru=use_gru, streaming=streaming)
+    weights = W.init_deepspeech2_weights(cfg, seed=seed)
+    cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
+    enc = CRNNEncoder(input_dim=cfg.input_dim, vocab_size=cfg.vocab_size, global_cmvn=cmvn, num_rnn_layers=cfg.num_rnn_layers,
+                      rnn_size=cfg.rnn_size, rnn_direction="forward" if streaming else "bidirect", use_gru=use_gru)
+    dec = CTCLoss(cfg.vocab_size, enc.output_size)
+    load_into(enc, weights, "encoder.")
+    load_into(dec, weights, "decoder.")
+    enc.eval(), dec.eval()
+    lens = np.array([131, 96, 57], dtype=np.int64)
+    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
+    for b, n in enumerate(lens):
+        feats[b, n:] = 0
+    out = {}
+    with torch.no_grad():
+        eouts, eouts_len, _, _ = enc(t(feats), t(lens, "int64"))
+        out["offline_logits"] = dec.ctc_lo(eouts).numpy()
+        out["offline_probs"] = dec.softmax(eouts).numpy()
+        out["offline_lens"] = eouts_len.numpy()
+        chunk_feats = np.zeros((0, 80), np.float32)
+        if streaming:
+            chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0]
+            h = c = None
+            logits = []
+            for (a, b) in stream_windows(chunk_feats.shape[0]):
+                x = t(chunk_feats[None, a:b])
+                eo, el, h, c = enc(x, t(np.array([b - a]), "int64"), h, c)
+                logits.append(dec.ctc_lo(eo).numpy()[0])
+            out["chunk_logits"] = np.concatenate(logits, 0)
+            out["chunk_state_h"] = h.numpy()
+            if c is not None:
+                out["chunk_state_c"] = c.numpy()
+    np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
+                        chunk_feats=chunk_feats, **out)
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["conformer"]
+    if "conformer" in which:
+        o = make_conformer(os.path.join(HERE, "encoder_golden_conformer_stream.npz"), streaming=True)
+        print("conformer stream", {k: v.shape for k, v in o.items()})
+        o = make_conformer(os.path.join(HERE, "encoder_golden_conformer_offline_bn.npz"), streaming=False, norm="batch_norm")
+        print("conformer offline/bn", {k: v.shape for k, v in o.items()})
+    if "squeezeformer" in which:
+        o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_stream.npz"), streaming=True)
+        print("squeezeformer stream", {k: v.shape for k, v in o.items()})
+        o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_offline.npz"), streaming=False)
+        print("squeezeformer offline", {k: v.shape for k, v in o.items()})
+    if "efficient_conformer" in which:
+        o = make_efficient_conformer(os.path.join(HERE, "encoder_golden_efficient_conformer_offline.npz"), streaming=False)
+        print("efficient_conformer offline", {k: v.shape for k, v in o.items()})
+        o = make_efficient_conformer(os.path.join(HERE, "encoder_golden_efficient_conformer_stream.npz"), streaming=True,
+                                     norm="layer_norm")
+        print("efficient_conformer stream", {k: v.shape for k, v in o.items()})
+    if "deepspeech2" in which:
+        for streaming, gru, tag in ((False, False, "offline_lstm"), (True, False, "stream_lstm"), (True, True, "stream_gru"),
+                                    (False, True, "offline_gru")):
+            o = make_deepspeech2(os.path.join(HERE, f"encoder_golden_deepspeech2_{tag}.npz"), streaming, gru)
+            print("deepspeech2", tag, {k: v.shape for k, v in o.items()})

@@ -84,7 +84,7 @@ def test_greedy_batch_oracle_matches_reference_golden():
     assert DO.greedy_decoder_batch([p, p[:100]], gold_vocab(97)) == m["texts"]
 
 
-# ---- encoder oracle self-consistency (parity of the encoder is unpinned: no Paddle, no reference tests) ----
+# ---- encoder oracle self-consistency (the pin against the reference code is tests/test_encoder_golden_cpu.py) ----
 @pytest.fixture(scope="module")
 def small():
     cfg = ConformerConfig(num_blocks=2, vocab_size=61)
@@ -185,7 +185,7 @@ def test_pruned_log_probs():
 
 
 # ------------------------------------------------------------------------------------------------
-# Squeezeformer oracle self-consistency (parity unpinned: no Paddle here; see oracle/squeezeformer_oracle.py)
+# Squeezeformer oracle self-consistency (pin against the reference code: tests/test_encoder_golden_cpu.py)
 # ------------------------------------------------------------------------------------------------
 def _squeeze(streaming=True, nb=3, **kw):
     from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
@@ -287,7 +287,7 @@ def test_deepspeech2_oracle_chunked_equals_offline_forward():
 
 
 # ------------------------------------------------------------------------------------------------
-# Efficient-Conformer oracle self-consistency (parity unpinned; oracle/efficient_conformer_oracle.py)
+# Efficient-Conformer oracle self-consistency (pin against the reference code: tests/test_encoder_golden_cpu.py)
 # ------------------------------------------------------------------------------------------------
 def test_efficient_conformer_oracle_shapes_and_batch_invariance():
     from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
