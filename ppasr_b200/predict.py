@@ -36,18 +36,40 @@ class AudioFeaturizer:
             mean_square = 1
         return 10 * np.log10(mean_square)
 
-    def featurize(self, samples, sample_rate=16000):
-        """samples: float32 in [-1, 1]. Returns fbank [T, n_mels] float32."""
+    @staticmethod
+    def to_float32(samples):
+        """audio.py:24-32,532-546 (AudioSegment.__init__): integer arrays are scaled to [-1, 1), floats are cast, a [N, C]
+        array is averaged over its channels. Always returns a fresh float32 array."""
+        samples = np.asarray(samples)
+        out = samples.astype('float32')
+        if samples.dtype in (np.int8, np.int16, np.int32, np.int64):
+            out *= (1. / 2 ** (np.iinfo(samples.dtype).bits - 1))
+        elif samples.dtype.kind != 'f':
+            raise TypeError("Unsupported sample type: %s." % samples.dtype)
+        if out.ndim >= 2:
+            out = np.mean(out, 1)
+        return out
+
+    def normalize_(self, samples):
+        """audio.py:256-264,287-304 normalize() -> gain_db(): IN PLACE on the float32 buffer, like the reference (the scaled
+        samples stay in the caller's buffer -- predict_stream relies on that, predict.py:262-274)."""
+        gain = self._target_dB - self._rms_db(samples)
+        if gain > 300.0:
+            raise ValueError(f"无法将段规范化到{self._target_dB}dB，音频增益{gain}增益已经超过max_gain_db (300.0dB)")
+        samples *= 10. ** (gain / 20.)
+        return samples
+
+    def featurize(self, samples, sample_rate=16000, inplace=False):
+        """samples: float32 in [-1, 1]. Returns fbank [T, n_mels] float32. With inplace=True `samples` must be a float32 array
+        and is left dB-normalised, as AudioFeaturizer.featurize leaves its AudioSegment (audio_featurizer.py:47-49)."""
         import torch
         import torchaudio
-        samples = np.asarray(samples, dtype=np.float32)
+        if not inplace:
+            samples = np.array(samples, dtype=np.float32)
         if sample_rate != self._target_sample_rate:
             raise Exception("resampling is outside the hot path: feed audio at %d Hz" % self._target_sample_rate)
-        if self._use_dB_normalization:  # audio.py:287-304 normalize(), gain_db()
-            gain = self._target_dB - self._rms_db(samples)
-            if gain > 300.0:
-                raise ValueError(f"无法将段规范化到{self._target_dB}dB，音频增益{gain}增益已经超过max_gain_db (300.0dB)")
-            samples = samples * (10.0 ** (gain / 20.0))
+        if self._use_dB_normalization:
+            self.normalize_(samples)
         # audio.py:549-574 to('int16'): scale by 2^15 and clip
         s16 = np.clip(samples * 32768.0, -32768, 32767).astype(np.int16)
         wav = torch.from_numpy(s16.astype(np.float32)).unsqueeze(0)
@@ -103,9 +125,10 @@ class PPASRPredictor:
 
     # predict.py:163-187
     def predict(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000):
-        if not isinstance(audio_data, np.ndarray):
+        if not isinstance(audio_data, np.ndarray):  # file paths / encoded bytes need a decoder: outside the hot path
             raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
-        audio_feature = self._audio_featurizer.featurize(audio_data, sample_rate)
+        samples = self._audio_featurizer.to_float32(audio_data)  # predict.py:152-153 AudioSegment.from_ndarray
+        audio_feature = self._audio_featurizer.featurize(samples, sample_rate, inplace=True)
         return self.predict_features(audio_feature, use_pun=use_pun, is_itn=is_itn)
 
     def predict_batch(self, audio_batch, n_samples=None):
@@ -139,19 +162,23 @@ class PPASRPredictor:
                        sample_rate=16000):
         if not self.streaming:
             raise Exception(f"不支持改该模型流式识别，当前模型：{self.use_model}")
-        if isinstance(audio_data, bytes):
-            if samp_width != 2 or channels != 1:
-                raise Exception("only 16-bit mono PCM bytes are supported")
-            audio_data = np.frombuffer(audio_data, dtype=np.int16).astype(np.float32) / 32768.0
-        elif not isinstance(audio_data, np.ndarray):
+        if isinstance(audio_data, np.ndarray):    # predict.py:253-254 AudioSegment.from_ndarray
+            audio_data = self._audio_featurizer.to_float32(audio_data)
+        elif isinstance(audio_data, bytes):       # predict.py:255-257 from_pcm_bytes -> buf_to_float (data_utils/utils.py:381-410)
+            scale = 1.0 / float(1 << ((8 * samp_width) - 1))
+            audio_data = scale * np.frombuffer(audio_data, "<i{:d}".format(samp_width)).astype(np.float32)
+            if channels > 1:
+                audio_data = audio_data.reshape(-1, channels)
+            audio_data = self._audio_featurizer.to_float32(audio_data)
+        else:
             raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
-        audio_data = np.asarray(audio_data, dtype=np.float32)
         if self.remained_wav is None:
             self.remained_wav = audio_data
         else:
-            self.remained_wav = np.concatenate([self.remained_wav, audio_data])
-        # featurise ALL remaining audio, then drop the consumed samples (predict.py:268-274)
-        x_chunk = self._audio_featurizer.featurize(self.remained_wav, sample_rate)
+            self.remained_wav = np.concatenate([self.remained_wav, audio_data]).astype(np.float32)
+        # featurise ALL remaining audio -- which dB-normalises it IN PLACE, so the unconsumed tail carried to the next call
+        # stays scaled exactly as in the reference (predict.py:262-274) -- then drop the consumed samples
+        x_chunk = self._audio_featurizer.featurize(self.remained_wav, sample_rate, inplace=True)
         x_chunk = np.array(x_chunk).astype(np.float32)[np.newaxis, :]
         self.remained_wav = self.remained_wav[160 * x_chunk.shape[1]:]
         return self.predict_stream_features(x_chunk, is_end=is_end, use_pun=use_pun, is_itn=is_itn)

@@ -1,0 +1,104 @@
+"""Host-side streaming logic of ppasr_b200.PPASRPredictor against the reference's own PPASRPredictor.
+
+tests/golden/stream_golden.json was recorded by tests/golden/make_stream_golden.py from the UNMODIFIED reference
+predict_stream / predict / reset_stream (ppasr/predict.py:163-187,232-347), AudioSegment and AudioFeaturizer.featurize, driven
+with tests/golden/stream_fake.py (a deterministic stand-in for the exported-model runner that logs every feature window it gets).
+Here the same script drives ppasr_b200.PPASRPredictor with the same stand-in. Must agree call by call: None vs result, the
+number and length of the decoding windows, the window contents (per-mel sums, 2e-3 relative: the features come from the same
+torchaudio Kaldi fbank in both), the samples left in `remained_wav` INCLUDING their in-place dB scaling, the cached frame count,
+the decoded text (exact) and score. The product greedy decoders need the GPU, so the oracle's (pinned bit-for-bit against the
+reference's in tests/test_oracle_cpu.py) are patched in.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLDEN)
+from stream_fake import VOCAB, FakePredictor, audio_script  # noqa: E402
+
+from oracle import decoders_oracle as DO  # noqa: E402
+from ppasr_b200 import predict as P  # noqa: E402
+
+
+@pytest.fixture
+def predictor(monkeypatch):
+    monkeypatch.setattr(P, "greedy_decoder_chunk", DO.greedy_decoder_chunk)
+    monkeypatch.setattr(P, "greedy_decoder", DO.greedy_decoder)
+    p = object.__new__(P.PPASRPredictor)  # __init__ builds the CUDA engine; the attributes it sets are assigned by hand
+    p.configs = {}
+    p.use_model, p.streaming, p.decoder = "conformer", True, "ctc_greedy"
+    p._audio_featurizer = P.AudioFeaturizer(feature_method="fbank", n_mels=80, use_dB_normalization=True, target_dB=-20)
+    p.vocab_list = VOCAB
+    p.running = False
+    p.remained_wav = p.cached_feat = p.greedy_last_max_prob_list = p.greedy_last_max_index_list = None
+    p.predictor = FakePredictor()
+    return p
+
+
+def _check(p, res, seen, g):
+    if g["result"] is None:
+        assert res is None
+    else:
+        assert res is not None and res["text"] == g["result"]["text"]
+        assert abs(float(res["score"]) - g["result"]["score"]) < 1e-3
+    wins = p.predictor.windows[seen:]
+    assert [n for n, _ in wins] == [w["frames"] for w in g["windows"]]
+    for (_, s), w in zip(wins, g["windows"]):
+        np.testing.assert_allclose(s, np.array(w["mel_sums"]), rtol=2e-3, atol=1e-2)
+
+
+def test_predict_stream_matches_reference_call_by_call(predictor):
+    g = json.load(open(os.path.join(GOLDEN, "stream_golden.json"), encoding="utf-8"))
+    assert g["vocab"] == VOCAB
+    it = iter(g["stream"])
+    n_none = n_res = 0
+    for rnd in range(2):
+        for kind, payload, is_end in audio_script(seed=11 + rnd):
+            rec = next(it)
+            assert (rec["round"], rec["kind"], rec["is_end"]) == (rnd, kind, is_end)
+            seen = len(predictor.predictor.windows)
+            res = predictor.predict_stream(payload, is_end=is_end)
+            _check(predictor, res, seen, rec)
+            assert len(predictor.remained_wav) == rec["remained_samples"]
+            got = float(np.abs(predictor.remained_wav.astype(np.float64)).sum())
+            assert abs(got - rec["remained_abs_sum"]) <= 1e-5 * max(1.0, rec["remained_abs_sum"])  # in-place dB scaling carried over
+            assert predictor.cached_feat.shape[1] == rec["cached_frames"]
+            n_none += res is None
+            n_res += res is not None
+        predictor.reset_stream()
+        assert predictor.remained_wav is None and predictor.cached_feat is None
+        assert predictor.greedy_last_max_index_list is None and predictor.greedy_last_max_prob_list is None
+    assert predictor.predictor.resets == g["resets"] == 2
+    assert n_none >= 4 and n_res >= 4  # both branches exercised
+
+
+def test_predict_offline_matches_reference(predictor):
+    g = json.load(open(os.path.join(GOLDEN, "stream_golden.json"), encoding="utf-8"))
+    it = iter(g["offline"])
+    n = 0
+    for kind, payload, _ in audio_script(seed=21):
+        if kind == "bytes" or len(payload) < 1000:
+            continue
+        rec = next(it)
+        assert rec["kind"] == kind
+        keep = payload.copy()
+        seen = len(predictor.predictor.windows)
+        res = predictor.predict(audio_data=payload)
+        _check(predictor, res, seen, rec)
+        assert np.array_equal(keep, payload)  # the caller's buffer is never scaled in place
+        n += 1
+    assert n == len(g["offline"]) >= 3
+
+
+def test_unsupported_inputs_raise_like_reference(predictor):
+    with pytest.raises(Exception, match="不支持该数据类型"):
+        predictor.predict_stream([0.0] * 1000)
+    with pytest.raises(Exception, match="不支持该数据类型"):
+        predictor.predict(audio_data=[0.0] * 1000)
+    predictor.streaming = False
+    with pytest.raises(Exception, match="不支持改该模型流式识别"):
+        predictor.predict_stream(np.zeros(1000, np.float32))
