@@ -98,32 +98,40 @@ def run_former(enc, ctc, feats, lens, chunk_feats):
     return out
 
 
-def make_conformer(path, streaming=True, norm="layer_norm", seed=1000):
-    cfg = W.ConformerConfig(input_dim=80, vocab_size=40, output_size=64, attention_heads=4, linear_units=128, num_blocks=3,
-                            cnn_module_kernel=15, streaming=streaming, cnn_module_norm=norm, max_len=600)
+SMALL = dict(output_size=64, attention_heads=4, linear_units=128, num_blocks=3, max_len=600)  # CPU-test fixtures
+LENS = (131, 96, 57)
+
+
+def inputs(lens, chunk_T, seed):
+    lens = np.array(lens, dtype=np.int64)
+    feats = W.synthetic_fbank(len(lens), int(lens.max()), 80, seed=seed + 2)
+    for b, n in enumerate(lens):
+        feats[b, n:] = 0
+    chunk_feats = W.synthetic_fbank(1, chunk_T, 80, seed=seed + 3)[0] if chunk_T else None
+    return feats, lens, chunk_feats
+
+
+def make_conformer(path, streaming=True, norm="layer_norm", seed=1000, lens=LENS, chunk_T=211, vocab=40, **kw):
+    cfg = W.ConformerConfig(input_dim=80, vocab_size=vocab, cnn_module_kernel=15, streaming=streaming, cnn_module_norm=norm,
+                            **(kw or SMALL))
     weights = W.init_conformer_weights(cfg, seed=seed)
     enc, ctc = build_conformer(cfg, weights, streaming)
     load_into(enc, weights, "encoder.")
     load_into(ctc, weights, "ctc.")
-    rng = np.random.RandomState(seed + 1)
-    lens = np.array([131, 96, 57], dtype=np.int64)
-    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
-    for b, n in enumerate(lens):
-        feats[b, n:] = 0
-    chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0] if streaming else None
+    feats, lens, chunk_feats = inputs(lens, chunk_T if streaming else 0, seed)
     out = run_former(enc, ctc, feats, lens, chunk_feats)
     np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
                         chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
     return out
 
 
-def make_squeezeformer(path, streaming=True, seed=1000):
+def make_squeezeformer(path, streaming=True, seed=1000, lens=LENS, chunk_T=211, vocab=40, norm="layer_norm", **kw):
     from ppasr.model_utils.loss.ctc import CTCLoss
     from ppasr.model_utils.squeezeformer.encoder import SqueezeformerEncoder
     from ppasr.model_utils.utils.cmvn import GlobalCMVN
-    cfg = W.SqueezeformerConfig(input_dim=80, vocab_size=40, encoder_dim=64, output_size=64, attention_heads=4, num_blocks=4,
-                                reduce_idx=1, recover_idx=3, feed_forward_expansion_factor=2, cnn_module_kernel=15,
-                                streaming=streaming, max_len=600)
+    kw = kw or dict(encoder_dim=64, output_size=64, attention_heads=4, num_blocks=4, reduce_idx=1, recover_idx=3,
+                    feed_forward_expansion_factor=2, cnn_module_kernel=15, max_len=600)
+    cfg = W.SqueezeformerConfig(input_dim=80, vocab_size=vocab, streaming=streaming, cnn_norm_type=norm, **kw)
     weights = W.init_squeezeformer_weights(cfg, seed=seed)
     cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
     # squeezeformer/model.py:35-50
@@ -137,24 +145,21 @@ def make_squeezeformer(path, streaming=True, seed=1000):
     ctc = CTCLoss(cfg.vocab_size, enc.output_size())
     load_into(enc, weights, "encoder.")
     load_into(ctc, weights, "ctc.")
-    lens = np.array([131, 96, 57], dtype=np.int64)
-    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
-    for b, n in enumerate(lens):
-        feats[b, n:] = 0
-    chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0] if streaming else None
+    feats, lens, chunk_feats = inputs(lens, chunk_T if streaming else 0, seed)
     out = run_former(enc, ctc, feats, lens, chunk_feats)
     np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
                         chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
     return out
 
 
-def make_efficient_conformer(path, streaming=False, seed=1000, norm="batch_norm"):
+def make_efficient_conformer(path, streaming=False, seed=1000, norm="batch_norm", lens=LENS, chunk_T=211, vocab=40, **kw):
     from ppasr.model_utils.efficient_conformer.encoder import EfficientConformerEncoder
     from ppasr.model_utils.loss.ctc import CTCLoss
     from ppasr.model_utils.utils.cmvn import GlobalCMVN
-    cfg = W.EfficientConformerConfig(input_dim=80, vocab_size=40, output_size=64, attention_heads=4, linear_units=128,
-                                     num_blocks=4, cnn_module_kernel=15, streaming=streaming, cnn_module_norm=norm,
-                                     max_len=600, stride_layer_idx=1, group_layer_idx=(0, 1), group_size=3)
+    kw = kw or dict(output_size=64, attention_heads=4, linear_units=128, num_blocks=4, max_len=600, stride_layer_idx=1,
+                    group_layer_idx=(0, 1))
+    cfg = W.EfficientConformerConfig(input_dim=80, vocab_size=vocab, cnn_module_kernel=15, streaming=streaming,
+                                     cnn_module_norm=norm, group_size=3, **kw)
     weights = W.init_efficient_conformer_weights(cfg, seed=seed)
     cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
     # efficient_conformer/model.py:34-47
@@ -170,18 +175,14 @@ def make_efficient_conformer(path, streaming=False, seed=1000, norm="batch_norm"
     # concat_after=True (:504-506), which no shipped config sets
     load_into(enc, weights, "encoder.", unused=("concat_linear",))
     load_into(ctc, weights, "ctc.")
-    lens = np.array([131, 96, 57], dtype=np.int64)
-    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
-    for b, n in enumerate(lens):
-        feats[b, n:] = 0
-    chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0] if streaming else None
+    feats, lens, chunk_feats = inputs(lens, chunk_T if streaming else 0, seed)
     out = run_former(enc, ctc, feats, lens, chunk_feats)
     np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
                         chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
     return out
 
 
-def make_deepspeech2(path, streaming, use_gru, seed=1000):
+def make_deepspeech2(path, streaming, use_gru, seed=1000, lens=LENS, chunk_T=211, chunk_B=1, vocab=40, nl=3, H=64):
     """deepspeech2/model.py:24-72: CRNNEncoder + CTC head `decoder`; offline get_encoder_out for a ragged batch and, for the
     streaming (forward-RNN) model, a get_encoder_out_chunk chain carrying the state boxes. The recurrent cells themselves are
     torch.nn.LSTM/GRU inside the shim (same gate order and equations as paddle.nn.LSTM/GRU), so this pins the wiring
@@ -189,7 +190,7 @@ def make_deepspeech2(path, streaming, use_gru, seed=1000):
     from ppasr.model_utils.deepspeech2.encoder import CRNNEncoder
     from ppasr.model_utils.loss.ctc import CTCLoss
     from ppasr.model_utils.utils.cmvn import GlobalCMVN
-    cfg = W.DeepSpeech2Config(input_dim=80, vocab_size=40, num_rnn_layers=3, rnn_size=64, use_gru=use_gru, streaming=streaming)
+    cfg = W.DeepSpeech2Config(input_dim=80, vocab_size=vocab, num_rnn_layers=nl, rnn_size=H, use_gru=use_gru, streaming=streaming)
     weights = W.init_deepspeech2_weights(cfg, seed=seed)
     cmvn = GlobalCMVN(t(weights["encoder.global_cmvn.mean"]), t(weights["encoder.global_cmvn.istd"]))
     enc = CRNNEncoder(input_dim=cfg.input_dim, vocab_size=cfg.vocab_size, global_cmvn=cmvn, num_rnn_layers=cfg.num_rnn_layers,
@@ -198,10 +199,7 @@ def make_deepspeech2(path, streaming, use_gru, seed=1000):
     load_into(enc, weights, "encoder.")
     load_into(dec, weights, "decoder.")
     enc.eval(), dec.eval()
-    lens = np.array([131, 96, 57], dtype=np.int64)
-    feats = W.synthetic_fbank(3, 131, 80, seed=seed + 2)
-    for b, n in enumerate(lens):
-        feats[b, n:] = 0
+    feats, lens, _ = inputs(lens, 0, seed)
     out = {}
     with torch.no_grad():
         eouts, eouts_len, _, _ = enc(t(feats), t(lens, "int64"))
@@ -210,14 +208,16 @@ def make_deepspeech2(path, streaming, use_gru, seed=1000):
         out["offline_lens"] = eouts_len.numpy()
         chunk_feats = np.zeros((0, 80), np.float32)
         if streaming:
-            chunk_feats = W.synthetic_fbank(1, 211, 80, seed=seed + 3)[0]
+            chunk_feats = W.synthetic_fbank(chunk_B, chunk_T, 80, seed=seed + 3)
             h = c = None
             logits = []
-            for (a, b) in stream_windows(chunk_feats.shape[0]):
-                x = t(chunk_feats[None, a:b])
-                eo, el, h, c = enc(x, t(np.array([b - a]), "int64"), h, c)
-                logits.append(dec.ctc_lo(eo).numpy()[0])
-            out["chunk_logits"] = np.concatenate(logits, 0)
+            for (a, b) in stream_windows(chunk_feats.shape[1]):
+                x = t(chunk_feats[:, a:b])
+                eo, el, h, c = enc(x, t(np.array([b - a] * chunk_B), "int64"), h, c)
+                logits.append(dec.ctc_lo(eo).numpy())
+            out["chunk_logits"] = np.concatenate(logits, 1)
+            if chunk_B == 1:
+                chunk_feats, out["chunk_logits"] = chunk_feats[0], out["chunk_logits"][0]
             out["chunk_state_h"] = h.numpy()
             if c is not None:
                 out["chunk_state_c"] = c.numpy()
@@ -249,3 +249,23 @@ if __name__ == "__main__":
                                     (False, True, "offline_gru")):
             o = make_deepspeech2(os.path.join(HERE, f"encoder_golden_deepspeech2_{tag}.npz"), streaming, gru)
             print("deepspeech2", tag, {k: v.shape for k, v in o.items()})
+    if "gpu" in which:
+        # Engine-size fixtures (d_model 256 / 4 heads / FFN 2048, the only widths the CUDA path is built for) for
+        # tests/test_gpu_reference_golden.py: the CUDA path against the reference's own code, no oracle in between. Shapes
+        # mirror cases of tests/test_gpu_parity.py that the engine is known to run.
+        G = lambda n: os.path.join(HERE, f"encoder_golden_{n}.npz")  # noqa: E731
+        make_conformer(G("conformer_gpu_stream"), streaming=True, lens=(131, 90), chunk_T=215, vocab=97, num_blocks=2)
+        make_conformer(G("conformer_gpu_offline_bn"), streaming=False, norm="batch_norm", lens=(300, 200), vocab=97,
+                       num_blocks=2)
+        make_squeezeformer(G("squeezeformer_gpu_stream"), streaming=True, lens=(203, 150, 99), chunk_T=67 + 64 * 3, vocab=120,
+                           num_blocks=4, reduce_idx=1, recover_idx=3)
+        make_squeezeformer(G("squeezeformer_gpu_offline"), streaming=False, lens=(207, 150, 5), vocab=120, num_blocks=3,
+                           reduce_idx=1, recover_idx=2)
+        make_efficient_conformer(G("efficient_conformer_gpu_causal"), streaming=True, norm="layer_norm", lens=(203, 150, 99),
+                                 chunk_T=0, vocab=120, num_blocks=2, group_layer_idx=(0, 1), stride_layer_idx=1)
+        make_efficient_conformer(G("efficient_conformer_gpu_offline"), streaming=False, norm="batch_norm", lens=(207, 150, 5),
+                                 vocab=120, num_blocks=2, group_layer_idx=(0, 1), stride_layer_idx=1)
+        make_deepspeech2(G("deepspeech2_gpu_stream_lstm"), True, False, lens=(203, 150, 99), chunk_T=67 + 64 * 2, chunk_B=2,
+                         vocab=120, nl=2, H=256)
+        make_deepspeech2(G("deepspeech2_gpu_offline_gru"), False, True, lens=(203, 150, 99), vocab=120, nl=2, H=256)
+        print("gpu fixtures written")

@@ -52,7 +52,7 @@ def _oracle(g, family):
 
 
 def test_fixtures_present():
-    assert len(FILES) >= 10, FILES
+    assert len(FILES) >= 18, FILES
     assert {_family(f) for f in FILES} == set(FAMILIES)
 
 
@@ -80,10 +80,11 @@ def test_chunk_chain_matches_reference_code(fname):
     outs = []
     if family == "deepspeech2":
         h = c = None
-        for (a, b) in stream_windows(cf.shape[0], is_end=True):
-            x, _, h, c = o.get_encoder_out_chunk(torch.from_numpy(cf[None, a:b]), torch.tensor([b - a]), h, c,
+        cfb = cf if cf.ndim == 3 else cf[None]  # the engine-size fixture streams a batch of 2
+        for (a, b) in stream_windows(cfb.shape[1], is_end=True):
+            x, _, h, c = o.get_encoder_out_chunk(torch.from_numpy(cfb[:, a:b]), torch.tensor([b - a] * cfb.shape[0]), h, c,
                                                  return_logits=True)
-            outs.append(x[0].numpy())
+            outs.append(x.numpy() if cf.ndim == 3 else x[0].numpy())
         np.testing.assert_allclose(h.numpy(), g["chunk_state_h"], rtol=0, atol=1e-5)
         if "chunk_state_c" in g.files:
             np.testing.assert_allclose(c.numpy(), g["chunk_state_c"], rtol=0, atol=1e-5)
@@ -96,6 +97,21 @@ def test_chunk_chain_matches_reference_code(fname):
         assert tuple(att.shape) == g["chunk_att_cache"].shape and tuple(cnn.shape) == g["chunk_cnn_cache"].shape
         np.testing.assert_allclose(att.numpy(), g["chunk_att_cache"], rtol=0, atol=1e-5)
         np.testing.assert_allclose(cnn.numpy(), g["chunk_cnn_cache"], rtol=0, atol=1e-5)
-    outs = np.concatenate(outs, 0)
+    outs = np.concatenate(outs, 1 if outs[0].ndim == 3 else 0)
     assert outs.shape == g["chunk_logits"].shape
     np.testing.assert_allclose(outs, g["chunk_logits"], rtol=0, atol=ATOL)
+
+
+@pytest.mark.parametrize("fname", [f for f in FILES if "stream" in f and "deepspeech2" not in f and "efficient" not in f])
+def test_streaming_predict_is_whole_utterance_forward_chunk(fname):
+    """InferencePredictor.predict on a streaming *former export feeds the forward_chunk graph with offset 0, no caches and
+    required_cache_size -1 (inference_predictor.py:127-137; model.py:188-198 exports get_encoder_out_chunk). The engine computes
+    the batched offline forward instead; for one utterance the two are the same function (odd and even subsampled lengths)."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    o = _oracle(g, _family(fname))
+    for T in (131, 135, 71):
+        x = torch.from_numpy(W.synthetic_fbank(1, T, 80, seed=T))
+        a = o.get_encoder_out(x, torch.tensor([T]), return_logits=True)
+        b, _, _ = o.get_encoder_out_chunk(x, 0, -1, torch.zeros(0, 0, 0, 0), torch.zeros(0, 0, 0, 0), return_logits=True)
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() < 1e-5

@@ -1,0 +1,133 @@
+"""The CUDA hot path against outputs of the reference's OWN model code -- no oracle in between (pytest -m gpu).
+
+tests/golden/encoder_golden_*_gpu_*.npz hold what the unmodified reference encoders (ConformerEncoder, SqueezeformerEncoder,
+EfficientConformerEncoder, CRNNEncoder + CTC head; imported from the reference tree on the torch-backed paddle stand-in by
+tests/golden/make_encoder_golden.py) produce for seeded weights at the engine's widths (d_model 256, 4 heads, FFN 2048 / LSTM
+256). Here the same weights (regenerated from the seed) and inputs go through the C-ABI engine. Tolerance as everywhere for the
+bf16 tensor-core path: max |logit diff| over valid frames < 1e-2 of max |logit| (north_star: 1e-2 rel for bf16); caches 2e-2.
+"""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "encoder_golden_*_gpu_*.npz")))
+FAMILIES = ("efficient_conformer", "squeezeformer", "conformer", "deepspeech2")
+
+
+def _family(fname):
+    stem = fname[len("encoder_golden_"):]
+    return next(f for f in FAMILIES if stem.startswith(f))
+
+
+def _config(g, family):
+    from ppasr_b200 import weights as W
+    cls, init = {"conformer": (W.ConformerConfig, W.init_conformer_weights),
+                 "squeezeformer": (W.SqueezeformerConfig, W.init_squeezeformer_weights),
+                 "efficient_conformer": (W.EfficientConformerConfig, W.init_efficient_conformer_weights),
+                 "deepspeech2": (W.DeepSpeech2Config, W.init_deepspeech2_weights)}[family]
+    cfg = cls(**ast.literal_eval(str(g["cfg"])))
+    return cfg, init(cfg, seed=int(g["seed"]))
+
+
+def _valid_frames(g, family, cfg):
+    n = ((g["lens"] - 1) // 2 - 1) // 2
+    if family == "efficient_conformer" and cfg.stride_layer_idx is not None:
+        n = (n + 1) // 2  # efficient_conformer/encoder.py:255-260
+    if family == "deepspeech2":
+        assert n.tolist() == g["offline_lens"].tolist()
+    return [int(v) for v in n]
+
+
+def _windows(num_frames, window=67, stride=64, context=7):
+    """predict.py:281-297 with is_end on the last call (the windows the fixtures were recorded with)."""
+    return [(cur, min(cur + window, num_frames)) for cur in range(0, num_frames - context + 1, stride)]
+
+
+def test_fixtures_present():
+    assert len(FILES) == 8 and {_family(f) for f in FILES} == set(FAMILIES)
+
+
+@pytest.mark.parametrize("fname", FILES)
+def test_offline_logits_match_reference_code(lib, cuda, fname):
+    from ppasr_b200.engine import ConformerEngine
+    g = np.load(os.path.join(GOLDEN, fname))
+    family = _family(fname)
+    cfg, w = _config(g, family)
+    eng = ConformerEngine(cfg, w)
+    eng.encode(torch.from_numpy(g["feats"]).to(cuda), [int(v) for v in g["lens"]])
+    logits = eng.ctc_logits().float().cpu().numpy()
+    probs = eng.ctc_probs().float().cpu().numpy()
+    eng.close()
+    ref, ref_p = g["offline_logits"], g["offline_probs"]
+    assert logits.shape == ref.shape
+    scale = float(np.abs(ref).max())
+    vl = _valid_frames(g, family, cfg)
+    assert max(vl) == ref.shape[1]
+    worst = max(float(np.abs(logits[b, :n] - ref[b, :n]).max()) for b, n in enumerate(vl) if n > 0) / scale
+    assert worst < 1e-2, f"{fname}: logits rel err {worst}"
+    # arg-max path agrees wherever the reference's own margin is far above bf16 noise
+    top2 = np.sort(ref, -1)[..., -2:]
+    big = (top2[..., 1] - top2[..., 0]) > 0.05 * scale
+    n_checked = 0
+    for b, n in enumerate(vl):
+        agree = (logits[b, :n].argmax(-1) == ref[b, :n].argmax(-1)) | ~big[b, :n]
+        assert bool(agree.all())
+        n_checked += int(big[b, :n].sum())
+        assert np.allclose(probs[b, :n].sum(-1), 1.0, atol=1e-4)
+        # probabilities: only where the reference is decided (a 1e-2-of-scale logit error moves an undecided softmax a lot)
+        sure = ref_p[b, :n].max(-1) > 0.99
+        assert float(np.abs(probs[b, :n][sure] - ref_p[b, :n][sure]).max()) < 5e-2 if sure.any() else True
+    assert n_checked > 0
+
+
+@pytest.mark.parametrize("fname", [f for f in FILES if "stream" in f])
+def test_chunk_chain_matches_reference_code(lib, cuda, fname):
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    g = np.load(os.path.join(GOLDEN, fname))
+    family = _family(fname)
+    cfg, w = _config(g, family)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, family, streaming=True,
+                              weights=w)
+    cf = g["chunk_feats"]
+    ref = g["chunk_logits"]
+    scale = float(np.abs(ref).max())
+    outs = []
+    if family == "deepspeech2":
+        assert cf.ndim == 3
+        for (a, b) in _windows(cf.shape[1]):
+            probs, lens = pred.predict_chunk_deepspeech(np.ascontiguousarray(cf[:, a:b]))
+            lg = pred.engine.ctc_logits().float().cpu().numpy()
+            assert lg.shape[0] == cf.shape[0] and lens.tolist() == [lg.shape[1]] * cf.shape[0]
+            outs.append(lg)
+        got = np.concatenate(outs, 1)
+        assert np.abs(pred.output_state_h - g["chunk_state_h"]).max() < 2e-2
+        if "chunk_state_c" in g.files:
+            assert np.abs(pred.output_state_c - g["chunk_state_c"]).max() < 5e-2
+    else:
+        assert cf.ndim == 2
+        off = 0
+        for (a, b) in _windows(cf.shape[0]):
+            probs = pred.predict_chunk_conformer(np.ascontiguousarray(cf[None, a:b]), -16)
+            lg = pred.engine.ctc_logits().float().cpu().numpy()
+            assert lg.shape == probs.shape and lg.shape[0] == 1
+            off += lg.shape[1]
+            assert int(pred.offset[0]) == off
+            outs.append(lg[0])
+        got = np.concatenate(outs, 0)
+        if family == "conformer":  # exported in the reference layout (inference_predictor.py:204-207)
+            att, cnn = pred.att_cache, pred.cnn_cache
+            ra, rc = g["chunk_att_cache"], g["chunk_cnn_cache"]
+            assert att.shape == ra.shape and cnn.shape == rc.shape
+            assert float(np.abs(att - ra).max()) / float(np.abs(ra).max()) < 2e-2
+            assert float(np.abs(cnn - rc).max()) / float(np.abs(rc).max()) < 2e-2
+    assert got.shape == ref.shape
+    worst = float(np.abs(got - ref).max()) / scale
+    assert worst < 1e-2, f"{fname}: chunk logits rel err {worst}"
+    pred.reset_stream()
