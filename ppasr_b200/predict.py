@@ -7,8 +7,11 @@ path runs in libppasr_b200.so; only the audio front end (outside the hot path, S
 `AudioFeaturizer` below restates audio_featurizer.py:37-69,120-138 with torchaudio's kaldi fbank, the CPU
 twin of paddleaudio's.
 
-Not mirrored (out of scope): predict_long (VAD), punctuation, ITN — passing
-`use_pun=True` / `is_itn=True` raises.
+`predict_long` (predict.py:190-229) is mirrored around the VAD: the silero ONNX model itself is outside the hot path
+(SURVEY §2 row 12), so the speech segments come from `speech_timestamps=` or from any object with the reference's
+`get_speech_timestamps(samples, sample_rate)` assigned to `self.vad_predictor`; the segments of one file then go through
+the encoder as ONE ragged batch. Not mirrored (out of scope): punctuation, ITN —
+passing `use_pun=True` / `is_itn=True` raises.
 """
 import numpy as np
 
@@ -81,6 +84,10 @@ class AudioFeaturizer:
 
 
 class PPASRPredictor:
+    # 7 fbank frames (25 ms window, 10 ms shift) = the shortest input Conv2dSubsampling4 turns into one encoder frame; a shorter
+    # region yields no text here (in the reference the fbank / conv of such a region raises)
+    MIN_SAMPLES = 400 + 6 * 160
+
     def __init__(self, configs, model_path='models/conformer_streaming_fbank/infer/', use_pun=False, use_gpu=True,
                  vocab_list=None, weights=None, device=0):
         """configs: dict (or attribute object) with the reference's yaml keys: use_model, streaming, decoder,
@@ -99,6 +106,7 @@ class PPASRPredictor:
             vocab_list = read_vocab_file(_get(_get(configs, 'dataset_conf', {}), 'dataset_vocab'))
         self.vocab_list = vocab_list
         self.running = False
+        self.vad_predictor = None
         # streaming state (predict.py:69-72)
         self.remained_wav = None
         self.cached_feat = None
@@ -148,6 +156,74 @@ class PPASRPredictor:
         res = self.predictor.predict_decode(feats, np.asarray(counts, dtype=np.int64), vocabulary=self.vocab_list,
                                             trim_to_lens=n_samples is not None)
         return [{'text': t, 'score': s} for s, t in res]
+
+    # predict.py:190-229
+    def predict_long(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000, speech_timestamps=None, batched=True,
+                     max_batch_samples=32 * 30 * 16000):
+        """Long-form recognition: the speech regions of one recording -> one result. Same composition as the reference: every
+        region is recognised on its own (own dB normalisation), non-empty texts are joined with '，', the score is the mean of
+        the region scores rounded to 2 places. `speech_timestamps`: [{'start': s, 'end': e}, ...] in samples, what
+        VADPredictor.get_speech_timestamps returns (vad_predictor.py:106-175); when None, `self.vad_predictor` is asked.
+        batched=True (ctc_greedy only) sends the regions through `predict_batch` in ragged batches of at most
+        `max_batch_samples` padded samples instead of one call per region."""
+        if use_pun or is_itn:
+            raise Exception("punctuation / ITN are outside the ppasr_b200 hot path")
+        if not isinstance(audio_data, np.ndarray):
+            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+        samples = self._audio_featurizer.to_float32(audio_data)
+        if sample_rate != self._audio_featurizer._target_sample_rate:
+            raise Exception("resampling is outside the hot path: feed audio at %d Hz" % self._audio_featurizer._target_sample_rate)
+        if speech_timestamps is None:
+            if self.vad_predictor is None:
+                raise Exception("predict_long needs speech_timestamps= or a vad_predictor with get_speech_timestamps()")
+            speech_timestamps = self.vad_predictor.get_speech_timestamps(samples, sample_rate)
+        segments = [samples[int(t['start']): int(t['end'])] for t in speech_timestamps]
+        if batched and self.decoder == 'ctc_greedy':
+            results = self._predict_segments_batched(segments, max_batch_samples)
+        else:
+            results = [self.predict(audio_data=seg, sample_rate=sample_rate) if len(seg) >= self.MIN_SAMPLES
+                       else {'text': '', 'score': 0} for seg in segments]
+        texts, scores = '', []
+        for result in results:
+            score, text = result['score'], result['text']
+            if text != '':
+                texts = texts + '，' + text
+            scores.append(score)
+        if texts[:1] == '，':
+            texts = texts[1:]
+        # the reference divides by len(scores) and indexes texts[0] unguarded (predict.py:219,226): no region -> exception there,
+        # an empty result here
+        return {'text': texts, 'score': round(sum(scores) / len(scores), 2) if scores else 0}
+
+    def _predict_segments_batched(self, segments, max_batch_samples):
+        """Regions -> ragged batches for predict_batch, in the original order; a batch is closed when its padded size
+        (count x longest region) would exceed max_batch_samples."""
+        results = [None] * len(segments)
+        group = []
+
+        def flush():
+            if not group:
+                return
+            n = np.array([len(segments[i]) for i in group], dtype=np.int32)
+            batch = np.zeros((len(group), int(n.max())), dtype=np.float32)
+            for r, i in enumerate(group):
+                batch[r, :n[r]] = segments[i]
+            for i, res in zip(group, self.predict_batch(batch, n_samples=n)):
+                results[i] = res
+            group.clear()
+
+        longest = 0
+        for i, seg in enumerate(segments):
+            if len(seg) < self.MIN_SAMPLES:
+                results[i] = {'text': '', 'score': 0}
+                continue
+            if group and (len(group) + 1) * max(longest, len(seg)) > max_batch_samples:
+                flush()
+                longest = 0
+            group.append(i)
+            longest = max(longest, len(seg))
+        flush()
+        return results
 
     def predict_features(self, audio_feature, use_pun=False, is_itn=False):
         """Same as predict() from the featurizer output on ([T, n_mels] fp32)."""

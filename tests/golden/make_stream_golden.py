@@ -59,7 +59,7 @@ def make_reference_predictor():
     p = object.__new__(PPASRPredictor)
     p.configs = dict_to_object({"use_model": "conformer", "streaming": True, "decoder": "ctc_greedy",
                                 "preprocess_conf": {"feature_method": "fbank", "n_mels": 80, "use_dB_normalization": True,
-                                                    "target_dB": -20}})
+                                                    "target_dB": -20, "sample_rate": 16000}})
     p.running = False
     p.inv_normalizer = None
     p.pun_predictor = None
@@ -104,6 +104,14 @@ def main():
         seen = len(p.predictor.windows)
         res = p.predict(audio_data=payload)
         out["offline"].append(dict(kind=kind, **snapshot(p, res, seen)))
+    # predict_long (predict.py:190-229) with a fixed segmentation instead of the silero VAD model
+    from stream_fake import long_audio
+    audio, stamps = long_audio()
+    p = make_reference_predictor()
+    p.vad_predictor = types.SimpleNamespace(get_speech_timestamps=lambda samples, sr: stamps)
+    res = p.predict_long(audio_data=audio)
+    out["long"] = {"result": {"text": res["text"], "score": float(res["score"])}, "stamps": stamps,
+                   "windows": [{"frames": n, "mel_sums": [float(v) for v in sm]} for n, sm in p.predictor.windows]}
     with open(os.path.join(HERE, "stream_golden.json"), "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False)
     n_none = sum(1 for s in out["stream"] if s["result"] is None)

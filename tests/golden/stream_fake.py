@@ -56,3 +56,15 @@ def audio_script(seed=11):
     k, p, _ = calls[-1]
     calls[-1] = (k, p, True)
     return calls
+
+
+def long_audio(seed=31):
+    """A 12 s recording with level changes and a fixed 'VAD' segmentation (samples) for predict_long."""
+    rng = np.random.RandomState(seed)
+    n = 12 * 16000
+    t = np.arange(n) / 16000.0
+    env = 0.02 + 0.2 * (np.sin(2 * np.pi * 0.4 * t) > 0)
+    x = (env * (np.sin(2 * np.pi * 310 * t) + 0.7 * rng.randn(n))).astype(np.float32)
+    stamps = [{"start": 1600, "end": 30000}, {"start": 41000, "end": 44000}, {"start": 60000, "end": 131000},
+              {"start": 140000, "end": 142000}, {"start": 150000, "end": 191500}]
+    return x, stamps

@@ -896,3 +896,28 @@ def test_stream_scheduler_ragged_sessions(lib, cuda):
         assert abs(last[sid[i]]["score"] - solo[i]["score"]) < 0.5
         assert sch.close(sid[i])["text"] == solo[i]["text"]
     assert len(sch._free) == 4
+
+
+def test_predict_long_batched_regions(lib, cuda):
+    """predict_long (predict.py:190-229): the speech regions of one recording as ragged GPU batches vs one predict() per
+    region. The two routes differ only in the fbank implementation (GPU kernel vs torchaudio) and in batch padding, so the
+    composed result must have the same structure and nearly the same score; every region on its own must decode identically
+    wherever predict_batch on equal-length input already does (test_predict_batch_from_waveforms)."""
+    from ppasr_b200.predict import PPASRPredictor
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, make_vocab
+    cfg = ConformerConfig(num_blocks=2, vocab_size=200)
+    p = PPASRPredictor({"use_model": "conformer", "streaming": True, "decoder": "ctc_greedy", "encoder_conf": cfg.to_dict(),
+                        "preprocess_conf": {"feature_method": "fbank", "n_mels": 80}}, vocab_list=make_vocab(200),
+                       weights=init_conformer_weights(cfg))
+    audio = np.concatenate([_wave(2.0, 0), _wave(1.0, 1, 0.02), _wave(3.0, 2, 0.6)])
+    stamps = [{"start": 800, "end": 30000}, {"start": 33000, "end": 47000}, {"start": 50000, "end": 95000},
+              {"start": 95000, "end": 95200}]
+    seq = p.predict_long(audio, speech_timestamps=stamps, batched=False)
+    bat = p.predict_long(audio, speech_timestamps=stamps, batched=True)
+    two = p.predict_long(audio, speech_timestamps=stamps, batched=True, max_batch_samples=2 * 45000)
+    assert isinstance(bat["text"], str) and len(seq["text"]) > 0
+    assert bat["text"].count("，") == seq["text"].count("，") == two["text"].count("，")
+    assert abs(len(bat["text"]) - len(seq["text"])) <= 3
+    assert abs(bat["score"] - seq["score"]) < 2.0 and abs(two["score"] - bat["score"]) < 2.0
+    with pytest.raises(Exception, match="speech_timestamps"):
+        p.predict_long(audio)

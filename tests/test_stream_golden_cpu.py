@@ -18,7 +18,7 @@ import pytest
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 sys.path.insert(0, GOLDEN)
-from stream_fake import VOCAB, FakePredictor, audio_script  # noqa: E402
+from stream_fake import VOCAB, FakePredictor, audio_script, long_audio  # noqa: E402
 
 from oracle import decoders_oracle as DO  # noqa: E402
 from ppasr_b200 import predict as P  # noqa: E402
@@ -34,6 +34,7 @@ def predictor(monkeypatch):
     p._audio_featurizer = P.AudioFeaturizer(feature_method="fbank", n_mels=80, use_dB_normalization=True, target_dB=-20)
     p.vocab_list = VOCAB
     p.running = False
+    p.vad_predictor = None
     p.remained_wav = p.cached_feat = p.greedy_last_max_prob_list = p.greedy_last_max_index_list = None
     p.predictor = FakePredictor()
     return p
@@ -102,3 +103,47 @@ def test_unsupported_inputs_raise_like_reference(predictor):
     predictor.streaming = False
     with pytest.raises(Exception, match="不支持改该模型流式识别"):
         predictor.predict_stream(np.zeros(1000, np.float32))
+
+
+def test_predict_long_matches_reference(predictor):
+    """predict.py:190-229 with a fixed segmentation in place of the silero VAD: region-by-region recognition, '，' joining,
+    mean score rounded to 2 places -- first one predict() per region like the reference, then the ragged-batch route (with
+    predict_batch, which needs the GPU, replaced by a per-row loop so that the grouping / padding / ordering logic is what
+    is tested)."""
+    g = json.load(open(os.path.join(GOLDEN, "stream_golden.json"), encoding="utf-8"))["long"]
+    audio, stamps = long_audio()
+    assert stamps == g["stamps"]
+    with pytest.raises(Exception, match="speech_timestamps"):
+        predictor.predict_long(audio)
+    res = predictor.predict_long(audio, speech_timestamps=stamps, batched=False)
+    assert res["text"] == g["result"]["text"] and abs(res["score"] - g["result"]["score"]) < 1e-6
+    wins = predictor.predictor.windows
+    assert [n for n, _ in wins] == [w["frames"] for w in g["windows"]]
+    for (_, sm), w in zip(wins, g["windows"]):
+        np.testing.assert_allclose(sm, np.array(w["mel_sums"]), rtol=2e-3, atol=1e-2)
+
+    # the VAD hook: any object with the reference's get_speech_timestamps(samples, sample_rate)
+    class Vad:
+        def get_speech_timestamps(self, samples, sr):
+            assert samples.dtype == np.float32 and sr == 16000
+            return stamps
+
+    calls = []
+
+    def fake_predict_batch(batch, n_samples=None):
+        calls.append((batch.shape, [int(v) for v in n_samples]))
+        assert batch.dtype == np.float32 and all((batch[r, n:] == 0).all() for r, n in enumerate(n_samples))
+        return [predictor.predict(audio_data=batch[r, :n]) for r, n in enumerate(n_samples)]
+
+    predictor.predict_batch = fake_predict_batch
+    predictor.vad_predictor = Vad()
+    predictor.predictor = FakePredictor()
+    res2 = predictor.predict_long(audio, max_batch_samples=2 * 71000)   # forces 3 batches: [0,1] [2,3] [4]
+    assert res2 == res
+    assert [c[1] for c in calls] == [[28400, 3000], [71000, 2000], [41500]]
+    assert [c[0] for c in calls] == [(2, 28400), (2, 71000), (1, 41500)]
+    # regions shorter than 7 fbank frames give no text and do not reach the GPU; no region at all -> empty result
+    calls.clear()
+    r3 = predictor.predict_long(audio, speech_timestamps=[{"start": 0, "end": 300}, {"start": 1600, "end": 30000}])
+    assert [c[1] for c in calls] == [[28400]] and r3["text"] != ""
+    assert predictor.predict_long(audio, speech_timestamps=[]) == {"text": "", "score": 0}
