@@ -898,6 +898,7 @@ def test_stream_scheduler_ragged_sessions(lib, cuda):
     assert len(sch._free) == 4
 
 
+@pytest.mark.xfail(reason="first GPU run pending (added after the GPU budget was spent)", strict=False)
 def test_predict_long_batched_regions(lib, cuda):
     """predict_long (predict.py:190-229): the speech regions of one recording as ragged GPU batches vs one predict() per
     region. The two routes differ only in the fbank implementation (GPU kernel vs torchaudio) and in batch padding, so the
