@@ -27,7 +27,7 @@ Weights are a dict name -> numpy array using the reference's Paddle parameter na
 (`Linear.weight` is [in, out]; `Conv*.weight` is [out, in/groups, k...]).
 """
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict
 
 import numpy as np
 import torch

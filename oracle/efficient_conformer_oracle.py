@@ -19,9 +19,6 @@ to 5e-5 (observed 1e-5). The reference's StrideConformerEncoderLayer also owns a
 (encoder.py:453, read only when concat_after=True): it appears in .pdparams files and is ignored by name here.
 """
 import math
-from typing import Dict
-
-import numpy as np
 import torch
 import torch.nn.functional as F
 

@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle.conformer_oracle import (ConformerOracle, add_optional_chunk_mask, layer_norm, linear, make_non_pad_mask,
-                                     positional_table, swish)
+                                     positional_table)
 
 
 class SqueezeformerConf:

@@ -4,8 +4,6 @@ ppasr_b200_greedy_decode (include/ppasr_b200.h). Detokenisation (ids -> string) 
 exactly as ctc_greedy_decoder.py:27-31. There is no NumPy fallback: without the CUDA library these
 functions raise.
 """
-import ctypes
-
 import numpy as np
 
 from .. import _lib as L

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from .. import _lib as L
-from ..engine import ConformerEngine, out_frames
+from ..engine import ConformerEngine
 from ..parallel import detokenize
 from ..weights import ConformerConfig, DeepSpeech2Config, EfficientConformerConfig, SqueezeformerConfig, load_npz, load_pdiparams, load_pdparams, read_mean_istd
 

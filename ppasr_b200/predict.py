@@ -143,7 +143,6 @@ class PPASRPredictor:
         """Extension: a batch of 16 kHz waveforms float32 [B, N] -> [{'text', 'score'}], everything from the fbank
         front end (csrc/fbank.cu) to the greedy decode on the GPU; only the decoded ids come back to the host."""
         from .featurizer import GpuFbank
-        from .parallel import detokenize
         if self.decoder != 'ctc_greedy':
             raise Exception("predict_batch implements the ctc_greedy decoder")
         if getattr(self, '_gpu_fbank', None) is None:

@@ -12,7 +12,6 @@ tests/test_oracle_cpu.py::test_encoder_oracle_vs_reference_code then checks orac
 """
 import os
 import sys
-import types
 
 import numpy as np
 
