@@ -165,7 +165,7 @@ def run_reference(args):
         "config": {"workload": workload, "rtf": dt / (sample_b * SECONDS)},
         "cpu_baseline": {"value": value, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample_b} of 32 utterances x 10 s per step, PyTorch-CPU fp32 oracle restatement "
-                                   "of the reference Paddle graph + reference greedy restatement (Paddle not installable)"},
+                                   "of the reference Paddle graph + reference greedy restatement (Paddle not installable; restatement pinned to the reference code, tests/test_encoder_golden_cpu.py)"},
         "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -393,7 +393,7 @@ def main():
         dt = (time.perf_counter() - t0) / n
         cpu = {"value": sb / dt, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{sb} of 32 utterances x 10 s, {n} passes (~10 s): PyTorch-CPU fp32 oracle restatement of the "
-                         "reference Paddle graph + greedy restatement (Paddle not installable offline)",
+                         "reference Paddle graph + greedy restatement (Paddle not installable offline; restatement pinned to the reference code, tests/test_encoder_golden_cpu.py)",
                "rtf": dt / (sb * SECONDS)}
 
     if rank == 0:
