@@ -134,3 +134,40 @@ def test_chunk_chain_matches_reference_code(lib, cuda, fname):
     worst = float(np.abs(got - ref).max()) / scale
     assert worst < 1e-2, f"{fname}: chunk logits rel err {worst}"
     pred.reset_stream()
+
+
+def test_model_level_api_matches_reference_code(lib, cuda):
+    """ppasr_b200.model_utils.ConformerModel driven exactly like the reference model (set_state_dict, get_encoder_out,
+    functional get_encoder_out_chunk loop with the caches handed back) against the reference code's own probabilities."""
+    from ppasr_b200.model_utils import ConformerModel
+    g = np.load(os.path.join(GOLDEN, "encoder_golden_conformer_gpu_stream.npz"))
+    cfg, w = _config(g, "conformer")
+    m = ConformerModel(input_dim=80, vocab_size=cfg.vocab_size, streaming=True,
+                       encoder_conf={k: v for k, v in cfg.to_dict().items() if k in (
+                           "output_size", "attention_heads", "linear_units", "num_blocks", "cnn_module_kernel", "cnn_module_norm",
+                           "max_len")})
+    m.set_state_dict(w)
+    probs = m.eval().get_encoder_out(g["feats"], g["lens"]).numpy()
+    ref = g["offline_probs"]
+    assert probs.shape == ref.shape
+    for b, n in enumerate(_valid_frames(g, "conformer", cfg)):
+        sure = ref[b, :n].max(-1) > 0.99
+        assert sure.any() and (probs[b, :n][sure].argmax(-1) == ref[b, :n][sure].argmax(-1)).all()
+        assert float(np.abs(probs[b, :n][sure] - ref[b, :n][sure]).max()) < 5e-2
+    cf = g["chunk_feats"]
+    ref_l = g["chunk_logits"]
+    ref_p = np.exp(ref_l - ref_l.max(-1, keepdims=True))
+    ref_p /= ref_p.sum(-1, keepdims=True)
+    att = np.zeros([0, 0, 0, 0], np.float32)
+    cnn = np.zeros([0, 0, 0, 0], np.float32)
+    offset, outs = 0, []
+    for (a, b) in _windows(cf.shape[0]):
+        pr, att, cnn = m.get_encoder_out_chunk(cf[None, a:b], np.array([offset], np.int32), np.array([-16], np.int32), att, cnn)
+        offset += pr.shape[1]
+        outs.append(pr.numpy()[0])
+    got = np.concatenate(outs, 0)
+    assert got.shape == ref_p.shape and att.shape == g["chunk_att_cache"].shape and cnn.shape == g["chunk_cnn_cache"].shape
+    sure = ref_p.max(-1) > 0.99
+    assert sure.any() and (got[sure].argmax(-1) == ref_p[sure].argmax(-1)).all()
+    assert float(np.abs(got[sure] - ref_p[sure]).max()) < 5e-2
+    m.close()

@@ -278,3 +278,98 @@ def test_read_vocab_file_matches_reference_golden(tmp_path):
     p = tmp_path / "vocabulary.txt"
     p.write_text(g["file"], encoding="utf-8")
     assert read_vocab_file(str(p)) == g["vocab_list"] and len(g["vocab_list"]) == g["vocab_size"]
+
+
+def test_model_utils_surface_cpu(monkeypatch, tmp_path):
+    """ppasr_b200.model_utils: the reference's model-level names (conformer/model.py:148-184, deepspeech2/model.py:62-72) over
+    InferencePredictor -- argument plumbing, lazy engine construction from set_state_dict + mean_istd.json, the
+    continuation rule of the device-resident caches, and the errors. The engine itself is replaced by a recorder (GPU only)."""
+    import json
+    import ppasr_b200.model_utils as MU
+
+    made = []
+
+    class FakePredictor:
+        def __init__(self, configs, use_model, streaming=True, weights=None, vocab_size=None, device=0, **kw):
+            self.args = dict(configs=configs, use_model=use_model, streaming=streaming, weights=weights, vocab_size=vocab_size, kw=kw)
+            self.offset = np.array([0], dtype=np.int32)
+            self.att_cache = np.zeros([0, 0, 0, 0], np.float32)
+            self.cnn_cache = np.zeros([0, 0, 0, 0], np.float32)
+            self.output_state_h = self.output_state_c = None
+            self.resets = 0
+            self.engine = self
+            made.append(self)
+
+        def close(self):
+            self.closed = True
+
+        def predict(self, speech, lens):
+            assert speech.dtype == np.float32 and lens.dtype == np.int64
+            return np.full((speech.shape[0], 3, 5), 0.2, np.float32)
+
+        def reset_stream(self):
+            self.resets += 1
+            self.offset = np.array([0], dtype=np.int32)
+            self.att_cache = np.zeros([0, 0, 0, 0], np.float32)
+            self.output_state_h = None
+
+        def predict_chunk_conformer(self, x, req):
+            assert x.dtype == np.float32 and isinstance(req, int)
+            self.offset = self.offset + 16
+            self.att_cache = np.ones([2, 4, int(self.offset[0]), 128], np.float32)
+            self.cnn_cache = np.ones([2, 1, 256, 14], np.float32)
+            return np.full((1, 16, 5), 0.2, np.float32)
+
+        def predict_chunk_deepspeech(self, x):
+            self.output_state_h = np.zeros((2, x.shape[0], 8), np.float32)
+            self.output_state_c = np.zeros((2, x.shape[0], 8), np.float32)
+            return np.full((x.shape[0], 16, 5), 0.2, np.float32), np.full([x.shape[0]], 16, np.int64)
+
+    monkeypatch.setattr(MU, "InferencePredictor", FakePredictor)
+    mi = tmp_path / "mean_istd.json"
+    mi.write_text(json.dumps({"mean": [1.0] * 80, "istd": [0.5] * 80}))
+    m = MU.ConformerModel(input_dim=80, vocab_size=5, mean_istd_path=str(mi), streaming=True,
+                          encoder_conf={"num_blocks": 2}, decoder_conf={"x": 1}, ctc_weight=0.3)
+    with pytest.raises(Exception, match="no parameters"):
+        m.get_encoder_out(np.zeros((1, 67, 80), np.float32), np.array([67]))
+    m.set_state_dict({"ctc.ctc_lo.weight": np.zeros((256, 5), np.float32)})
+    out = m.eval().get_encoder_out(np.zeros((2, 67, 80)), [67, 60])
+    assert out.numpy().shape == (2, 3, 5) and isinstance(out.numpy(), np.ndarray)
+    a = made[-1].args
+    assert a["use_model"] == "conformer" and a["streaming"] is True and a["vocab_size"] == 5
+    assert a["configs"]["encoder_conf"] == {"num_blocks": 2} and a["configs"]["preprocess_conf"] == {"n_mels": 80}
+    assert np.allclose(a["weights"]["encoder.global_cmvn.istd"], 0.5) and "ctc.ctc_lo.weight" in a["weights"]
+    # chunk API: empty caches start a stream, afterwards only the continuation is accepted
+    x = np.zeros((1, 67, 80), np.float32)
+    p1, att, cnn = m.get_encoder_out_chunk(x, np.array([0], np.int32), np.array([-16], np.int32), np.zeros([0, 0, 0, 0]), np.zeros([0, 0, 0, 0]))
+    assert p1.shape == (1, 16, 5) and att.shape == (2, 4, 16, 128) and cnn.shape == (2, 1, 256, 14) and made[-1].resets == 1
+    p2, att, cnn = m.get_encoder_out_chunk(x, 16, -16, att, cnn)
+    assert att.shape == (2, 4, 32, 128) and made[-1].resets == 1
+    with pytest.raises(Exception, match="continue the previous call"):
+        m.get_encoder_out_chunk(x, 16, -16, att, cnn)
+    with pytest.raises(Exception, match="offset 0"):
+        m.get_encoder_out_chunk(x, 16, -16, None, None)
+    m.get_encoder_out_chunk(x, 0, -16)              # restart
+    assert made[-1].resets == 3
+    with pytest.raises(Exception, match="outside the ppasr_b200 hot path"):
+        m(x, [67], None, None)
+    with pytest.raises(Exception, match="export"):
+        m.export()
+    n_before = len(made)
+    m.set_state_dict({"ctc.ctc_lo.weight": np.zeros((256, 5), np.float32)})   # new parameters -> new engine on next use
+    assert made[-1].closed
+    m.get_encoder_out(np.zeros((1, 67, 80)), [67])
+    assert len(made) == n_before + 1
+    # DeepSpeech2: states instead of caches; EfficientConformer chunk API raises
+    d = MU.DeepSpeech2Model(80, 5, str(mi), streaming=True, encoder_conf={"num_rnn_layers": 2, "rnn_size": 8},
+                            weights={"decoder.ctc_lo.weight": np.zeros((8, 5), np.float32)})
+    pr, ln, h, c = d.get_encoder_out_chunk(np.zeros((3, 67, 80)), np.array([67] * 3))
+    assert pr.shape == (3, 16, 5) and ln.tolist() == [16] * 3 and h.shape == (2, 3, 8) and c.shape == (2, 3, 8)
+    d.get_encoder_out_chunk(np.zeros((3, 67, 80)), np.array([67] * 3), h, c)
+    assert made[-1].args["use_model"] == "deepspeech2" and made[-1].resets == 1
+    e = MU.EfficientConformerModel(80, 5, str(mi), weights={"ctc.ctc_lo.weight": np.zeros((256, 5), np.float32)})
+    assert e.get_encoder_out(np.zeros((1, 67, 80)), [67]).shape == (1, 3, 5)
+    with pytest.raises(Exception, match="not implemented on the GPU"):
+        e.get_encoder_out_chunk(x, 0, -16)
+    assert {c.use_model for c in (MU.ConformerModel, MU.SqueezeformerModel, MU.EfficientConformerModel, MU.DeepSpeech2Model)} == \
+        {"conformer", "squeezeformer", "efficient_conformer", "deepspeech2"}
