@@ -14,7 +14,8 @@ Differences, all stated:
     and layouts) or from `weights=` / `model_dir=` at construction; the engine is built on first use;
   * `get_encoder_out_chunk` is functional in the reference (caches in, caches out). Here the K/V and conv caches live on the
     device: an EMPTY `att_cache` starts a new stream, anything else must be the continuation of the previous call (same
-    `offset`) -- feeding caches from elsewhere raises. The returned caches are host copies in the reference layout;
+    `offset`) -- feeding caches from elsewhere raises. The returned caches are host copies in the reference layout for the
+    Conformer and opaque continuation tokens for the Squeezeformer;
   * training (`forward`, losses, the attention decoder) and `export` are outside the hot path and raise;
   * results are host NumPy arrays wrapped so that `.numpy()` works like on a Paddle tensor.
 """
@@ -110,7 +111,12 @@ class _HotPathModel:
             raise Exception(f"device-resident caches: the chunk must continue the previous call (offset {int(p.offset[0])}), "
                             f"got offset {offset}")
         probs = p.predict_chunk_conformer(np.asarray(speech, dtype=np.float32), int(np.asarray(required_cache_size).reshape(-1)[0]))
-        return _wrap(probs), _wrap(p.att_cache), _wrap(p.cnn_cache)
+        if self.use_model == "conformer":
+            return _wrap(probs), _wrap(p.att_cache), _wrap(p.cnn_cache)
+        # Squeezeformer keeps the caches of its half-rate blocks at half rate on the device; the reference layout (every key
+        # repeated, squeezeformer/encoder.py:355-358) is not exported: the caller gets opaque non-empty continuation tokens
+        token = np.full([1, 1, 1, 1], float(int(p.offset[0])), dtype=np.float32)
+        return _wrap(probs), _wrap(token), _wrap(token.copy())
 
     # -- outside the hot path ----------------------------------------------------------------------------------------
     def forward(self, *a, **k):
