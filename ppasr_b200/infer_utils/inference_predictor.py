@@ -30,6 +30,32 @@ def _get(obj, key, default=None):
     return getattr(obj, key, default)
 
 
+def model_config_from(use_model, enc, n_mels, vocab_size, streaming):
+    """yaml `encoder_conf` (a dict) -> the engine's config object, keeping the keys that shape the inference graph and
+    dropping the training-only ones (dropout rates, activation_type 'swish', input_layer 'conv2d', ...), the way the
+    reference model classes pass `**encoder_conf` to their encoders (conformer/model.py:43-47 etc.)."""
+    if use_model == 'efficient_conformer':
+        allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
+                   'cnn_module_norm', 'max_len', 'stride_layer_idx', 'stride', 'group_layer_idx', 'group_size',
+                   'stride_kernel')
+        kw = {k: enc[k] for k in allowed if k in enc}
+        return EfficientConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+    if use_model == 'deepspeech2':
+        # configs/deepspeech2.yml encoder_conf (deepspeech2/encoder.py:8-16); streaming => forward-only RNN (model.py:40)
+        kw = {k: enc[k] for k in ('num_rnn_layers', 'rnn_size', 'use_gru') if k in enc}
+        return DeepSpeech2Config(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+    if use_model == 'squeezeformer':
+        # keys of configs/squeezeformer.yml encoder_conf (squeezeformer/encoder.py:24-53)
+        allowed = ('encoder_dim', 'output_size', 'attention_heads', 'num_blocks', 'reduce_idx', 'recover_idx',
+                   'feed_forward_expansion_factor', 'cnn_module_kernel', 'cnn_norm_type', 'adaptive_scale', 'max_len')
+        kw = {k: enc[k] for k in allowed if k in enc}
+        return SqueezeformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+    allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
+               'cnn_module_norm', 'max_len')
+    kw = {k: enc[k] for k in allowed if k in enc}
+    return ConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+
+
 class InferencePredictor:
     def __init__(self,
                  configs,
@@ -85,27 +111,7 @@ class InferencePredictor:
         if vocab_size is None:
             key = 'decoder.ctc_lo.weight' if use_model == 'deepspeech2' else 'ctc.ctc_lo.weight'
             vocab_size = int(weights[key].shape[1])
-        if use_model == 'efficient_conformer':
-            allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
-                       'cnn_module_norm', 'max_len', 'stride_layer_idx', 'stride', 'group_layer_idx', 'group_size',
-                       'stride_kernel')
-            kw = {k: enc[k] for k in allowed if k in enc}
-            self.model_config = EfficientConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
-        elif use_model == 'deepspeech2':
-            # configs/deepspeech2.yml encoder_conf (deepspeech2/encoder.py:8-16); streaming => forward-only RNN (model.py:40)
-            kw = {k: enc[k] for k in ('num_rnn_layers', 'rnn_size', 'use_gru') if k in enc}
-            self.model_config = DeepSpeech2Config(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
-        elif use_model == 'squeezeformer':
-            # keys of configs/squeezeformer.yml encoder_conf (squeezeformer/encoder.py:24-53)
-            allowed = ('encoder_dim', 'output_size', 'attention_heads', 'num_blocks', 'reduce_idx', 'recover_idx',
-                       'feed_forward_expansion_factor', 'cnn_module_kernel', 'cnn_norm_type', 'adaptive_scale', 'max_len')
-            kw = {k: enc[k] for k in allowed if k in enc}
-            self.model_config = SqueezeformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
-        else:
-            allowed = ('output_size', 'attention_heads', 'linear_units', 'num_blocks', 'cnn_module_kernel',
-                       'cnn_module_norm', 'max_len')
-            kw = {k: enc[k] for k in allowed if k in enc}
-            self.model_config = ConformerConfig(input_dim=n_mels, vocab_size=vocab_size, streaming=streaming, **kw)
+        self.model_config = model_config_from(use_model, enc, n_mels, vocab_size, streaming)
         self._weights_ref = weights  # kept for DecodePipeline (extra engines pack their own copy)
         self.engine = ConformerEngine(self.model_config, weights, device=device)
 

@@ -373,3 +373,30 @@ def test_model_utils_surface_cpu(monkeypatch, tmp_path):
         e.get_encoder_out_chunk(x, 0, -16)
     assert {c.use_model for c in (MU.ConformerModel, MU.SqueezeformerModel, MU.EfficientConformerModel, MU.DeepSpeech2Model)} == \
         {"conformer", "squeezeformer", "efficient_conformer", "deepspeech2"}
+
+
+def test_param_tables_match_reference_state_dict():
+    """ppasr_b200/weights.py against the reference's own model classes (tests/golden/state_dict_golden.json, recorded by
+    make_state_dict_golden.py from the reference <Family>Model classes built from the reference's shipped configs/*.yml, both
+    `streaming` settings): the yaml encoder_conf goes through the same mapping InferencePredictor uses, and the parameter
+    table the weight packer expects must be exactly the reference state_dict minus the attention decoder (never read by CTC
+    inference) and minus parameters the reference constructs but never reads."""
+    import json
+    from ppasr_b200 import weights as W
+    from ppasr_b200.infer_utils.inference_predictor import model_config_from
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_golden.json"), encoding="utf-8"))
+    tables = {"conformer": W.conformer_param_shapes, "squeezeformer": W.squeezeformer_param_shapes,
+              "efficient_conformer": W.efficient_conformer_param_shapes, "deepspeech2": W.deepspeech2_param_shapes}
+    # built by the reference but unused at inference: StrideConformerEncoderLayer.concat_linear (efficient_conformer/encoder.py:453,
+    # read only when concat_after=True)
+    unused = ("concat_linear",)
+    assert len(g["models"]) == 8
+    for m in g["models"]:
+        cfg = model_config_from(m["use_model"], m["encoder_conf"], g["n_mels"], g["vocab_size"], m["streaming"])
+        mine = {k: list(v) for k, v in tables[m["use_model"]](cfg).items()}
+        ref = {k: v for k, v in m["state_dict"].items() if not any(u in k for u in unused)}
+        assert set(mine) == set(ref), (m["use_model"], m["streaming"], sorted(set(mine) ^ set(ref))[:8])
+        bad = {k: (mine[k], ref[k]) for k in mine if mine[k] != ref[k]}
+        assert not bad, (m["use_model"], m["streaming"], list(bad.items())[:5])
+        if m["use_model"] != "deepspeech2":
+            assert m["attention_decoder_tensors"] > 0
