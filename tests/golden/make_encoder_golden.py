@@ -237,6 +237,9 @@ if __name__ == "__main__":
         print("squeezeformer stream", {k: v.shape for k, v in o.items()})
         o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_offline.npz"), streaming=False)
         print("squeezeformer offline", {k: v.shape for k, v in o.items()})
+        o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_offline_bn.npz"), streaming=False,
+                               norm="batch_norm", seed=1001)
+        print("squeezeformer offline/bn", {k: v.shape for k, v in o.items()})
     if "efficient_conformer" in which:
         o = make_efficient_conformer(os.path.join(HERE, "encoder_golden_efficient_conformer_offline.npz"), streaming=False)
         print("efficient_conformer offline", {k: v.shape for k, v in o.items()})
