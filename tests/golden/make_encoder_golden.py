@@ -73,7 +73,7 @@ def build_conformer(cfg, weights, streaming):
     return enc, ctc
 
 
-def run_former(enc, ctc, feats, lens, chunk_feats):
+def run_former(enc, ctc, feats, lens, chunk_feats, required=-16):
     """model.py:148-184 get_encoder_out / get_encoder_out_chunk, called on the reference encoder + CTC head."""
     enc.eval(), ctc.eval()
     out = {}
@@ -87,7 +87,7 @@ def run_former(enc, ctc, feats, lens, chunk_feats):
             offset = 0
             logits = []
             for (a, b) in stream_windows(chunk_feats.shape[0]):
-                xs, att, cnn = enc.forward_chunk(xs=t(chunk_feats[None, a:b]), offset=offset, required_cache_size=-16,
+                xs, att, cnn = enc.forward_chunk(xs=t(chunk_feats[None, a:b]), offset=offset, required_cache_size=required,
                                                  att_cache=att, cnn_cache=cnn)
                 offset += int(xs.shape[1])
                 logits.append(logits_of(ctc, xs).numpy()[0])
@@ -110,7 +110,7 @@ def inputs(lens, chunk_T, seed):
     return feats, lens, chunk_feats
 
 
-def make_conformer(path, streaming=True, norm="layer_norm", seed=1000, lens=LENS, chunk_T=211, vocab=40, **kw):
+def make_conformer(path, streaming=True, norm="layer_norm", seed=1000, lens=LENS, chunk_T=211, vocab=40, required=-16, **kw):
     cfg = W.ConformerConfig(input_dim=80, vocab_size=vocab, cnn_module_kernel=15, streaming=streaming, cnn_module_norm=norm,
                             **(kw or SMALL))
     weights = W.init_conformer_weights(cfg, seed=seed)
@@ -118,7 +118,8 @@ def make_conformer(path, streaming=True, norm="layer_norm", seed=1000, lens=LENS
     load_into(enc, weights, "encoder.")
     load_into(ctc, weights, "ctc.")
     feats, lens, chunk_feats = inputs(lens, chunk_T if streaming else 0, seed)
-    out = run_former(enc, ctc, feats, lens, chunk_feats)
+    out = run_former(enc, ctc, feats, lens, chunk_feats, required)
+    out["required_cache_size"] = np.array(required)
     np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
                         chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
     return out
@@ -232,6 +233,10 @@ if __name__ == "__main__":
         print("conformer stream", {k: v.shape for k, v in o.items()})
         o = make_conformer(os.path.join(HERE, "encoder_golden_conformer_offline_bn.npz"), streaming=False, norm="batch_norm")
         print("conformer offline/bn", {k: v.shape for k, v in o.items()})
+        for req in (32, 0):  # bounded / no attention history (encoder.py:255-260 next_cache_start)
+            o = make_conformer(os.path.join(HERE, f"encoder_golden_conformer_stream_req{req}.npz"), streaming=True, seed=1002,
+                               lens=(71,), required=req)
+            print("conformer stream required", req, {k: np.shape(v) for k, v in o.items()})
     if "squeezeformer" in which:
         o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_stream.npz"), streaming=True)
         print("squeezeformer stream", {k: v.shape for k, v in o.items()})

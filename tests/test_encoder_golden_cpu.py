@@ -52,7 +52,7 @@ def _oracle(g, family):
 
 
 def test_fixtures_present():
-    assert len(FILES) >= 18, FILES
+    assert len(FILES) >= 21, FILES
     assert {_family(f) for f in FILES} == set(FAMILIES)
 
 
@@ -90,8 +90,9 @@ def test_chunk_chain_matches_reference_code(fname):
             np.testing.assert_allclose(c.numpy(), g["chunk_state_c"], rtol=0, atol=1e-5)
     else:
         att, cnn, off = torch.zeros(0, 0, 0, 0), torch.zeros(0, 0, 0, 0), 0
+        required = int(g["required_cache_size"]) if "required_cache_size" in g.files else -16  # 32 / 0: bounded / no history
         for (a, b) in stream_windows(cf.shape[0], is_end=True):
-            x, att, cnn = o.get_encoder_out_chunk(torch.from_numpy(cf[None, a:b]), off, -16, att, cnn, return_logits=True)
+            x, att, cnn = o.get_encoder_out_chunk(torch.from_numpy(cf[None, a:b]), off, required, att, cnn, return_logits=True)
             off += x.shape[1]
             outs.append(x[0].numpy())
         assert tuple(att.shape) == g["chunk_att_cache"].shape and tuple(cnn.shape) == g["chunk_cnn_cache"].shape
