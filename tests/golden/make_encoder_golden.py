@@ -125,7 +125,8 @@ def make_conformer(path, streaming=True, norm="layer_norm", seed=1000, lens=LENS
     return out
 
 
-def make_squeezeformer(path, streaming=True, seed=1000, lens=LENS, chunk_T=211, vocab=40, norm="layer_norm", **kw):
+def make_squeezeformer(path, streaming=True, seed=1000, lens=LENS, chunk_T=211, vocab=40, norm="layer_norm", required=-16,
+                       **kw):
     from ppasr.model_utils.loss.ctc import CTCLoss
     from ppasr.model_utils.squeezeformer.encoder import SqueezeformerEncoder
     from ppasr.model_utils.utils.cmvn import GlobalCMVN
@@ -146,7 +147,8 @@ def make_squeezeformer(path, streaming=True, seed=1000, lens=LENS, chunk_T=211, 
     load_into(enc, weights, "encoder.")
     load_into(ctc, weights, "ctc.")
     feats, lens, chunk_feats = inputs(lens, chunk_T if streaming else 0, seed)
-    out = run_former(enc, ctc, feats, lens, chunk_feats)
+    out = run_former(enc, ctc, feats, lens, chunk_feats, required)
+    out["required_cache_size"] = np.array(required)
     np.savez_compressed(path, cfg=np.array(repr(cfg.to_dict())), seed=seed, feats=feats.astype(np.float32), lens=lens,
                         chunk_feats=(chunk_feats if chunk_feats is not None else np.zeros((0, 80), np.float32)), **out)
     return out
@@ -245,6 +247,9 @@ if __name__ == "__main__":
         o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_offline_bn.npz"), streaming=False,
                                norm="batch_norm", seed=1001)
         print("squeezeformer offline/bn", {k: v.shape for k, v in o.items()})
+        o = make_squeezeformer(os.path.join(HERE, "encoder_golden_squeezeformer_stream_req32.npz"), streaming=True, seed=1003,
+                               lens=(71,), chunk_T=67 + 64 * 2 + 21, required=32)
+        print("squeezeformer stream required 32", {k: np.shape(v) for k, v in o.items()})
     if "efficient_conformer" in which:
         o = make_efficient_conformer(os.path.join(HERE, "encoder_golden_efficient_conformer_offline.npz"), streaming=False)
         print("efficient_conformer offline", {k: v.shape for k, v in o.items()})
