@@ -5,7 +5,8 @@ arguments, same `{'text', 'score'}` results, same window logic (67-frame window,
 frames), same `None` returns when too few frames are buffered, same exceptions. The encoder + decode call
 path runs in libppasr_b200.so; only the audio front end (outside the hot path) is host code:
 `AudioFeaturizer` below restates audio_featurizer.py:37-69,120-138 with torchaudio's kaldi fbank, the CPU
-twin of paddleaudio's.
+twin of paddleaudio's. Inputs as in `_load_audio` (predict.py:142-161): ndarray (float, or integer scaled to [-1, 1)), path /
+open file / bytes of a complete RIFF/WAVE PCM file (other containers need soundfile / PyAV: decode them first).
 
 `predict_long` (predict.py:190-229) is mirrored around the VAD: the silero ONNX model itself is outside the hot path
 (SURVEY §2 row 12), so the speech segments come from `speech_timestamps=` or from any object with the reference's
@@ -83,6 +84,33 @@ class AudioFeaturizer:
         return mat.numpy().astype(np.float32)
 
 
+def _read_wav(src):
+    """RIFF/WAVE integer PCM through the standard library (the reference reads files with soundfile / PyAV, predict.py:143-161,
+    audio.py:56-71,110-119, which also decode FLAC, MP3, ...: those need a decoder and stay outside the hot path).
+    Returns (float32 samples in [-1, 1) -- [N] or [N, channels] like soundfile.read(dtype='float32') --, sample_rate)."""
+    import io
+    import wave
+    if isinstance(src, (bytes, bytearray)):
+        src = io.BytesIO(bytes(src))
+    try:
+        with wave.open(src, 'rb') as w:
+            nch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+            raw = w.readframes(n)
+    except (wave.Error, EOFError) as e:
+        raise Exception(f'only RIFF/WAVE PCM files are decoded here ({e}); decode other formats to a NumPy array first')
+    if width == 1:    # 8-bit WAV is unsigned
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    elif width == 2:
+        x = np.frombuffer(raw, dtype='<i2').astype(np.float32) / 32768.0
+    elif width == 4:
+        x = np.frombuffer(raw, dtype='<i4').astype(np.float32) / 2147483648.0
+    else:
+        raise Exception(f'unsupported WAV sample width: {width} bytes')
+    if nch > 1:
+        x = x.reshape(-1, nch)
+    return x, rate
+
+
 class PPASRPredictor:
     # 7 fbank frames (25 ms window, 10 ms shift) = the shortest input Conv2dSubsampling4 turns into one encoder frame; a shorter
     # region yields no text here (in the reference the fbank / conv of such a region raises)
@@ -131,11 +159,25 @@ class PPASRPredictor:
             result = greedy_decoder(probs_seq=output_data, vocabulary=self.vocab_list)
         return result[0], result[1]
 
+    # predict.py:142-161
+    @staticmethod
+    def _load_audio(audio_data, sample_rate=16000):
+        """str path / open binary file / bytes of a complete WAV file / ndarray -> (samples, sample_rate)."""
+        from io import BufferedReader
+        if isinstance(audio_data, np.ndarray):
+            return audio_data, sample_rate
+        if isinstance(audio_data, str):
+            import os
+            assert os.path.exists(audio_data), f'文件不存在，请检查路径：{audio_data}'
+            return _read_wav(audio_data)
+        if isinstance(audio_data, (BufferedReader, bytes)):
+            return _read_wav(audio_data)
+        raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+
     # predict.py:163-187
     def predict(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000):
-        if not isinstance(audio_data, np.ndarray):  # file paths / encoded bytes need a decoder: outside the hot path
-            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
-        samples = self._audio_featurizer.to_float32(audio_data)  # predict.py:152-153 AudioSegment.from_ndarray
+        audio_data, sample_rate = self._load_audio(audio_data, sample_rate)
+        samples = self._audio_featurizer.to_float32(audio_data)  # AudioSegment.__init__ (audio.py:24-32)
         audio_feature = self._audio_featurizer.featurize(samples, sample_rate, inplace=True)
         return self.predict_features(audio_feature, use_pun=use_pun, is_itn=is_itn)
 
@@ -167,8 +209,7 @@ class PPASRPredictor:
         `max_batch_samples` padded samples instead of one call per region."""
         if use_pun or is_itn:
             raise Exception("punctuation / ITN are outside the ppasr_b200 hot path")
-        if not isinstance(audio_data, np.ndarray):
-            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+        audio_data, sample_rate = self._load_audio(audio_data, sample_rate)
         samples = self._audio_featurizer.to_float32(audio_data)
         if sample_rate != self._audio_featurizer._target_sample_rate:
             raise Exception("resampling is outside the hot path: feed audio at %d Hz" % self._audio_featurizer._target_sample_rate)

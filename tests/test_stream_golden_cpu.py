@@ -147,3 +147,45 @@ def test_predict_long_matches_reference(predictor):
     r3 = predictor.predict_long(audio, speech_timestamps=[{"start": 0, "end": 300}, {"start": 1600, "end": 30000}])
     assert [c[1] for c in calls] == [[28400]] and r3["text"] != ""
     assert predictor.predict_long(audio, speech_timestamps=[]) == {"text": "", "score": 0}
+
+
+def test_predict_accepts_wav_files_like_reference_load_audio(predictor, tmp_path):
+    """predict.py:142-161 _load_audio: path / open file / bytes of a complete file / ndarray. WAV PCM is decoded with the
+    standard library; the result must equal feeding the same int16 samples as an array (soundfile.read(dtype='float32')
+    scales int16 by 1/32768, exactly what AudioSegment does with an int16 array)."""
+    import wave
+    x = next(p for k, p, _ in audio_script(seed=21) if k == "int16" and len(p) > 1000)
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1), w.setsampwidth(2), w.setframerate(16000)
+        w.writeframes(x.tobytes())
+
+    def run(arg):
+        predictor.predictor = FakePredictor()
+        return predictor.predict(audio_data=arg)
+
+    ref = run(x)
+    assert run(path) == ref
+    assert run(open(path, "rb").read()) == ref
+    with open(path, "rb") as f:
+        assert run(f) == ref
+    def run_long(arg):
+        predictor.predictor = FakePredictor()   # the stand-in's output depends on its call count
+        return predictor.predict_long(arg, speech_timestamps=[{"start": 0, "end": len(x)}], batched=False)
+
+    assert run_long(path) == run_long(x) and run_long(x)["text"] == ref["text"]
+    # stereo: channels are averaged (audio.py:31-32)
+    st = str(tmp_path / "st.wav")
+    with wave.open(st, "wb") as w:
+        w.setnchannels(2), w.setsampwidth(2), w.setframerate(16000)
+        w.writeframes(np.stack([x, x], 1).tobytes())
+    assert run(st) == ref
+    with pytest.raises(Exception, match="RIFF/WAVE"):
+        run(b"ID3\x03 not a wav file at all")
+    with pytest.raises(AssertionError, match="文件不存在"):
+        run(str(tmp_path / "missing.wav"))
+    with wave.open(st, "wb") as w:
+        w.setnchannels(1), w.setsampwidth(2), w.setframerate(8000)
+        w.writeframes(x.tobytes())
+    with pytest.raises(Exception, match="resampling"):
+        run(st)
