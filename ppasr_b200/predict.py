@@ -54,6 +54,15 @@ class AudioFeaturizer:
             out = np.mean(out, 1)
         return out
 
+    @classmethod
+    def from_pcm_bytes(cls, data, channels=1, samp_width=2):
+        """audio.py:122-139 from_pcm_bytes -> buf_to_float (data_utils/utils.py:381-410): headerless little-endian PCM."""
+        scale = 1.0 / float(1 << ((8 * samp_width) - 1))
+        x = scale * np.frombuffer(data, "<i{:d}".format(samp_width)).astype(np.float32)
+        if channels > 1:
+            x = x.reshape(-1, channels)
+        return cls.to_float32(x)
+
     def normalize_(self, samples):
         """audio.py:256-264,287-304 normalize() -> gain_db(): IN PLACE on the float32 buffer, like the reference (the scaled
         samples stay in the caller's buffer -- predict_stream relies on that, predict.py:262-274)."""
@@ -280,12 +289,8 @@ class PPASRPredictor:
             raise Exception(f"不支持改该模型流式识别，当前模型：{self.use_model}")
         if isinstance(audio_data, np.ndarray):    # predict.py:253-254 AudioSegment.from_ndarray
             audio_data = self._audio_featurizer.to_float32(audio_data)
-        elif isinstance(audio_data, bytes):       # predict.py:255-257 from_pcm_bytes -> buf_to_float (data_utils/utils.py:381-410)
-            scale = 1.0 / float(1 << ((8 * samp_width) - 1))
-            audio_data = scale * np.frombuffer(audio_data, "<i{:d}".format(samp_width)).astype(np.float32)
-            if channels > 1:
-                audio_data = audio_data.reshape(-1, channels)
-            audio_data = self._audio_featurizer.to_float32(audio_data)
+        elif isinstance(audio_data, bytes):       # predict.py:255-257
+            audio_data = self._audio_featurizer.from_pcm_bytes(audio_data, channels=channels, samp_width=samp_width)
         else:
             raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
         if self.remained_wav is None:

@@ -189,3 +189,66 @@ def test_predict_accepts_wav_files_like_reference_load_audio(predictor, tmp_path
         w.writeframes(x.tobytes())
     with pytest.raises(Exception, match="resampling"):
         run(st)
+
+
+def test_stream_scheduler_feed_audio_matches_reference_predict_stream(monkeypatch):
+    """StreamScheduler.feed_audio (many sessions on one engine) must cut each session's audio into exactly the feature windows
+    the reference's single-stream predict_stream produced (stream_golden.json: per-window frame count and per-mel sums, incl.
+    the in-place dB normalisation carried between calls) -- here with the two recorded rounds running as two INTERLEAVED
+    sessions, and the transcripts must equal the reference's final results. The engine is a stand-in built on the same
+    FakePredictor (its output depends on how many windows it has seen, so each session gets its own)."""
+    from ppasr_b200.infer_utils import stream_scheduler as SS
+    g = json.load(open(os.path.join(GOLDEN, "stream_golden.json"), encoding="utf-8"))
+    fakes = {}
+
+    class Engine:
+        def sessions_init(self, n):
+            pass
+
+        def sessions_reset(self, slot):
+            fakes[slot] = FakePredictor()
+
+        def sessions_step(self, batch, slots, required):
+            assert required == -16 and len(set(slots)) == len(slots)
+            self.out = [fakes[s].predict_chunk_conformer(batch[b:b + 1], required)[0] for b, s in enumerate(slots)]
+
+        def ctc_probs(self, to_host=True):
+            return np.stack(self.out)
+
+    class Pred:
+        use_model, streaming = "conformer", True
+        configs = {"preprocess_conf": {"feature_method": "fbank", "n_mels": 80, "use_dB_normalization": True, "target_dB": -20}}
+
+        class model_config:
+            input_dim = 80
+
+        engine = Engine()
+
+    monkeypatch.setattr(SS, "greedy_decoder_chunk", DO.greedy_decoder_chunk)
+    sch = SS.StreamScheduler(Pred(), VOCAB, max_sessions=4, required_cache_size=-16)
+    scripts = {rnd: audio_script(seed=11 + rnd) for rnd in range(2)}
+    sids = {rnd: sch.open() for rnd in range(2)}
+    # the reference run used ONE stand-in for both rounds: round 1 started after the windows of round 0
+    n0 = sum(len(r["windows"]) for r in g["stream"] if r["round"] == 0)
+    fakes[sch._sessions[sids[1]].slot].windows = [(0, None)] * n0
+    last = {}
+    for i in range(len(scripts[0])):
+        for rnd in range(2):
+            kind, payload, is_end = scripts[rnd][i]
+            sch.feed_audio(sids[rnd], payload, is_end=is_end)
+        while sch.pending():
+            last.update(sch.step())
+    for rnd in range(2):
+        recs = [r for r in g["stream"] if r["round"] == rnd]
+        ref_wins = [w for r in recs for w in r["windows"]]
+        slot = sch._sessions[sids[rnd]].slot
+        wins = fakes[slot].windows[n0 if rnd == 1 else 0:]
+        assert [n for n, _ in wins] == [w["frames"] for w in ref_wins]
+        for (_, sm), w in zip(wins, ref_wins):
+            np.testing.assert_allclose(sm, np.array(w["mel_sums"]), rtol=2e-3, atol=1e-2)
+        final = recs[-1]["result"]
+        assert last[sids[rnd]]["text"] == final["text"] and abs(last[sids[rnd]]["score"] - final["score"]) < 1e-3
+        assert len(sch._sessions[sids[rnd]].wav) == recs[-1]["remained_samples"]
+        assert sch.close(sids[rnd])["text"] == final["text"]
+    with pytest.raises(Exception, match="不支持该数据类型"):
+        sch.feed_audio(sch.open(), [0.0] * 100)
