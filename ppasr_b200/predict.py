@@ -21,6 +21,9 @@ from .infer_utils.inference_predictor import InferencePredictor, _get
 from .weights import read_vocab_file
 
 
+SUPPORT_MODEL = ['squeezeformer', 'efficient_conformer', 'conformer', 'deepspeech2']  # ppasr/__init__.py:3
+
+
 class AudioFeaturizer:
     """ppasr/data_utils/featurizer/audio_featurizer.py:13-138 for feature_method='fbank' (the shipped default)."""
 
@@ -125,15 +128,18 @@ class PPASRPredictor:
     # region yields no text here (in the reference the fbank / conv of such a region raises)
     MIN_SAMPLES = 400 + 6 * 160
 
-    def __init__(self, configs, model_path='models/conformer_streaming_fbank/infer/', use_pun=False, use_gpu=True,
-                 vocab_list=None, weights=None, device=0):
-        """configs: dict (or attribute object) with the reference's yaml keys: use_model, streaming, decoder,
-        encoder_conf, preprocess_conf, dataset_conf.dataset_vocab. `vocab_list` / `weights` let tests pass
-        in-memory objects instead of files."""
+    def __init__(self, configs=None, model_path='models/conformer_streaming_fbank/infer/', use_pun=False, use_gpu=True,
+                 vocab_list=None, weights=None, device=0, model_tag=None, pun_model_dir=None):
+        """configs: path of a reference yaml config (predict.py:36-41), or the loaded dict / attribute object, with the
+        reference's keys: use_model, streaming, decoder, encoder_conf, preprocess_conf, dataset_conf.dataset_vocab,
+        ctc_beam_search_decoder_conf. `vocab_list` / `weights` let tests pass in-memory objects instead of files. `model_tag`
+        (download of a published model, predict.py:42-58) needs the network and is not supported."""
         if use_pun:
             raise Exception("punctuation restoration is outside the ppasr_b200 hot path")
+        configs = self.load_configs(configs, model_tag)
         self.configs = configs
         self.use_model = _get(configs, 'use_model', 'conformer')
+        assert self.use_model in SUPPORT_MODEL, f'没有该模型：{self.use_model}'   # predict.py:61
         self.streaming = bool(_get(configs, 'streaming', True))
         self.decoder = _get(configs, 'decoder', 'ctc_greedy')
         pre = _get(configs, 'preprocess_conf', {}) or {}
@@ -157,6 +163,18 @@ class PPASRPredictor:
         self.predictor = InferencePredictor(configs=configs, use_model=self.use_model, streaming=self.streaming,
                                             model_dir=model_path, use_gpu=use_gpu, weights=weights,
                                             vocab_size=len(vocab_list), device=device)
+
+    @staticmethod
+    def load_configs(configs, model_tag=None):
+        """predict.py:36-60: a str is the path of a yaml file; dicts / attribute objects pass through."""
+        if configs is None:
+            raise Exception(f"no configs given: downloading the published model '{model_tag}' needs the network; pass the "
+                            "yaml config of an exported model instead")
+        if isinstance(configs, str):
+            import yaml
+            with open(configs, 'r', encoding='utf-8') as f:
+                configs = yaml.load(f.read(), Loader=yaml.FullLoader)
+        return configs
 
     # predict.py:114-140
     def decode(self, output_data, use_pun=False, is_itn=False):

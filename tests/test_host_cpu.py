@@ -400,3 +400,19 @@ def test_param_tables_match_reference_state_dict():
         assert not bad, (m["use_model"], m["streaming"], list(bad.items())[:5])
         if m["use_model"] != "deepspeech2":
             assert m["attention_decoder_tensors"] > 0
+
+
+def test_predictor_config_loading(tmp_path):
+    """PPASRPredictor.load_configs (predict.py:36-60): yaml path or loaded config; no configs (model download) raises."""
+    from ppasr_b200.predict import PPASRPredictor, SUPPORT_MODEL
+    y = tmp_path / "c.yml"
+    y.write_text("use_model: squeezeformer\nstreaming: True\ndecoder: ctc_greedy\nencoder_conf:\n  num_blocks: 12\n"
+                 "preprocess_conf:\n  feature_method: fbank\n  n_mels: 80\n", encoding="utf-8")
+    c = PPASRPredictor.load_configs(str(y))
+    assert c["use_model"] == "squeezeformer" and c["encoder_conf"]["num_blocks"] == 12 and c["streaming"] is True
+    assert PPASRPredictor.load_configs(c) is c
+    with pytest.raises(Exception, match="needs the network"):
+        PPASRPredictor.load_configs(None, "conformer_streaming_fbank_wenetspeech")
+    assert set(SUPPORT_MODEL) == {"conformer", "squeezeformer", "efficient_conformer", "deepspeech2"}
+    with pytest.raises(AssertionError, match="没有该模型"):
+        PPASRPredictor({"use_model": "whisper"})
