@@ -48,6 +48,19 @@ def _detok(ids, vocabulary):
     return "".join([vocabulary[i] for i in ids]).replace("<space>", " ")
 
 
+def collapse_frames(frame_ids, frame_probs, vocabulary, n_frames=None, blank_index=0):
+    """Host half of ctc_greedy_decoder.py:18-31 on per-frame arg-max ids / probabilities that the GPU already produced
+    (ppasr_b200_ctc_greedy `frame_ids` / `frame_probs`): merge repeats, drop blanks, join; score = 100 x mean probability of the
+    non-blank frames, summed in frame order in float32 like Python's sum() over np.float32. `n_frames` cuts a padded row."""
+    from itertools import groupby
+    ids = [int(i) for i in frame_ids[:n_frames]]
+    kept = [np.float32(frame_probs[t]) for t, i in enumerate(ids) if i != blank_index]
+    index_list = [i for i in (g[0] for g in groupby(ids)) if i != blank_index]
+    text = "".join([vocabulary[i] for i in index_list])
+    score = float(sum(kept) / len(kept)) * 100.0 if len(kept) > 0 else 0
+    return score, text.replace("<space>", " ")
+
+
 def greedy_decoder(probs_seq, vocabulary, blank_index=0):
     """ctc_greedy_decoder.py:6-31 -> (score, text)."""
     ids, ol, sc, _, _ = greedy_decode_ids(probs_seq, None, blank_index)

@@ -221,9 +221,22 @@ class PPASRPredictor:
                                        use_dB_normalization=pre.get('use_dB_normalization', True),
                                        target_dB=pre.get('target_dB', -20))
         feats, counts = self._gpu_fbank.featurize_batch(audio_batch, n_samples)
-        res = self.predictor.predict_decode(feats, np.asarray(counts, dtype=np.int64), vocabulary=self.vocab_list,
-                                            trim_to_lens=n_samples is not None)
-        return [{'text': t, 'score': s} for s, t in res]
+        if n_samples is None:
+            res = self.predictor.predict_decode(feats, np.asarray(counts, dtype=np.int64), vocabulary=self.vocab_list)
+            return [{'text': t, 'score': s} for s, t in res]
+        # ragged batch: every utterance is decoded over exactly the frames a run of its own would produce
+        # (out_frames(its fbank frames), not the 1-2 extra frames the batch mask keeps, subsampling.py:115), from the per-frame
+        # arg-max ids / probabilities of the fused CTC head
+        from .decoders.ctc_greedy_decoder import collapse_frames
+        eng = self.predictor.engine
+        eng.encode(feats, np.asarray(counts, dtype=np.int64))
+        _, _, _, frame_ids, frame_probs = eng.ctc_greedy(to_host=True, with_frames=True)
+        out = []
+        for b, c in enumerate(counts):
+            n = int(eng.lib.ppasr_b200_out_frames(eng._ctx, int(c))) if c > 0 else 0
+            score, text = collapse_frames(frame_ids[b], frame_probs[b], self.vocab_list, n_frames=max(n, 0))
+            out.append({'text': text, 'score': score})
+        return out
 
     # predict.py:190-229
     def predict_long(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000, speech_timestamps=None, batched=True,

@@ -493,3 +493,24 @@ def test_audio_normalisation_oracle_matches_reference_golden():
     from ppasr_b200.predict import AudioFeaturizer
     x = g["tone/float32"]
     assert np.abs(AudioFeaturizer().featurize(x) - FO.kaldi_fbank(g["tone/int16"].astype(np.float32))).max() < 2e-3
+
+
+def test_collapse_frames_matches_reference_golden():
+    """ppasr_b200.decoders.ctc_greedy_decoder.collapse_frames (the host half of the ragged-batch decode: per-frame arg-max
+    ids / probabilities -> text, score) against the reference decoder's own outputs, bit for bit, incl. a padded row cut by
+    n_frames."""
+    from ppasr_b200.decoders.ctc_greedy_decoder import collapse_frames
+    z, meta = _gold()
+    for m in meta:
+        if m["name"] == "__batch__":
+            continue
+        probs = z[m["name"] + "_probs"]
+        ids, mx = probs.argmax(-1), probs.max(-1)
+        score, text = collapse_frames(ids, mx, gold_vocab(m["V"]))
+        assert text == m["text"] and repr(float(score)) == m["score"], m["name"]
+        pad_ids = np.concatenate([ids, np.full(5, 3, ids.dtype)])
+        pad_mx = np.concatenate([mx, np.full(5, 0.9, mx.dtype)])
+        score2, text2 = collapse_frames(pad_ids, pad_mx, gold_vocab(m["V"]), n_frames=len(ids))
+        assert (text2, repr(float(score2))) == (m["text"], m["score"])
+    assert collapse_frames(np.zeros(4, np.int64), np.ones(4, np.float32), ["<blank>", "a"]) == (0, "")
+    assert collapse_frames(np.array([1, 1, 0, 1]), np.ones(4, np.float32), ["<blank>", "a"], n_frames=0) == (0, "")
