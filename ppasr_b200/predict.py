@@ -229,7 +229,12 @@ class PPASRPredictor:
         # arg-max ids / probabilities of the fused CTC head
         from .decoders.ctc_greedy_decoder import collapse_frames
         eng = self.predictor.engine
-        eng.encode(feats, np.asarray(counts, dtype=np.int64))
+        # a padded batch marks frame j valid iff 4 j < len (subsampling.py:115), 1-2 frames more than the utterance has on its
+        # own; lengths of the form 4 T' - 3 make the batch mask end exactly at T' = ((frames - 1) // 2 - 1) // 2, so that
+        # attention and the conv masks see what a stand-alone run sees
+        t_own = [max(((int(c) - 1) // 2 - 1) // 2, 0) for c in counts]
+        lens = counts if self.use_model == 'deepspeech2' else [4 * t - 3 if t > 0 else 0 for t in t_own]  # DS2: conv.py:20 rule
+        eng.encode(feats, np.asarray(lens, dtype=np.int64))
         _, _, _, frame_ids, frame_probs = eng.ctc_greedy(to_host=True, with_frames=True)
         out = []
         for b, c in enumerate(counts):
