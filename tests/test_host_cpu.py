@@ -416,3 +416,36 @@ def test_predictor_config_loading(tmp_path):
     assert set(SUPPORT_MODEL) == {"conformer", "squeezeformer", "efficient_conformer", "deepspeech2"}
     with pytest.raises(AssertionError, match="没有该模型"):
         PPASRPredictor({"use_model": "whisper"})
+
+
+def test_inference_predictor_config_roundtrip(monkeypatch):
+    """InferencePredictor builds the engine config from the yaml-style encoder_conf: a config's own to_dict() must survive the
+    trip unchanged for all four families (the engine itself is replaced: it needs the GPU)."""
+    from ppasr_b200 import weights as W
+    from ppasr_b200.infer_utils import inference_predictor as IP
+    made = []
+
+    class FakeEngine:
+        def __init__(self, cfg, w, device=0):
+            made.append((cfg, w))
+
+    monkeypatch.setattr(IP, "ConformerEngine", FakeEngine)
+    cases = [("conformer", W.ConformerConfig(num_blocks=2, vocab_size=50, cnn_module_norm="batch_norm", streaming=False),
+              W.init_conformer_weights),
+             ("squeezeformer", W.SqueezeformerConfig(num_blocks=3, vocab_size=50, reduce_idx=1, recover_idx=2),
+              W.init_squeezeformer_weights),
+             ("efficient_conformer", W.EfficientConformerConfig(num_blocks=2, vocab_size=50, stride_layer_idx=1,
+                                                                group_layer_idx=(0, 1)), W.init_efficient_conformer_weights),
+             ("deepspeech2", W.DeepSpeech2Config(num_rnn_layers=2, rnn_size=64, vocab_size=50, use_gru=True),
+              W.init_deepspeech2_weights)]
+    for use_model, cfg, init in cases:
+        w = init(cfg)
+        p = IP.InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, use_model,
+                                  streaming=cfg.streaming, weights=w)
+        got, gw = made[-1]
+        assert got.to_dict() == cfg.to_dict() and gw is w and p.model_config is got
+        assert type(got) is type(cfg)
+    with pytest.raises(Exception, match="use_gpu=False"):
+        IP.InferencePredictor({}, "conformer", use_gpu=False)
+    with pytest.raises(Exception, match="当前模型不支持该方法"):
+        IP.InferencePredictor({}, "whisper")
