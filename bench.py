@@ -378,6 +378,13 @@ def main():
                 "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic.get(top), "peak_source": pk["src"] + " (burst cuBLAS bf16)",
                 "us_per_launch": us, "share_of_step": prof[top][1] / total,
                 "step_tensor_frac_sustained": (gflop_per_utt * B / ms) / pk["bf16_tflops_sustained"]}
+        try:  # a row-tile kernel launch covers ceil(B*T'/128) CTAs: how much of the GPU one launch can use at all
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            ctas = (B * Tp + 127) // 128
+            if top in ("fused_ffn", "fused_attn_out") and 0 < ctas < sms:
+                roof.update({"ctas_per_launch": ctas, "sms": sms, "frac_per_occupied_sm": roof["frac"] * sms / ctas})
+        except Exception:
+            pass
 
     # ---- CPU baseline: oracle restatement on the host cores, bounded sample ----
     cpu = None
