@@ -106,12 +106,12 @@ class BeamSearchDecoder:
                 if lens[b, k] < 0:
                     continue
                 toks = [self.vocab_list[i] for i in ids[b, k, :lens[b, k]]]
-                approx = float(sc[b, k])
+                score = float(sc[b, k])
                 if self._ext_scorer is not None and approx:
                     # approx_ctc: take the word-insertion and LM terms out again (ctc_beam_search_decoder.cpp, end of decoding)
                     es = self._ext_scorer
-                    approx = approx - len(toks) * es.beta - es.get_sent_log_prob(toks) * es.alpha
-                res.append((-approx, "".join(toks)))
+                    score = score - len(toks) * es.beta - es.get_sent_log_prob(toks) * es.alpha
+                res.append((-score, "".join(toks)))
             out.append(res)
         return out
 
