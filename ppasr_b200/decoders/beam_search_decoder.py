@@ -81,6 +81,7 @@ class BeamSearchDecoder:
         if self._lm_dev is not None:
             keys, vals, in_lm, cap = self._lm_dev
             sc = self._ext_scorer
+            sc.reset_params(self.alpha, self.beta)  # beam_search_decoder.py:46-47,60-61: alpha / beta may be retuned between calls
             L.check(self.lib.ppasr_b200_beam_advance_lm(L.ptr(probs), B, T, V, L.ptr(fl), self.beam_size,
                                                         ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
                                                         L.ptr(state), max_frames, L.ptr(ws), L.ptr(keys), L.ptr(vals),
