@@ -42,6 +42,8 @@ class BeamSearchDecoder:
         self.max_frames = int(max_frames)
         self.lib = L.load()
         self._ext_scorer = ext_scorer
+        if ext_scorer is not None:  # a ready-made scorer carries its own weights (swig_wrapper.py:35-41 ext_scoring_func)
+            self.alpha, self.beta = ext_scorer.alpha, ext_scorer.beta
         if language_model_path is not None and ext_scorer is None:
             from .ngram_lm import Scorer
             with open(language_model_path, "rb") as f:
