@@ -82,6 +82,10 @@ class ConformerEngine:
         self._ctx = ctypes.c_void_p()
         L.check(self.lib.ppasr_b200_create(ctypes.byref(c), ctypes.byref(self._ctx)))
         for name, arr in weights.items():
+            # a trained checkpoint also holds the attention decoder of the *former models (`decoder.*`, 166 tensors that
+            # CTC inference never reads; in DeepSpeech2 `decoder` IS the CTC head) and may hold 0-d bookkeeping entries
+            if (c.model_type != 2 and name.startswith("decoder.")) or np.ndim(arr) == 0 or np.ndim(arr) > 4:
+                continue
             a = np.ascontiguousarray(arr, dtype=np.float32)
             shape = (ctypes.c_int64 * a.ndim)(*a.shape)
             L.check(self.lib.ppasr_b200_load_tensor(self._ctx, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
