@@ -20,13 +20,17 @@ import numpy as np
 from .. import _lib as L
 
 
+class UnsupportedDecoderConfig(Exception):
+    """The requested beam-search configuration is outside what the GPU decoder of this build implements."""
+
+
 class BeamSearchDecoder:
     def __init__(self, alpha=2.2, beta=4.3, beam_size=300, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=None,
                  num_processes=10, blank_id=0, language_model_path=None, max_frames=5000, ext_scorer=None):
         if beam_size > 128:
-            raise Exception(f"beam_size {beam_size} > 128 is not supported by the GPU decoder in this build")
+            raise UnsupportedDecoderConfig(f"beam_size {beam_size} > 128 is not supported by the GPU decoder in this build")
         if cutoff_top_n > 64:
-            raise Exception(f"cutoff_top_n {cutoff_top_n} > 64 is not supported by the GPU decoder in this build")
+            raise UnsupportedDecoderConfig(f"cutoff_top_n {cutoff_top_n} > 64 is not supported by the GPU decoder in this build")
         import torch
         if not torch.cuda.is_available():
             raise L.PPASRB200Error("ppasr_b200 decoders need a CUDA device (no CPU fallback)")
@@ -49,16 +53,16 @@ class BeamSearchDecoder:
             with open(language_model_path, "rb") as f:
                 head = f.read(64)
             if not head.lstrip().startswith(b"\\data\\"):
-                raise Exception("language model must be an ARPA text file (KenLM binary formats are not supported): "
+                raise UnsupportedDecoderConfig("language model must be an ARPA text file (KenLM binary formats are not supported): "
                                 + str(language_model_path))
             self._ext_scorer = Scorer(alpha, beta, language_model_path, vocab_list)
         self._lm_dev = None
         if self._ext_scorer is not None:
             sc = self._ext_scorer
             if not sc.is_character_based():
-                raise Exception("only character-based language models are supported by the GPU scorer")
+                raise UnsupportedDecoderConfig("only character-based language models are supported by the GPU scorer")
             if sc.get_max_order() > 4:
-                raise Exception("n-gram order > 4 is not supported by the GPU scorer")
+                raise UnsupportedDecoderConfig("n-gram order > 4 is not supported by the GPU scorer")
             keys, vals, in_lm = sc.lm.device_tables(vocab_list)
             self._lm_dev = (torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(vals).cuda(),
                             torch.from_numpy(in_lm).cuda(), int(keys.shape[0]))

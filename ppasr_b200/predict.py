@@ -129,7 +129,7 @@ class PPASRPredictor:
     MIN_SAMPLES = 400 + 6 * 160
 
     def __init__(self, configs=None, model_path='models/conformer_streaming_fbank/infer/', use_pun=False, use_gpu=True,
-                 vocab_list=None, weights=None, device=0, model_tag=None, pun_model_dir=None):
+                 vocab_list=None, weights=None, device=0, model_tag=None, pun_model_dir=None, decoder_fallback=True):
         """configs: path of a reference yaml config (predict.py:36-41), or the loaded dict / attribute object, with the
         reference's keys: use_model, streaming, decoder, encoder_conf, preprocess_conf, dataset_conf.dataset_vocab,
         ctc_beam_search_decoder_conf. `vocab_list` / `weights` let tests pass in-memory objects instead of files. `model_tag`
@@ -155,14 +155,31 @@ class PPASRPredictor:
         self.cached_feat = None
         self.greedy_last_max_prob_list = None
         self.greedy_last_max_index_list = None
-        if self.decoder == 'ctc_beam_search':
-            from .decoders.beam_search_decoder import BeamSearchDecoder
-            bconf = _get(configs, 'ctc_beam_search_decoder_conf', {}) or {}
-            bconf = dict(bconf) if isinstance(bconf, dict) else vars(bconf)
-            self.beam_search_decoder = BeamSearchDecoder(vocab_list=vocab_list, **bconf)
+        self._init_decoder(decoder_fallback)
         self.predictor = InferencePredictor(configs=configs, use_model=self.use_model, streaming=self.streaming,
                                             model_dir=model_path, use_gpu=use_gpu, weights=weights,
                                             vocab_size=len(vocab_list), device=device)
+
+    # predict.py:92-105
+    def _init_decoder(self, decoder_fallback=True):
+        """ctc_beam_search: build the GPU beam-search decoder from `ctc_beam_search_decoder_conf`. The reference switches to
+        ctc_greedy with a warning when its decoder cannot be initialised (missing paddlespeech_ctcdecoders, predict.py:98-105);
+        the same happens here when the configuration is outside what the GPU decoder implements (e.g. the shipped
+        beam_size 300 > 128, or a KenLM binary / word-based language model) unless decoder_fallback=False."""
+        if self.decoder != 'ctc_beam_search':
+            return
+        from .decoders.beam_search_decoder import BeamSearchDecoder, UnsupportedDecoderConfig
+        bconf = _get(self.configs, 'ctc_beam_search_decoder_conf', {}) or {}
+        bconf = dict(bconf) if isinstance(bconf, dict) else vars(bconf)
+        try:
+            self.beam_search_decoder = BeamSearchDecoder(vocab_list=self.vocab_list, **bconf)
+        except UnsupportedDecoderConfig as e:
+            if not decoder_fallback:
+                raise
+            import warnings
+            warnings.warn(f"ctc_beam_search is not available with this configuration ({e}); "
+                          "【注意】现在已自动切换为ctc_greedy解码器，ctc_greedy解码器准确率相对较低。")
+            self.decoder = 'ctc_greedy'
 
     @staticmethod
     def load_configs(configs, model_tag=None):

@@ -449,3 +449,24 @@ def test_inference_predictor_config_roundtrip(monkeypatch):
         IP.InferencePredictor({}, "conformer", use_gpu=False)
     with pytest.raises(Exception, match="当前模型不支持该方法"):
         IP.InferencePredictor({}, "whisper")
+
+
+def test_decoder_fallback_like_reference():
+    """predict.py:92-105: a beam-search decoder that cannot be initialised degrades to ctc_greedy with a warning. Here that covers
+    configurations outside the GPU decoder (the shipped beam_size 300, a KenLM binary LM); decoder_fallback=False raises."""
+    from ppasr_b200.decoders.beam_search_decoder import UnsupportedDecoderConfig
+    from ppasr_b200.predict import PPASRPredictor
+    p = object.__new__(PPASRPredictor)
+    p.configs = {"ctc_beam_search_decoder_conf": {"alpha": 2.2, "beta": 4.3, "beam_size": 300, "cutoff_prob": 0.99,
+                                                  "cutoff_top_n": 40, "num_processes": 10,
+                                                  "language_model_path": "lm/zh_giga.no_cna_cmn.prune01244.klm"}}
+    p.vocab_list = ["<blank>", "a"]
+    p.decoder = "ctc_beam_search"
+    with pytest.warns(UserWarning, match="ctc_greedy"):
+        p._init_decoder()
+    assert p.decoder == "ctc_greedy" and not hasattr(p, "beam_search_decoder")
+    p.decoder = "ctc_beam_search"
+    with pytest.raises(UnsupportedDecoderConfig, match="beam_size 300"):
+        p._init_decoder(decoder_fallback=False)
+    p.decoder = "ctc_greedy"
+    p._init_decoder()   # nothing to do
