@@ -18,10 +18,8 @@ import numpy as np
 
 from .decoders.ctc_greedy_decoder import greedy_decoder, greedy_decoder_chunk
 from .infer_utils.inference_predictor import InferencePredictor, _get
+from . import SUPPORT_MODEL
 from .weights import read_vocab_file
-
-
-SUPPORT_MODEL = ['squeezeformer', 'efficient_conformer', 'conformer', 'deepspeech2']  # ppasr/__init__.py:3
 
 
 class AudioFeaturizer:
