@@ -82,3 +82,20 @@ def test_ragged_length_trick_ends_the_mask_at_the_own_frame_count(frames):
 
 def test_hypothesis_is_bounded():
     assert FAST.max_examples <= 100
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 40000))
+def test_fbank_frame_count_of_the_library_matches_kaldi(n):
+    """ppasr_b200_fbank_frames (pure host arithmetic inside the C-ABI library) == the frame count of Kaldi's snip-edges
+    framing (25 ms window, 10 ms shift: 1 + (n - 400) // 160, nothing below one window) == what torchaudio's Kaldi fbank (the
+    CPU twin of the reference's paddleaudio call, audio_featurizer.py:120-138) actually returns."""
+    import torch
+    import torchaudio
+    from ppasr_b200 import _lib as L
+    got = int(L.load().ppasr_b200_fbank_frames(int(n)))
+    assert got == (1 + (n - 400) // 160 if n >= 400 else 0)
+    if n >= 400:
+        m = torchaudio.compliance.kaldi.fbank(torch.zeros(1, n) + 1.0, num_mel_bins=80, frame_length=25, frame_shift=10,
+                                              dither=0.0, sample_frequency=16000.0)
+        assert m.shape == (got, 80)
