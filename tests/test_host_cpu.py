@@ -470,3 +470,58 @@ def test_decoder_fallback_like_reference():
         p._init_decoder(decoder_fallback=False)
     p.decoder = "ctc_greedy"
     p._init_decoder()   # nothing to do
+
+
+def _abi_config(**kw):
+    from ppasr_b200.engine import Config
+    c = Config()
+    base = dict(model_type=0, feat_dim=80, d_model=256, n_heads=4, ffn_dim=2048, n_layers=2, conv_kernel=15, causal=1,
+                conv_norm=0, vocab_size=50, max_len=5000, reduce_idx=-1, recover_idx=-1, time_reduce_kernel=0, use_gru=0,
+                stride_layer_idx=-1, group_layer_mask=0, group_size=0, stride_kernel=0)
+    base.update(kw)
+    for k, v in base.items():
+        setattr(c, k, v)
+    return c
+
+
+def test_c_abi_create_validates_configs_without_a_gpu():
+    """ppasr_b200_create / out_frames / load_tensor / destroy are host-only: configuration errors come back as a status code
+    plus ppasr_b200_last_error() (never a crash), valid configurations give a context whose out_frames follows the model's
+    subsampling rule, and finalize (which needs the device) fails cleanly on a machine without one."""
+    import ctypes
+    from ppasr_b200 import _lib as L
+    lib = L.load()
+
+    def create(cfg):
+        ctx = ctypes.c_void_p()
+        return lib.ppasr_b200_create(ctypes.byref(cfg), ctypes.byref(ctx)), ctx
+
+    for bad, msg in [(dict(d_model=512, n_heads=8), "d_model must be 256"), (dict(n_heads=8), "head dim"),
+                     (dict(ffn_dim=1000), "ffn_dim"), (dict(conv_kernel=9), "conv_kernel"), (dict(model_type=7), "model_type"),
+                     (dict(model_type=1, reduce_idx=3, recover_idx=1, time_reduce_kernel=1), "reduce_idx"),
+                     (dict(model_type=2, d_model=2048), "rnn_size"),
+                     (dict(model_type=3, group_size=2), "group_size"),
+                     (dict(model_type=3, group_size=3, n_layers=4, stride_layer_idx=1, group_layer_mask=0b1100), "up to the stride"),
+                     (dict(vocab_size=1), "bad config")]:
+        rc, ctx = create(_abi_config(**bad))
+        assert rc != 0 and not ctx.value, bad
+        assert msg in lib.ppasr_b200_last_error().decode(), (bad, lib.ppasr_b200_last_error())
+    # valid contexts: the output-frame rule (two k3/s2 convs; the Efficient Conformer's stride block halves again, ceil)
+    rc, ctx = create(_abi_config())
+    assert rc == 0 and ctx.value
+    for T in (0, 6, 7, 10, 11, 67, 498, 998, 2998):
+        want = ((T - 1) // 2 - 1) // 2 if T >= 7 else 0
+        assert lib.ppasr_b200_out_frames(ctx, T) == want
+    x = np.zeros((4, 4, 4, 4, 4), np.float32)
+    shape = (ctypes.c_int64 * 5)(4, 4, 4, 4, 4)
+    assert lib.ppasr_b200_load_tensor(ctx, b"x", x.ctypes.data_as(ctypes.c_void_p), 5, shape) != 0   # ndim > 4 rejected
+    if not __import__("torch").cuda.is_available():
+        assert lib.ppasr_b200_finalize(ctx) != 0 and lib.ppasr_b200_last_error()                      # needs the device
+    assert lib.ppasr_b200_destroy(ctx) == 0 and lib.ppasr_b200_destroy(None) == 0
+    rc, ctx = create(_abi_config(model_type=3, group_size=3, n_layers=4, stride_layer_idx=1, group_layer_mask=0b0011, stride_kernel=1))
+    assert rc == 0
+    assert [lib.ppasr_b200_out_frames(ctx, T) for T in (7, 67, 131, 135, 498)] == [1, 8, 16, 17, 62]
+    lib.ppasr_b200_destroy(ctx)
+    rc, ctx = create(_abi_config(model_type=2, d_model=1024, n_layers=5, causal=0))
+    assert rc == 0 and lib.ppasr_b200_out_frames(ctx, 498) == 123
+    lib.ppasr_b200_destroy(ctx)
