@@ -525,3 +525,33 @@ def test_c_abi_create_validates_configs_without_a_gpu():
     rc, ctx = create(_abi_config(model_type=2, d_model=1024, n_layers=5, causal=0))
     assert rc == 0 and lib.ppasr_b200_out_frames(ctx, 498) == 123
     lib.ppasr_b200_destroy(ctx)
+
+
+def test_c_abi_state_errors_and_host_helpers_without_a_gpu():
+    """Calls in the wrong state fail with a status + message before touching the device; the sizing / naming helpers are
+    pure host code."""
+    import ctypes
+    from ppasr_b200 import _lib as L
+    lib = L.load()
+    ctx = ctypes.c_void_p()
+    assert lib.ppasr_b200_create(ctypes.byref(_abi_config()), ctypes.byref(ctx)) == 0
+    feats = np.zeros((1, 67, 80), np.float32)
+    p = feats.ctypes.data_as(ctypes.c_void_p)
+    assert lib.ppasr_b200_encode(ctx, p, 0, None, 1, 67, None) != 0
+    assert "finalize" in lib.ppasr_b200_last_error().decode()
+    assert lib.ppasr_b200_encode(ctx, None, 0, None, 1, 67, None) != 0 and lib.ppasr_b200_encode(ctx, p, 0, None, 0, 67, None) != 0
+    out = np.zeros((1, 16, 50), np.float32)
+    assert lib.ppasr_b200_ctc_logits(ctx, out.ctypes.data_as(ctypes.c_void_p), 0, None) != 0
+    assert "encode first" in lib.ppasr_b200_last_error().decode()
+    assert lib.ppasr_b200_set_option(ctx, b"fused_ffn", 0) == 0 and lib.ppasr_b200_set_option(ctx, b"fused_ffn", 1) == 0
+    assert lib.ppasr_b200_set_option(ctx, b"no_such_option", 1) != 0
+    assert lib.ppasr_b200_set_option(None, b"fused_ffn", 1) != 0
+    lib.ppasr_b200_destroy(ctx)
+    # sizes grow with the problem and are positive
+    s1, s2, s3 = (lib.ppasr_b200_beam_state_bytes(1, 100, 10), lib.ppasr_b200_beam_state_bytes(2, 100, 10),
+                  lib.ppasr_b200_beam_state_bytes(2, 200, 20))
+    assert 0 < s1 < s2 < s3
+    assert 0 < lib.ppasr_b200_beam_workspace_bytes(1, 50) < lib.ppasr_b200_beam_workspace_bytes(4, 500)
+    names = [lib.ppasr_b200_profile_class_name(i).decode() for i in range(lib.ppasr_b200_profile_num_classes())]
+    assert len(names) == len(set(names)) >= 8 and {"fused_ffn", "attention", "qkv_gemm"} <= set(names)
+    assert lib.ppasr_b200_abi_version() == 2
