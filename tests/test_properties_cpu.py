@@ -12,7 +12,7 @@ from oracle.conformer_oracle import stream_windows
 from ppasr_b200.decoders.ctc_greedy_decoder import collapse_frames
 from ppasr_b200.parallel import shard_range
 
-FAST = settings(max_examples=60, deadline=None)
+FAST = settings(max_examples=60, deadline=None, derandomize=True)  # same examples on every run
 
 
 @FAST
@@ -84,7 +84,7 @@ def test_hypothesis_is_bounded():
     assert FAST.max_examples <= 100
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(st.integers(0, 40000))
 def test_fbank_frame_count_of_the_library_matches_kaldi(n):
     """ppasr_b200_fbank_frames (pure host arithmetic inside the C-ABI library) == the frame count of Kaldi's snip-edges
