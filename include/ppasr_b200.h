@@ -61,6 +61,14 @@ int64_t ppasr_b200_launch_count(void);
  * throughput pipeline switches it off. */
 int ppasr_b200_set_pdl(int32_t enable);
 
+/* Process-wide: fused feed-forward kernel variant (env PPASR_B200_FFN_SPLIT). 1 (default) = each 128-row tile is
+ * computed by a 2-CTA thread-block cluster, the 2048-wide hidden dimension split over the pair and the two partial
+ * outputs reduced through distributed shared memory (2 x ceil(M/128) CTAs per launch: lowest latency of one launch);
+ * 2 = the same two-team Swish pipeline on one CTA per tile (least SM time: used when several batches are in flight);
+ * 0 = the round-1 kernel. Replaces nothing in the reference (a tuning switch of positionwise.py:30-39's kernel);
+ * results agree to fp32 summation order. */
+int ppasr_b200_set_ffn_split(int32_t mode);
+
 /* ---- life cycle ------------------------------------------------------------------------------
  * replaces: InferencePredictor.__init__ loading model.pdmodel/.pdiparams
  *           (infer_utils/inference_predictor.py:12-45). */
@@ -155,9 +163,12 @@ int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V
  *           (decoders/swig_wrapper.py:35-121 -> paddlespeech_ctcdecoders, ext_scoring_func=None).
  * `states` (ppasr_b200_beam_state_bytes) holds the beam and the prefix table of B utterances across calls,
  * so advance() can be fed chunk by chunk (decode_chunk) or once (offline). probs: fp32 [B,T,V] dense
- * probabilities (not logs), like the reference. beam <= 128, cutoff_top_n is capped at 64.
+ * probabilities (not logs), like the reference. beam <= 512 (configs/conformer.yml:84 ships 300), cutoff_top_n is capped
+ * at 64 (ships 40), V < 65535. advance() refuses to run past the `max_frames` the state was sized for: the state is left
+ * untouched, flagged, and result() then reports out_lens = -2 for every entry.
  * result(): out_ids int32 [B, beam, lmax], out_lens int32 [B, beam] (-1 = no such entry), out_scores fp32
- * [B, beam] = log P(prefix) sorted best first (the reference returns -score to Python). */
+ * [B, beam] = log P(prefix) sorted best first (the reference returns -score to Python); result_nbest() writes only the
+ * first nbest <= beam entries ([B, nbest, lmax], [B, nbest]). */
 int64_t ppasr_b200_beam_state_bytes(int32_t B, int32_t max_frames, int32_t beam);
 int64_t ppasr_b200_beam_workspace_bytes(int32_t B, int32_t T);
 int ppasr_b200_beam_reset(void* states, int32_t B, int32_t max_frames, int32_t beam, void* stream);
@@ -175,6 +186,8 @@ int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t
                                int64_t lm_capacity, int32_t lm_order, float alpha, float beta, void* stream);
 int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
                            int32_t lmax, int32_t* out_lens, float* out_scores, void* stream);
+int ppasr_b200_beam_result_nbest(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t nbest,
+                                 int32_t* out_ids, int32_t lmax, int32_t* out_lens, float* out_scores, void* stream);
 /* The pruning scan of the posterior alone (decoder_utils.cpp get_pruned_log_probs), for the HBM roofline. */
 int ppasr_b200_op_ctc_prune(const float* probs, int32_t rows, int32_t V, float cutoff_prob, int32_t cutoff_top_n,
                             void* workspace, void* stream);

@@ -52,6 +52,7 @@ I = c_int32
 PROTOTYPES = {
     "ppasr_b200_launch_count": (c_int64, []),
     "ppasr_b200_set_pdl": (c_int, [I]),
+    "ppasr_b200_set_ffn_split": (c_int, [I]),
     "ppasr_b200_create": (c_int, [P, ctypes.POINTER(P)]),
     "ppasr_b200_destroy": (c_int, [P]),
     "ppasr_b200_load_tensor": (c_int, [P, c_char_p, P, I, P]),
@@ -77,6 +78,7 @@ PROTOTYPES = {
     "ppasr_b200_beam_advance": (c_int, [P, I, I, I, P, I, c_float, I, I, P, I, P, P]),
     "ppasr_b200_beam_advance_lm": (c_int, [P, I, I, I, P, I, c_float, I, I, P, I, P, P, P, P, c_int64, I, c_float, c_float, P]),
     "ppasr_b200_beam_result": (c_int, [P, I, I, I, P, I, P, P, P]),
+    "ppasr_b200_beam_result_nbest": (c_int, [P, I, I, I, I, P, I, P, P, P]),
     "ppasr_b200_op_ctc_prune": (c_int, [P, I, I, c_float, I, P, P]),
     "ppasr_b200_greedy_decode": (c_int, [P, I, I, I, P, I, P, I, P, P, P, P, P]),
     "ppasr_b200_op_linear": (c_int, [P, c_int64, P, c_int64, P, P, c_int64, I, I, I, I, I, c_float, I, P, I, I, P]),

@@ -1,37 +1,42 @@
-// CTC prefix beam search on the GPU (no external scorer).
+// CTC prefix beam search on the GPU (optionally with a character n-gram scorer).
 //
 // Replaces the C++ library behind ppasr/decoders/swig_wrapper.py:35-121 / beam_search_decoder.py:45-96
 // (`paddlespeech_ctcdecoders`: ctc_beam_search_decoder.cpp, decoder_utils.cpp, path_trie.cpp -- not vendored
 // in the reference, restated in oracle/decoders_oracle.py).
 //
 // Two kernels:
-//  (1) ctc_prune_kernel -- the HBM-bound scan of the posterior [B,T,V]: one warp per frame stages the
-//      row in shared memory with 16-byte loads and extracts, in descending probability order (ties: lower
-//      index first), the smallest head whose cumulative probability reaches cutoff_prob, capped at
-//      cutoff_top_n (decoder_utils.cpp get_pruned_log_probs). Output per frame: n, ids[n], log(p + FLT_MIN)[n].
-//      Every frame is independent, so the scan runs at full grid width; the sequential part never touches
-//      the [B,T,V] tensor.
-//  (2) ctc_prefix_beam_kernel -- one CTA per utterance walks the frames over the compact candidate lists.
-//      The prefix trie of the reference is replaced by an equivalent flat form: a beam entry carries a 64-bit
-//      hash of its id string (its identity) and an id into a (parent id, char) table used only to read the
-//      string back; an extension (prefix i, char c) merges into beam entry j iff hash[j] == H(hash[i], c),
-//      otherwise it is a fresh prefix (a revived trie node is reset to -inf in path_trie.cpp, i.e.
-//      indistinguishable from a fresh one).
-//      Top-`beam` selection per frame = `beam` rounds of a block-wide arg-max (score desc, then char asc
-//      like prefix_compare). State (beam + id table) lives in global memory so the same kernel serves the
-//      streaming decode_chunk API.
+//  (1) ctc_prune_kernel -- the HBM-bound scan of the posterior [B,T,V]: one warp per frame. Pass 1 streams the row
+//      with 16-byte loads keeping each lane's two largest values; the 64 kept values are sorted in registers (warp
+//      bitonic network) and a double-precision prefix sum over them gives a threshold tau that is a lower bound of
+//      everything that can be selected (decoder_utils.cpp get_pruned_log_probs: descending probability, ties lower
+//      index first, smallest head whose cumulative probability reaches cutoff_prob, capped at cutoff_top_n). Pass 2
+//      re-reads the row (L2 hits) and compacts the elements >= tau; the <= 64 survivors are sorted once by
+//      (probability desc, index asc) in registers and cut with the same prefix sum. Output per frame: n, ids[n],
+//      log(p + FLT_MIN)[n]. Every frame is independent, so the scan runs at full grid width; the sequential part
+//      never touches the [B,T,V] tensor.
+//  (2) ctc_prefix_beam_kernel<NT> -- one CTA of NT threads per utterance (a single warp for beams <= 32 without a
+//      scorer) walks the frames over the compact candidate lists. The prefix trie of the reference is replaced by an
+//      equivalent flat form: a beam entry carries a 64-bit hash of its id string (its identity) and an id into a
+//      (parent id, char) table used only to read the string back; an extension (prefix i, char c) merges into beam
+//      entry j iff hash[j] == H(hash[i], c) (looked up in a shared-memory hash table of the beam), otherwise it is a
+//      fresh prefix (a revived trie node is reset to -inf in path_trie.cpp, i.e. indistinguishable from a fresh one).
+//      Top-`beam` selection per frame: every live candidate becomes one 64-bit key (score desc | last char asc | slot
+//      asc, all distinct), the keys are sorted once (register bitonic network for <= 32 keys, shared-memory bitonic
+//      sort otherwise) and the first `beam` are kept -- prefix_compare's order, beam sorted best first as in the
+//      reference. State (beam + id table) lives in global memory so the same kernel serves the streaming decode_chunk API.
 #include <float.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <mutex>
+
 namespace ppasr {
 
 void count_launch();
 
-constexpr int BEAM_MAXB = 128;   // max beam size
-constexpr int BEAM_MAXC = 64;    // max cutoff_top_n
-constexpr int BEAM_THREADS = 256;
+constexpr int BEAM_MAXB = BEAM_MAX_BEAM;   // max beam size (512)
+constexpr int BEAM_MAXC = BEAM_MAX_TOPN;   // max cutoff_top_n (64)
 
 // ------------------------------------------------------------------------------------------------
 // (1) pruning scan
@@ -42,11 +47,82 @@ DEVINL bool prune_before(float pa, int ia, float pb, int ib) { return pa > pb ||
 constexpr int PRUNE_CAND_MAX = 256;  // compacted candidates per row; more (mass ties) falls back to full-row rounds
 constexpr int PRUNE_WARPS = 4;
 
-// One warp per frame, no row staging (occupancy, i.e. bytes in flight, is what saturates HBM):
-//   pass 1 streams the row from HBM with 16-byte loads (8 in flight per lane) keeping each lane's two largest values;
-//          the limit-th largest of those 64 values is a lower bound tau of the limit-th largest of the row;
-//   pass 2 re-reads the row (L2 hits: 17 KB touched microseconds earlier) and compacts every element >= tau;
-//   then at most `limit` arg-max rounds over the (typically ~64) candidates, with the cumulative cut-off.
+// probability (>= 0, or -inf = empty) and index -> one key whose ASCENDING order is (probability desc, index asc)
+DEVINL unsigned long long prune_key(float p, int idx) {
+  const unsigned u = (p == -INFINITY) ? 0u : (__float_as_uint(p) | 0x80000000u);  // monotone for p >= 0; empty sorts last
+  return ((unsigned long long)(~u) << 32) | (unsigned)idx;
+}
+DEVINL float prune_key_prob(unsigned long long k) {
+  const unsigned u = ~(unsigned)(k >> 32);
+  return u == 0u ? -INFINITY : __uint_as_float(u & 0x7fffffffu);
+}
+
+// 64 values, element e = r * 32 + lane in register a_r: bitonic network, result DESCENDING in e
+DEVINL void warp_sort64_desc(float& a0, float& a1, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j == 32) {
+        const float hi = fmaxf(a0, a1), lo = fminf(a0, a1);
+        a0 = hi, a1 = lo;
+      } else {
+        const float p0 = __shfl_xor_sync(0xffffffffu, a0, j);
+        const float p1 = __shfl_xor_sync(0xffffffffu, a1, j);
+        const bool lower = (lane & j) == 0;
+        const bool desc0 = (lane & k) == 0;          // e = lane      : (e & k) == 0 (k <= 32), always for k = 64
+        const bool desc1 = ((32 + lane) & k) == 0;   // e = 32 + lane
+        a0 = (desc0 == lower) ? fmaxf(a0, p0) : fminf(a0, p0);
+        a1 = (desc1 == lower) ? fmaxf(a1, p1) : fminf(a1, p1);
+      }
+    }
+  }
+}
+// same network on 64-bit keys, result ASCENDING in e
+DEVINL void warp_sort64_keys(unsigned long long& a0, unsigned long long& a1, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j == 32) {
+        const unsigned long long lo = a0 < a1 ? a0 : a1, hi = a0 < a1 ? a1 : a0;
+        a0 = lo, a1 = hi;
+      } else {
+        const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, a0, j);
+        const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, a1, j);
+        const bool lower = (lane & j) == 0;
+        const bool asc0 = (lane & k) == 0;
+        const bool asc1 = ((32 + lane) & k) == 0;
+        a0 = (asc0 == lower) ? (a0 < p0 ? a0 : p0) : (a0 < p0 ? p0 : a0);
+        a1 = (asc1 == lower) ? (a1 < p1 ? a1 : p1) : (a1 < p1 ? p1 : a1);
+      }
+    }
+  }
+}
+// 32 keys, one per lane, ascending in lane
+DEVINL void warp_sort32_keys(unsigned long long& a, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long p = __shfl_xor_sync(0xffffffffu, a, j);
+      const bool lower = (lane & j) == 0;
+      const bool asc = (lane & k) == 0 || k == 32;
+      a = (asc == lower) ? (a < p ? a : p) : (a < p ? p : a);
+    }
+  }
+}
+// inclusive prefix sum in double over element order e = r * 32 + lane (values in x0, x1)
+DEVINL void warp_scan64(double& x0, double& x1, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y0 = __shfl_up_sync(0xffffffffu, x0, o);
+    const double y1 = __shfl_up_sync(0xffffffffu, x1, o);
+    if (lane >= o) x0 += y0, x1 += y1;
+  }
+  x1 += __shfl_sync(0xffffffffu, x0, 31);
+}
+
 __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float* __restrict__ probs, int V, int rows,
                                                                       float cutoff_prob, int top_n, int* __restrict__ cnt,
                                                                       int* __restrict__ cid, float* __restrict__ clp) {
@@ -83,28 +159,28 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
     upd4(a0), upd4(a1), upd4(a2), upd4(a3), upd4(a4), upd4(a5), upd4(a6), upd4(a7);
   }
   for (; i < n4; i += 32) upd4(__ldg(v4 + i));
-  // ---- threshold: walk the 64 per-lane maxima in descending order. They are row elements, so the k-th of them is a lower
-  //      bound of the k-th largest of the row and their running sum a lower bound of the true cumulative mass: as soon as it
-  //      reaches cutoff_prob (or k = limit) everything that can be selected is >= tau = the value just taken.
+  // ---- threshold: the 64 per-lane maxima in descending order. They are row elements, so the k-th of them is a lower
+  //      bound of the k-th largest of the row and their running sum a lower bound of the true cumulative mass: at the
+  //      first k where it reaches cutoff_prob (or k = limit) everything that can be selected is >= tau = that value.
   float tau = -INFINITY;
-  {
-    float a1 = t1, a2 = t2;
-    float cumx = 0.f;
-    for (int k = 0; k < limit; ++k) {
-      const float m = warp_max(fmaxf(a1, a2));
-      tau = m;
-      if (m == -INFINITY) break;
-      cumx += m;
-      if (cutoff_prob < 1.0f && cumx >= cutoff_prob * 1.0001f) break;  // margin: fp32 sum vs the Kahan sum used below
-      const unsigned has = __ballot_sync(0xffffffffu, a1 == m || a2 == m);
-      if (lane == __ffs(has) - 1) {
-        if (a1 == m)
-          a1 = -INFINITY;
-        else
-          a2 = -INFINITY;
-      }
+  if (prune) {
+    float a0 = t1, a1 = t2;
+    warp_sort64_desc(a0, a1, lane);
+    double c0 = a0 > -INFINITY ? (double)a0 : 0.0, c1 = a1 > -INFINITY ? (double)a1 : 0.0;
+    warp_scan64(c0, c1, lane);
+    const double thr = (double)cutoff_prob * 1.0001;  // margin: lower-bound sum vs the exact sum used below
+    const bool stop0 = (cutoff_prob < 1.0f && c0 >= thr) || (lane + 1 >= limit) || a0 == -INFINITY;
+    const bool stop1 = (cutoff_prob < 1.0f && c1 >= thr) || (lane + 33 >= limit) || a1 == -INFINITY;
+    const unsigned b0 = __ballot_sync(0xffffffffu, stop0);
+    const unsigned b1 = __ballot_sync(0xffffffffu, stop1);
+    if (b0) {
+      tau = __shfl_sync(0xffffffffu, a0, __ffs(b0) - 1);
+    } else if (b1) {
+      tau = __shfl_sync(0xffffffffu, a1, __ffs(b1) - 1);
+    } else {
+      tau = __shfl_sync(0xffffffffu, a1, 31);
     }
-    if (!prune) tau = -INFINITY;
+    // an exhausted list (-inf reached before the stop) means every finite element is a candidate
   }
   // ---- pass 2: compact elements >= tau (warp-uniform control flow; lane 0 writes) ----
   int c = 0;
@@ -156,9 +232,41 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
     }
   }
   __syncwarp();
+  if (c <= 64) {
+    // ---- the common case: sort the survivors once, cut with an exact (double) running sum ----
+    unsigned long long k0 = lane < c ? prune_key(cp[lane], ci[lane]) : ~0ull;
+    unsigned long long k1 = 32 + lane < c ? prune_key(cp[32 + lane], ci[32 + lane]) : ~0ull;
+    if (c <= 32) {
+      warp_sort32_keys(k0, lane);
+    } else {
+      warp_sort64_keys(k0, k1, lane);
+    }
+    const float p0 = k0 != ~0ull ? prune_key_prob(k0) : -INFINITY;
+    const float p1 = k1 != ~0ull ? prune_key_prob(k1) : -INFINITY;
+    double c0 = p0 > -INFINITY ? (double)p0 : 0.0, c1 = p1 > -INFINITY ? (double)p1 : 0.0;
+    warp_scan64(c0, c1, lane);
+    int n = min(c, limit);
+    if (cutoff_prob < 1.0f) {
+      const unsigned b0 = __ballot_sync(0xffffffffu, lane < c && c0 >= (double)cutoff_prob);
+      const unsigned b1 = __ballot_sync(0xffffffffu, 32 + lane < c && c1 >= (double)cutoff_prob);
+      if (b0) n = min(n, __ffs(b0));
+      else if (b1) n = min(n, 32 + __ffs(b1));
+    }
+    if (lane < n) {
+      oid[lane] = (int)(unsigned)k0;
+      olp[lane] = logf(p0 + FLT_MIN);
+    }
+    if (32 + lane < n) {
+      oid[32 + lane] = (int)(unsigned)k1;
+      olp[32 + lane] = logf(p1 + FLT_MIN);
+    }
+    if (lane == 0) cnt[row] = n;
+    return;
+  }
+  // ---- many ties at tau (e.g. uniform rows): arg-max rounds with a Kahan-compensated running sum ----
   float last_p = INFINITY;
   int last_i = -1;
-  float cum = 0.f, cum_c = 0.f;  // Kahan-compensated fp32 running sum (stands in for the reference's double)
+  float cum = 0.f, cum_c = 0.f;
   int n = 0;
   const bool compact = c <= PRUNE_CAND_MAX;
   while (n < limit) {
@@ -173,7 +281,7 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
           bi = iv;
         }
       }
-    } else {  // mass ties (e.g. uniform rows): rounds over the whole row
+    } else {
       for (int j = lane; j < V; j += 32) {
         const float pv = __ldg(src + j);
         if (prune_before(last_p, last_i, pv, j) && prune_before(pv, j, bm, bi)) {
@@ -265,58 +373,134 @@ DEVINL float lm_log_cond_prob(const BeamLm& lm, const BeamEntry& e, int c) {
   return -1000.0f;
 }
 
-__global__ void __launch_bounds__(BEAM_THREADS)
+// candidate -> 64-bit key whose ASCENDING order is prefix_compare's: score desc, then last char asc, then slot asc
+DEVINL unsigned long long beam_key(float score, int last, int slot) {
+  const unsigned u = __float_as_uint(score);
+  const unsigned up = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone increasing in score (-inf lowest)
+  return ((unsigned long long)(~up) << 32) | ((unsigned long long)(unsigned)(last + 1) << 16) | (unsigned)slot;
+}
+DEVINL float beam_key_score(unsigned long long k) {
+  const unsigned up = ~(unsigned)(k >> 32);
+  return __uint_as_float((up & 0x80000000u) ? (up & 0x7fffffffu) : ~up);
+}
+
+struct BeamSmemLayout {  // byte offsets into dynamic shared memory
+  int ebuf, stay_b, stay_nb, merge_nb, htab, fid, flp, keys, total;
+  int bcap, hcap, kcap;
+};
+__host__ __device__ inline int beam_pow2_ge(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+__host__ __device__ inline BeamSmemLayout beam_smem_layout(int beam, int topn) {
+  BeamSmemLayout L;
+  L.bcap = (beam + 3) & ~3;
+  L.hcap = beam_pow2_ge(4 * beam < 64 ? 64 : 4 * beam);
+  L.kcap = beam_pow2_ge(beam * topn + beam < 32 ? 32 : beam * topn + beam);
+  int o = 0;
+  L.keys = o, o += L.kcap * 8;
+  L.ebuf = o, o += 2 * L.bcap * (int)sizeof(BeamEntry);
+  L.stay_b = o, o += L.bcap * 4;
+  L.stay_nb = o, o += L.bcap * 4;
+  L.merge_nb = o, o += L.bcap * 4;
+  L.htab = o, o += L.hcap * 4;
+  L.fid = o, o += BEAM_MAXC * 4;
+  L.flp = o, o += BEAM_MAXC * 4;
+  L.total = o;
+  return L;
+}
+
+template <int NT>
+DEVINL void beam_sync() {
+  if (NT == 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
 ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid, const float* __restrict__ clp, int T,
-                       const int* __restrict__ frame_lens, int beam, int blank, BeamStateHeader* __restrict__ states,
-                       size_t state_stride_bytes, int node_cap, const float* __restrict__ probs, int V, const BeamLm lm) {
+                       const int* __restrict__ frame_lens, int beam, int topn, int blank, int max_frames,
+                       BeamStateHeader* __restrict__ states, size_t state_stride_bytes, int node_cap,
+                       const float* __restrict__ probs, int V, const BeamLm lm) {
   const int b = blockIdx.x;
   uint8_t* sp = reinterpret_cast<uint8_t*>(states) + (size_t)b * state_stride_bytes;
   BeamStateHeader* hdr = reinterpret_cast<BeamStateHeader*>(sp);
   BeamEntry* gbeam = reinterpret_cast<BeamEntry*>(sp + sizeof(BeamStateHeader));
   int2* nodes = reinterpret_cast<int2*>(sp + sizeof(BeamStateHeader) + sizeof(BeamEntry) * BEAM_MAXB);
 
-  __shared__ BeamEntry ebuf[2][BEAM_MAXB];
-  __shared__ float stay_b[BEAM_MAXB], stay_nb[BEAM_MAXB], merge_nb[BEAM_MAXB];
-  extern __shared__ uint8_t dyn_smem[];
-  float* cscore = reinterpret_cast<float*>(dyn_smem);                                   // [beam*MAXC + beam]
-  int* ckey = reinterpret_cast<int*>(dyn_smem) + (beam * BEAM_MAXC + beam);             // tie-break key (char); INT_MAX = consumed
-  __shared__ int sel[BEAM_MAXB];
-  __shared__ int fid[BEAM_MAXC];
-  __shared__ float flp[BEAM_MAXC];
-  __shared__ float red_s[BEAM_THREADS / 32];
-  __shared__ int red_k[BEAM_THREADS / 32], red_i[BEAM_THREADS / 32];
-  __shared__ int s_nb, s_next_id;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const BeamSmemLayout L = beam_smem_layout(beam, topn);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dyn_smem + L.keys);
+  BeamEntry* ebuf = reinterpret_cast<BeamEntry*>(dyn_smem + L.ebuf);
+  float* stay_b = reinterpret_cast<float*>(dyn_smem + L.stay_b);
+  float* stay_nb = reinterpret_cast<float*>(dyn_smem + L.stay_nb);
+  float* merge_nb = reinterpret_cast<float*>(dyn_smem + L.merge_nb);
+  int* htab = reinterpret_cast<int*>(dyn_smem + L.htab);
+  int* fid = reinterpret_cast<int*>(dyn_smem + L.fid);
+  float* flp = reinterpret_cast<float*>(dyn_smem + L.flp);
+  __shared__ int s_nb, s_next_id, s_ncand, s_full_beam;
   __shared__ float s_min_cutoff;
-  __shared__ int s_full_beam;
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int nframes = frame_lens ? min(T, frame_lens[b]) : T;
+  // a stream fed past the capacity the state was sized for: refuse (the id table would overflow) and flag it
+  if (hdr->frames + nframes > max_frames) {
+    if (tid == 0) hdr->pad = 1;
+    return;
+  }
   if (tid == 0) {
     s_nb = hdr->nb;
     s_next_id = hdr->next_id;
   }
-  __syncthreads();
+  beam_sync<NT>();
   int cur = 0;
-  for (int i = tid; i < s_nb; i += BEAM_THREADS) ebuf[0][i] = gbeam[i];
-  __syncthreads();
+  for (int i = tid; i < s_nb; i += NT) ebuf[i] = gbeam[i];
 
-  const int nframes = frame_lens ? min(T, frame_lens[b]) : T;
+  // candidate list of the next frame, prefetched into registers while the current frame is processed
+  constexpr int PF = (BEAM_MAXC + NT - 1) / NT;
+  int pf_id[PF];
+  float pf_lp[PF];
+  int pf_nc = 0;
+  auto prefetch = [&](int t) {
+    if (t < nframes) {
+      const size_t row = (size_t)b * T + t;
+      pf_nc = __ldg(cnt + row);
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int i = tid + u * NT;
+        if (i < BEAM_MAXC) {
+          pf_id[u] = __ldg(cid + row * BEAM_MAXC + i);
+          pf_lp[u] = __ldg(clp + row * BEAM_MAXC + i);
+        }
+      }
+    }
+  };
+  prefetch(0);
+  beam_sync<NT>();
+
   for (int t = 0; t < nframes; ++t) {
     const size_t row = (size_t)b * T + t;
-    const int nc = cnt[row];
+    const int nc = pf_nc;
     const int nb = s_nb;
-    BeamEntry* E = ebuf[cur];
-    BeamEntry* N = ebuf[cur ^ 1];
-    for (int i = tid; i < nc; i += BEAM_THREADS) {
-      fid[i] = cid[row * BEAM_MAXC + i];
-      flp[i] = clp[row * BEAM_MAXC + i];
+    BeamEntry* E = ebuf + cur * L.bcap;
+    BeamEntry* N = ebuf + (cur ^ 1) * L.bcap;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int i = tid + u * NT;
+      if (i < nc) {
+        fid[i] = pf_id[u];
+        flp[i] = pf_lp[u];
+      }
     }
-    for (int i = tid; i < nb; i += BEAM_THREADS) stay_b[i] = stay_nb[i] = merge_nb[i] = -INFINITY;
-    const int npair = nb * nc;
-    for (int i = tid; i < npair + nb; i += BEAM_THREADS) {
-      cscore[i] = -INFINITY;
-      ckey[i] = 0;
-    }
+    prefetch(t + 1);
+    for (int i = tid; i < nb; i += NT) stay_b[i] = stay_nb[i] = merge_nb[i] = -INFINITY;
+    for (int i = tid; i < L.hcap; i += NT) htab[i] = 0;
     if (tid == 0) {
+      s_ncand = 0;
       // with a scorer: min_cutoff = worst beam score + ln p(blank) - max(0, beta); applies when the beam is full
       // (ctc_beam_search_decoder.cpp; the beam is kept sorted best-first, so E[nb-1] is the worst entry)
       s_full_beam = 0;
@@ -327,9 +511,16 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
         s_full_beam = nb == beam;
       }
     }
-    __syncthreads();
+    beam_sync<NT>();
+    // identity table of the beam: hash -> entry index + 1 (open addressing)
+    for (int k = tid; k < nb; k += NT) {
+      unsigned slot = (unsigned)(E[k].hash >> 24) & (unsigned)(L.hcap - 1);
+      while (atomicCAS(&htab[slot], 0, k + 1) != 0) slot = (slot + 1) & (unsigned)(L.hcap - 1);
+    }
+    beam_sync<NT>();
     // every (prefix i, char c) pair
-    for (int pidx = tid; pidx < npair; pidx += BEAM_THREADS) {
+    const int npair = nb * nc;
+    for (int pidx = tid; pidx < npair; pidx += NT) {
       const int i = pidx / nc, ci = pidx - i * nc;
       const int c = fid[ci];
       const float lp = flp[ci];
@@ -350,81 +541,67 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
       // does the extension land on a prefix that is already in the beam? (identity = hash of the id string)
       const unsigned long long hx = e.hash * 0x9E3779B97F4A7C15ull + (unsigned long long)(c + 1);
       int j = -1;
-      for (int k = 0; k < nb; ++k)
-        if (E[k].hash == hx && E[k].len == e.len + 1 && E[k].last == c) {
-          j = k;
-          break;
+      {
+        unsigned slot = (unsigned)(hx >> 24) & (unsigned)(L.hcap - 1);
+        for (;;) {
+          const int k1 = htab[slot];
+          if (k1 == 0) break;
+          const BeamEntry& o = E[k1 - 1];
+          if (o.hash == hx && o.len == e.len + 1 && o.last == c) {
+            j = k1 - 1;
+            break;
+          }
+          slot = (slot + 1) & (unsigned)(L.hcap - 1);
         }
+      }
       if (j >= 0) {
         merge_nb[j] = log_p;
-      } else {
-        cscore[pidx] = log_p;
-        ckey[pidx] = c;
+      } else if (log_p > -INFINITY) {  // fresh extensions need a finite score
+        keys[atomicAdd(&s_ncand, 1)] = beam_key(log_p, c, pidx);
       }
     }
-    __syncthreads();
-    for (int j = tid; j < nb; j += BEAM_THREADS) {
+    beam_sync<NT>();
+    // prefixes already in the beam stay candidates even at -inf
+    for (int j = tid; j < nb; j += NT) {
       const float nbn = lse2(stay_nb[j], merge_nb[j]);
       stay_nb[j] = nbn;
-      cscore[npair + j] = lse2(stay_b[j], nbn);
-      ckey[npair + j] = E[j].last;
+      keys[atomicAdd(&s_ncand, 1)] = beam_key(lse2(stay_b[j], nbn), E[j].last, npair + j);
     }
-    __syncthreads();
-    // top-`beam` selection: rounds of block-wide arg-max (score desc, char asc, slot asc)
-    const int nslots = npair + nb;
-    int nsel = 0;
-    for (int r = 0; r < beam; ++r) {
-      float bs = -INFINITY;
-      int bk = 0x7fffffff, bi = -1;
-      for (int i = tid; i < nslots; i += BEAM_THREADS) {
-        const float sc = cscore[i];
-        const int k = ckey[i];
-        // fresh extensions need a finite score; prefixes already in the beam stay candidates even at -inf
-        if (k != 0x7fffffff && (i >= npair || sc > -INFINITY)) {
-          if (bi < 0 || sc > bs || (sc == bs && (k < bk || (k == bk && i < bi)))) {
-            bs = sc;
-            bk = k;
-            bi = i;
+    beam_sync<NT>();
+    // ---- top-`beam` = the first `beam` keys in ascending order ----
+    const int n = s_ncand;
+    if (n <= 32) {
+      if (tid < 32) {
+        unsigned long long k = lane < n ? keys[lane] : ~0ull;
+        warp_sort32_keys(k, lane);
+        keys[lane] = k;
+      }
+    } else {
+      const int np2 = beam_pow2_ge(n);
+      for (int i = n + tid; i < np2; i += NT) keys[i] = ~0ull;
+      beam_sync<NT>();
+      for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int x = tid; x < (np2 >> 1); x += NT) {
+            const int lo = ((x & ~(j - 1)) << 1) | (x & (j - 1));
+            const int hi = lo | j;
+            const unsigned long long a = keys[lo], bq = keys[hi];
+            const bool asc = (lo & k) == 0;
+            if ((a > bq) == asc) {
+              keys[lo] = bq;
+              keys[hi] = a;
+            }
           }
+          beam_sync<NT>();
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (oi >= 0 && (bi < 0 || os > bs || (os == bs && (ok < bk || (ok == bk && oi < bi))))) {
-          bs = os;
-          bk = ok;
-          bi = oi;
-        }
-      }
-      if ((tid & 31) == 0) {
-        red_s[tid >> 5] = bs;
-        red_k[tid >> 5] = bk;
-        red_i[tid >> 5] = bi;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        for (int w = 1; w < BEAM_THREADS / 32; ++w) {
-          const float os = red_s[w];
-          const int ok = red_k[w], oi = red_i[w];
-          if (oi >= 0 && (bi < 0 || os > bs || (os == bs && (ok < bk || (ok == bk && oi < bi))))) {
-            bs = os;
-            bk = ok;
-            bi = oi;
-          }
-        }
-        sel[r] = bi;
-        if (bi >= 0) ckey[bi] = 0x7fffffff;  // consumed
-      }
-      __syncthreads();
-      if (sel[r] < 0) break;
-      ++nsel;
     }
-    // build the next beam
-    for (int r = tid; r < nsel; r += BEAM_THREADS) {
-      const int slot = sel[r];
+    beam_sync<NT>();
+    // build the next beam (already in best-first order)
+    const int nsel = min(n, beam);
+    for (int r = tid; r < nsel; r += NT) {
+      const unsigned long long k = keys[r];
+      const int slot = (int)(k & 0xffffu);
       BeamEntry ne;
       if (slot >= npair) {
         const int j = slot - npair;
@@ -436,7 +613,7 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
         const int i = slot / nc, ci = slot - i * nc;
         const BeamEntry e = E[i];
         const int c = fid[ci];
-        const float log_p = cscore[slot];  // as computed above (includes the scorer terms)
+        const float log_p = beam_key_score(k);  // as computed above (includes the scorer terms)
         const int id = atomicAdd(&s_next_id, 1);
         ne.id = id;
         ne.hash = e.hash * 0x9E3779B97F4A7C15ull + (unsigned long long)(c + 1);
@@ -445,6 +622,7 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
         ne.prev1 = e.last;
         ne.prev2 = e.prev1;
         ne.len = e.len + 1;
+        ne.pad = 0;
         ne.b_prev = -INFINITY;
         ne.nb_prev = log_p;
         ne.score = log_p;
@@ -452,13 +630,13 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
       }
       N[r] = ne;
     }
-    __syncthreads();
+    beam_sync<NT>();
     if (tid == 0) s_nb = nsel;
     cur ^= 1;
-    __syncthreads();
+    beam_sync<NT>();
   }
   // write the state back
-  for (int i = tid; i < s_nb; i += BEAM_THREADS) gbeam[i] = ebuf[cur][i];
+  for (int i = tid; i < s_nb; i += NT) gbeam[i] = ebuf[cur * L.bcap + i];
   if (tid == 0) {
     hdr->nb = s_nb;
     hdr->next_id = s_next_id;
@@ -466,9 +644,11 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
   }
 }
 
-// Results: beam entries sorted by score (desc; ties char asc), ids by walking the (parent, char) table.
+// Results: the beam is kept best first (score desc; ties char asc), so entry r IS rank r; ids by walking the
+// (parent, char) table. Only the first `nbest` entries are written: out_ids [B, nbest, lmax], out_lens / out_scores
+// [B, nbest]; out_lens = -1 where the beam has fewer entries, -2 if the state overflowed its max_frames.
 __global__ void ctc_beam_result_kernel(const BeamStateHeader* __restrict__ states, size_t state_stride_bytes,
-                                       int node_cap, int beam, int* __restrict__ out_ids, int lmax,
+                                       int node_cap, int nbest, int* __restrict__ out_ids, int lmax,
                                        int* __restrict__ out_lens, float* __restrict__ out_scores) {
   const int b = blockIdx.x;
   const uint8_t* sp = reinterpret_cast<const uint8_t*>(states) + (size_t)b * state_stride_bytes;
@@ -476,31 +656,29 @@ __global__ void ctc_beam_result_kernel(const BeamStateHeader* __restrict__ state
   const BeamEntry* gbeam = reinterpret_cast<const BeamEntry*>(sp + sizeof(BeamStateHeader));
   const int2* nodes = reinterpret_cast<const int2*>(sp + sizeof(BeamStateHeader) + sizeof(BeamEntry) * BEAM_MAXB);
   const int nb = hdr->nb;
-  const int r = threadIdx.x;
-  if (r >= beam) return;
-  int* ids = out_ids + ((size_t)b * beam + r) * lmax;
-  if (r >= nb) {
-    out_lens[b * beam + r] = -1;
-    out_scores[b * beam + r] = -INFINITY;
-    return;
+  for (int r = threadIdx.x; r < nbest; r += blockDim.x) {
+    if (hdr->pad != 0) {
+      out_lens[b * nbest + r] = -2;
+      out_scores[b * nbest + r] = -INFINITY;
+      continue;
+    }
+    if (r >= nb) {
+      out_lens[b * nbest + r] = -1;
+      out_scores[b * nbest + r] = -INFINITY;
+      continue;
+    }
+    const BeamEntry me = gbeam[r];
+    int* ids = out_ids + ((size_t)b * nbest + r) * lmax;
+    const int len = min(me.len, lmax);
+    int id = me.id;
+    for (int pos = me.len - 1; pos >= 0 && id > 0; --pos) {
+      const int2 nd = (id < node_cap) ? nodes[id] : make_int2(0, 0);
+      if (pos < lmax) ids[pos] = nd.y;
+      id = nd.x;
+    }
+    out_lens[b * nbest + r] = len;
+    out_scores[b * nbest + r] = me.score;
   }
-  // rank of entry r
-  const BeamEntry me = gbeam[r];
-  int rank = 0;
-  for (int k = 0; k < nb; ++k) {
-    const BeamEntry o = gbeam[k];
-    if (k != r && (o.score > me.score || (o.score == me.score && (o.last < me.last || (o.last == me.last && k < r))))) ++rank;
-  }
-  ids = out_ids + ((size_t)b * beam + rank) * lmax;
-  const int len = min(me.len, lmax);
-  int id = me.id;
-  for (int pos = me.len - 1; pos >= 0 && id > 0; --pos) {
-    const int2 nd = (id < node_cap) ? nodes[id] : make_int2(0, 0);
-    if (pos < lmax) ids[pos] = nd.y;
-    id = nd.x;
-  }
-  out_lens[b * beam + rank] = len;
-  out_scores[b * beam + rank] = me.score;
 }
 
 __global__ void ctc_beam_reset_kernel(BeamStateHeader* states, size_t state_stride_bytes) {
@@ -511,6 +689,7 @@ __global__ void ctc_beam_reset_kernel(BeamStateHeader* states, size_t state_stri
     hdr->nb = 1;
     hdr->next_id = 1;  // id 0 = root (empty prefix)
     hdr->frames = 0;
+    hdr->pad = 0;      // overflow flag
     BeamEntry root;
     root.id = 0, root.parent_id = -1, root.last = -1, root.len = 0;
     root.prev1 = root.prev2 = -1, root.pad = 0;
@@ -533,31 +712,45 @@ cudaError_t launch_beam_reset(void* states, int B, int node_cap, cudaStream_t st
   return cudaGetLastError();
 }
 
-cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp, int B, int T, const int* frame_lens,
-                                int beam, int blank, void* states, int node_cap, cudaStream_t st, const float* probs, int V,
-                                const BeamLm* lm) {
-  if (beam < 1 || beam > BEAM_MAXB) return cudaErrorInvalidValue;
-  const size_t dyn = (size_t)(beam * BEAM_MAXC + beam) * 8;
-  static size_t configured = 0;
-  if (dyn > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ctc_prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)(BEAM_MAXB * BEAM_MAXC + BEAM_MAXB) * 8));
-    if (e != cudaSuccess) return e;
-    configured = (size_t)(BEAM_MAXB * BEAM_MAXC + BEAM_MAXB) * 8;
-  }
-  BeamLm none{};
-  ctc_prefix_beam_kernel<<<B, BEAM_THREADS, dyn, st>>>(cnt, cid, clp, T, frame_lens, beam, blank,
-                                                     reinterpret_cast<BeamStateHeader*>(states),
-                                                     beam_state_stride(node_cap), node_cap, probs, V, lm ? *lm : none);
+template <int NT>
+static cudaError_t launch_beam_advance_nt(const int* cnt, const int* cid, const float* clp, int B, int T,
+                                          const int* frame_lens, int beam, int topn, int blank, int max_frames, void* states,
+                                          int node_cap, cudaStream_t st, const float* probs, int V, const BeamLm& lm) {
+  const BeamSmemLayout L = beam_smem_layout(beam, topn);
+  static std::once_flag once;
+  static cudaError_t cfg_err = cudaSuccess;
+  std::call_once(once, [] {
+    cfg_err = cudaFuncSetAttribute(ctc_prefix_beam_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  });
+  if (cfg_err != cudaSuccess) return cfg_err;
+  if (L.total > 226 * 1024) return cudaErrorInvalidValue;
+  ctc_prefix_beam_kernel<NT><<<B, NT, L.total, st>>>(cnt, cid, clp, T, frame_lens, beam, topn, blank, max_frames,
+                                                      reinterpret_cast<BeamStateHeader*>(states), beam_state_stride(node_cap),
+                                                      node_cap, probs, V, lm);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_beam_result(const void* states, int B, int node_cap, int beam, int* out_ids, int lmax, int* out_lens,
+cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp, int B, int T, const int* frame_lens,
+                                int beam, int topn, int blank, int max_frames, void* states, int node_cap, cudaStream_t st,
+                                const float* probs, int V, const BeamLm* lm) {
+  if (beam < 1 || beam > BEAM_MAXB || topn < 1 || topn > BEAM_MAXC) return cudaErrorInvalidValue;
+  BeamLm none{};
+  const BeamLm& l = lm ? *lm : none;
+  // one warp per utterance when the per-frame work is tiny; the n-gram scorer's dependent table probes want more threads
+  if (beam <= 32 && lm == nullptr)
+    return launch_beam_advance_nt<32>(cnt, cid, clp, B, T, frame_lens, beam, topn, blank, max_frames, states, node_cap, st, probs, V, l);
+  if (beam <= 32)
+    return launch_beam_advance_nt<128>(cnt, cid, clp, B, T, frame_lens, beam, topn, blank, max_frames, states, node_cap, st, probs, V, l);
+  if (beam <= 128)
+    return launch_beam_advance_nt<256>(cnt, cid, clp, B, T, frame_lens, beam, topn, blank, max_frames, states, node_cap, st, probs, V, l);
+  return launch_beam_advance_nt<512>(cnt, cid, clp, B, T, frame_lens, beam, topn, blank, max_frames, states, node_cap, st, probs, V, l);
+}
+
+cudaError_t launch_beam_result(const void* states, int B, int node_cap, int nbest, int* out_ids, int lmax, int* out_lens,
                                float* out_scores, cudaStream_t st) {
-  ctc_beam_result_kernel<<<B, BEAM_MAXB, 0, st>>>(reinterpret_cast<const BeamStateHeader*>(states),
-                                                 beam_state_stride(node_cap), node_cap, beam, out_ids, lmax, out_lens,
-                                                 out_scores);
+  ctc_beam_result_kernel<<<B, 128, 0, st>>>(reinterpret_cast<const BeamStateHeader*>(states), beam_state_stride(node_cap),
+                                            node_cap, nbest, out_ids, lmax, out_lens, out_scores);
   count_launch();
   return cudaGetLastError();
 }

@@ -59,6 +59,14 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
                              cudaStream_t st, int y_affine = 0, const int* ylens = nullptr, const float* pre_ys = nullptr,
                              const float* pre_yb = nullptr, const FfnDw* dw = nullptr);
 
+// fused_ffn variant (process-wide; env PPASR_B200_FFN_SPLIT=0/1/2 or ppasr_b200_set_option(ctx, "ffn_split", v)):
+//   1 (default) = 2-CTA cluster per row tile, hidden dimension split over the pair, distributed-shared-memory reduction
+//                 (2 x ceil(M/128) CTAs per launch: shortest single-launch latency);
+//   2 = the same two-team pipeline on one CTA per row tile (least SM time per launch; the throughput pipeline uses it);
+//   0 = the round-1 kernel (one CTA per row tile, single Swish team; still used for the opt-in fused_dwconv mode).
+int ffn_split_mode();
+void set_ffn_split_mode(int mode);
+
 // Fused attention out-projection + residual + norm_conv + pointwise_conv1 + GLU (fused_attn_out.cu)
 cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& tm_wo, const CUtensorMap& tm_wpw1, int M,
                                   float* x, __nv_bfloat16* g, const float* bo, const float* ln_g, const float* ln_b,
@@ -116,12 +124,13 @@ cudaError_t launch_ctc_prune(const float* probs, int V, int rows, float cutoff_p
                              float* clp, cudaStream_t st);
 cudaError_t launch_beam_reset(void* states, int B, int node_cap, cudaStream_t st);
 cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp, int B, int T, const int* frame_lens,
-                                int beam, int blank, void* states, int node_cap, cudaStream_t st,
+                                int beam, int topn, int blank, int max_frames, void* states, int node_cap, cudaStream_t st,
                                 const float* probs = nullptr, int V = 0, const BeamLm* lm = nullptr);
-cudaError_t launch_beam_result(const void* states, int B, int node_cap, int beam, int* out_ids, int lmax, int* out_lens,
+// writes the first `nbest` beam entries (best first): out_ids [B, nbest, lmax], out_lens / out_scores [B, nbest]
+cudaError_t launch_beam_result(const void* states, int B, int node_cap, int nbest, int* out_ids, int lmax, int* out_lens,
                                float* out_scores, cudaStream_t st);
 constexpr int BEAM_MAX_TOPN = 64;
-constexpr int BEAM_MAX_BEAM = 128;
+constexpr int BEAM_MAX_BEAM = 512;
 
 // Relative-position attention (attention.cu). Tensor maps are built by the caller.
 struct AttnParams {

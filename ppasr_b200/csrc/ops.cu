@@ -74,6 +74,11 @@ int ppasr_b200_set_pdl(int32_t enable) {
   return PPASR_OK;
 }
 
+int ppasr_b200_set_ffn_split(int32_t enable) {
+  set_ffn_split_mode(enable);
+  return PPASR_OK;
+}
+
 // C = epilogue(A[M,K] * W[N,K]^T + bias).  See include/ppasr_b200.h for the epilogue codes.
 int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t w_rows, const float* bias,
                          void* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t act,
@@ -170,15 +175,17 @@ int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V,
                             int32_t max_frames, void* workspace, void* stream) {
   PPASR_REQUIRE(probs && states && workspace, "null pointer");
   PPASR_REQUIRE(B > 0 && T > 0 && V > 1, "bad sizes");
-  PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,128] in this build");
-  PPASR_REQUIRE(cutoff_top_n >= 1, "cutoff_top_n must be >= 1");
+  PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,512] in this build");
+  PPASR_REQUIRE(cutoff_top_n >= 1 && V < 65535, "cutoff_top_n must be >= 1 and the vocabulary below 65535");
+  PPASR_REQUIRE(max_frames >= 1, "max_frames must be >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int top_n = cutoff_top_n < BEAM_MAX_TOPN ? cutoff_top_n : BEAM_MAX_TOPN;
   int* cnt = reinterpret_cast<int*>(workspace);
   int* cid = cnt + (((size_t)B * T + 63) & ~size_t(63));
   float* clp = reinterpret_cast<float*>(cid + (size_t)B * T * BEAM_MAX_TOPN);
   PPASR_CUDA_CHECK(launch_ctc_prune(probs, V, B * T, cutoff_prob, top_n, cnt, cid, clp, st));
-  PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, blank_id, states, max_frames * beam + 1, st));
+  PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, top_n < V ? top_n : V, blank_id, max_frames, states,
+                                       max_frames * beam + 1, st));
   return PPASR_OK;
 }
 int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens, int32_t beam,
@@ -187,8 +194,8 @@ int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t
                                int64_t lm_capacity, int32_t lm_order, float alpha, float beta, void* stream) {
   PPASR_REQUIRE(probs && states && workspace && lm_keys && lm_vals && lm_in_vocab, "null pointer");
   PPASR_REQUIRE(B > 0 && T > 0 && V > 1 && V + 2 < 65536, "bad sizes (the scorer packs token ids in 16 bits)");
-  PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,128] in this build");
-  PPASR_REQUIRE(cutoff_top_n >= 1, "cutoff_top_n must be >= 1");
+  PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,512] in this build");
+  PPASR_REQUIRE(cutoff_top_n >= 1 && max_frames >= 1, "cutoff_top_n and max_frames must be >= 1");
   PPASR_REQUIRE(lm_order >= 1 && lm_order <= 4, "the scorer supports n-gram orders 1..4");
   PPASR_REQUIRE(lm_capacity >= 2 && (lm_capacity & (lm_capacity - 1)) == 0, "lm_capacity must be a power of two");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -204,14 +211,19 @@ int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t
   lm.mask = (unsigned)(lm_capacity - 1);
   lm.order = lm_order;
   lm.alpha = alpha, lm.beta = beta;
-  PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, blank_id, states, max_frames * beam + 1, st, probs,
-                                       V, &lm));
+  PPASR_CUDA_CHECK(launch_beam_advance(cnt, cid, clp, B, T, frame_lens, beam, top_n < V ? top_n : V, blank_id, max_frames, states,
+                                       max_frames * beam + 1, st, probs, V, &lm));
   return PPASR_OK;
 }
 int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
                            int32_t lmax, int32_t* out_lens, float* out_scores, void* stream) {
+  return ppasr_b200_beam_result_nbest(states, B, max_frames, beam, beam, out_ids, lmax, out_lens, out_scores, stream);
+}
+int ppasr_b200_beam_result_nbest(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t nbest,
+                                 int32_t* out_ids, int32_t lmax, int32_t* out_lens, float* out_scores, void* stream) {
   PPASR_REQUIRE(states && out_ids && out_lens && out_scores && lmax > 0, "bad arguments");
-  PPASR_CUDA_CHECK(launch_beam_result(states, B, max_frames * beam + 1, beam, out_ids, lmax, out_lens, out_scores,
+  PPASR_REQUIRE(B > 0 && beam >= 1 && beam <= BEAM_MAX_BEAM && nbest >= 1 && nbest <= beam, "bad sizes");
+  PPASR_CUDA_CHECK(launch_beam_result(states, B, max_frames * beam + 1, nbest, out_ids, lmax, out_lens, out_scores,
                                       reinterpret_cast<cudaStream_t>(stream)));
   return PPASR_OK;
 }

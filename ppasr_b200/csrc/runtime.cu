@@ -1348,6 +1348,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
     c->host_sync = value != 0;
     return PPASR_OK;
   }
+  if (n == "ffn_split") {  // process-wide: which fused_ffn kernel launch_fused_ffn dispatches to
+    set_ffn_split_mode(value);
+    return PPASR_OK;
+  }
   if (n == "fused_dwconv") {
     c->fused_dwconv = value != 0;
     return PPASR_OK;

@@ -8,7 +8,7 @@ Same constructor arguments and methods (beam_search_decoder.py:9-96). Difference
     (order <= 4) that is character based (every LM word is one vocabulary token), as the reference's Chinese setups
     are; it is turned into a device hash table and scored inside the beam kernel (ppasr_b200/decoders/ngram_lm.py).
     KenLM *binary* files (.klm / trie) and word-based LMs (English, needs the dictionary FST) raise.
-  * beam_size <= 128 and cutoff_top_n <= 64 in this build; larger values raise.
+  * beam_size <= 512 and cutoff_top_n <= 64 in this build (the shipped configs use 300 / 40); larger values raise.
   * `num_processes` is accepted and ignored (utterances are decoded by one CTA each, all in parallel).
 Returned scores follow the upstream convention: -log P(prefix) of the total CTC probability
 (decoder_utils.cpp get_beam_search_result, `-approx_ctc`), best first.
@@ -27,14 +27,11 @@ class UnsupportedDecoderConfig(Exception):
 class BeamSearchDecoder:
     def __init__(self, alpha=2.2, beta=4.3, beam_size=300, cutoff_prob=0.99, cutoff_top_n=40, vocab_list=None,
                  num_processes=10, blank_id=0, language_model_path=None, max_frames=5000, ext_scorer=None):
-        if beam_size > 128:
-            raise UnsupportedDecoderConfig(f"beam_size {beam_size} > 128 is not supported by the GPU decoder in this build")
+        if beam_size > 512:
+            raise UnsupportedDecoderConfig(f"beam_size {beam_size} > 512 is not supported by the GPU decoder in this build")
         if cutoff_top_n > 64:
             raise UnsupportedDecoderConfig(f"cutoff_top_n {cutoff_top_n} > 64 is not supported by the GPU decoder in this build")
-        import torch
-        if not torch.cuda.is_available():
-            raise L.PPASRB200Error("ppasr_b200 decoders need a CUDA device (no CPU fallback)")
-        self.torch = torch
+        # ---- configuration checks first (they do not need a device) ----
         self.alpha = alpha
         self.beta = beta
         self.beam_size = int(beam_size)
@@ -44,17 +41,26 @@ class BeamSearchDecoder:
         self.num_processes = num_processes
         self.blank_id = int(blank_id)
         self.max_frames = int(max_frames)
-        self.lib = L.load()
         self._ext_scorer = ext_scorer
         if ext_scorer is not None:  # a ready-made scorer carries its own weights (swig_wrapper.py:35-41 ext_scoring_func)
             self.alpha, self.beta = ext_scorer.alpha, ext_scorer.beta
         if language_model_path is not None and ext_scorer is None:
-            from .ngram_lm import Scorer
+            import os
+            if not os.path.isfile(str(language_model_path)):
+                # the reference downloads a missing LM (beam_search_decoder.py:19-25); there is no network here
+                raise UnsupportedDecoderConfig("language model file not found: " + str(language_model_path))
             with open(language_model_path, "rb") as f:
                 head = f.read(64)
             if not head.lstrip().startswith(b"\\data\\"):
                 raise UnsupportedDecoderConfig("language model must be an ARPA text file (KenLM binary formats are not supported): "
                                 + str(language_model_path))
+        import torch
+        if not torch.cuda.is_available():
+            raise L.PPASRB200Error("ppasr_b200 decoders need a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.lib = L.load()
+        if language_model_path is not None and ext_scorer is None:
+            from .ngram_lm import Scorer
             self._ext_scorer = Scorer(alpha, beta, language_model_path, vocab_list)
         self._lm_dev = None
         if self._ext_scorer is not None:
@@ -100,16 +106,21 @@ class BeamSearchDecoder:
 
     def _results(self, state, B, max_frames, lmax, nbest=None, approx=True):
         torch = self.torch
-        ids = torch.zeros((B, self.beam_size, lmax), dtype=torch.int32, device="cuda")
-        lens = torch.zeros((B, self.beam_size), dtype=torch.int32, device="cuda")
-        sc = torch.zeros((B, self.beam_size), dtype=torch.float32, device="cuda")
-        L.check(self.lib.ppasr_b200_beam_result(L.ptr(state), B, max_frames, self.beam_size, L.ptr(ids), lmax,
-                                                L.ptr(lens), L.ptr(sc), L.stream_ptr()))
+        nb = self.beam_size if nbest is None else max(1, min(int(nbest), self.beam_size))
+        lmax = max(1, int(lmax))
+        ids = torch.zeros((B, nb, lmax), dtype=torch.int32, device="cuda")
+        lens = torch.zeros((B, nb), dtype=torch.int32, device="cuda")
+        sc = torch.zeros((B, nb), dtype=torch.float32, device="cuda")
+        L.check(self.lib.ppasr_b200_beam_result_nbest(L.ptr(state), B, max_frames, self.beam_size, nb, L.ptr(ids), lmax,
+                                                      L.ptr(lens), L.ptr(sc), L.stream_ptr()))
         ids, lens, sc = ids.cpu().numpy(), lens.cpu().numpy(), sc.cpu().numpy()
+        if (lens == -2).any():
+            raise L.PPASRB200Error("beam-search state overflow: more frames were fed than the max_frames the decoder "
+                                   "was created with (call reset_decoder(), or construct it with a larger max_frames)")
         out = []
         for b in range(B):
             res = []
-            for k in range(self.beam_size if nbest is None else min(nbest, self.beam_size)):
+            for k in range(nb):
                 if lens[b, k] < 0:
                     continue
                 toks = [self.vocab_list[i] for i in ids[b, k, :lens[b, k]]]
@@ -162,12 +173,19 @@ class BeamSearchDecoder:
         if p.dim() == 2:
             p = p.unsqueeze(0)
         lens = np.asarray(logits_lens).astype(np.int32)
+        n_new = int(min(int(lens[0]), p.shape[1]))
+        if self._stream_frames + n_new > self.max_frames:
+            raise L.PPASRB200Error(f"decode_chunk: {self._stream_frames + n_new} frames exceed max_frames={self.max_frames} "
+                                   "of this decoder (reset_decoder() between utterances, or construct with a larger max_frames)")
         self._advance(self._stream_state, p[:1], lens[:1], self.max_frames)
-        return self._results(self._stream_state, 1, self.max_frames, self.max_frames, nbest=1)[0][0]
+        self._stream_frames += n_new
+        # a prefix is never longer than the number of frames consumed: copy back only that much
+        return self._results(self._stream_state, 1, self.max_frames, self._stream_frames, nbest=1)[0][0]
 
     def reset_decoder(self):
         """beam_search_decoder.py:93-96."""
         self._stream_state = self._alloc_state(1, self.max_frames)
+        self._stream_frames = 0
 
 
 def ctc_beam_search_decoding(probs_seq, vocabulary, beam_size, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0,

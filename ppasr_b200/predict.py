@@ -127,7 +127,7 @@ class PPASRPredictor:
     MIN_SAMPLES = 400 + 6 * 160
 
     def __init__(self, configs=None, model_path='models/conformer_streaming_fbank/infer/', use_pun=False, use_gpu=True,
-                 vocab_list=None, weights=None, device=0, model_tag=None, pun_model_dir=None, decoder_fallback=True):
+                 vocab_list=None, weights=None, device=0, model_tag=None, pun_model_dir=None, decoder_fallback=False):
         """configs: path of a reference yaml config (predict.py:36-41), or the loaded dict / attribute object, with the
         reference's keys: use_model, streaming, decoder, encoder_conf, preprocess_conf, dataset_conf.dataset_vocab,
         ctc_beam_search_decoder_conf. `vocab_list` / `weights` let tests pass in-memory objects instead of files. `model_tag`
@@ -159,11 +159,13 @@ class PPASRPredictor:
                                             vocab_size=len(vocab_list), device=device)
 
     # predict.py:92-105
-    def _init_decoder(self, decoder_fallback=True):
-        """ctc_beam_search: build the GPU beam-search decoder from `ctc_beam_search_decoder_conf`. The reference switches to
-        ctc_greedy with a warning when its decoder cannot be initialised (missing paddlespeech_ctcdecoders, predict.py:98-105);
-        the same happens here when the configuration is outside what the GPU decoder implements (e.g. the shipped
-        beam_size 300 > 128, or a KenLM binary / word-based language model) unless decoder_fallback=False."""
+    def _init_decoder(self, decoder_fallback=False):
+        """ctc_beam_search: build the GPU beam-search decoder from `ctc_beam_search_decoder_conf` (the shipped beam_size 300 /
+        cutoff_top_n 40 run on the GPU). A configuration outside what the GPU decoder implements (a KenLM binary or
+        word-based language model, a missing LM file, beam_size > 512) RAISES UnsupportedDecoderConfig: silently decoding
+        with another decoder would change the results of a stock config. Only with decoder_fallback=True does it degrade
+        to ctc_greedy with a warning, as the reference does when its own decoder cannot be initialised (missing
+        paddlespeech_ctcdecoders, predict.py:98-105)."""
         if self.decoder != 'ctc_beam_search':
             return
         from .decoders.beam_search_decoder import BeamSearchDecoder, UnsupportedDecoderConfig

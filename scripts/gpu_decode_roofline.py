@@ -28,9 +28,15 @@ for name, (B, T, V, beam, temp) in {"C2 [32,248,4233]": (32, 248, 4233, 10, 8.0)
         L.check(lib.ppasr_b200_beam_reset(L.ptr(st), B, T, beam, L.stream_ptr()))
         L.check(lib.ppasr_b200_beam_advance(L.ptr(probs), B, T, V, None, beam, 0.99, 40, 0, L.ptr(st), T, L.ptr(ws), L.stream_ptr()))
     ms_b = timeit(beam_fn, reps=5)
-    r = {"bytes": nbytes, "greedy_ms": ms_g, "greedy_gbs": nbytes / ms_g / 1e6, "greedy_frac": nbytes / ms_g / 1e6 / peak,
+    st300 = torch.empty(lib.ppasr_b200_beam_state_bytes(B, T, 300), dtype=torch.uint8, device=dev)
+    def beam300_fn():
+        L.check(lib.ppasr_b200_beam_reset(L.ptr(st300), B, T, 300, L.stream_ptr()))
+        L.check(lib.ppasr_b200_beam_advance(L.ptr(probs), B, T, V, None, 300, 0.99, 40, 0, L.ptr(st300), T, L.ptr(ws), L.stream_ptr()))
+    ms_b300 = timeit(beam300_fn, reps=2)
+    del st300
+    r = {"beam300_total_ms": ms_b300, "bytes": nbytes, "greedy_ms": ms_g, "greedy_gbs": nbytes / ms_g / 1e6, "greedy_frac": nbytes / ms_g / 1e6 / peak,
          "prune_ms": ms_p, "prune_gbs": nbytes / ms_p / 1e6, "prune_frac": nbytes / ms_p / 1e6 / peak,
          "beam10_total_ms": ms_b, "beam10_utt_per_s": B / ms_b * 1e3}
     out[name] = r
     print(name, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()}, flush=True)
-json.dump({"hbm_peak_gbs": peak, "cases": out}, open('gpurun_out/decode_roofline_r1.json', 'w'), indent=1)
+json.dump({"hbm_peak_gbs": peak, "cases": out}, open('gpurun_out/decode_roofline_r2.json', 'w'), indent=1)

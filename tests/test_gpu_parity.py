@@ -65,6 +65,77 @@ def test_gemm_epilogues(lib, cuda, M, N, K, epi, act, bn):
     assert rel_err(got, ref) < tol
 
 
+# ------------------------------------------------------------------------------------------------
+# fused feed-forward block: one CTA per row tile (split 0) and 2-CTA cluster with the hidden split (split 1)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("split", [0, 1, 2])
+@pytest.mark.parametrize("M,FF,dbl", [(7936, 2048, 0), (7936, 2048, 1), (1000, 2048, 0), (77, 512, 1), (128, 1024, 0)])
+def test_fused_ffn_op_both_variants(lib, cuda, split, M, FF, dbl):
+    """positionwise.py:30-39 + residual + LayerNorm(s) (encoder.py:380-386,419-429) on raw pointers; tolerance 2e-2 of
+    max|.| on the bf16 y output (bf16 hidden activation), 5e-3 on the fp32 residual stream."""
+    from ppasr_b200 import _lib as L
+    torch.manual_seed(M + FF + dbl)
+    y = torch.randn(M, 256, device=cuda).to(torch.bfloat16)
+    w1 = (torch.randn(FF, 256, device=cuda) / 16).to(torch.bfloat16)
+    w2 = (torch.randn(256, FF, device=cuda) / FF ** 0.5 * 0.5).to(torch.bfloat16)
+    b1 = torch.randn(FF, device=cuda) * 0.1
+    b2 = torch.randn(256, device=cuda) * 0.1
+    g1 = torch.rand(256, device=cuda) + 0.5
+    bn1 = torch.randn(256, device=cuda) * 0.1
+    g2 = torch.rand(256, device=cuda) + 0.5
+    bn2 = torch.randn(256, device=cuda) * 0.1
+    x0 = torch.randn(M, 256, device=cuda)
+    x = x0.clone()
+    yo = torch.zeros(M, 256, device=cuda, dtype=torch.bfloat16)
+    L.check(lib.ppasr_b200_set_ffn_split(split))
+    try:
+        L.check(lib.ppasr_b200_op_fused_ffn(L.ptr(y), L.ptr(w1), L.ptr(w2), L.ptr(x), L.ptr(yo), L.ptr(b1), L.ptr(b2),
+                                            L.ptr(g1), L.ptr(bn1), L.ptr(g2) if dbl else None, L.ptr(bn2) if dbl else None,
+                                            M, FF, 1e-5, L.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        lib.ppasr_b200_set_ffn_split(1)
+    h = y.float() @ w1.float().t() + b1
+    h = (h * torch.sigmoid(h)).to(torch.bfloat16).float()
+    xr = x0 + h @ w2.float().t() + b2
+    if dbl:
+        xr = F.layer_norm(xr, (256,), g1, bn1, 1e-5)
+        yr = F.layer_norm(xr, (256,), g2, bn2, 1e-5)
+    else:
+        yr = F.layer_norm(xr, (256,), g1, bn1, 1e-5)
+    assert rel_err(x, xr) < 5e-3
+    assert rel_err(yo, yr) < 2e-2
+
+
+@pytest.mark.parametrize("family", ["conformer", "squeezeformer"])
+def test_fused_ffn_split_matches_single_cta_model_level(lib, cuda, family):
+    """The kernel variants differ only in fp32 summation order (which can flip a bf16 rounding of the LayerNorm output,
+    1 ulp = 0.4 %): whole-model logits (plain + chained + post-norm chained modes are all exercised by these two
+    families) agree to 5e-3 of max|logit|, i.e. inside the bf16 noise the oracle comparison allows (1e-2)."""
+    from ppasr_b200 import engine as E, weights as W
+    if family == "conformer":
+        cfg = W.ConformerConfig(num_blocks=3, vocab_size=301)
+        w = W.init_conformer_weights(cfg)
+        mk = lambda: E.ConformerEngine(cfg, w, device=0)
+    else:
+        cfg = W.SqueezeformerConfig(num_blocks=4, vocab_size=301, reduce_idx=1, recover_idx=3)
+        w = W.init_squeezeformer_weights(cfg)
+        mk = lambda: E.ConformerEngine(cfg, w, device=0)
+    feats = torch.from_numpy(W.synthetic_fbank(3, 523)).cuda()
+    lens = [523, 3, 260]
+    outs = []
+    for split in (0, 1, 2):
+        lib.ppasr_b200_set_ffn_split(split)
+        try:
+            eng = mk()
+            eng.encode(feats, lens)
+            outs.append(eng.ctc_logits().float().cpu())
+        finally:
+            lib.ppasr_b200_set_ffn_split(1)
+    assert rel_err(outs[1], outs[0]) < 5e-3
+    assert rel_err(outs[2], outs[0]) < 5e-3
+
+
 def test_gemm_residual_row_mask(lib, cuda):
     from ppasr_b200 import _lib as L
     B, T, N, K = 4, 248, 256, 256
@@ -498,6 +569,84 @@ def test_beam_search_matches_oracle(lib, cuda, T, V, beam, cp, topn, temp):
     s1, t1 = dec.decode_beam_search_offline(probs[0])
     assert t1 == got[0][0][1]
     assert dec.decode_batch_beam_search_offline([probs[0], probs[1][: T // 2]])[0] == t1
+
+
+@pytest.mark.parametrize("T,V,beam,cp,topn,temp", [(60, 120, 300, 0.99, 40, 1.5), (40, 60, 200, 1.0, 40, 1.0)])
+def test_beam_search_shipped_beam_size_matches_oracle(lib, cuda, T, V, beam, cp, topn, temp):
+    """configs/conformer.yml:80-90 ships beam_size 300 / cutoff_top_n 40: the wide-beam path (512 threads per utterance,
+    shared-memory bitonic selection over up to beam * top_n candidates) against the oracle restatement."""
+    from oracle import decoders_oracle as DO
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    rng = np.random.RandomState(T + V + beam)
+    vocab = [f"<{i}>" for i in range(V)]
+    dec = BeamSearchDecoder(beam_size=beam, cutoff_prob=cp, cutoff_top_n=topn, vocab_list=vocab)
+    probs = np.stack([_peaky_probs(rng, T, V, temp, bb) for bb in (0.0, 1.5)])
+    got = dec.decode_ids_batch(probs)
+    for b in range(probs.shape[0]):
+        ref = DO.ctc_beam_search_decoding(probs[b], vocab, beam, cp, topn)
+        assert got[b][0][1] == ref[0][1], f"best hypothesis differs (utt {b})"
+        assert abs(got[b][0][0] - ref[0][0]) < 1e-3 * max(1.0, abs(ref[0][0]))
+        assert len(got[b]) == len(ref)
+        rd = dict((t, s) for s, t in ref)
+        hits = sum(1 for s, t in got[b] if t in rd and abs(rd[t] - s) < 1e-3 * max(1.0, abs(s)))
+        assert hits >= int(0.9 * len(ref)), f"only {hits} of {len(ref)} beam entries agree"
+        # best first
+        sc = [s for s, _ in got[b]]
+        assert all(sc[i] <= sc[i + 1] + 1e-6 for i in range(len(sc) - 1))
+
+
+def test_ctc_prune_matches_oracle_rows(lib, cuda):
+    """decoder_utils.cpp get_pruned_log_probs on peaked, flat and tie-heavy rows (the tie rows take the fallback path)."""
+    from oracle import decoders_oracle as DO
+    from ppasr_b200 import _lib as L
+    rng = np.random.RandomState(5)
+    V = 4233
+    rows = []
+    for temp in (8.0, 3.0, 1.0, 0.2):
+        lg = rng.randn(6, V).astype(np.float32) * temp
+        e = np.exp(lg - lg.max(-1, keepdims=True))
+        rows.append((e / e.sum(-1, keepdims=True)).astype(np.float32))
+    rows.append(np.full((2, V), 1.0 / V, np.float32))                    # uniform: every element ties
+    tie = np.zeros((2, V), np.float32); tie[:, 100:170] = 1.0 / 70       # 70 equal candidates > 64
+    rows.append(tie)
+    probs = torch.from_numpy(np.concatenate(rows)).to(cuda).contiguous()
+    R = probs.shape[0]
+    for cp, topn in ((0.99, 40), (1.0, 40), (0.5, 64), (0.999, 5)):
+        ws = torch.zeros(lib.ppasr_b200_beam_workspace_bytes(1, R), dtype=torch.uint8, device=cuda)
+        L.check(lib.ppasr_b200_op_ctc_prune(L.ptr(probs), R, V, cp, topn, L.ptr(ws), L.stream_ptr()))
+        torch.cuda.synchronize()
+        w = ws.cpu().numpy()
+        cnt = w[:R * 4].view(np.int32)
+        off = ((R + 63) // 64 * 64) * 4
+        cid = w[off:off + R * 64 * 4].view(np.int32).reshape(R, 64)
+        clp = w[off + R * 64 * 4:off + 2 * R * 64 * 4].view(np.float32).reshape(R, 64)
+        pn = probs.cpu().numpy()
+        for r in range(R):
+            ref = DO.get_pruned_log_probs(pn[r], cp, topn)
+            assert cnt[r] == len(ref), (r, cp, topn, cnt[r], len(ref))
+            assert cid[r, :cnt[r]].tolist() == [i for i, _ in ref], (r, cp, topn)
+            np.testing.assert_allclose(clp[r, :cnt[r]], [l for _, l in ref], rtol=1e-5, atol=1e-5)
+
+
+def test_beam_search_stream_overflow_raises(lib, cuda):
+    """A stream fed past max_frames must fail loudly instead of returning truncated transcripts."""
+    from ppasr_b200 import _lib as L
+    from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+    rng = np.random.RandomState(2)
+    V = 30
+    vocab = [f"<{i}>" for i in range(V)]
+    dec = BeamSearchDecoder(beam_size=8, vocab_list=vocab, max_frames=40)
+    probs = _peaky_probs(rng, 64, V, 3.0, 0.5)
+    dec.decode_chunk(probs[None, :32], np.array([32]))
+    with pytest.raises(L.PPASRB200Error):
+        dec.decode_chunk(probs[None, 32:64], np.array([32]))
+    # the C-ABI itself refuses as well: the state is flagged and result() reports -2
+    st = dec._alloc_state(1, 16)
+    dec._advance(st, dec._to_cuda(probs[None, :32]), None, 16)
+    with pytest.raises(L.PPASRB200Error):
+        dec._results(st, 1, 16, 16, nbest=1)
+    dec.reset_decoder()
+    assert dec.decode_chunk(probs[None, :32], np.array([32]))[1] is not None
 
 
 def test_beam_search_streaming_equals_offline(lib, cuda):

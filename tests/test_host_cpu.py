@@ -451,23 +451,31 @@ def test_inference_predictor_config_roundtrip(monkeypatch):
         IP.InferencePredictor({}, "whisper")
 
 
-def test_decoder_fallback_like_reference():
-    """predict.py:92-105: a beam-search decoder that cannot be initialised degrades to ctc_greedy with a warning. Here that covers
-    configurations outside the GPU decoder (the shipped beam_size 300, a KenLM binary LM); decoder_fallback=False raises."""
+def test_decoder_fallback_like_reference(tmp_path):
+    """predict.py:92-105: the reference degrades to ctc_greedy with a warning when its beam-search decoder cannot be
+    initialised. Here an unsupported configuration (KenLM binary LM, missing LM file, beam > 512) raises by default -- a
+    stock config must not silently decode differently -- and degrades only with decoder_fallback=True."""
     from ppasr_b200.decoders.beam_search_decoder import UnsupportedDecoderConfig
     from ppasr_b200.predict import PPASRPredictor
+    klm = tmp_path / "zh_giga.no_cna_cmn.prune01244.klm"
+    klm.write_bytes(b"mmap lm http://kheafield.com/code format version 5\n\x00" + bytes(64))
     p = object.__new__(PPASRPredictor)
     p.configs = {"ctc_beam_search_decoder_conf": {"alpha": 2.2, "beta": 4.3, "beam_size": 300, "cutoff_prob": 0.99,
-                                                  "cutoff_top_n": 40, "num_processes": 10,
-                                                  "language_model_path": "lm/zh_giga.no_cna_cmn.prune01244.klm"}}
+                                                  "cutoff_top_n": 40, "num_processes": 10, "language_model_path": str(klm)}}
     p.vocab_list = ["<blank>", "a"]
     p.decoder = "ctc_beam_search"
-    with pytest.warns(UserWarning, match="ctc_greedy"):
+    with pytest.raises(UnsupportedDecoderConfig, match="ARPA"):
         p._init_decoder()
+    with pytest.warns(UserWarning, match="ctc_greedy"):
+        p._init_decoder(decoder_fallback=True)
     assert p.decoder == "ctc_greedy" and not hasattr(p, "beam_search_decoder")
     p.decoder = "ctc_beam_search"
-    with pytest.raises(UnsupportedDecoderConfig, match="beam_size 300"):
-        p._init_decoder(decoder_fallback=False)
+    p.configs["ctc_beam_search_decoder_conf"]["language_model_path"] = str(tmp_path / "missing.klm")
+    with pytest.raises(UnsupportedDecoderConfig, match="not found"):
+        p._init_decoder()
+    p.configs["ctc_beam_search_decoder_conf"].update(language_model_path=None, beam_size=600)
+    with pytest.raises(UnsupportedDecoderConfig, match="beam_size 600"):
+        p._init_decoder()
     p.decoder = "ctc_greedy"
     p._init_decoder()   # nothing to do
 
