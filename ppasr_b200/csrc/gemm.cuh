@@ -546,9 +546,14 @@ struct EpiQKVGrouped {
   const float* bias_u;  // [H*192]
   const float* bias_v;  // [H*192]
   int M, T, H, Tg, Tgp;
+  // chunk streaming: K / V go to the append-only grouped cache at ABSOLUTE frame kofs + t (group = frame / 3, the cache
+  // starts zeroed so a partially filled last group reads zeros), queries stay grouped from the chunk start.
+  // Tgk = group pitch of the K cache per (b, h) (0 = offline: Tg); the V^T pitch is Tgp in both modes.
+  int kofs = 0, Tgk = 0;
   DEVINL void put(int b, int t, int which, int c0, const float (&v)[32]) const {
-    const int i0 = (t % 3) * 256 + c0;
-    const int g = t / 3;
+    const int tf = which == 0 ? t : t + kofs;
+    const int i0 = (tf % 3) * 256 + c0;
+    const int g = tf / 3;
     const int hp = i0 / 192;
     const int dp = i0 - hp * 192;
     const size_t bh = (size_t)b * H + hp;
@@ -570,7 +575,7 @@ struct EpiQKVGrouped {
         dv[j] = make_uint4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
       }
     } else if (which == 1) {
-      __nv_bfloat16* dst = kkg + (bh * Tg + g) * 192 + dp;
+      __nv_bfloat16* dst = kkg + (bh * (Tgk > 0 ? Tgk : Tg) + g) * 192 + dp;
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -599,7 +604,7 @@ struct EpiQKVGrouped {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sbias[cc + j];
       put(b, t, which, c0, v);
-      if (t == T - 1) {
+      if (t == T - 1 && (Tgk == 0 || which == 0)) {  // streaming: only the query padding; the cache is append-only
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
         for (int tp = T; tp < 3 * Tg; ++tp) put(b, tp, which, c0, v);

@@ -56,8 +56,10 @@ grouped_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   const int h = blockIdx.y, b = blockIdx.z;
   const int bh = b * p.H + h;
   const int row0 = blockIdx.x * 128;
-  const int klen = p.klens ? min(p.Tg, (__ldg(p.klens + b) + 2) / 3) : p.Tg;  // keys g with 3g < len
-  const int nblk = (p.Tg + 63) / 64;
+  const int Tgk = p.Tgk > 0 ? p.Tgk : p.Tg;           // key groups (streaming: the whole cache, queries: this chunk)
+  const int kpitch = p.k_pitch > 0 ? p.k_pitch : p.Tg;
+  const int klen = p.klens ? min(Tgk, (__ldg(p.klens + b) + 2) / 3) : Tgk;  // keys g with 3g < len
+  const int nblk = (Tgk + 63) / 64;
 
   if (warp_idx == 4) {
     if (elect_one()) {
@@ -98,7 +100,7 @@ grouped_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         if (j > 0) mbar_wait(bar_s + j - 1, 0);  // MMAs reading the K|P tiles of block j-1 are done
         mbar_arrive_expect_tx(bar_kp, 6 * GA_KT);
         for (int kt = 0; kt < 3; ++kt) {
-          tma_load_2d(s_kp + kt * GA_KT, &tm_k, bar_kp, kt * 64, bh * p.Tg + k0);
+          tma_load_2d(s_kp + kt * GA_KT, &tm_k, bar_kp, kt * 64, bh * kpitch + k0);
           tma_load_2d(s_kp + (3 + kt) * GA_KT, &tm_p, bar_kp, h * 192 + kt * 64, k0);
         }
         if (j == 0) mbar_wait(bar_q, 0);
@@ -212,7 +214,7 @@ grouped_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 
 cudaError_t launch_grouped_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_p,
                                      const CUtensorMap& tm_vt, const GroupedAttnParams& p, cudaStream_t st) {
-  if (p.Tg > GA_MAX_BLOCKS * 64 || p.H != 4) return cudaErrorInvalidValue;
+  if (p.Tg > GA_MAX_BLOCKS * 64 || p.Tgk > GA_MAX_BLOCKS * 64 || p.H != 4) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(grouped_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GA_SMEM_TOTAL);

@@ -157,10 +157,13 @@ cudaError_t launch_rel_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_
 // Grouped rel-pos attention of the Efficient Conformer (grouped_attention.cu)
 struct GroupedAttnParams {
   int B, H;
-  int T;    // frames per utterance
-  int Tg;   // groups per utterance = ceil(T / 3) (queries == keys)
-  const int* klens;     // per-utterance valid frame count (nullable)
+  int T;    // query frames per utterance
+  int Tg;   // query groups per utterance = ceil(T / 3); also the key groups when Tgk == 0 (offline: queries == keys)
+  const int* klens;     // per-utterance valid KEY frame count (nullable)
   __nv_bfloat16* out;   // [B*T, 256]
+  // chunk streaming (forward_chunk, attention.py:128-193 with a cache): the keys are the append-only grouped cache
+  int Tgk = 0;          // key groups to attend (0: = Tg)
+  int k_pitch = 0;      // rows of the K operand per (b, h) (0: = Tg); the cache's group capacity when streaming
 };
 cudaError_t launch_grouped_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_p,
                                      const CUtensorMap& tm_vt, const GroupedAttnParams& p, cudaStream_t st);

@@ -176,6 +176,10 @@ struct ppasr_b200_ctx {
     __nv_bfloat16* vt = nullptr;   // [L][B,H,64,Tcap]
     __nv_bfloat16* cnn = nullptr;  // [L][B,lorder,D]
     std::vector<CUtensorMap> tm_k, tm_vt;  // per layer, rebuilt every chunk (extent = kend)
+    // Efficient Conformer streaming: positional operands of the (<= 4) grouped blocks [4][256 groups][768], rebuilt per
+    // chunk, and the map of this chunk's grouped queries
+    __nv_bfloat16* pgc = nullptr;
+    CUtensorMap tm_pgc[4], tm_qgc;
     // ragged sessions (ppasr_b200_sessions_*): every cache slot is an independent stream with its own positions
     bool ragged = false;                        // set for the duration of a sessions_step
     std::vector<int> s_kstart, s_kend, s_offset;  // per slot (host)
@@ -347,6 +351,7 @@ int ppasr_b200_destroy(ppasr_b200_ctx* ctx) {
   if (ctx->ss.kk) cudaFree(ctx->ss.kk);
   if (ctx->ss.vt) cudaFree(ctx->ss.vt);
   if (ctx->ss.cnn) cudaFree(ctx->ss.cnn);
+  if (ctx->ss.pgc) cudaFree(ctx->ss.pgc);
   if (ctx->ss.d_step) cudaFree(ctx->ss.d_step);
   if (ctx->ds.h_state) cudaFree(ctx->ds.h_state);
   if (ctx->ds.c_state) cudaFree(ctx->ds.c_state);
@@ -1002,6 +1007,12 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
     set_last_error("ppasr_b200_finalize has not been called");
     return PPASR_ERR_STATE;
   }
+  // the memsets below run on the legacy default stream while chunks run on caller streams (PyTorch streams are
+  // non-blocking): a reset is rare, so order it against everything queued before and after with device-wide syncs
+  struct SyncBothSides {
+    SyncBothSides() { cudaDeviceSynchronize(); }
+    ~SyncBothSides() { cudaDeviceSynchronize(); }
+  } sync_both_sides;
   if (c->cfg.model_type == 2) {
     // zero LSTM / GRU states [L*nd, B, H] (inference_predictor.py:157-164)
     auto& ds = c->ds;
@@ -1019,8 +1030,8 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
     PPASR_CUDA_CHECK(cudaMemset(ds.c_state, 0, n * 4));
     return PPASR_OK;
   }
-  if (c->cfg.model_type != 0 && c->cfg.model_type != 1) {
-    set_last_error("chunk streaming (forward_chunk) is implemented for conformer, squeezeformer and deepspeech2");
+  if (c->cfg.model_type != 0 && c->cfg.model_type != 1 && c->cfg.model_type != 3) {
+    set_last_error("chunk streaming (forward_chunk) is implemented for conformer, squeezeformer, efficient_conformer and deepspeech2");
     return PPASR_ERR_STATE;
   }
   if (!c->cfg.causal) {
@@ -1049,6 +1060,15 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
   }
   // empty conv cache == the reference's zero left padding of the first chunk (convolution.py:109-110)
   PPASR_CUDA_CHECK(cudaMemset(ss.cnn, 0, (size_t)L * B * lorder * D * 2));
+  if (cfg.model_type == 3) {
+    // grouped blocks append into zeroed caches: the missing frames of a partially filled last group must read as zero
+    PPASR_REQUIRE(ss.Tcap >= 768, "efficient_conformer streaming needs max_len >= 768");
+    const size_t n = (size_t)L * B * H * ss.Tcap * 64;
+    PPASR_CUDA_CHECK(cudaMemset(ss.kk, 0, n * 2));
+    PPASR_CUDA_CHECK(cudaMemset(ss.vt, 0, n * 2));
+    if (!ss.pgc) PPASR_CUDA_CHECK(cudaMalloc(&ss.pgc, (size_t)4 * 256 * 768 * 2));
+    PPASR_CUDA_CHECK(cudaMemset(ss.pgc, 0, (size_t)4 * 256 * 768 * 2));
+  }
   ss.kstart = ss.kend = ss.offset = 0;
   return PPASR_OK;
 }
@@ -1104,6 +1124,50 @@ int ppasr_b200_encode_chunk(ppasr_b200_ctx* c, const float* feats, int32_t feats
                       (required_cache_size < 0 || required_cache_size % 2 == 0),
                   "squeezeformer chunk streaming needs even chunk sizes (all but the last chunk) and an even required_cache_size");
   }
+  const bool eff = cfg.model_type == 3;
+  if (eff) {
+    // forward_chunk of the Efficient Conformer: append-only caches (runtime_effconf.inl)
+    PPASR_REQUIRE(required_cache_size < 0, "efficient_conformer streaming keeps the whole history (required_cache_size < 0, "
+                                           "as PPASRPredictor passes, predict.py:304-306)");
+    PPASR_REQUIRE(c->eff_stride_idx < 0 || ss.kend % 2 == 0,
+                  "efficient_conformer chunk streaming needs even chunk sizes (all but the last chunk of a stream)");
+    if (c->eff_group_mask != 0 && (kend_new + 2) / 3 > 256) {
+      set_last_error("efficient_conformer stream longer than 768 encoder frames (30.7 s): the grouped attention keeps at most "
+                     "256 key groups; call reset_stream");
+      return PPASR_ERR_STATE;
+    }
+    int gi = 0;
+    for (int l = 0; l < L; ++l) {
+      const size_t lk = (size_t)l * B * H * ss.Tcap * 64;
+      const int rate = (c->eff_stride_idx >= 0 && l > c->eff_stride_idx) ? 2 : 1;
+      const int kv = (kend_new + rate - 1) / rate;  // keys valid after this chunk, at the block's rate
+      bool ok;
+      if ((c->eff_group_mask >> l) & 1) {
+        ok = gi < 4 && make_tmap_2d(&ss.tm_k[l], ss.kk + lk, 192, (uint64_t)B * H * 256, 192 * 2, 64, &err) &&
+             make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, (uint64_t)((kv + 2) / 3), (uint64_t)B * H * 192, 256 * 2, 192, &err) &&
+             make_tmap_2d(&ss.tm_pgc[gi], ss.pgc + (size_t)gi * 256 * 768, 768, 256, 768 * 2, 64, &err);
+        if (gi >= 4) err = "more than 4 grouped blocks are not supported";
+        ++gi;
+      } else {
+        ok = make_tmap_2d(&ss.tm_k[l], ss.kk + lk, 64, (uint64_t)B * H * ss.Tcap, 128, 128, &err) &&
+             make_tmap_2d(&ss.tm_vt[l], ss.vt + lk, kv, (uint64_t)B * H * 64, (uint64_t)ss.Tcap * 2, 64, &err);
+      }
+      if (!ok) {
+        set_last_error(err);
+        return PPASR_ERR_CUDA;
+      }
+    }
+    if (c->eff_group_mask != 0 &&
+        !make_tmap_2d(&ss.tm_qgc, p.q2g, 384, (uint64_t)B * H * ((p.Tp + 2) / 3), 384 * 2, 128, &err)) {
+      set_last_error(err);
+      return PPASR_ERR_CUDA;
+    }
+    rc = run_encoder_effconf_chunk(c, st);
+    if (rc) return rc;
+    ss.kend = kend_new;
+    ss.offset += p.Tp;
+    return PPASR_OK;
+  }
   for (int l = 0; l < L; ++l) {
     const size_t lk = (size_t)l * B * H * ss.Tcap * 64;
     const int rate = (sqz && c->sq.reduce_idx >= 0 && l >= c->sq.reduce_idx && l < c->sq.recover_idx) ? 2 : 1;
@@ -1147,8 +1211,11 @@ int ppasr_b200_sessions_reset(ppasr_b200_ctx* c, int32_t slot) {
   const auto& cfg = c->cfg;
   const int lorder = cfg.conv_kernel - 1, D = cfg.d_model;
   ss.s_kstart[slot] = ss.s_kend[slot] = ss.s_offset[slot] = 0;
+  // ordered against the steps queued on caller (non-blocking) streams before and after: a slot is recycled rarely
+  PPASR_CUDA_CHECK(cudaDeviceSynchronize());
   for (int l = 0; l < cfg.n_layers; ++l)  // empty conv cache == zero left padding of the first chunk
     PPASR_CUDA_CHECK(cudaMemset(ss.cnn + ((size_t)l * ss.B + slot) * lorder * D, 0, (size_t)lorder * D * 2));
+  PPASR_CUDA_CHECK(cudaDeviceSynchronize());
   return PPASR_OK;
 }
 

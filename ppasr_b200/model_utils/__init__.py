@@ -137,10 +137,11 @@ class SqueezeformerModel(_HotPathModel):
 
 
 class EfficientConformerModel(_HotPathModel):
+    """efficient_conformer/model.py:16-63,147-183. get_encoder_out_chunk (forward_chunk, encoder.py:266-394) keeps its
+    append-only grouped / half-rate caches on the device (csrc/runtime_effconf.inl); like the Squeezeformer the caller gets
+    opaque continuation tokens instead of the reference's cache tensors. Streams are limited to 768 encoder frames (30.7 s)
+    between reset_stream() calls and need required_cache_size < 0 (what PPASRPredictor passes, predict.py:304-306)."""
     use_model = "efficient_conformer"
-
-    def get_encoder_out_chunk(self, *a, **k):
-        raise Exception("EfficientConformerModel.get_encoder_out_chunk is not implemented on the GPU yet (DESIGN.md 7.1)")
 
 
 class DeepSpeech2Model(_HotPathModel):

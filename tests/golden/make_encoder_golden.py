@@ -277,6 +277,15 @@ if __name__ == "__main__":
                                  chunk_T=0, vocab=120, num_blocks=2, group_layer_idx=(0, 1), stride_layer_idx=1)
         make_efficient_conformer(G("efficient_conformer_gpu_offline"), streaming=False, norm="batch_norm", lens=(207, 150, 5),
                                  vocab=120, num_blocks=2, group_layer_idx=(0, 1), stride_layer_idx=1)
+        # forward_chunk of the Efficient Conformer (encoder.py:266-394): grouped attention on cache + chunk, the stride block and
+        # half-rate blocks behind it; 67-frame windows incl. an odd last window. The 12-block one has the shipped layout
+        # (configs/efficient_conformer.yml: group_layer_idx 0-3, stride_layer_idx 3).
+        make_efficient_conformer(G("efficient_conformer_gpu_stream"), streaming=True, norm="layer_norm", lens=(203, 150, 99),
+                                 chunk_T=67 + 64 * 3 + 24, vocab=120, num_blocks=4, group_layer_idx=(0, 1), stride_layer_idx=1,
+                                 seed=1005)
+        make_efficient_conformer(G("efficient_conformer_gpu_stream12"), streaming=True, norm="layer_norm", lens=(99,),
+                                 chunk_T=67 + 64 * 5, vocab=120, num_blocks=12, group_layer_idx=(0, 1, 2, 3), stride_layer_idx=3,
+                                 seed=1006)
         make_deepspeech2(G("deepspeech2_gpu_stream_lstm"), True, False, lens=(203, 150, 99), chunk_T=67 + 64 * 2, chunk_B=2,
                          vocab=120, nl=2, H=256)
         make_deepspeech2(G("deepspeech2_gpu_offline_gru"), False, True, lens=(203, 150, 99), vocab=120, nl=2, H=256)

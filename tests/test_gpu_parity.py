@@ -326,13 +326,25 @@ def _run_model(cuda, num_blocks, B, T, lens, vocab=4233, streaming=True, norm="l
     scale = ref_logits.abs().max().item()
     worst = max((logits[b, :vl[b]] - ref_logits[b, :vl[b]]).abs().max().item() for b in range(B) if vl[b] > 0) / scale
     assert worst < 1e-2, f"logits rel err {worst}"
-    # greedy ids: identical wherever the oracle's arg-max margin is far above bf16 noise
+    # greedy ids vs the fp32 oracle. Bit-exact is what the decode kernels deliver ON A GIVEN posterior (checked below and
+    # against the reference's own outputs in test_greedy_decoder_golden_bit_exact); end to end the bf16 encoder may flip an
+    # arg-max only where the oracle's top-2 margin is below twice the logit error. So: every frame whose margin exceeds
+    # 3 x the MEASURED max |logit error| must agree, and the unfiltered agreement rate is reported and bounded.
     top2 = ref_logits.topk(2, -1).values
-    big = (top2[..., 0] - top2[..., 1]) > 0.05 * scale
+    margin = top2[..., 0] - top2[..., 1]
+    big = margin > 3.0 * worst * scale
     ref_ids = ref_logits.argmax(-1)
+    n_frames = n_agree = n_small = 0
     for b in range(B):
-        agree = (torch.from_numpy(fi)[b, :vl[b]] == ref_ids[b, :vl[b]]) | ~big[b, :vl[b]]
-        assert bool(agree.all())
+        same = torch.from_numpy(fi)[b, :vl[b]] == ref_ids[b, :vl[b]]
+        assert bool((same | ~big[b, :vl[b]]).all())
+        n_frames += int(vl[b])
+        n_agree += int(same.sum())
+        n_small += int((~big[b, :vl[b]]).sum())
+    rate = n_agree / max(1, n_frames)
+    print(f"[greedy ids] model={model} L={num_blocks} B={B} T={T}: logits rel err {worst:.3e}; unfiltered frame agreement "
+          f"{n_agree}/{n_frames} = {rate:.5f}; frames inside the 3x-error margin: {n_small}")
+    assert rate >= 0.95, f"unfiltered greedy agreement {rate}"
     # fused head == reference greedy on the materialised posterior of the same engine (bit-exact ids)
     pn = probs.numpy()
     for b in range(B):
@@ -931,6 +943,47 @@ def test_squeezeformer_chunk_streaming_matches_oracle(lib, cuda, nb, reduce_idx,
     pred.reset_stream()
 
 
+@pytest.mark.parametrize("nb,group_idx,stride_idx,batch", [(4, (0, 1), 1, 1), (4, (0, 1, 2), 2, 3), (3, (), None, 2), (12, (0, 1, 2, 3), 3, 2)])
+def test_efficient_conformer_chunk_streaming_matches_oracle(lib, cuda, nb, group_idx, stride_idx, batch):
+    """efficient_conformer/encoder.py:266-394 forward_chunk on the device (append-only grouped K / V^T caches, per-chunk padded
+    positional operand, stride block over [cache | chunk], half-rate blocks behind it): 67-frame windows with stride 64 and a
+    short last window, `batch` lock-step streams, chunk by chunk on the logits against the oracle's forward_chunk chain (which
+    is pinned to the reference code's own streaming outputs, tests/test_encoder_golden_cpu.py)."""
+    from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
+    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+    from ppasr_b200.weights import EfficientConformerConfig, init_efficient_conformer_weights, synthetic_fbank
+    cfg = EfficientConformerConfig(num_blocks=nb, vocab_size=120, group_layer_idx=group_idx, stride_layer_idx=stride_idx)
+    w = init_efficient_conformer_weights(cfg)
+    orc = EfficientConformerOracle(EfficientConformerConf(**cfg.to_dict()), w)
+    pred = InferencePredictor({"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}, "efficient_conformer",
+                              streaming=True, weights=w)
+    feats = synthetic_fbank(batch, 67 + 64 * 3 + 24)
+    states = [(torch.zeros(0, 0, 0, 0), torch.zeros(0, 0, 0, 0), 0) for _ in range(batch)]
+    total = 0
+    for s in range(0, feats.shape[1] - 6, 64):
+        ch = feats[:, s:s + 67]
+        refs = []
+        for b in range(batch):   # the oracle streams one utterance at a time like the reference
+            att, cnn, off = states[b]
+            ref, att, cnn = orc.get_encoder_out_chunk(torch.from_numpy(ch[b:b + 1]), off, -16, att, cnn, return_logits=True)
+            states[b] = (att, cnn, off + ref.shape[1])
+            refs.append(ref)
+        ref = torch.cat(refs, 0)
+        total += ref.shape[1]
+        probs = pred.predict_chunk_conformer(ch, -16)
+        assert probs.shape == tuple(ref.shape) and np.allclose(probs.sum(-1), 1.0, atol=1e-4)
+        lg = pred.engine.ctc_logits().float().cpu()
+        assert ((lg - ref).abs().max() / ref.abs().max()).item() < 1e-2, s
+        assert int(pred.offset[0]) == total
+    # bounded histories are not what PPASRPredictor asks for and are refused; so is a stream past the grouped capacity
+    with pytest.raises(Exception):
+        pred.predict_chunk_conformer(feats[:, :67], 32)
+    pred.reset_stream()
+    probs = pred.predict_chunk_conformer(feats[:, :67], -16)
+    assert probs.shape[1] == (16 if stride_idx is None else 8)
+    pred.reset_stream()
+
+
 @pytest.mark.parametrize("model", ["conformer", "squeezeformer"])
 def test_fused_dwconv_bit_identical(lib, cuda, model):
     """The depthwise conv + norm + swish stage computed inside the chained FFN kernel (option fused_dwconv, default) equals the
@@ -1047,7 +1100,6 @@ def test_stream_scheduler_ragged_sessions(lib, cuda):
     assert len(sch._free) == 4
 
 
-@pytest.mark.xfail(reason="first GPU run pending (added after the GPU budget was spent)", strict=False)
 def test_predict_long_batched_regions(lib, cuda):
     """predict_long (predict.py:190-229): the speech regions of one recording as ragged GPU batches vs one predict() per
     region. The two routes differ only in the fbank implementation (GPU kernel vs torchaudio) and in batch padding, so the

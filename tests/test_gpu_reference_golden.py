@@ -14,10 +14,8 @@ import numpy as np
 import pytest
 import torch
 
-# Written after this round's GPU minutes were spent (dry-run on CPU against oracle-backed stand-ins of the engine): the first
-# real run is the round-end one, so a mismatch is reported as xfail (and a pass as XPASS) instead of stopping the suite. To be
-# promoted to hard assertions once seen green on a B200.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first GPU run pending (added after the GPU budget was spent)", strict=False)]
+# Hard assertions: seen green on a B200 at the end of round 1 (GPUTEST_r01: all XPASS), the non-strict xfail marks are gone.
+pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "encoder_golden_*_gpu_*.npz")))
@@ -54,7 +52,7 @@ def _windows(num_frames, window=67, stride=64, context=7):
 
 
 def test_fixtures_present():
-    assert len(FILES) == 8 and {_family(f) for f in FILES} == set(FAMILIES)
+    assert len(FILES) == 10 and {_family(f) for f in FILES} == set(FAMILIES)
 
 
 @pytest.mark.parametrize("fname", FILES)
@@ -75,14 +73,20 @@ def test_offline_logits_match_reference_code(lib, cuda, fname):
     assert max(vl) == ref.shape[1]
     worst = max(float(np.abs(logits[b, :n] - ref[b, :n]).max()) for b, n in enumerate(vl) if n > 0) / scale
     assert worst < 1e-2, f"{fname}: logits rel err {worst}"
-    # arg-max path agrees wherever the reference's own margin is far above bf16 noise
+    # arg-max path: every frame whose reference top-2 margin exceeds 3 x the MEASURED max |logit error| must agree (an arg-max
+    # can only flip below twice the error); the unfiltered agreement rate is reported and bounded
     top2 = np.sort(ref, -1)[..., -2:]
-    big = (top2[..., 1] - top2[..., 0]) > 0.05 * scale
-    n_checked = 0
+    big = (top2[..., 1] - top2[..., 0]) > 3.0 * worst * scale
+    n_checked = n_frames = n_agree = 0
     for b, n in enumerate(vl):
-        agree = (logits[b, :n].argmax(-1) == ref[b, :n].argmax(-1)) | ~big[b, :n]
-        assert bool(agree.all())
+        same = logits[b, :n].argmax(-1) == ref[b, :n].argmax(-1)
+        assert bool((same | ~big[b, :n]).all())
         n_checked += int(big[b, :n].sum())
+        n_frames += int(n)
+        n_agree += int(same.sum())
+    print(f"[{fname}] logits rel err {worst:.3e}; unfiltered arg-max agreement {n_agree}/{n_frames}")
+    assert n_agree >= 0.95 * n_frames
+    for b, n in enumerate(vl):
         assert np.allclose(probs[b, :n].sum(-1), 1.0, atol=1e-4)
         # probabilities: only where the reference is decided (a 1e-2-of-scale logit error moves an undecided softmax a lot)
         sure = ref_p[b, :n].max(-1) > 0.99

@@ -360,7 +360,7 @@ def test_model_utils_surface_cpu(monkeypatch, tmp_path):
     assert made[-1].closed
     m.get_encoder_out(np.zeros((1, 67, 80)), [67])
     assert len(made) == n_before + 1
-    # DeepSpeech2: states instead of caches; EfficientConformer chunk API raises
+    # DeepSpeech2: states instead of caches; EfficientConformer: device-resident caches like the Squeezeformer
     d = MU.DeepSpeech2Model(80, 5, str(mi), streaming=True, encoder_conf={"num_rnn_layers": 2, "rnn_size": 8},
                             weights={"decoder.ctc_lo.weight": np.zeros((8, 5), np.float32)})
     pr, ln, h, c = d.get_encoder_out_chunk(np.zeros((3, 67, 80)), np.array([67] * 3))
@@ -369,8 +369,8 @@ def test_model_utils_surface_cpu(monkeypatch, tmp_path):
     assert made[-1].args["use_model"] == "deepspeech2" and made[-1].resets == 1
     e = MU.EfficientConformerModel(80, 5, str(mi), weights={"ctc.ctc_lo.weight": np.zeros((256, 5), np.float32)})
     assert e.get_encoder_out(np.zeros((1, 67, 80)), [67]).shape == (1, 3, 5)
-    with pytest.raises(Exception, match="not implemented on the GPU"):
-        e.get_encoder_out_chunk(x, 0, -16)
+    pe, tok_a, tok_c = e.get_encoder_out_chunk(x, 0, -16)   # forward_chunk runs on the device; opaque continuation tokens
+    assert tok_a.shape == (1, 1, 1, 1) and tok_c.shape == (1, 1, 1, 1) and made[-1].args["use_model"] == "efficient_conformer"
     assert {c.use_model for c in (MU.ConformerModel, MU.SqueezeformerModel, MU.EfficientConformerModel, MU.DeepSpeech2Model)} == \
         {"conformer", "squeezeformer", "efficient_conformer", "deepspeech2"}
 
