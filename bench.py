@@ -1,16 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the B200-native PPASR hot path (contract: see the task statement / DESIGN.md §Measurement).
 
-Workload (BASELINE.json configs[1]): conformer.yml streaming model, batch 32 x 10 s synthetic fbank
-([32, 998, 80] fp32) per GPU, fused CTC head + ctc_greedy. A "step" = one pass of the hot path over one
-batch: encoder forward -> CTC projection -> greedy decode (-> one NCCL all-gather of the decoded ids
-when N > 1). Weak scaling: every GPU processes its own 32 utterances.
+Default workload = BASELINE.json configs[1] (the config the headline metric is quoted on): conformer.yml streaming model,
+batch 32 x 10 s synthetic fbank ([32, 998, 80] fp32) per GPU, fused CTC head + ctc_greedy. A "step" = one pass of the hot
+path over one batch: encoder forward -> CTC projection -> decode (-> one NCCL all-gather of the decoded ids when N > 1).
+Weak scaling: every GPU processes its own batch.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (torchrun for N > 1)
-  python bench.py --impl reference [--steps K] [--warmup W]      # CPU reference arm (oracle port, all host threads)
+  python bench.py [--gpus N] [--steps K] [--warmup W]               # our arm (torchrun for N > 1)
+  python bench.py --impl reference [--steps K] [--warmup W]         # CPU reference arm (oracle port, host threads)
+  python bench.py --config {c1,c2,c3,c4,c5} ...                     # the other BASELINE configs, same JSON schema
+
+--config: c2 (default) conformer streaming b32x10s greedy; c1 deepspeech2 non-streaming 1x5s greedy (CPU arm: one core);
+c3 conformer non-streaming b64x30s ctc_beam_search beam 10; c4 squeezeformer streaming b32x10s per GPU greedy; c5
+efficient_conformer streaming chunk 16, b64x5s per GPU, ctc_beam_search beam 20 + 4-gram LM.
+
+Timing: W >= 3 warm-up steps; the timed region is R repetitions of exactly K steps, each repetition bracketed by CUDA events on
+the launching streams (barrier + synchronize on both sides, max over ranks); R is chosen so that the repetitions cover >= 1 s.
+`ms_per_step` / `value` are the MEDIAN repetition; p10 / p90 are reported beside it.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -22,35 +32,76 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH_PER_GPU = 32
-SECONDS = 10
-FRAMES = 1 + (16000 * SECONDS - 400) // 160  # 998 (kaldi snip-edges, audio_featurizer.py:125-136)
 VOCAB = 4233
-GFLOP_PER_UTT = 23.17  # SURVEY.md §8d algorithmic FLOPs of the conformer path at 10 s
 METRIC = "utterances_per_sec"
 
+# algorithmic GFLOP per utterance: SURVEY.md §8(d) / BASELINE.md §2 (2 * MAC of the GEMM-shaped work)
+CONFIGS = {
+    "c1": dict(model="deepspeech2", streaming=False, batch=1, seconds=5, decoder="ctc_greedy", gflop_per_utt=30.2,
+               name="deepspeech2 non-streaming 1x5s fbank[1,498,80] ctc_greedy (BASELINE configs[0])"),
+    "c2": dict(model="conformer", streaming=True, batch=32, seconds=10, decoder="ctc_greedy", gflop_per_utt=23.17,
+               name="conformer-streaming b32x10s fbank[32,998,80] ctc_greedy (BASELINE configs[1])"),
+    "c3": dict(model="conformer", streaming=False, batch=64, seconds=30, decoder="ctc_beam_search", beam=10, gflop_per_utt=76.8,
+               name="conformer non-streaming b64x30s fbank[64,2998,80] ctc_beam_search beam 10 (BASELINE configs[2])"),
+    "c4": dict(model="squeezeformer", streaming=True, batch=32, seconds=10, decoder="ctc_greedy", gflop_per_utt=19.0,
+               name="squeezeformer-streaming b32x10s per GPU fbank[32,998,80] ctc_greedy (BASELINE configs[3] shard)"),
+    # 494 frames = 4.96 s: the reference's forward_chunk cannot take an ODD number of subsampled frames in the last window of a
+    # stream (efficient_conformer/encoder.py:390 concatenates full-rate caches with x2-repeated half-rate ones; 5.00 s = 498
+    # frames would end on an 11-frame chunk and raise there), so both arms run the longest length it accepts
+    "c5": dict(model="efficient_conformer", streaming=True, batch=64, seconds=5, frames=494, decoder="ctc_beam_search", beam=20,
+               lm=True, chunked=True, gflop_per_utt=8.24,
+               name="efficient_conformer streaming chunk 16 (67-frame windows, stride 64) b64x5s per GPU "
+                    "ctc_beam_search beam 20 + 4-gram LM (BASELINE configs[4] shard)"),
+}
 
-def model_setup(model):
-    """(config, weights, workload name, use_model, algorithmic GFLOP/utt) for --model: conformer = BASELINE configs[1]
-    (the headline metric); squeezeformer = the per-GPU share of configs[3] (256 x 10 s over 8 GPUs = 32 per GPU)."""
-    from ppasr_b200.weights import (ConformerConfig, SqueezeformerConfig, init_conformer_weights,
-                                    init_squeezeformer_weights)
-    if model == "squeezeformer":
-        cfg = SqueezeformerConfig(vocab_size=VOCAB)
-        return (cfg, init_squeezeformer_weights(cfg),
-                "squeezeformer-streaming b32x10s per GPU fbank[32,998,80] ctc_greedy (BASELINE configs[3] shard)",
-                "squeezeformer", 19.0)
-    cfg = ConformerConfig(vocab_size=VOCAB)
-    return (cfg, init_conformer_weights(cfg),
-            "conformer-streaming b32x10s fbank[32,998,80] ctc_greedy (BASELINE configs[1])", "conformer", GFLOP_PER_UTT)
+
+def frames_of(seconds):
+    return 1 + (16000 * seconds - 400) // 160  # kaldi snip-edges (audio_featurizer.py:125-136): 5 s 498, 10 s 998, 30 s 2998
 
 
-def make_oracle(model, cfg, w):
-    if model == "squeezeformer":
+def model_setup(conf):
+    from ppasr_b200 import weights as W
+    m = conf["model"]
+    if m == "squeezeformer":
+        cfg = W.SqueezeformerConfig(vocab_size=VOCAB, streaming=conf["streaming"])
+        return cfg, W.init_squeezeformer_weights(cfg)
+    if m == "efficient_conformer":
+        cfg = W.EfficientConformerConfig(vocab_size=VOCAB, streaming=conf["streaming"])
+        return cfg, W.init_efficient_conformer_weights(cfg)
+    if m == "deepspeech2":
+        cfg = W.DeepSpeech2Config(vocab_size=VOCAB, streaming=conf["streaming"])
+        return cfg, W.init_deepspeech2_weights(cfg)
+    cfg = W.ConformerConfig(vocab_size=VOCAB, streaming=conf["streaming"])
+    return cfg, W.init_conformer_weights(cfg)
+
+
+def make_oracle(conf, cfg, w):
+    m = conf["model"]
+    if m == "squeezeformer":
         from oracle.squeezeformer_oracle import SqueezeformerConf, SqueezeformerOracle
         return SqueezeformerOracle(SqueezeformerConf(**cfg.to_dict()), w)
+    if m == "efficient_conformer":
+        from oracle.efficient_conformer_oracle import EfficientConformerConf, EfficientConformerOracle
+        return EfficientConformerOracle(EfficientConformerConf(**cfg.to_dict()), w)
+    if m == "deepspeech2":
+        from oracle.deepspeech2_oracle import DeepSpeech2Conf, DeepSpeech2Oracle
+        return DeepSpeech2Oracle(DeepSpeech2Conf(**cfg.to_dict()), w)
     from oracle.conformer_oracle import ConformerConf, ConformerOracle
     return ConformerOracle(ConformerConf(**cfg.to_dict()), w)
+
+
+def synthetic_lm(vocab, order=4):
+    """Seeded synthetic character 4-gram LM over the synthetic vocabulary (no LM ships with the reference)."""
+    from ppasr_b200.decoders.ngram_lm import NGramLM
+    rng = np.random.RandomState(0)
+    V = len(vocab)
+    sents = [[vocab[2 + int(z) % (V - 3)] for z in rng.zipf(1.3, size=rng.randint(5, 30))] for _ in range(20000)]
+    return NGramLM.from_counts(sents, order=order)
+
+
+def stream_windows(num_frames, window=67, stride=64, context=7):
+    """predict.py:281-297 with is_end on the last call."""
+    return [(cur, min(cur + window, num_frames)) for cur in range(0, num_frames - context + 1, stride)]
 
 
 def peaks():
@@ -64,6 +115,17 @@ def peaks():
         return fallback
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture of this kernel is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        v = d.get(kernel)
+        return float(v["dram_bytes_per_launch"]) if v else None
+    except (OSError, ValueError, KeyError, TypeError):
+        return None
+
+
 def host_cores():
     """Usable host cores: CPU affinity capped by the cgroup CPU quota (the GPU boxes expose 128 logical CPUs
     but a 16-CPU quota; running the CPU arm with 128 threads is 100x slower than with 16)."""
@@ -75,6 +137,23 @@ def host_cores():
     except Exception:
         pass
     return n
+
+
+def pin_to_gpu_numa(index):
+    """Bind this rank to the CPUs NVML reports as local to its GPU (8-GPU boxes: two sockets). Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        use = (cpus & cur) or cur
+        os.sched_setaffinity(0, use)
+        return len(use)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -129,48 +208,210 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_step(orc, feats, lens, vocab):
-    """One pass of the reference-equivalent CPU path (oracle restatement; Paddle is not installable here):
-    get_encoder_out -> greedy_decoder_batch."""
-    import torch
-    from oracle import decoders_oracle as DO
-    probs = orc.get_encoder_out(torch.from_numpy(feats), torch.tensor(lens))
-    return DO.greedy_decoder_batch([p for p in probs.numpy()], vocab)
+def quantiles(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    q = lambda f: xs[min(n - 1, max(0, int(round(f * (n - 1)))))]
+    return {"p10": q(0.1), "p50": statistics.median(xs), "p90": q(0.9), "repetitions": n}
 
 
-def run_reference(args):
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle restatement of the reference graph (PyTorch-CPU fp32) + the reference decoders' restatement.
+# Paddle is not installable offline, so kind = "port"; the restatement is pinned to the reference's own code
+# (tests/test_encoder_golden_cpu.py, tests/golden/greedy_golden.*).
+# ----------------------------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, conf, cfg, weights, vocab):
+        import torch
+        self.torch = torch
+        self.conf, self.cfg, self.vocab = conf, cfg, vocab
+        self.orc = make_oracle(conf, cfg, weights)
+        self.frames = conf.get("frames") or frames_of(conf["seconds"])
+        self.scorer = None
+        if conf.get("lm"):
+            from ppasr_b200.decoders.ngram_lm import Scorer
+            self.scorer = Scorer(2.2, 4.3, None, vocab, lm=synthetic_lm(vocab))
+        # full per-GPU batch for the greedy configs; the pure-Python beam search restatement is ~1 s per 10 s utterance, so
+        # the beam configs time a bounded sample of the batch (declared in `sample`)
+        self.sample_b = conf["batch"] if conf["decoder"] == "ctc_greedy" else min(conf["batch"], 2)
+
+    def probs(self, feats, lens):
+        torch = self.torch
+        if self.conf.get("chunked"):
+            outs = []
+            for b in range(feats.shape[0]):
+                att, cnn, off, rows = torch.zeros(0, 0, 0, 0), torch.zeros(0, 0, 0, 0), 0, []
+                for (a, e) in stream_windows(int(lens[b])):
+                    p, att, cnn = self.orc.get_encoder_out_chunk(torch.from_numpy(feats[b:b + 1, a:e]), off, -16, att, cnn)
+                    off += p.shape[1]
+                    rows.append(p[0])
+                outs.append(torch.cat(rows, 0).numpy())
+            return outs
+        p = self.orc.get_encoder_out(torch.from_numpy(feats), torch.tensor(lens))
+        return [x for x in p.numpy()]
+
+    def step(self, feats, lens):
+        from oracle import decoders_oracle as DO
+        ps = self.probs(feats, lens)
+        if self.conf["decoder"] == "ctc_greedy":
+            return DO.greedy_decoder_batch(ps, self.vocab)
+        return [DO.ctc_beam_search_decoding(p, self.vocab, self.conf["beam"], 0.99, 40, ext_scorer=self.scorer)[0][1] for p in ps]
+
+    def choose_threads(self, feats, lens):
+        """3-point probe of the intra-op thread count (all usable cores, half, a quarter) on a 4-utterance slice."""
+        torch = self.torch
+        cores = 1 if self.conf["model"] == "deepspeech2" else host_cores()  # BASELINE configs[0]: single core
+        cands = sorted({max(1, cores), max(1, cores // 2), max(1, cores // 4)}, reverse=True)
+        if len(cands) == 1:
+            torch.set_num_threads(cands[0])
+            return cands[0], {}
+        nb = min(4, feats.shape[0])
+        f, l = feats[:nb], lens[:nb]
+        probe = {}
+        for n in cands:
+            torch.set_num_threads(n)
+            self.probs(f, l)
+            t0 = time.perf_counter()
+            self.probs(f, l)
+            probe[n] = time.perf_counter() - t0
+        best = min(probe, key=probe.get)
+        torch.set_num_threads(best)
+        return best, {str(k): round(v, 4) for k, v in probe.items()}
+
+    def describe(self, n_steps):
+        c = self.conf
+        what = f"{self.sample_b} of {c['batch']} utterances x {c['seconds']} s per step" if self.sample_b != c["batch"] else \
+            f"the full batch of {c['batch']} utterances x {c['seconds']} s per step"
+        return (f"{what}, {n_steps} timed steps: PyTorch-CPU fp32 oracle restatement of the reference Paddle graph + "
+                f"{c['decoder']} restatement (Paddle not installable offline; restatement pinned to the reference code, "
+                "tests/test_encoder_golden_cpu.py)")
+
+
+def run_reference(args, conf):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from ppasr_b200.weights import make_vocab, synthetic_fbank
-    cores = host_cores()
-    torch.set_num_threads(cores)
-    cfg, w, workload, _, _ = model_setup(args.model)
-    orc = make_oracle(args.model, cfg, w)
+    cfg, w = model_setup(conf)
     vocab = make_vocab(VOCAB)
-    sample_b = 8  # bounded sample of the 32-utterance batch per step
-    feats = synthetic_fbank(sample_b, FRAMES)
-    lens = [FRAMES] * sample_b
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_step(orc, feats, lens, vocab)
-    steps = max(1, min(args.steps, 5))
+    ref = CpuReference(conf, cfg, w, vocab)
+    feats = synthetic_fbank(ref.sample_b, ref.frames, seed=1234)
+    lens = [ref.frames] * ref.sample_b
+    threads, probe = ref.choose_threads(feats, lens)
+    W = max(1, args.warmup)
+    K = max(1, args.steps)
+    # keep the whole run within a few minutes: one step of the full C2 batch is ~1.5-3 s on 16 cores
     t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_step(orc, feats, lens, vocab)
-    dt = (time.perf_counter() - t0) / steps
-    value = sample_b / dt
+    ref.step(feats, lens)
+    one = time.perf_counter() - t0
+    budget_s = 240.0
+    if one * (W + K) > budget_s:
+        K = max(1, int(budget_s / one) - min(W, 2))
+        W = min(W, 2)
+    for _ in range(max(0, W - 1)):
+        ref.step(feats, lens)
+    times = []
+    for _ in range(K):
+        t0 = time.perf_counter()
+        ref.step(feats, lens)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    value = ref.sample_b / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (BATCH_PER_GPU / sample_b), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "rtf": dt / (sample_b * SECONDS)},
+        "config": {"workload": conf["name"], "rtf": dt / (ref.sample_b * conf["seconds"]), "batch_per_step": ref.sample_b,
+                   "step_ms_quantiles": quantiles([t * 1e3 for t in times]), "thread_probe_s": probe},
         "cpu_baseline": {"value": value, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample_b} of 32 utterances x 10 s per step, PyTorch-CPU fp32 oracle restatement "
-                                   "of the reference Paddle graph + reference greedy restatement (Paddle not installable; restatement pinned to the reference code, tests/test_encoder_golden_cpu.py)"},
+                         "sample": ref.describe(K)},
         "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class GpuWorkload:
+    """One BASELINE config on one GPU: device-resident step (`value`), host-buffer step through the public API (`e2e`)."""
+
+    def __init__(self, conf, cfg, weights, vocab, dev, rank, world):
+        import torch
+        from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
+        from ppasr_b200.weights import synthetic_fbank
+        self.torch, self.conf, self.cfg, self.vocab, self.dev, self.rank, self.world = torch, conf, cfg, vocab, dev, rank, world
+        self.B = conf["batch"]
+        self.frames = conf.get("frames") or frames_of(conf["seconds"])
+        configs = {"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}
+        self.pred = InferencePredictor(configs, conf["model"], streaming=conf["streaming"], weights=weights, device=dev.index)
+        self.eng = self.pred.engine
+        self.pipelined = conf["decoder"] == "ctc_greedy" and conf["model"] != "deepspeech2"
+        npool = 16 if self.B * self.frames * 320 * 16 < (8 << 30) else 2
+        if conf["model"] == "conformer" and not conf["streaming"]:
+            npool = 3  # 64 x 2998 x 80 fp32 = 61 MB per batch: three distinct batches exceed the 126 MB L2
+        self.host = torch.from_numpy(synthetic_fbank(self.B, self.frames, seed=1234 + rank)).pin_memory()
+        self.pool = [self.host.to(dev)] + [torch.from_numpy(synthetic_fbank(self.B, self.frames, seed=5000 + 97 * rank + i)).to(dev)
+                                            for i in range(npool - 1)]
+        self.pool_bytes = sum(t.numel() * 4 for t in self.pool)
+        self.dec = None
+        if conf["decoder"] == "ctc_beam_search":
+            from ppasr_b200.decoders.beam_search_decoder import BeamSearchDecoder
+            kw = {}
+            if conf.get("lm"):
+                from ppasr_b200.decoders.ngram_lm import Scorer
+                kw = dict(alpha=2.2, beta=4.3, ext_scorer=Scorer(2.2, 4.3, None, vocab, lm=synthetic_lm(vocab)))
+            self.dec = BeamSearchDecoder(beam_size=conf["beam"], cutoff_prob=0.99, cutoff_top_n=40, vocab_list=vocab, **kw)
+        self.windows = stream_windows(self.frames) if conf.get("chunked") else None
+        self.Tp = self.eng.encode(self.pool[0]).Tp if not self.windows else None
+        if self.windows:
+            self.eng.stream_reset(self.B)
+            self.Tp = sum(int(self.eng.lib.ppasr_b200_out_frames(self.eng._ctx, b - a)) for a, b in self.windows)
+
+    # -- one step, sync-style (no pipeline): results stay on the device ------------------------------------------------
+    def step_device(self, feats):
+        eng, conf = self.eng, self.conf
+        if self.windows:
+            eng.stream_reset(self.B)
+            st = self.dec._alloc_state(self.B, self.Tp)
+            for (a, b) in self.windows:
+                eng.encode_chunk(feats[:, a:b].contiguous(), -16)
+                self.dec._advance(st, eng.ctc_probs(), None, self.Tp)
+            return self.dec._results_device(st, self.B, self.Tp, self.Tp, 1)
+        eng.encode(feats)
+        if conf["decoder"] == "ctc_greedy":
+            return eng.ctc_greedy(to_host=False)
+        return self.dec.decode_device(eng.ctc_probs(), None, 1)
+
+    def texts_from(self, res):
+        from ppasr_b200.parallel import detokenize
+        ids, lens = res[0], res[1]
+        if ids.dim() == 3:
+            ids, lens = ids[:, 0], lens[:, 0]
+        return detokenize(ids.cpu().numpy(), np.maximum(lens.cpu().numpy(), 0), self.vocab)
+
+    def step_e2e(self):
+        """Host fbank in (pinned), texts out: H2D of the step's features and D2H of its ids inside."""
+        if self.windows:
+            eng = self.eng
+            eng.stream_reset(self.B)
+            st = self.dec._alloc_state(self.B, self.Tp)
+            hn = self.host.numpy()
+            for (a, b) in self.windows:
+                eng.encode_chunk(hn[:, a:b], -16)      # host window -> device inside the call
+                self.dec._advance(st, eng.ctc_probs(), None, self.Tp)
+            return self.texts_from(self.dec._results_device(st, self.B, self.Tp, self.Tp, 1))
+        self.eng.encode(self.host)                      # pinned host features -> device inside the call
+        if self.conf["decoder"] == "ctc_greedy":
+            return self.texts_from(self.eng.ctc_greedy(to_host=False))
+        return self.texts_from(self.dec.decode_device(self.eng.ctc_probs(), None, 1))
+
+    def h2d_bytes(self):
+        return self.B * self.frames * 80 * 4
+
+    def d2h_bytes(self):
+        return self.B * self.Tp * 4 + self.B * 4
 
 
 def main():
@@ -180,22 +421,25 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="conformer", choices=["conformer", "squeezeformer"],
-                    help="conformer = the headline BASELINE metric (default); squeezeformer = configs[3] per-GPU shard")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="BASELINE config to run (default c2 = configs[1], the config the headline metric is quoted on)")
+    ap.add_argument("--model", default=None, choices=["conformer", "squeezeformer"], help="deprecated alias: squeezeformer = --config c4")
     args = ap.parse_args()
+    cname = args.config or ("c4" if args.model == "squeezeformer" else "c2")
+    conf = CONFIGS[cname]
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, conf)
 
     import torch
     import torch.distributed as dist
     from ppasr_b200 import _lib as L
-    from ppasr_b200.infer_utils.inference_predictor import InferencePredictor
     from ppasr_b200.parallel import all_gather_results, detokenize
-    from ppasr_b200.weights import make_vocab, synthetic_fbank
+    from ppasr_b200.weights import make_vocab
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = pin_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -206,28 +450,24 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
-    cfg, weights, workload, use_model, gflop_per_utt = model_setup(args.model)
+    cfg, weights = model_setup(conf)
     vocab = make_vocab(VOCAB)
-    configs = {"encoder_conf": cfg.to_dict(), "preprocess_conf": {"n_mels": 80}}
-    pred = InferencePredictor(configs, use_model, streaming=True, weights=weights, device=local_rank)
-    eng = pred.engine
-    lib = L.load()
-
-    B = BATCH_PER_GPU
+    wl = GpuWorkload(conf, cfg, weights, vocab, dev, rank, world)
+    pred, eng, lib = wl.pred, wl.eng, L.load()
+    B, Tp = wl.B, wl.Tp
     total_utts = B * world
-    feats_host = torch.from_numpy(synthetic_fbank(B, FRAMES, seed=1234 + rank)).pin_memory()
-    feats_dev = feats_host.to(dev)
-    Tp = eng.encode(feats_dev).Tp
     lmax = Tp
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    # ---- (a) single-stream latency-style measurement: one batch at a time, L2 flushed between steps ----
+    def gather(res):
+        ids, ol, sc = res
+        if ids.dim() == 3:
+            ids, ol, sc = ids[:, 0].contiguous(), ol[:, 0].contiguous(), sc[:, 0].contiguous()
+        return all_gather_results(ids, ol, sc, total_utts, lmax) if world > 1 else (ids, ol, sc)
+
+    # ---- (a) single-stream: one batch at a time, L2 flushed between steps ----
     def step():
-        eng.encode(feats_dev)
-        ids, ol, sc = eng.ctc_greedy(to_host=False)
-        if world > 1:
-            ids, ol, sc = all_gather_results(ids, ol, sc, total_utts, lmax)
-        return ids, ol, sc
+        return gather(wl.step_device(wl.pool[0]))
 
     for _ in range(W):
         step()
@@ -240,13 +480,15 @@ def main():
         step()
         ev[k][1].record()
     torch.cuda.synchronize()
-    single_ms = sum(a.elapsed_time(b) for a, b in ev) / ks
+    single = [a.elapsed_time(b) for a, b in ev]
+    single_ms = sum(single) / ks
 
-    # ---- (b) throughput mode = `value`: two batches in flight (two engines / streams), inputs cycle over a pool of
-    #      distinct device-resident batches larger than L2 (16 x 10.2 MB = 163 MB > 126 MB), no explicit flush ----
-    pool = [feats_dev] + [torch.from_numpy(synthetic_fbank(B, FRAMES, seed=5000 + 97 * rank + i)).to(dev) for i in range(15)]
-    depth = int(os.environ.get("PPASR_B200_DEPTH", "3"))
-    pipe = pred.pipeline(depth=depth)
+    # ---- (b) `value`: whole-job throughput, inputs device resident and cycling over a pool of distinct batches larger than
+    #      L2 (no explicit flush). Greedy configs run the public throughput pipeline (several batches in flight on private
+    #      streams); beam / chunked / DS2 configs run one batch at a time on the current stream. ----
+    depth = int(os.environ.get("PPASR_B200_DEPTH", "3")) if wl.pipelined else 1
+    pipe = pred.pipeline(depth=depth) if wl.pipelined else None
+    pool = wl.pool
 
     def finish(ticket):
         if world > 1:
@@ -255,6 +497,10 @@ def main():
                 all_gather_results(ids, ol, sc, total_utts, lmax)
 
     def run_steps(n):
+        if pipe is None:
+            for i in range(n):
+                gather(wl.step_device(pool[i % len(pool)]))
+            return
         pending = []
         for i in range(n):
             pending.append(pipe.submit(pool[i % len(pool)], to_host=False))
@@ -263,57 +509,91 @@ def main():
         while pending:
             finish(pending.pop(0))
 
+    def timed_rep(n):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        if pipe is not None:
+            for sl in pipe.slots:
+                sl["stream"].wait_event(e0)
+        run_steps(n)
+        if pipe is not None:
+            for sl in pipe.slots:
+                torch.cuda.current_stream().wait_stream(sl["stream"])
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(t.item())
+
     run_steps(max(W, 4))
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    probe_ms = timed_rep(K)
+    reps = int(min(200, max(5, math.ceil(1000.0 / max(probe_ms, 1e-3)))))  # >= 1 s of timed region in total
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        rt = torch.tensor([reps], device=dev)
+        dist.broadcast(rt, 0)
+        reps = int(rt.item())
+    sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = lib.ppasr_b200_launch_count()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for sl in pipe.slots:
-        sl["stream"].wait_event(e0)
-    run_steps(K)
-    for sl in pipe.slots:
-        torch.cuda.current_stream().wait_stream(sl["stream"])
-    e1.record()
-    torch.cuda.synchronize()
+    rep_ms = [timed_rep(K) for _ in range(reps)]
     launches1 = lib.ppasr_b200_launch_count()
     sampler.stop_flag = True
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1) / K
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = statistics.median(rep_ms) / K
     value = total_utts / (ms * 1e-3)
-    pipe.close()
+    q_ms = quantiles([r / K for r in rep_ms])
+    if pipe is not None:
+        pipe.close()
 
     # ---- e2e through the public API with host buffers (H2D of the features, D2H of ids/lens/scores) ----
-    # DecodePipeline = the throughput-mode public API: two engines on two streams, so the pinned H2D copy of batch
-    # i+1 overlaps the kernels of batch i. Every step still copies its own inputs in and its own results out.
-    pipe = pred.pipeline(depth=depth)
+    # Greedy configs: DecodePipeline = the throughput-mode public API (the pinned H2D copy of batch i+1 overlaps the kernels of
+    # batch i). Every step copies its own inputs in and its own results out. With N > 1 every rank contributes its shard to the
+    # single all-gather (the gathered ids stay on every GPU), copies back and detokenises ITS OWN shard; rank 0, the consumer
+    # of the whole job, additionally copies the gathered records back and detokenises all N x B utterances.
+    brk = {"submit_ms": 0.0, "wait_d2h_ms": 0.0, "allgather_enqueue_ms": 0.0, "detok_ms": 0.0}
+    pipe = pred.pipeline(depth=depth) if wl.pipelined else None
+    gathered_pin = torch.empty((total_utts, lmax + 1), dtype=torch.int32).pin_memory() if world > 1 and rank == 0 else None
 
     def e2e_finish(ticket):
+        t0 = time.perf_counter()
+        g = None
         if world > 1:
-            # results stay on the device until the single all-gather, then ONE D2H of the gathered records
-            ids, ol, sc = pipe.device_result(ticket)
+            dids, dol, dsc = pipe.device_result(ticket)
             with torch.cuda.stream(pipe.stream(ticket)):
-                g = all_gather_results(ids, ol, sc, total_utts, lmax)
-                ids, ol = g[0].cpu().numpy(), g[1].cpu().numpy()
-        else:
-            ids, ol, scores = pipe.result(ticket)
-        return detokenize(ids, ol, vocab)
+                g = all_gather_results(dids, dol, dsc, total_utts, lmax)
+                if gathered_pin is not None:
+                    gathered_pin[:, :lmax].copy_(g[0], non_blocking=True)
+                    gathered_pin[:, lmax].copy_(g[1], non_blocking=True)
+        t1 = time.perf_counter()
+        ids, ol, _ = pipe.result(ticket)             # synchronises the slot stream; own shard on the host
+        t2 = time.perf_counter()
+        texts = detokenize(ids, ol, vocab)
+        if gathered_pin is not None:
+            gp = gathered_pin.numpy()
+            texts = detokenize(gp[:, :lmax], gp[:, lmax], vocab)
+        t3 = time.perf_counter()
+        brk["allgather_enqueue_ms"] += (t1 - t0) * 1e3
+        brk["wait_d2h_ms"] += (t2 - t1) * 1e3
+        brk["detok_ms"] += (t3 - t2) * 1e3
+        return texts
 
     def e2e_run(n):
         texts = None
+        if pipe is None:
+            for _ in range(n):
+                res_texts = wl.step_e2e()
+                texts = res_texts
+            return texts
         pending = []
         for _ in range(n):
-            pending.append(pipe.submit(feats_host, to_host=(world == 1)))
+            t0 = time.perf_counter()
+            pending.append(pipe.submit(wl.host, to_host=True))
+            brk["submit_ms"] += (time.perf_counter() - t0) * 1e3
             if len(pending) == depth:
                 texts = e2e_finish(pending.pop(0))
         while pending:
@@ -324,105 +604,158 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ke = max(10, min(K, 40))
-    t0 = time.perf_counter()
-    texts = e2e_run(ke)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / ke * 1e3
-    t = torch.tensor([e2e_ms], device=dev)
+    ke = max(10, min(K, 40)) if ms < 20 else max(3, min(K, 10))
+    ereps = int(min(50, max(3, math.ceil(500.0 / max(ms * ke, 1e-3)))))
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    pipe.close()
-    h2d = B * FRAMES * 80 * 4
-    d2h = B * Tp * 4 + B * 4 + B * 4
+        rt = torch.tensor([ereps], device=dev)
+        dist.broadcast(rt, 0)
+        ereps = int(rt.item())
+    for k in brk:
+        brk[k] = 0.0
+    e2e_reps = []
+    texts = None
+    for _ in range(ereps):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        texts = e2e_run(ke)
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / ke * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_reps.append(float(t.item()))
+    e2e_ms = statistics.median(e2e_reps)
+    if pipe is not None:
+        pipe.close()
+    brk = {k: v / (ereps * ke) for k, v in brk.items()}
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events around every launch ----
+    # ---- roofline of the dominant kernel, measured live with CUDA events ----
     pk = peaks()
     roof = None
     prof_table = None
     if rank == 0:
-        eng.profile_enable(True)
-        reps = 5
-        for _ in range(reps):
-            flush.zero_()
-            eng.encode(feats_dev)
-            eng.ctc_greedy(to_host=False)
-        prof = eng.profile_read()
-        eng.profile_enable(False)
-        M = B * Tp
-        D, FF = cfg.output_size, cfg.linear_units
-        ffn_m = 0.75 if args.model == "squeezeformer" else 1.0  # half of the squeezeformer blocks run at T'/2
-        T1 = (FRAMES - 1) // 2
-        Th = (T1 + 1) // 2
-        flops = {  # algorithmic FLOPs per launch (2*M*N*K)
-            "ffn1_gemm": 2.0 * M * FF * D, "ffn2_gemm": 2.0 * M * D * FF, "qkv_gemm": 2.0 * M * 3 * D * D,
-            "outproj_gemm": 2.0 * M * D * D, "pw1_glu_gemm": 2.0 * M * 2 * D * D, "pw2_gemm": 2.0 * M * D * D,
-            "conv2_gemm": 2.0 * (B * Tp * 19) * D * 9 * D, "embed_gemm": 2.0 * M * D * 19 * D,
-            "ctc_stats_gemm": 2.0 * M * VOCAB * D, "attention": 2.0 * B * 4 * Tp * Tp * (128 + 64),
-            # fused_ffn: W1 + W2 GEMMs (+ the chained pointwise_conv2 in every second launch: averaged)
-            "fused_ffn": (2.0 * M * D * FF * 2) * ffn_m + (0.5 * 2.0 * M * D * D if args.model == "conformer" else 0.0),
-            "fused_attn_out": 2.0 * M * D * D + 2.0 * M * 2 * D * D,
-            "conv_front": 2.0 * (B * Tp * 19) * D * 9 * D,
-        }
-        total = sum(v[1] for v in prof.values())
-        prof_table = {k: {"launches_per_step": v[0] // reps, "us_per_launch": v[1] / v[0] * 1e3,
-                          "share": v[1] / total} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-        top = max((k for k in prof if k in flops), key=lambda k: prof[k][1])
-        us = prof[top][1] / prof[top][0] * 1e3
-        ach = flops[top] / (us * 1e-6) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # kernel (profiles/r1_final_ncu_fused_ffn.txt: 14.35 MB read + 0 written, the outputs still sit in L2)
-        ncu_traffic = {"fused_ffn": 14.35e6}
-        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic.get(top), "peak_source": pk["src"] + " (burst cuBLAS bf16)",
-                "us_per_launch": us, "share_of_step": prof[top][1] / total,
-                "step_tensor_frac_sustained": (gflop_per_utt * B / ms) / pk["bf16_tflops_sustained"]}
-        try:  # a row-tile kernel launch covers ceil(B*T'/128) CTAs: how much of the GPU one launch can use at all
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            ctas = (B * Tp + 127) // 128
-            if top in ("fused_ffn", "fused_attn_out") and 0 < ctas < sms:
-                roof.update({"ctas_per_launch": ctas, "sms": sms, "frac_per_occupied_sm": roof["frac"] * sms / ctas})
-        except Exception:
-            pass
+        if conf["decoder"] == "ctc_beam_search":
+            # the decode's HBM-bound kernel: the pruning scan of the posterior [B, T', V] fp32 (reads every byte once)
+            if wl.windows:
+                eng.stream_reset(B)
+                eng.encode_chunk(wl.pool[0][:, wl.windows[0][0]:wl.windows[0][1]].contiguous(), -16)
+            else:
+                eng.encode(wl.pool[0])
+            probs = eng.ctc_probs()
+            rows = probs.shape[0] * probs.shape[1]
+            ws = torch.empty(lib.ppasr_b200_beam_workspace_bytes(probs.shape[0], probs.shape[1]), dtype=torch.uint8, device=dev)
+            prune = lambda: L.check(lib.ppasr_b200_op_ctc_prune(L.ptr(probs), rows, VOCAB, 0.99, 40, L.ptr(ws), L.stream_ptr()))
+            prune()
+            torch.cuda.synchronize()
+            tot, n = 0.0, 10
+            for _ in range(n):
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                prune()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            us = tot / n * 1e3
+            nbytes = rows * VOCAB * 4.0
+            ach = nbytes / (us * 1e-6) / 1e9
+            roof = {"kernel": "ctc_prune", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("ctc_prune"), "peak_source": pk["src"] + " (copy bandwidth)",
+                    "us_per_launch": us, "algorithmic_bytes_per_launch": nbytes,
+                    "rows_per_launch": rows, "note": "posterior [B,T',V] fp32 read once; L2 flushed before every timed launch"}
+        elif conf["model"] != "deepspeech2":
+            eng.profile_enable(True)
+            reps_p = 5
+            for _ in range(reps_p):
+                flush.zero_()
+                eng.encode(wl.pool[0])
+                eng.ctc_greedy(to_host=False)
+            prof = eng.profile_read()
+            eng.profile_enable(False)
+            M = B * Tp
+            D, FF = cfg.output_size, cfg.linear_units
+            ffn_m = 0.75 if conf["model"] == "squeezeformer" else 1.0  # half of the squeezeformer blocks run at T'/2
+            flops = {  # algorithmic FLOPs per launch (2*M*N*K)
+                "ffn1_gemm": 2.0 * M * FF * D, "ffn2_gemm": 2.0 * M * D * FF, "qkv_gemm": 2.0 * M * 3 * D * D,
+                "outproj_gemm": 2.0 * M * D * D, "pw1_glu_gemm": 2.0 * M * 2 * D * D, "pw2_gemm": 2.0 * M * D * D,
+                "conv2_gemm": 2.0 * (B * Tp * 19) * D * 9 * D, "embed_gemm": 2.0 * M * D * 19 * D,
+                "ctc_stats_gemm": 2.0 * M * VOCAB * D, "attention": 2.0 * B * 4 * Tp * Tp * (128 + 64),
+                # fused_ffn: W1 + W2 GEMMs (+ the chained pointwise_conv2 in every second launch: averaged)
+                "fused_ffn": (2.0 * M * D * FF * 2) * ffn_m + (0.5 * 2.0 * M * D * D if conf["model"] == "conformer" else 0.0),
+                "fused_attn_out": 2.0 * M * D * D + 2.0 * M * 2 * D * D,
+                "conv_front": 2.0 * (B * Tp * 19) * D * 9 * D,
+            }
+            total = sum(v[1] for v in prof.values())
+            prof_table = {k: {"launches_per_step": v[0] // reps_p, "us_per_launch": v[1] / v[0] * 1e3,
+                              "share": v[1] / total} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+            top = max((k for k in prof if k in flops), key=lambda k: prof[k][1])
+            us = prof[top][1] / prof[top][0] * 1e3
+            ach = flops[top] / (us * 1e-6) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops"], "traffic": ncu_traffic(top), "peak_source": pk["src"] + " (burst cuBLAS bf16)",
+                    "us_per_launch": us, "share_of_step": prof[top][1] / total,
+                    "algorithmic_flops_per_launch": flops[top],
+                    "step_tensor_frac_sustained": (conf["gflop_per_utt"] * B / ms) / pk["bf16_tflops_sustained"],
+                    "note": "CUDA-event pairs around every launch of 5 profiled single-batch steps (L2 flushed per step); the "
+                            "pairs add a few us to kernels this short, so frac is a lower bound"}
+            try:
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                ctas = (B * Tp + 127) // 128 * (2 if lib.ppasr_b200_get_ffn_split() == 1 else 1)
+                if top == "fused_ffn":
+                    roof.update({"ctas_per_launch": ctas, "sms": sms})
+            except Exception:
+                pass
 
-    # ---- CPU baseline: oracle restatement on the host cores, bounded sample ----
+    # ---- CPU baseline: the same CPU reference arm, bounded to ~10-20 s (rank 0, N = 1) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(host_cores())
-        orc = make_oracle(args.model, cfg, weights)
-        sb = 4
-        f = feats_host[:sb].numpy()
-        cpu_reference_step(orc, f, [FRAMES] * sb, vocab)
+        ref = CpuReference(conf, cfg, weights, vocab)
+        f = wl.host[:ref.sample_b].numpy()
+        lens = [wl.frames] * ref.sample_b
+        threads, probe = ref.choose_threads(f, lens)
+        ref.step(f, lens)
         t0 = time.perf_counter()
         n = 0
-        while time.perf_counter() - t0 < 10.0:
-            ref_texts = cpu_reference_step(orc, f, [FRAMES] * sb, vocab)
+        while n < 2 or time.perf_counter() - t0 < 10.0:
+            ref.step(f, lens)
             n += 1
+            if n >= 50:
+                break
         dt = (time.perf_counter() - t0) / n
-        cpu = {"value": sb / dt, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{sb} of 32 utterances x 10 s, {n} passes (~10 s): PyTorch-CPU fp32 oracle restatement of the "
-                         "reference Paddle graph + greedy restatement (Paddle not installable offline; restatement pinned to the reference code, tests/test_encoder_golden_cpu.py)",
-               "rtf": dt / (sb * SECONDS)}
+        cpu = {"value": ref.sample_b / dt, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": ref.describe(n), "rtf": dt / (ref.sample_b * conf["seconds"]), "thread_probe_s": probe}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if conf["model"] != "deepspeech2" else "bf16 (recurrent weights) / f32 (state)",
             "data": "synthetic",
-            "config": {"workload": workload + "; per GPU, fused CTC head + ctc_greedy",
-                       "global_batch": total_utts, "frames": FRAMES, "out_frames": Tp, "vocab": VOCAB,
+            "config": {"workload": conf["name"] + "; per GPU", "config": cname,
+                       "global_batch": total_utts, "frames": wl.frames, "out_frames": Tp, "vocab": VOCAB,
                        "parallelism": f"dp{world} (batch sharded, one all-gather of ids)" if world > 1 else "single GPU",
-                       "mode": f"throughput: {depth} batches in flight ({depth} engines on {depth} CUDA streams per GPU)",
-                       "l2": "inputs larger than L2: 16 distinct device-resident batches (163 MB) cycled; no explicit flush",
+                       "mode": (f"throughput: {depth} batches in flight ({depth} engines on {depth} CUDA streams per GPU)"
+                                if wl.pipelined else "one batch at a time on one stream"),
+                       "l2": f"inputs larger than L2: {len(pool)} distinct device-resident batches ({wl.pool_bytes / 1e6:.0f} MB) "
+                             "cycled; no explicit flush",
+                       "timed_region": {"repetitions_of_k_steps": reps, "total_s": sum(rep_ms) / 1e3,
+                                        "ms_per_step_quantiles": q_ms, "statistic": "median repetition"},
                        "single_stream_ms_per_step": single_ms,
+                       "single_stream_quantiles": quantiles(single),
                        "single_stream_note": "one batch at a time, 256 MiB memset L2 flush between steps (outside the events)",
-                       "rtf": ms * 1e-3 / (B * SECONDS), "gflop_per_step_per_gpu": gflop_per_utt * B},
+                       "rtf": ms * 1e-3 / (B * conf["seconds"]), "gflop_per_step_per_gpu": conf["gflop_per_utt"] * B,
+                       "ffn_variant": {"single_stream": int(lib.ppasr_b200_get_ffn_split()),
+                                       "pipeline": int(os.environ.get("PPASR_B200_FFN_PIPE", "2"))},
+                       "numa_pinned_cpus": numa_cpus},
             "clocks": sampler.result(),
             "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": f"InferencePredictor.pipeline(depth={depth}).submit(host fbank)/result() + host detokenisation"},
-            "gpu_launches": int(launches1 - launches0),
+                    "ms_per_step_quantiles": quantiles(e2e_reps),
+                    "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(),
+                    "host_ms_per_step_rank0": brk,
+                    "api": (f"InferencePredictor.pipeline(depth={depth}).submit(host fbank)/result() + host detokenisation"
+                            if wl.pipelined else "engine.encode/encode_chunk(host fbank) + decoder + D2H of the best ids + host detokenisation")},
+            "gpu_launches": int((launches1 - launches0) // max(1, reps)),
             "roofline": roof, "cpu_baseline": cpu, "kernel_profile": prof_table,
             "sample_text_len": len(texts[0]) if texts else 0,
         }

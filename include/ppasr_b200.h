@@ -68,6 +68,7 @@ int ppasr_b200_set_pdl(int32_t enable);
  * 0 = the round-1 kernel. Replaces nothing in the reference (a tuning switch of positionwise.py:30-39's kernel);
  * results agree to fp32 summation order. */
 int ppasr_b200_set_ffn_split(int32_t mode);
+int ppasr_b200_get_ffn_split(void);
 
 /* ---- life cycle ------------------------------------------------------------------------------
  * replaces: InferencePredictor.__init__ loading model.pdmodel/.pdiparams

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "ppasr_b200_launch_count": (c_int64, []),
     "ppasr_b200_set_pdl": (c_int, [I]),
     "ppasr_b200_set_ffn_split": (c_int, [I]),
+    "ppasr_b200_get_ffn_split": (c_int, []),
     "ppasr_b200_create": (c_int, [P, ctypes.POINTER(P)]),
     "ppasr_b200_destroy": (c_int, [P]),
     "ppasr_b200_load_tensor": (c_int, [P, c_char_p, P, I, P]),

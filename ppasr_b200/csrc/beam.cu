@@ -385,7 +385,7 @@ DEVINL float beam_key_score(unsigned long long k) {
 }
 
 struct BeamSmemLayout {  // byte offsets into dynamic shared memory
-  int ebuf, stay_b, stay_nb, merge_nb, htab, fid, flp, keys, total;
+  int ebuf, stay_b, stay_nb, merge_nb, htab, fid, flp, keys, keys2, total;
   int bcap, hcap, kcap;
 };
 __host__ __device__ inline int beam_pow2_ge(int x) {
@@ -400,6 +400,7 @@ __host__ __device__ inline BeamSmemLayout beam_smem_layout(int beam, int topn) {
   L.kcap = beam_pow2_ge(beam * topn + beam < 32 ? 32 : beam * topn + beam);
   int o = 0;
   L.keys = o, o += L.kcap * 8;
+  L.keys2 = o, o += (beam <= 32 ? (L.kcap / 2 < 32 ? 32 : L.kcap / 2) : 0) * 8;  // tournament ping-pong buffer (small beams)
   L.ebuf = o, o += 2 * L.bcap * (int)sizeof(BeamEntry);
   L.stay_b = o, o += L.bcap * 4;
   L.stay_nb = o, o += L.bcap * 4;
@@ -434,6 +435,7 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const BeamSmemLayout L = beam_smem_layout(beam, topn);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(dyn_smem + L.keys);
+  unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(dyn_smem + L.keys2);
   BeamEntry* ebuf = reinterpret_cast<BeamEntry*>(dyn_smem + L.ebuf);
   float* stay_b = reinterpret_cast<float*>(dyn_smem + L.stay_b);
   float* stay_nb = reinterpret_cast<float*>(dyn_smem + L.stay_nb);
@@ -575,6 +577,34 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
         unsigned long long k = lane < n ? keys[lane] : ~0ull;
         warp_sort32_keys(k, lane);
         keys[lane] = k;
+      }
+    } else if (beam <= 32) {
+      // tournament: every warp sorts 64-key chunks in registers and keeps each chunk's best `keep` >= beam keys; the
+      // survivors are sorted again until one chunk is left. The overall best `beam` keys survive every round.
+      const int keep = beam <= 4 ? 4 : (beam <= 8 ? 8 : (beam <= 16 ? 16 : 32));
+      const int warp = tid >> 5;
+      constexpr int NW = NT / 32;
+      unsigned long long* src = keys;
+      unsigned long long* dst = keys2;
+      int cur_n = n;
+      for (;;) {
+        const int nch = (cur_n + 63) >> 6;
+        for (int ch = warp; ch < nch; ch += NW) {
+          const int base = ch << 6;
+          unsigned long long k0 = base + lane < cur_n ? src[base + lane] : ~0ull;
+          unsigned long long k1 = base + 32 + lane < cur_n ? src[base + 32 + lane] : ~0ull;
+          warp_sort64_keys(k0, k1, lane);
+          if (lane < keep) dst[ch * keep + lane] = k0;
+        }
+        beam_sync<NT>();
+        cur_n = nch * keep;
+        unsigned long long* t2 = src;
+        src = dst;
+        dst = t2;
+        if (nch == 1) break;
+      }
+      if (src != keys) {
+        if (tid < keep) keys[tid] = src[tid];
       }
     } else {
       const int np2 = beam_pow2_ge(n);
@@ -737,9 +767,7 @@ cudaError_t launch_beam_advance(const int* cnt, const int* cid, const float* clp
   if (beam < 1 || beam > BEAM_MAXB || topn < 1 || topn > BEAM_MAXC) return cudaErrorInvalidValue;
   BeamLm none{};
   const BeamLm& l = lm ? *lm : none;
-  // one warp per utterance when the per-frame work is tiny; the n-gram scorer's dependent table probes want more threads
-  if (beam <= 32 && lm == nullptr)
-    return launch_beam_advance_nt<32>(cnt, cid, clp, B, T, frame_lens, beam, topn, blank, max_frames, states, node_cap, st, probs, V, l);
+  // beams <= 32: four warps per utterance, top-`beam` by a register-sort tournament; wider beams: shared-memory bitonic sort
   if (beam <= 32)
     return launch_beam_advance_nt<128>(cnt, cid, clp, B, T, frame_lens, beam, topn, blank, max_frames, states, node_cap, st, probs, V, l);
   if (beam <= 128)

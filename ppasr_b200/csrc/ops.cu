@@ -78,6 +78,7 @@ int ppasr_b200_set_ffn_split(int32_t enable) {
   set_ffn_split_mode(enable);
   return PPASR_OK;
 }
+int ppasr_b200_get_ffn_split(void) { return ffn_split_mode(); }
 
 // C = epilogue(A[M,K] * W[N,K]^T + bias).  See include/ppasr_b200.h for the epilogue codes.
 int ppasr_b200_op_linear(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t w_rows, const float* bias,

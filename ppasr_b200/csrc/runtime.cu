@@ -1063,9 +1063,14 @@ int ppasr_b200_stream_reset(ppasr_b200_ctx* c, int32_t B) {
   if (cfg.model_type == 3) {
     // grouped blocks append into zeroed caches: the missing frames of a partially filled last group must read as zero
     PPASR_REQUIRE(ss.Tcap >= 768, "efficient_conformer streaming needs max_len >= 768");
-    const size_t n = (size_t)L * B * H * ss.Tcap * 64;
-    PPASR_CUDA_CHECK(cudaMemset(ss.kk, 0, n * 2));
-    PPASR_CUDA_CHECK(cudaMemset(ss.vt, 0, n * 2));
+    // only the grouped blocks read beyond what was written (their K [B*H*256, 192] / V^T [B*H*192, 256] views are the
+    // first B*H*49152 elements of the block's slice); the plain blocks are bounded by the tensor-map extents
+    const size_t slice = (size_t)B * H * ss.Tcap * 64, gview = (size_t)B * H * 256 * 192;
+    for (int l = 0; l < L; ++l) {
+      if (!((c->eff_group_mask >> l) & 1)) continue;
+      PPASR_CUDA_CHECK(cudaMemset(ss.kk + (size_t)l * slice, 0, gview * 2));
+      PPASR_CUDA_CHECK(cudaMemset(ss.vt + (size_t)l * slice, 0, gview * 2));
+    }
     if (!ss.pgc) PPASR_CUDA_CHECK(cudaMalloc(&ss.pgc, (size_t)4 * 256 * 768 * 2));
     PPASR_CUDA_CHECK(cudaMemset(ss.pgc, 0, (size_t)4 * 256 * 768 * 2));
   }

@@ -104,15 +104,21 @@ class BeamSearchDecoder:
                                                  ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
                                                  L.ptr(state), max_frames, L.ptr(ws), L.stream_ptr()))
 
-    def _results(self, state, B, max_frames, lmax, nbest=None, approx=True):
+    def _results_device(self, state, B, max_frames, lmax, nb):
+        """First `nb` beam entries as device tensors: ids int32 [B, nb, lmax], lens int32 [B, nb] (-1 none, -2 overflow),
+        scores fp32 [B, nb] = log P(prefix), best first."""
         torch = self.torch
-        nb = self.beam_size if nbest is None else max(1, min(int(nbest), self.beam_size))
-        lmax = max(1, int(lmax))
         ids = torch.zeros((B, nb, lmax), dtype=torch.int32, device="cuda")
         lens = torch.zeros((B, nb), dtype=torch.int32, device="cuda")
         sc = torch.zeros((B, nb), dtype=torch.float32, device="cuda")
         L.check(self.lib.ppasr_b200_beam_result_nbest(L.ptr(state), B, max_frames, self.beam_size, nb, L.ptr(ids), lmax,
                                                       L.ptr(lens), L.ptr(sc), L.stream_ptr()))
+        return ids, lens, sc
+
+    def _results(self, state, B, max_frames, lmax, nbest=None, approx=True):
+        nb = self.beam_size if nbest is None else max(1, min(int(nbest), self.beam_size))
+        lmax = max(1, int(lmax))
+        ids, lens, sc = self._results_device(state, B, max_frames, lmax, nb)
         ids, lens, sc = ids.cpu().numpy(), lens.cpu().numpy(), sc.cpu().numpy()
         if (lens == -2).any():
             raise L.PPASRB200Error("beam-search state overflow: more frames were fed than the max_frames the decoder "
@@ -132,6 +138,14 @@ class BeamSearchDecoder:
                 res.append((-score, "".join(toks)))
             out.append(res)
         return out
+
+    def decode_device(self, probs, frame_lens=None, nbest=1):
+        """probs: CUDA fp32 [B,T,V] -> device tensors (ids [B,nbest,T], lens [B,nbest], log-prob scores [B,nbest]) without any
+        host synchronisation (batch pipelines: bench.py, predict_batch)."""
+        B, T, V = probs.shape
+        st = self._alloc_state(B, T)
+        self._advance(st, probs, frame_lens, T)
+        return self._results_device(st, B, T, T, max(1, min(int(nbest), self.beam_size)))
 
     def _to_cuda(self, probs):
         torch = self.torch

@@ -47,16 +47,51 @@ def all_gather_results(ids, out_lens, scores, num_items: int, lmax: int, group=N
 
 
 def detokenize(ids, out_lens, vocabulary):
-    """Host-side string assembly (ppasr/decoders/ctc_greedy_decoder.py:27-31)."""
+    """Host-side string assembly (ppasr/decoders/ctc_greedy_decoder.py:27-31): "".join(vocabulary[i]) with "<space>" -> " ".
+
+    Vectorised over the whole batch: tokens that are a single character (every entry of a Chinese character vocabulary, and
+    "<space>" after its replacement) are gathered as UTF-32 code points in ONE NumPy take over all utterances and decoded in
+    one call; the per-utterance strings are slices of that. An utterance containing any other multi-character token
+    (<blank>, <unk>, <eos>, word pieces) takes the reference's join."""
     ids = np.asarray(ids)
-    out_lens = np.asarray(out_lens)
+    out_lens = np.asarray(out_lens).astype(np.int64)
     key = id(vocabulary)
-    tab = _VOCAB_ARRAYS.get(key)
-    if tab is None or len(tab) != len(vocabulary) or tab[0] != vocabulary[0] or tab[-1] != vocabulary[-1]:
-        tab = np.asarray(vocabulary, dtype=object)  # one object-array gather per utterance instead of a Python loop per token
+    ent = _VOCAB_ARRAYS.get(key)
+    if ent is None or len(ent[0]) != len(vocabulary) or ent[0][0] != vocabulary[0] or ent[0][-1] != vocabulary[-1]:
+        tab = np.asarray(vocabulary, dtype=object)
+        cp = np.zeros(len(vocabulary), dtype=np.uint32)   # code point of single-character tokens, 0 = needs the slow path
+        for i, tok in enumerate(vocabulary):
+            t = " " if tok == "<space>" else tok
+            if len(t) == 1:
+                cp[i] = ord(t)
         _VOCAB_ARRAYS.clear()
-        _VOCAB_ARRAYS[key] = tab
-    return ["".join(tab[ids[b, :int(out_lens[b])]].tolist()).replace("<space>", " ") for b in range(ids.shape[0])]
+        ent = (tab, cp)
+        _VOCAB_ARRAYS[key] = ent
+    tab, cp = ent
+    B = ids.shape[0]
+    if B == 0:
+        return []
+    L = ids.shape[1]
+    lens = np.minimum(out_lens, L)
+    mask = np.arange(L)[None, :] < lens[:, None]
+    flat = ids[mask]                                   # all tokens of all utterances, utterance-major
+    pts = cp[flat]
+    text = pts.astype("<u4").tobytes().decode("utf-32-le") if pts.size else ""
+    ends = np.cumsum(lens)
+    slow = np.zeros(B, dtype=bool)
+    if pts.size and not pts.all():
+        bad = np.flatnonzero(pts == 0)
+        slow[np.searchsorted(ends, bad, side="right")] = True
+    out = []
+    start = 0
+    for b in range(B):
+        e = int(ends[b])
+        if slow[b]:
+            out.append("".join(tab[ids[b, :int(lens[b])]].tolist()).replace("<space>", " "))
+        else:
+            out.append(text[start:e])
+        start = e
+    return out
 
 
 _VOCAB_ARRAYS = {}
