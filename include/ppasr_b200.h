@@ -239,7 +239,9 @@ int ppasr_b200_set_option(ppasr_b200_ctx* ctx, const char* name, int32_t value);
 
 /* Per-kernel-class device timing of the model-level calls (cudaEvent pairs around every launch).
  * enable, run encode/ctc_* once, then read: counts[i] launches and total_ms[i] for class i in
- * [0, ppasr_b200_profile_num_classes()). Used by bench.py for the live roofline figure. */
+ * [0, ppasr_b200_profile_num_classes()). Used by bench.py for the live roofline figure. enable = 1: every class (the
+ * event records between back-to-back kernels of a few microseconds inflate them); enable = 2 + class id: event pairs around
+ * the launches of that class only, the rest of the step runs undisturbed. */
 int ppasr_b200_profile_enable(ppasr_b200_ctx* ctx, int32_t enable);
 int ppasr_b200_profile_num_classes(void);
 const char* ppasr_b200_profile_class_name(int32_t cls);

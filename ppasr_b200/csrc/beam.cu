@@ -29,6 +29,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace ppasr {
@@ -182,55 +183,43 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
     }
     // an exhausted list (-inf reached before the stop) means every finite element is a candidate
   }
-  // ---- pass 2: compact elements >= tau (warp-uniform control flow; lane 0 writes) ----
-  int c = 0;
-  auto emit = [&](float ev, int idx) {  // called with warp-uniform arguments
+  // ---- pass 2: compact elements >= tau. Only the lanes that hold a candidate do any work: the slot comes from a
+  //      shared-memory counter (order irrelevant: the survivors are sorted by (probability, index) below) ----
+  __shared__ int s_cnt[PRUNE_WARPS];
+  if (lane == 0) s_cnt[warp] = 0;
+  __syncwarp();
+  auto emit = [&](float ev, int idx) {
     if (ev >= tau && ev > -INFINITY) {
-      if (c < PRUNE_CAND_MAX && lane == 0) {
-        cp[c] = ev;
-        ci[c] = idx;
+      const int pos = atomicAdd(&s_cnt[warp], 1);
+      if (pos < PRUNE_CAND_MAX) {
+        cp[pos] = ev;
+        ci[pos] = idx;
       }
-      ++c;
     }
   };
-  {
-    const float hv = (lane < head) ? src[lane] : -INFINITY;
-    const float tv = (tail0 + lane < V) ? src[tail0 + lane] : -INFINITY;
-    unsigned hit = __ballot_sync(0xffffffffu, hv >= tau && hv > -INFINITY);
-    while (hit) {
-      const int sl = __ffs(hit) - 1;
-      hit &= hit - 1;
-      emit(__shfl_sync(0xffffffffu, hv, sl), sl);
-    }
-    hit = __ballot_sync(0xffffffffu, tv >= tau && tv > -INFINITY);
-    while (hit) {
-      const int sl = __ffs(hit) - 1;
-      hit &= hit - 1;
-      emit(__shfl_sync(0xffffffffu, tv, sl), tail0 + sl);
-    }
-  }
-  for (int q0 = 0; q0 < n4; q0 += 128) {
-    float4 x[4];
+  if (lane < head) emit(src[lane], lane);
+  if (tail0 + lane < V) emit(src[tail0 + lane], tail0 + lane);
+  for (int q0 = 0; q0 < n4; q0 += 256) {
+    float4 x[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int q = q0 + u * 32 + lane;
       x[u] = (q < n4) ? __ldg(v4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const float mx = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
-      unsigned hit = __ballot_sync(0xffffffffu, mx >= tau && mx > -INFINITY);
-      while (hit) {
-        const int sl = __ffs(hit) - 1;
-        hit &= hit - 1;
-        const int base = head + 4 * (q0 + u * 32 + sl);
-        emit(__shfl_sync(0xffffffffu, x[u].x, sl), base);
-        emit(__shfl_sync(0xffffffffu, x[u].y, sl), base + 1);
-        emit(__shfl_sync(0xffffffffu, x[u].z, sl), base + 2);
-        emit(__shfl_sync(0xffffffffu, x[u].w, sl), base + 3);
+      if (mx >= tau && mx > -INFINITY) {
+        const int base = head + 4 * (q0 + u * 32 + lane);
+        emit(x[u].x, base);
+        emit(x[u].y, base + 1);
+        emit(x[u].z, base + 2);
+        emit(x[u].w, base + 3);
       }
     }
   }
+  __syncwarp();
+  const int c = s_cnt[warp];
   __syncwarp();
   if (c <= 64) {
     // ---- the common case: sort the survivors once, cut with an exact (double) running sum ----
@@ -316,11 +305,32 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
   if (lane == 0) cnt[row] = n;
 }
 
+// Rows in flight = resident warps. Pass 2 re-reads each row from L2, which only works while the rows in flight fit there:
+// at full occupancy (48 warps / SM x 148 SMs x 17 KB = 120 MB, the whole L2) the first pass of the other rows evicts a row
+// before its second pass and the DRAM traffic doubles (ncu: 241 MB read for a 134 MB posterior). A dynamic shared-memory
+// reservation caps the resident CTAs per SM (default 4 = 16 warps / SM = 40 MB in flight, still > 60 KB of loads in flight
+// per SM); PPASR_B200_PRUNE_CTAS overrides it for experiments.
+static int prune_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PPASR_B200_PRUNE_CTAS");
+    v = e ? atoi(e) : 4;
+    if (v < 1 || v > 16) v = 4;
+  }
+  return v;
+}
+
 cudaError_t launch_ctc_prune(const float* probs, int V, int rows, float cutoff_prob, int top_n, int* cnt, int* cid,
                              float* clp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  ctc_prune_kernel<<<(rows + PRUNE_WARPS - 1) / PRUNE_WARPS, PRUNE_WARPS * 32, 0, st>>>(probs, V, rows, cutoff_prob, top_n, cnt,
-                                                                                 cid, clp);
+  const int per_sm = prune_ctas_per_sm();
+  const int dyn = (225 * 1024) / per_sm - 10 * 1024;  // static 8 KB + 1 KB system reservation per CTA
+  static std::once_flag once;
+  static cudaError_t cfg_err = cudaSuccess;
+  std::call_once(once, [] { cfg_err = cudaFuncSetAttribute(ctc_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); });
+  if (cfg_err != cudaSuccess) return cfg_err;
+  ctc_prune_kernel<<<(rows + PRUNE_WARPS - 1) / PRUNE_WARPS, PRUNE_WARPS * 32, dyn > 0 ? dyn : 0, st>>>(probs, V, rows, cutoff_prob,
+                                                                                                 top_n, cnt, cid, clp);
   count_launch();
   return cudaGetLastError();
 }
@@ -336,8 +346,18 @@ DEVINL float lse2(float a, float b) {  // decoder_utils.h log_sum_exp
 }
 
 // ---- external scorer: back-off n-gram query (scorer.cpp get_log_cond_prob over make_ngram(prefix), character based) ----
+// home slot = murmur3 finaliser of the packed token ids (ppasr_b200/decoders/ngram_lm.py::lm_hash64 builds the table with
+// the same function): every 16-bit token field reaches the low bits
+DEVINL unsigned lm_home_slot(unsigned long long x, unsigned mask) {
+  x ^= x >> 33;
+  x *= 0xFF51AFD7ED558CCDull;
+  x ^= x >> 33;
+  x *= 0xC4CEB9FE1A85EC53ull;
+  x ^= x >> 33;
+  return (unsigned)x & mask;
+}
 DEVINL bool lm_find(const BeamLm& lm, unsigned long long key, float2* out) {
-  unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 17) & lm.mask;
+  unsigned slot = lm_home_slot(key, lm.mask);
   for (;;) {
     const unsigned long long k = __ldg(lm.keys + slot);
     if (k == key) {

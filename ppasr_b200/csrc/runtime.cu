@@ -199,6 +199,7 @@ struct ppasr_b200_ctx {
   bool fused_conv = false;
   bool host_sync = true;  // ctc_* with host outputs synchronise the stream before returning
   bool profiling = false;
+  int prof_only = -1;  // >= 0: event pairs only around launches of this kernel class (undisturbed neighbours)
   struct ProfRec {
     int cls;
     cudaEvent_t e0, e1;
@@ -224,7 +225,7 @@ struct ProfScope {
   cudaStream_t st;
   cudaEvent_t e1 = nullptr;
   ProfScope(ppasr_b200_ctx* c_, int cls, cudaStream_t st_) : c(c_), st(st_) {
-    if (!c->profiling) return;
+    if (!c->profiling || (c->prof_only >= 0 && c->prof_only != cls)) return;
     if (c->prof_used == c->prof_pool.size()) {
       cudaEvent_t a, b;
       cudaEventCreate(&a);
@@ -1443,6 +1444,7 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
 int ppasr_b200_profile_enable(ppasr_b200_ctx* c, int32_t enable) {
   PPASR_REQUIRE(c, "null ctx");
   c->profiling = enable != 0;
+  c->prof_only = enable >= 2 ? enable - 2 : -1;  // enable = 2 + class id: profile that class only
   c->prof.clear();
   c->prof_used = 0;
   return PPASR_OK;

@@ -176,14 +176,26 @@ class NGramLM:
         vals = np.zeros((cap, 2), dtype=np.float32)
         mask = cap - 1
         for key, p, bo in items:
-            h = ((key * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF) >> 17
-            slot = h & mask
+            slot = lm_hash64(key) & mask
             while keys[slot] != 0:
                 slot = (slot + 1) & mask
             keys[slot] = key
             vals[slot] = (p, bo)
         in_lm = np.array([1 if w in self.vocab else 0 for w in vocab_list], dtype=np.int32)
         return keys, vals, in_lm
+
+
+def lm_hash64(x):
+    """Home slot hash of the device table (the same finaliser runs in csrc/beam.cu::lm_find). The keys are token ids packed
+    16 bits each, so the hash must mix the HIGH fields into the low bits: a plain multiplicative hash taken from the middle
+    of the product ignores the oldest tokens of a 4-gram and piles thousands of n-grams onto the same slots."""
+    x &= 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 33
+    x = (x * 0xFF51AFD7ED558CCD) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 33
+    x = (x * 0xC4CEB9FE1A85EC53) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 33
+    return x
 
 
 class Scorer:

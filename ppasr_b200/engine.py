@@ -242,8 +242,14 @@ class ConformerEngine:
     def set_option(self, name, value):
         L.check(self.lib.ppasr_b200_set_option(self._ctx, name.encode(), int(value)))
 
-    def profile_enable(self, on=True):
-        L.check(self.lib.ppasr_b200_profile_enable(self._ctx, int(on)))
+    def profile_enable(self, on=True, only=None):
+        """on: time every kernel class; only='fused_ffn': event pairs around that class alone (the rest runs undisturbed)."""
+        mode = int(bool(on))
+        if on and only is not None:
+            n = self.lib.ppasr_b200_profile_num_classes()
+            names = [self.lib.ppasr_b200_profile_class_name(i).decode() for i in range(n)]
+            mode = 2 + names.index(only)
+        L.check(self.lib.ppasr_b200_profile_enable(self._ctx, mode))
 
     def profile_read(self):
         """Returns {class_name: (launches, total_ms)} for the launches since profile_enable(True)."""

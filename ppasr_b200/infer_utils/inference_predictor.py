@@ -126,10 +126,18 @@ class InferencePredictor:
         self.engine.encode(speech, speech_lengths)
         return self.engine.ctc_probs(to_host=True)
 
-    def predict_decode(self, speech, speech_lengths=None, vocabulary=None, trim_to_lens=False, blank_id=0):
+    def predict_decode(self, speech, speech_lengths=None, vocabulary=None, trim_to_lens=None, blank_id=0):
         """Extension: fused encoder + CTC head + greedy decode. speech may be host NumPy (copied H2D inside) or
         a CUDA tensor. Returns (ids [B,T'] int32, out_lens [B], scores [B] in the reference's 0..100 scale)
-        or, when `vocabulary` is given, a list of (score, text) like greedy_decoder."""
+        or, when `vocabulary` is given, a list of (score, text) like greedy_decoder.
+        trim_to_lens (default: True whenever speech_lengths is given) collapses each utterance over its own valid encoder
+        frames only -- the frames the reference's subsampled mask keeps (4 j < len, utils/mask.py:22-68 after
+        subsampling.py:113-115) -- so the padding frames of shorter utterances never add tokens or skew the score. Pass
+        trim_to_lens=False to decode all T' frames of every row, which is what the reference's batched evaluation does
+        (trainer.py:347-349 hands outs[i, :, :] to greedy_decoder_batch without slicing). PPASRPredictor.predict_batch trims
+        further, to the frame count of a stand-alone run of each utterance."""
+        if trim_to_lens is None:
+            trim_to_lens = speech_lengths is not None
         self.engine.encode(speech, speech_lengths)
         ids, ol, sc = self.engine.ctc_greedy(to_host=True, trim_to_lens=trim_to_lens, blank_id=blank_id)
         scores = [float(s) * 100.0 if n > 0 else 0 for s, n in zip(sc, ol)]

@@ -1,7 +1,11 @@
-"""Summarise an .ncu-rep: key raw metrics per kernel + top stall lines from the source page."""
-import csv, subprocess, sys, collections
+"""Summarise an .ncu-rep: key raw metrics per kernel + top stall lines from the source page.
+    python scripts/ncu_summary.py <rep> [top_n] [traffic_key]
+With `traffic_key` the measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the first kernel in the
+report is recorded in profiles/ncu_traffic.json under that key -- bench.py reads `roofline.traffic` from there."""
+import csv, json, os, subprocess, sys, collections
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 14
+traffic_key = sys.argv[3] if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -12,6 +16,18 @@ keys = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
         'smsp__inst_executed_pipe_xu.sum', 'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum']
+def _bytes(v, unit):
+    v = float(v.replace(',', ''))
+    return v * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1.0)
+if traffic_key and len(rows) > 2:
+    r = rows[2]
+    tot = _bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + \
+          _bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_traffic.json')
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[traffic_key] = {'dram_bytes_per_launch': tot, 'kernel': r[idx['Kernel Name']][:90], 'report': os.path.basename(rep),
+                      'duration_us_under_ncu': r[idx['gpu__time_duration.sum']] + ' ' + units[idx['gpu__time_duration.sum']]}
+    json.dump(d, open(path, 'w'), indent=1)
 seen = set()
 for r in rows[2:]:
     name = r[idx['Kernel Name']][:70]

@@ -450,6 +450,42 @@ def test_full_size_properties(lib, cuda):
     eng.close()
 
 
+def test_conformer_non_streaming_12_layers_30s(lib, cuda):
+    """BASELINE configs[2] geometry: conformer.yml non-streaming (symmetric conv, full attention), 12 blocks, 30 s utterances
+    (T = 2998 -> T' = 748 keys per query: the attention kernel's multi-block key loop at full depth), ragged, vs the oracle."""
+    _run_model(cuda, 12, 2, 2998, [2998, 2501], streaming=False)
+
+
+def test_full_size_batch_matches_oracle_on_a_subset(lib, cuda):
+    """BASELINE configs[1] at its real size, B = 32 x 998 frames, 12 blocks: the logits of utterances 0, 13 and 31 of the
+    batched run against the oracle run on each of them alone (utterances are independent; all 32 are full length)."""
+    from oracle.conformer_oracle import ConformerConf, ConformerOracle
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+    cfg = ConformerConfig()
+    w = init_conformer_weights(cfg)
+    feats = synthetic_fbank(32, 998)
+    eng = ConformerEngine(cfg, w)
+    eng.encode(torch.from_numpy(feats).to(cuda))
+    logits = eng.ctc_logits().float().cpu()
+    eng.close()
+    orc = ConformerOracle(ConformerConf(**cfg.to_dict()), w)
+    n_frames = n_agree = 0
+    for b in (0, 13, 31):
+        ref = orc.get_encoder_out(torch.from_numpy(feats[b:b + 1]), torch.tensor([998]), return_logits=True)[0]
+        scale = ref.abs().max().item()
+        err = (logits[b] - ref).abs().max().item() / scale
+        assert err < 1e-2, f"utterance {b}: logits rel err {err}"
+        top2 = ref.topk(2, -1).values
+        big = (top2[:, 0] - top2[:, 1]) > 3.0 * err * scale
+        same = logits[b].argmax(-1) == ref.argmax(-1)
+        assert bool((same | ~big).all())
+        n_frames += ref.shape[0]
+        n_agree += int(same.sum())
+    print(f"[C2 full size] unfiltered arg-max agreement {n_agree}/{n_frames}")
+    assert n_agree >= 0.95 * n_frames
+
+
 def test_inference_predictor_api(lib, cuda):
     """Drop-in surface: predict -> probs [B,T',V] host; predict_decode == reference greedy on those probs."""
     from oracle import decoders_oracle as DO
