@@ -115,13 +115,20 @@ def peaks():
         return fallback
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, grid=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture of this kernel is committed."""
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture of this kernel is committed.
+    `grid`: CTAs of the launch being reported -- a capture taken at another grid size (same bytes per CTA: one CTA = four
+    posterior rows / one row tile) is scaled by the ratio."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         v = d.get(kernel)
-        return float(v["dram_bytes_per_launch"]) if v else None
+        if not v:
+            return None
+        t = float(v["dram_bytes_per_launch"])
+        if grid and v.get("grid_size"):
+            t *= float(grid) / float(v["grid_size"])
+        return t
     except (OSError, ValueError, KeyError, TypeError):
         return None
 
@@ -559,18 +566,26 @@ def main():
     pipe = pred.pipeline(depth=depth) if wl.pipelined else None
     gathered_pin = torch.empty((total_utts, lmax + 1), dtype=torch.int32).pin_memory() if world > 1 and rank == 0 else None
 
+    own_pin = (torch.empty((B, lmax), dtype=torch.int32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory()) \
+        if world > 1 else None
+
     def e2e_finish(ticket):
         t0 = time.perf_counter()
-        g = None
         if world > 1:
-            dids, dol, dsc = pipe.device_result(ticket)
+            dids, dol, dsc = pipe.device_result(ticket)      # device tensors (submitted with to_host=False)
             with torch.cuda.stream(pipe.stream(ticket)):
                 g = all_gather_results(dids, dol, dsc, total_utts, lmax)
+                own_pin[0].copy_(dids[:, :lmax], non_blocking=True)
+                own_pin[1].copy_(dol, non_blocking=True)
                 if gathered_pin is not None:
                     gathered_pin[:, :lmax].copy_(g[0], non_blocking=True)
                     gathered_pin[:, lmax].copy_(g[1], non_blocking=True)
-        t1 = time.perf_counter()
-        ids, ol, _ = pipe.result(ticket)             # synchronises the slot stream; own shard on the host
+            t1 = time.perf_counter()
+            pipe.stream(ticket).synchronize()
+            ids, ol = own_pin[0].numpy(), own_pin[1].numpy()
+        else:
+            t1 = time.perf_counter()
+            ids, ol, _ = pipe.result(ticket)             # synchronises the slot stream; results in pinned host buffers
         t2 = time.perf_counter()
         texts = detokenize(ids, ol, vocab)
         if gathered_pin is not None:
@@ -592,7 +607,7 @@ def main():
         pending = []
         for _ in range(n):
             t0 = time.perf_counter()
-            pending.append(pipe.submit(wl.host, to_host=True))
+            pending.append(pipe.submit(wl.host, to_host=(world == 1)))
             brk["submit_ms"] += (time.perf_counter() - t0) * 1e3
             if len(pending) == depth:
                 texts = e2e_finish(pending.pop(0))
@@ -661,15 +676,16 @@ def main():
             nbytes = rows * VOCAB * 4.0
             ach = nbytes / (us * 1e-6) / 1e9
             roof = {"kernel": "ctc_prune", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("ctc_prune"), "peak_source": pk["src"] + " (copy bandwidth)",
+                    "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("ctc_prune", (rows + 3) // 4), "peak_source": pk["src"] + " (copy bandwidth)",
                     "us_per_launch": us, "algorithmic_bytes_per_launch": nbytes,
                     "rows_per_launch": rows, "note": "posterior [B,T',V] fp32 read once; L2 flushed before every timed launch"}
         elif conf["model"] != "deepspeech2":
+            # like the `value` measurement: inputs cycle over the pool of distinct device-resident batches (larger than L2), no
+            # explicit flush -- a 256 MiB flush would also evict the 70 MB of weights a serving process keeps L2 resident
             eng.profile_enable(True)
-            reps_p = 5
-            for _ in range(reps_p):
-                flush.zero_()
-                eng.encode(wl.pool[0])
+            reps_p = 6
+            for i in range(reps_p):
+                eng.encode(wl.pool[i % len(wl.pool)])
                 eng.ctc_greedy(to_host=False)
             prof = eng.profile_read()
             eng.profile_enable(False)
@@ -694,9 +710,8 @@ def main():
             # second pass: event pairs around the dominant class ONLY, so the other ~70 launches of the step stay back to back
             # and the CPU-side event records do not open gaps in front of the timed kernel
             eng.profile_enable(True, only=top)
-            for _ in range(reps_p):
-                flush.zero_()
-                eng.encode(wl.pool[0])
+            for i in range(reps_p):
+                eng.encode(wl.pool[i % len(wl.pool)])
                 eng.ctc_greedy(to_host=False)
             prof1 = eng.profile_read()
             eng.profile_enable(False)
@@ -707,9 +722,9 @@ def main():
                     "us_per_launch": us, "us_per_launch_all_classes_timed": us_all, "share_of_step": prof[top][1] / total,
                     "algorithmic_flops_per_launch": flops[top],
                     "step_tensor_frac_sustained": (conf["gflop_per_utt"] * B / ms) / pk["bf16_tflops_sustained"],
-                    "note": "us_per_launch: CUDA-event pairs around the launches of this kernel class only, 5 single-batch steps "
-                            "with the L2 flushed before each (average over the plain and the chained launches); shares: a "
-                            "first pass with pairs around every launch"}
+                    "note": "us_per_launch: CUDA-event pairs around the launches of this kernel class only, 6 single-batch steps "
+                            "over distinct input batches (pool larger than L2, no flush; average over the plain and the "
+                            "chained launches); shares: a first pass with pairs around every launch"}
             try:
                 sms = torch.cuda.get_device_properties(dev).multi_processor_count
                 ctas = (B * Tp + 127) // 128 * (2 if lib.ppasr_b200_get_ffn_split() == 1 else 1)

@@ -5,7 +5,8 @@
 // in the reference, restated in oracle/decoders_oracle.py).
 //
 // Two kernels:
-//  (1) ctc_prune_kernel -- the HBM-bound scan of the posterior [B,T,V]: one warp per frame. Pass 1 streams the row
+//  (1) ctc_prune_cta_kernel (V >= 512; ctc_prune_kernel = the same algorithm with one WARP per frame, small vocabularies)
+//      -- the HBM-bound scan of the posterior [B,T,V]: one CTA of four warps per frame. Pass 1 streams the row
 //      with 16-byte loads keeping each lane's two largest values; the 64 kept values are sorted in registers (warp
 //      bitonic network) and a double-precision prefix sum over them gives a threshold tau that is a lower bound of
 //      everything that can be selected (decoder_utils.cpp get_pruned_log_probs: descending probability, ties lower
@@ -14,16 +15,16 @@
 //      (probability desc, index asc) in registers and cut with the same prefix sum. Output per frame: n, ids[n],
 //      log(p + FLT_MIN)[n]. Every frame is independent, so the scan runs at full grid width; the sequential part
 //      never touches the [B,T,V] tensor.
-//  (2) ctc_prefix_beam_kernel<NT> -- one CTA of NT threads per utterance (a single warp for beams <= 32 without a
-//      scorer) walks the frames over the compact candidate lists. The prefix trie of the reference is replaced by an
+//  (2) ctc_prefix_beam_kernel<NT> -- one CTA of NT threads per utterance (128 for beams <= 32, 256 / 512 above)
+//      walks the frames over the compact candidate lists. The prefix trie of the reference is replaced by an
 //      equivalent flat form: a beam entry carries a 64-bit hash of its id string (its identity) and an id into a
 //      (parent id, char) table used only to read the string back; an extension (prefix i, char c) merges into beam
 //      entry j iff hash[j] == H(hash[i], c) (looked up in a shared-memory hash table of the beam), otherwise it is a
 //      fresh prefix (a revived trie node is reset to -inf in path_trie.cpp, i.e. indistinguishable from a fresh one).
 //      Top-`beam` selection per frame: every live candidate becomes one 64-bit key (score desc | last char asc | slot
-//      asc, all distinct), the keys are sorted once (register bitonic network for <= 32 keys, shared-memory bitonic
-//      sort otherwise) and the first `beam` are kept -- prefix_compare's order, beam sorted best first as in the
-//      reference. State (beam + id table) lives in global memory so the same kernel serves the streaming decode_chunk API.
+//      asc, all distinct); beams <= 32 keep the best keys by a tournament of register sorts (each warp sorts 64-key
+//      chunks with a shuffle network and keeps each chunk's best 2^ceil(log2 beam)), wider beams by one shared-memory
+//      bitonic sort -- prefix_compare's order, beam sorted best first as in the reference. State (beam + id table) lives in global memory so the same kernel serves the streaming decode_chunk API.
 #include <float.h>
 
 #include "kernels.h"
@@ -124,7 +125,7 @@ DEVINL void warp_scan64(double& x0, double& x1, int lane) {
   x1 += __shfl_sync(0xffffffffu, x0, 31);
 }
 
-__global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float* __restrict__ probs, int V, int rows,
+__global__ void __launch_bounds__(PRUNE_WARPS * 32, 12) ctc_prune_kernel(const float* __restrict__ probs, int V, int rows,
                                                                       float cutoff_prob, int top_n, int* __restrict__ cnt,
                                                                       int* __restrict__ cid, float* __restrict__ clp) {
   __shared__ float s_cp[PRUNE_WARPS][PRUNE_CAND_MAX];
@@ -199,15 +200,15 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
   };
   if (lane < head) emit(src[lane], lane);
   if (tail0 + lane < V) emit(src[tail0 + lane], tail0 + lane);
-  for (int q0 = 0; q0 < n4; q0 += 256) {
-    float4 x[8];
+  for (int q0 = 0; q0 < n4; q0 += 128) {
+    float4 x[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int q = q0 + u * 32 + lane;
       x[u] = (q < n4) ? __ldg(v4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const float mx = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
       if (mx >= tau && mx > -INFINITY) {
         const int base = head + 4 * (q0 + u * 32 + lane);
@@ -305,17 +306,243 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) ctc_prune_kernel(const float
   if (lane == 0) cnt[row] = n;
 }
 
-// Rows in flight = resident warps. Pass 2 re-reads each row from L2, which only works while the rows in flight fit there:
-// at full occupancy (48 warps / SM x 148 SMs x 17 KB = 120 MB, the whole L2) the first pass of the other rows evicts a row
-// before its second pass and the DRAM traffic doubles (ncu: 241 MB read for a 134 MB posterior). A dynamic shared-memory
-// reservation caps the resident CTAs per SM (default 4 = 16 warps / SM = 40 MB in flight, still > 60 KB of loads in flight
-// per SM); PPASR_B200_PRUNE_CTAS overrides it for experiments.
+// ------------------------------------------------------------------------------------------------
+// CTA-per-row variant (default for V >= 512): the four warps of a CTA share ONE row, a quarter each. Same algorithm, but
+//  * the rows in flight are the resident CTAs, not the resident warps: 12 CTAs x 148 SMs x 17 KB = 30 MB instead of
+//    120 MB, so the second pass really hits L2 (the warp-per-row kernel re-read 80 % of the posterior from DRAM: ncu
+//    241 MB for 134 MB) while 48 warps per SM keep the loads in flight;
+//  * every thread's share of the row is requested in batches of 5 float4 (two DRAM round trips per 4233-wide row);
+//  * threshold: the 128 per-thread maxima (row elements, hence lower bounds as before) -- sorted per warp in registers,
+//    merged pairwise with bitonic merges (2 x 6 + 6 shuffle stages), prefix-summed in double precision by warp 0.
+// ------------------------------------------------------------------------------------------------
+DEVINL void warp_sort32_desc_f(float& a, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float p = __shfl_xor_sync(0xffffffffu, a, j);
+      const bool lower = (lane & j) == 0;
+      const bool desc = (lane & k) == 0 || k == 32;
+      a = (desc == lower) ? fmaxf(a, p) : fminf(a, p);
+    }
+  }
+}
+// (a0, a1) = a bitonic sequence of 64 (element e = r * 32 + lane) -> sorted DESCENDING
+DEVINL void warp_bitonic_merge64_desc(float& a0, float& a1, int lane) {
+  {
+    const float hi = fmaxf(a0, a1), lo = fminf(a0, a1);
+    a0 = hi, a1 = lo;
+  }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const float p0 = __shfl_xor_sync(0xffffffffu, a0, j);
+    const float p1 = __shfl_xor_sync(0xffffffffu, a1, j);
+    const bool lower = (lane & j) == 0;
+    a0 = lower ? fmaxf(a0, p0) : fminf(a0, p0);
+    a1 = lower ? fmaxf(a1, p1) : fminf(a1, p1);
+  }
+}
+
+__global__ void __launch_bounds__(128, 12) ctc_prune_cta_kernel(const float* __restrict__ probs, int V, int rows,
+                                                                 float cutoff_prob, int top_n, int* __restrict__ cnt,
+                                                                 int* __restrict__ cid, float* __restrict__ clp) {
+  __shared__ float s_top[128];        // per-thread maxima, sorted descending per warp
+  __shared__ float s_m[2][64];        // pairwise merges
+  __shared__ float s_cp[PRUNE_CAND_MAX];
+  __shared__ int s_ci[PRUNE_CAND_MAX];
+  __shared__ int s_c;
+  __shared__ float s_tau;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = blockIdx.x;
+  const float* src = probs + (size_t)row * V;
+  const bool prune = (cutoff_prob < 1.0f) || (top_n < V);
+  const int limit = min(prune ? min(top_n, V) : V, BEAM_MAXC);
+  const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+  const int head = mis ? min(4 - mis, V) : 0;
+  const float4* v4 = reinterpret_cast<const float4*>(src + head);
+  const int n4 = (V - head) >> 2;
+  const int tail0 = head + 4 * n4;
+  int* oid = cid + (size_t)row * BEAM_MAXC;
+  float* olp = clp + (size_t)row * BEAM_MAXC;
+  if (tid == 0) s_c = 0;
+  // ---- pass 1: per-thread maximum; the whole row is requested at once (<= 5 + 4 float4 per thread for V <= 4608) ----
+  float m = -INFINITY;
+  if (tid < head) m = fmaxf(m, src[tid]);
+  if (tail0 + tid < V) m = fmaxf(m, src[tail0 + tid]);
+  for (int q0 = 0; q0 < n4; q0 += 640) {
+    float4 x[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int q = q0 + u * 128 + tid;
+      x[u] = (q < n4) ? __ldg(v4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) m = fmaxf(m, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+  }
+  // ---- threshold from the 128 maxima ----
+  float tau = -INFINITY;
+  if (prune) {
+    warp_sort32_desc_f(m, lane);
+    s_top[tid] = m;
+    __syncthreads();
+    if ((warp & 1) == 0) {  // warps 0 and 2: merge their run with the next warp's (reversed) -> sorted 64
+      float a0 = s_top[warp * 32 + lane], a1 = s_top[(warp + 1) * 32 + 31 - lane];
+      warp_bitonic_merge64_desc(a0, a1, lane);
+      s_m[warp >> 1][lane] = a0;
+      s_m[warp >> 1][32 + lane] = a1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // top 64 of the union of two sorted runs of 64: max(X[e], Y[63 - e]) is bitonic
+      float a0 = fmaxf(s_m[0][lane], s_m[1][63 - lane]);
+      float a1 = fmaxf(s_m[0][32 + lane], s_m[1][31 - lane]);
+      warp_bitonic_merge64_desc(a0, a1, lane);
+      double c0 = a0 > -INFINITY ? (double)a0 : 0.0, c1 = a1 > -INFINITY ? (double)a1 : 0.0;
+      warp_scan64(c0, c1, lane);
+      const double thr = (double)cutoff_prob * 1.0001;  // margin: lower-bound sum vs the exact sum used below
+      const bool stop0 = (cutoff_prob < 1.0f && c0 >= thr) || (lane + 1 >= limit) || a0 == -INFINITY;
+      const bool stop1 = (cutoff_prob < 1.0f && c1 >= thr) || (lane + 33 >= limit) || a1 == -INFINITY;
+      const unsigned b0 = __ballot_sync(0xffffffffu, stop0);
+      const unsigned b1 = __ballot_sync(0xffffffffu, stop1);
+      float t;
+      if (b0) t = __shfl_sync(0xffffffffu, a0, __ffs(b0) - 1);
+      else if (b1) t = __shfl_sync(0xffffffffu, a1, __ffs(b1) - 1);
+      else t = __shfl_sync(0xffffffffu, a1, 31);
+      if (lane == 0) s_tau = t;
+    }
+    __syncthreads();
+    tau = s_tau;
+  } else {
+    __syncthreads();
+  }
+  // ---- pass 2 (L2): compact the elements >= tau ----
+  auto emit = [&](float ev, int idx) {
+    if (ev >= tau && ev > -INFINITY) {
+      const int pos = atomicAdd(&s_c, 1);
+      if (pos < PRUNE_CAND_MAX) {
+        s_cp[pos] = ev;
+        s_ci[pos] = idx;
+      }
+    }
+  };
+  if (tid < head) emit(src[tid], tid);
+  if (tail0 + tid < V) emit(src[tail0 + tid], tail0 + tid);
+  for (int q0 = 0; q0 < n4; q0 += 640) {
+    float4 x[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int q = q0 + u * 128 + tid;
+      x[u] = (q < n4) ? __ldg(v4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const float mx = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+      if (mx >= tau && mx > -INFINITY) {
+        const int base = head + 4 * (q0 + u * 128 + tid);
+        emit(x[u].x, base);
+        emit(x[u].y, base + 1);
+        emit(x[u].z, base + 2);
+        emit(x[u].w, base + 3);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  const int c = s_c;
+  if (c <= 64) {
+    unsigned long long k0 = lane < c ? prune_key(s_cp[lane], s_ci[lane]) : ~0ull;
+    unsigned long long k1 = 32 + lane < c ? prune_key(s_cp[32 + lane], s_ci[32 + lane]) : ~0ull;
+    if (c <= 32) {
+      warp_sort32_keys(k0, lane);
+    } else {
+      warp_sort64_keys(k0, k1, lane);
+    }
+    const float p0 = k0 != ~0ull ? prune_key_prob(k0) : -INFINITY;
+    const float p1 = k1 != ~0ull ? prune_key_prob(k1) : -INFINITY;
+    double c0 = p0 > -INFINITY ? (double)p0 : 0.0, c1 = p1 > -INFINITY ? (double)p1 : 0.0;
+    warp_scan64(c0, c1, lane);
+    int n = min(c, limit);
+    if (cutoff_prob < 1.0f) {
+      const unsigned b0 = __ballot_sync(0xffffffffu, lane < c && c0 >= (double)cutoff_prob);
+      const unsigned b1 = __ballot_sync(0xffffffffu, 32 + lane < c && c1 >= (double)cutoff_prob);
+      if (b0) n = min(n, __ffs(b0));
+      else if (b1) n = min(n, 32 + __ffs(b1));
+    }
+    if (lane < n) {
+      oid[lane] = (int)(unsigned)k0;
+      olp[lane] = logf(p0 + FLT_MIN);
+    }
+    if (32 + lane < n) {
+      oid[32 + lane] = (int)(unsigned)k1;
+      olp[32 + lane] = logf(p1 + FLT_MIN);
+    }
+    if (lane == 0) cnt[row] = n;
+    return;
+  }
+  // ---- many ties at tau (e.g. uniform rows): arg-max rounds with a Kahan-compensated running sum (warp 0) ----
+  float last_p = INFINITY;
+  int last_i = -1;
+  float cum = 0.f, cum_c = 0.f;
+  int n = 0;
+  const bool compact = c <= PRUNE_CAND_MAX;
+  while (n < limit) {
+    float bm = -INFINITY;
+    int bi = 0x7fffffff;
+    if (compact) {
+      for (int j = lane; j < c; j += 32) {
+        const float pv = s_cp[j];
+        const int iv = s_ci[j];
+        if (prune_before(last_p, last_i, pv, iv) && prune_before(pv, iv, bm, bi)) {
+          bm = pv;
+          bi = iv;
+        }
+      }
+    } else {
+      for (int j = lane; j < V; j += 32) {
+        const float pv = __ldg(src + j);
+        if (prune_before(last_p, last_i, pv, j) && prune_before(pv, j, bm, bi)) {
+          bm = pv;
+          bi = j;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (prune_before(om, oi, bm, bi)) {
+        bm = om;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff) break;
+    if (lane == 0) {
+      oid[n] = bi;
+      olp[n] = logf(bm + FLT_MIN);
+    }
+    last_p = bm;
+    last_i = bi;
+    ++n;
+    const float yk = bm - cum_c;
+    const float tk = cum + yk;
+    cum_c = (tk - cum) - yk;
+    cum = tk;
+    if (cutoff_prob < 1.0f && cum >= cutoff_prob) break;
+  }
+  if (lane == 0) cnt[row] = n;
+}
+
+// Occupancy: the scan is latency bound per warp (serial phases: stream, sort, re-read, sort), so what saturates HBM is the
+// number of rows in flight -- measured on [64,748,4233] (scripts/gpu_prune_sweep.py): 2 / 4 / 8 / 9+ resident CTAs per SM ->
+// 25 % / 41 % / 50 % / 61 % of the copy bandwidth. The kernel is therefore built for 12 CTAs (48 warps) per SM (<= 40
+// registers, 8 KB static shared memory). PPASR_B200_PRUNE_CTAS caps the residency through a dynamic shared-memory
+// reservation (experiments only; default: no cap).
 static int prune_ctas_per_sm() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PPASR_B200_PRUNE_CTAS");
-    v = e ? atoi(e) : 4;
-    if (v < 1 || v > 16) v = 4;
+    v = e ? atoi(e) : 16;
+    if (v < 1 || v > 16) v = 16;
   }
   return v;
 }
@@ -324,13 +551,21 @@ cudaError_t launch_ctc_prune(const float* probs, int V, int rows, float cutoff_p
                              float* clp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   const int per_sm = prune_ctas_per_sm();
-  const int dyn = (225 * 1024) / per_sm - 10 * 1024;  // static 8 KB + 1 KB system reservation per CTA
+  const int dyn = per_sm >= 12 ? 0 : (225 * 1024) / per_sm - 10 * 1024;  // static 8 KB + 1 KB system reservation per CTA
   static std::once_flag once;
   static cudaError_t cfg_err = cudaSuccess;
   std::call_once(once, [] { cfg_err = cudaFuncSetAttribute(ctc_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); });
   if (cfg_err != cudaSuccess) return cfg_err;
-  ctc_prune_kernel<<<(rows + PRUNE_WARPS - 1) / PRUNE_WARPS, PRUNE_WARPS * 32, dyn > 0 ? dyn : 0, st>>>(probs, V, rows, cutoff_prob,
-                                                                                                 top_n, cnt, cid, clp);
+  static int use_cta = -1;
+  if (use_cta < 0) {
+    const char* e = getenv("PPASR_B200_PRUNE_KERNEL");  // "warp" selects the warp-per-row kernel for A/B runs
+    use_cta = (e != nullptr && e[0] == 'w') ? 0 : 1;
+  }
+  if (use_cta && V >= 512)
+    ctc_prune_cta_kernel<<<rows, 128, 0, st>>>(probs, V, rows, cutoff_prob, top_n, cnt, cid, clp);
+  else
+    ctc_prune_kernel<<<(rows + PRUNE_WARPS - 1) / PRUNE_WARPS, PRUNE_WARPS * 32, dyn > 0 ? dyn : 0, st>>>(probs, V, rows, cutoff_prob,
+                                                                                                   top_n, cnt, cid, clp);
   count_launch();
   return cudaGetLastError();
 }

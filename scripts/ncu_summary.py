@@ -25,7 +25,8 @@ if traffic_key and len(rows) > 2:
           _bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_traffic.json')
     d = json.load(open(path)) if os.path.exists(path) else {}
-    d[traffic_key] = {'dram_bytes_per_launch': tot, 'kernel': r[idx['Kernel Name']][:90], 'report': os.path.basename(rep),
+    d[traffic_key] = {'dram_bytes_per_launch': tot, 'grid_size': int(float(r[idx['launch__grid_size']].replace(',', ''))),
+                      'kernel': r[idx['Kernel Name']][:90], 'report': os.path.basename(rep),
                       'duration_us_under_ncu': r[idx['gpu__time_duration.sum']] + ' ' + units[idx['gpu__time_duration.sum']]}
     json.dump(d, open(path, 'w'), indent=1)
 seen = set()

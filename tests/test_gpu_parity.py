@@ -643,12 +643,14 @@ def test_beam_search_shipped_beam_size_matches_oracle(lib, cuda, T, V, beam, cp,
         assert all(sc[i] <= sc[i + 1] + 1e-6 for i in range(len(sc) - 1))
 
 
-def test_ctc_prune_matches_oracle_rows(lib, cuda):
-    """decoder_utils.cpp get_pruned_log_probs on peaked, flat and tie-heavy rows (the tie rows take the fallback path)."""
+@pytest.mark.parametrize("V", [4233, 5003, 300])
+def test_ctc_prune_matches_oracle_rows(lib, cuda, V):
+    """decoder_utils.cpp get_pruned_log_probs on peaked, flat and tie-heavy rows (the tie rows take the fallback path). The
+    vocabulary sizes cover both kernels: CTA per row (V >= 512; 4233 = two load batches, 5003 = a third partial one) and warp
+    per row (V = 300)."""
     from oracle import decoders_oracle as DO
     from ppasr_b200 import _lib as L
     rng = np.random.RandomState(5)
-    V = 4233
     rows = []
     for temp in (8.0, 3.0, 1.0, 0.2):
         lg = rng.randn(6, V).astype(np.float32) * temp
