@@ -676,7 +676,7 @@ def main():
             nbytes = rows * VOCAB * 4.0
             ach = nbytes / (us * 1e-6) / 1e9
             roof = {"kernel": "ctc_prune", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("ctc_prune", (rows + 3) // 4), "peak_source": pk["src"] + " (copy bandwidth)",
+                    "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("ctc_prune", rows),  # one CTA per posterior row "peak_source": pk["src"] + " (copy bandwidth)",
                     "us_per_launch": us, "algorithmic_bytes_per_launch": nbytes,
                     "rows_per_launch": rows, "note": "posterior [B,T',V] fp32 read once; L2 flushed before every timed launch"}
         elif conf["model"] != "deepspeech2":

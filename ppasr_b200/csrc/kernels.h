@@ -67,7 +67,10 @@ cudaError_t launch_fused_ffn(const CUtensorMap& tm_a, const CUtensorMap* tm_wp, 
 int ffn_split_mode();
 void set_ffn_split_mode(int mode);
 
-// Fused attention out-projection + residual + norm_conv + pointwise_conv1 + GLU (fused_attn_out.cu)
+// Fused attention out-projection + residual + norm_conv + pointwise_conv1 + GLU (fused_attn_out.cu). Variant (process-wide,
+// env PPASR_B200_ATTN_OUT_V2 / set_option "attn_out_v2"): 1 (default) = no serial residual preload, 0 = round-1 kernel.
+int attn_out_variant();
+void set_attn_out_variant(int v);
 cudaError_t launch_fused_attn_out(const CUtensorMap& tm_att, const CUtensorMap& tm_wo, const CUtensorMap& tm_wpw1, int M,
                                   float* x, __nv_bfloat16* g, const float* bo, const float* ln_g, const float* ln_b,
                                   const float* bpw1, const int* lens, int T, float eps, cudaStream_t st);

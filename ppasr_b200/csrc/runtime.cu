@@ -1421,6 +1421,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
     c->host_sync = value != 0;
     return PPASR_OK;
   }
+  if (n == "attn_out_v2") {  // process-wide: fused_attn_out kernel variant
+    set_attn_out_variant(value);
+    return PPASR_OK;
+  }
   if (n == "ffn_split") {  // process-wide: which fused_ffn kernel launch_fused_ffn dispatches to
     set_ffn_split_mode(value);
     return PPASR_OK;
