@@ -493,7 +493,7 @@ def main():
     # ---- (b) `value`: whole-job throughput, inputs device resident and cycling over a pool of distinct batches larger than
     #      L2 (no explicit flush). Greedy configs run the public throughput pipeline (several batches in flight on private
     #      streams); beam / chunked / DS2 configs run one batch at a time on the current stream. ----
-    depth = int(os.environ.get("PPASR_B200_DEPTH", "3")) if wl.pipelined else 1
+    depth = int(os.environ.get("PPASR_B200_DEPTH", "4")) if wl.pipelined else 1
     pipe = pred.pipeline(depth=depth) if wl.pipelined else None
     pool = wl.pool
 

@@ -1083,7 +1083,7 @@ def test_fused_dwconv_bit_identical(lib, cuda, model):
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("use_model", ["deepspeech2", "squeezeformer"])
+@pytest.mark.parametrize("use_model", ["deepspeech2", "squeezeformer", "efficient_conformer"])
 def test_predict_stream_other_models(lib, cuda, use_model):
     """PPASRPredictor.predict_stream_features dispatches to predict_chunk_deepspeech / predict_chunk_conformer by model
     (predict.py:302-311); feeding arbitrary slices equals feeding the reference's 67/64 windows by hand."""
@@ -1094,6 +1094,9 @@ def test_predict_stream_other_models(lib, cuda, use_model):
     if use_model == "deepspeech2":
         cfg = W.DeepSpeech2Config(num_rnn_layers=2, rnn_size=256, vocab_size=150, streaming=True)
         w = W.init_deepspeech2_weights(cfg)
+    elif use_model == "efficient_conformer":   # forward_chunk on the device: grouped blocks 0-1, stride block 1, odd last chunk
+        cfg = W.EfficientConformerConfig(num_blocks=4, vocab_size=150, group_layer_idx=(0, 1), stride_layer_idx=1)
+        w = W.init_efficient_conformer_weights(cfg)
     else:
         cfg = W.SqueezeformerConfig(num_blocks=3, vocab_size=150, reduce_idx=1, recover_idx=2)
         w = W.init_squeezeformer_weights(cfg)
