@@ -337,7 +337,7 @@ def _toy_lm(V=20, order=4, seed=0):
 
 
 def test_ngram_lm_backoff_semantics_and_arpa_roundtrip(tmp_path):
-    from ppasr_b200.decoders.ngram_lm import NGramLM, OOV_SCORE, LOG10_E
+    from ppasr_b200.decoders.ngram_lm import NGramLM, OOV_SCORE, LOG10_E, lm_hash64, lm_hash64
     vocab, sents, lm = _toy_lm()
     assert lm.is_character_based() and lm.order == 4
     # P(. | seen context) sums to ~1 (discounted mass redistributed through the back-off weights)
@@ -365,11 +365,17 @@ def test_ngram_lm_backoff_semantics_and_arpa_roundtrip(tmp_path):
         key = 0
         for w in ng:
             key = (key << 16) | tok[w]
-        slot = (((key * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF) >> 17) & mask
+        slot = lm_hash64(key) & mask
         while int(keys[slot]) != key:
             assert int(keys[slot]) != 0
             slot = (slot + 1) & mask
         assert abs(vals[slot][0] - lp / LOG10_E) < 1e-4
+    # the home-slot hash mixes every token field: no long probe runs (a multiplicative hash taken from the middle of the
+    # product ignored the oldest tokens and produced runs of thousands of slots on a 4-gram table)
+    occ = (keys != 0).astype(np.int8)
+    edges = np.diff(np.concatenate([[0], occ, [0]]))
+    runs = np.flatnonzero(edges == -1) - np.flatnonzero(edges == 1)
+    assert occ.mean() <= 0.5 and runs.max() <= 64
 
 
 def test_oracle_beam_search_with_scorer():
