@@ -347,9 +347,11 @@ __global__ void __launch_bounds__(128, 12) ctc_prune_cta_kernel(const float* __r
                                                                  float cutoff_prob, int top_n, int* __restrict__ cnt,
                                                                  int* __restrict__ cid, float* __restrict__ clp) {
   __shared__ float s_top[128];        // per-thread maxima, sorted descending per warp
+  __shared__ float s_m[2][64];        // pairwise merges
   __shared__ float s_cp[PRUNE_CAND_MAX];
   __shared__ int s_ci[PRUNE_CAND_MAX];
   __shared__ int s_c;
+  __shared__ float s_tau;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = blockIdx.x;
   const float* src = probs + (size_t)row * V;
@@ -383,27 +385,33 @@ __global__ void __launch_bounds__(128, 12) ctc_prune_cta_kernel(const float* __r
     warp_sort32_desc_f(m, lane);
     s_top[tid] = m;
     __syncthreads();
-    // every warp merges the four sorted runs itself (identical result in all warps: one barrier instead of three and no
-    // warp waits for another): runs (0, 1) and (2, 3) -> two sorted 64s, their element-wise max against the reversed
-    // partner is the bitonic top 64 of all 128
-    float x0 = s_top[lane], x1 = s_top[32 + 31 - lane];
-    warp_bitonic_merge64_desc(x0, x1, lane);
-    float y0 = s_top[64 + lane], y1 = s_top[96 + 31 - lane];
-    warp_bitonic_merge64_desc(y0, y1, lane);
-    // Y reversed: element e of Y^R = Y[63 - e] -> register (1 - r) of lane (31 - lane)
-    float a0 = fmaxf(x0, __shfl_sync(0xffffffffu, y1, 31 - lane));
-    float a1 = fmaxf(x1, __shfl_sync(0xffffffffu, y0, 31 - lane));
-    warp_bitonic_merge64_desc(a0, a1, lane);
-    double c0 = a0 > -INFINITY ? (double)a0 : 0.0, c1 = a1 > -INFINITY ? (double)a1 : 0.0;
-    warp_scan64(c0, c1, lane);
-    const double thr = (double)cutoff_prob * 1.0001;  // margin: lower-bound sum vs the exact sum used below
-    const bool stop0 = (cutoff_prob < 1.0f && c0 >= thr) || (lane + 1 >= limit) || a0 == -INFINITY;
-    const bool stop1 = (cutoff_prob < 1.0f && c1 >= thr) || (lane + 33 >= limit) || a1 == -INFINITY;
-    const unsigned b0 = __ballot_sync(0xffffffffu, stop0);
-    const unsigned b1 = __ballot_sync(0xffffffffu, stop1);
-    if (b0) tau = __shfl_sync(0xffffffffu, a0, __ffs(b0) - 1);
-    else if (b1) tau = __shfl_sync(0xffffffffu, a1, __ffs(b1) - 1);
-    else tau = __shfl_sync(0xffffffffu, a1, 31);
+    if ((warp & 1) == 0) {  // warps 0 and 2: merge their run with the next warp's (reversed) -> sorted 64
+      float a0 = s_top[warp * 32 + lane], a1 = s_top[(warp + 1) * 32 + 31 - lane];
+      warp_bitonic_merge64_desc(a0, a1, lane);
+      s_m[warp >> 1][lane] = a0;
+      s_m[warp >> 1][32 + lane] = a1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // top 64 of the union of two sorted runs of 64: max(X[e], Y[63 - e]) is bitonic
+      float a0 = fmaxf(s_m[0][lane], s_m[1][63 - lane]);
+      float a1 = fmaxf(s_m[0][32 + lane], s_m[1][31 - lane]);
+      warp_bitonic_merge64_desc(a0, a1, lane);
+      double c0 = a0 > -INFINITY ? (double)a0 : 0.0, c1 = a1 > -INFINITY ? (double)a1 : 0.0;
+      warp_scan64(c0, c1, lane);
+      const double thr = (double)cutoff_prob * 1.0001;  // margin: lower-bound sum vs the exact sum used below
+      const bool stop0 = (cutoff_prob < 1.0f && c0 >= thr) || (lane + 1 >= limit) || a0 == -INFINITY;
+      const bool stop1 = (cutoff_prob < 1.0f && c1 >= thr) || (lane + 33 >= limit) || a1 == -INFINITY;
+      const unsigned b0 = __ballot_sync(0xffffffffu, stop0);
+      const unsigned b1 = __ballot_sync(0xffffffffu, stop1);
+      float t;
+      if (b0) t = __shfl_sync(0xffffffffu, a0, __ffs(b0) - 1);
+      else if (b1) t = __shfl_sync(0xffffffffu, a1, __ffs(b1) - 1);
+      else t = __shfl_sync(0xffffffffu, a1, 31);
+      if (lane == 0) s_tau = t;
+    }
+    __syncthreads();
+    tau = s_tau;
   } else {
     __syncthreads();
   }
