@@ -178,13 +178,16 @@ int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V,
                             int32_t max_frames, void* workspace, void* stream);
 /* Same with an external scorer (replaces Scorer + ext_scoring_func of swig_wrapper.py:4-19,35-64): a character-based
  * back-off n-gram LM as an open-addressing hash table on the device (built by ppasr_b200/decoders/ngram_lm.py from an ARPA
- * file): lm_keys uint64 [lm_capacity] (0 = empty; token ids packed 16 bits each, <s> = 1, vocabulary id v = v + 2, most
- * recent token in the low bits), lm_vals float [lm_capacity][2] = (ln p, ln backoff), lm_in_vocab int32 [V].
+ * file): lm_keys uint64 [lm_capacity] (0 = empty; the four most recent token ids packed 16 bits each, <s> = 1, vocabulary id
+ * v = v + 2, most recent token in the low bits), lm_keys_hi uint32 [lm_capacity] (the oldest token of a 5-gram, 0 for shorter
+ * n-grams; may be NULL when lm_order <= 4), lm_vals float [lm_capacity][2] = (ln p, ln backoff), lm_in_vocab int32 [V]; home
+ * slot = murmur3 finaliser of lo ^ hi * 0x9E3779B97F4A7C15, linear probing. lm_order <= 5 (the reference trains `-o 5`).
  * Every emitted character adds alpha * ln P(c | history) + beta; the published min_cutoff pruning is applied. */
 int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens, int32_t beam,
                                float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states, int32_t max_frames,
-                               void* workspace, const uint64_t* lm_keys, const float* lm_vals, const int32_t* lm_in_vocab,
-                               int64_t lm_capacity, int32_t lm_order, float alpha, float beta, void* stream);
+                               void* workspace, const uint64_t* lm_keys, const uint32_t* lm_keys_hi, const float* lm_vals,
+                               const int32_t* lm_in_vocab, int64_t lm_capacity, int32_t lm_order, float alpha, float beta,
+                               void* stream);
 int ppasr_b200_beam_result(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t* out_ids,
                            int32_t lmax, int32_t* out_lens, float* out_scores, void* stream);
 int ppasr_b200_beam_result_nbest(const void* states, int32_t B, int32_t max_frames, int32_t beam, int32_t nbest,

@@ -77,7 +77,7 @@ PROTOTYPES = {
     "ppasr_b200_beam_workspace_bytes": (c_int64, [I, I]),
     "ppasr_b200_beam_reset": (c_int, [P, I, I, I, P]),
     "ppasr_b200_beam_advance": (c_int, [P, I, I, I, P, I, c_float, I, I, P, I, P, P]),
-    "ppasr_b200_beam_advance_lm": (c_int, [P, I, I, I, P, I, c_float, I, I, P, I, P, P, P, P, c_int64, I, c_float, c_float, P]),
+    "ppasr_b200_beam_advance_lm": (c_int, [P, I, I, I, P, I, c_float, I, I, P, I, P, P, P, P, P, c_int64, I, c_float, c_float, P]),
     "ppasr_b200_beam_result": (c_int, [P, I, I, I, P, I, P, P, P]),
     "ppasr_b200_beam_result_nbest": (c_int, [P, I, I, I, I, P, I, P, P, P]),
     "ppasr_b200_op_ctc_prune": (c_int, [P, I, I, c_float, I, P, P]),

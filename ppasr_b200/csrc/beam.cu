@@ -591,11 +591,11 @@ DEVINL unsigned lm_home_slot(unsigned long long x, unsigned mask) {
   x ^= x >> 33;
   return (unsigned)x & mask;
 }
-DEVINL bool lm_find(const BeamLm& lm, unsigned long long key, float2* out) {
-  unsigned slot = lm_home_slot(key, lm.mask);
+DEVINL bool lm_find(const BeamLm& lm, unsigned long long key, unsigned hi, float2* out) {
+  unsigned slot = lm_home_slot(key ^ ((unsigned long long)hi * 0x9E3779B97F4A7C15ull), lm.mask);
   for (;;) {
     const unsigned long long k = __ldg(lm.keys + slot);
-    if (k == key) {
+    if (k == key && (lm.keys_hi == nullptr || __ldg(lm.keys_hi + slot) == hi)) {
       *out = __ldg(lm.vals + slot);
       return true;
     }
@@ -606,24 +606,30 @@ DEVINL bool lm_find(const BeamLm& lm, unsigned long long key, float2* out) {
 // ln P(c | last order-1 tokens of the prefix, left-padded with <s>); any token without a unigram -> OOV_SCORE (-1000)
 DEVINL float lm_log_cond_prob(const BeamLm& lm, const BeamEntry& e, int c) {
   if (!__ldg(lm.in_lm + c)) return -1000.0f;
-  const int n = lm.order - 1;  // context length
-  unsigned long long ctx[3];   // oldest .. most recent
+  const int n = lm.order - 1;  // context length (<= 4)
+  unsigned long long ctx[4];   // oldest .. most recent
   {
-    const int raw[3] = {e.prev2, e.prev1, e.last};
-    for (int i = 0; i < 3; ++i) {
+    const int raw[4] = {e.prev3, e.prev2, e.prev1, e.last};
+    for (int i = 0; i < 4; ++i) {
       const int v = raw[i];
-      if (i >= 3 - n && v >= 0 && !__ldg(lm.in_lm + v)) return -1000.0f;  // only tokens inside the n-gram window
+      if (i >= 4 - n && v >= 0 && !__ldg(lm.in_lm + v)) return -1000.0f;  // only tokens inside the n-gram window
       ctx[i] = v >= 0 ? (unsigned long long)(v + 2) : 1ull;  // <s> padding
     }
   }
   const unsigned long long w = (unsigned long long)(c + 2);
   float bo = 0.f;
-  for (int start = 3 - n; start <= 3; ++start) {
+  for (int start = 4 - n; start <= 4; ++start) {
+    // n-gram ctx[start..3] + w: the four most recent tokens go to the 64-bit key, a fifth (oldest) one to `hi`
+    const int len = 4 - start;  // context tokens in this n-gram
     unsigned long long kc = 0ull;
-    for (int i = start; i < 3; ++i) kc = (kc << 16) | ctx[i];
+    for (int i = start; i < 4; ++i) kc = (kc << 16) | ctx[i];
     float2 v;
-    if (lm_find(lm, (kc << 16) | w, &v)) return bo + v.x;
-    if (start < 3 && lm_find(lm, kc, &v)) bo += v.y;
+    {
+      const unsigned long long lo = (kc << 16) | w;  // with four context tokens the 64-bit shift drops the oldest one
+      const unsigned hi = (len == 4) ? (unsigned)ctx[start] : 0u;
+      if (lm_find(lm, lo, hi, &v)) return bo + v.x;
+    }
+    if (start < 4 && lm_find(lm, kc, 0u, &v)) bo += v.y;  // back-off weight of the context (<= 4 tokens)
   }
   return -1000.0f;
 }
@@ -906,8 +912,8 @@ ctc_prefix_beam_kernel(const int* __restrict__ cnt, const int* __restrict__ cid,
         ne.last = c;
         ne.prev1 = e.last;
         ne.prev2 = e.prev1;
+        ne.prev3 = e.prev2;
         ne.len = e.len + 1;
-        ne.pad = 0;
         ne.b_prev = -INFINITY;
         ne.nb_prev = log_p;
         ne.score = log_p;
@@ -977,7 +983,7 @@ __global__ void ctc_beam_reset_kernel(BeamStateHeader* states, size_t state_stri
     hdr->pad = 0;      // overflow flag
     BeamEntry root;
     root.id = 0, root.parent_id = -1, root.last = -1, root.len = 0;
-    root.prev1 = root.prev2 = -1, root.pad = 0;
+    root.prev1 = root.prev2 = root.prev3 = -1;
     root.hash = 0x243F6A8885A308D3ull;
     root.b_prev = 0.f;  // root.log_prob_b_prev = 0.0, root.score = 0.0 (ctc_beam_search_decoder.cpp)
     root.nb_prev = -INFINITY;

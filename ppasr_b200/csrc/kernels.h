@@ -109,17 +109,19 @@ struct BeamEntry {
   unsigned long long hash;  // identity of the prefix string
   int id, parent_id, last, len;
   float b_prev, nb_prev, score;
-  int prev1, prev2;  // the two tokens before `last` (-1 = none): n-gram context of the external scorer
-  int pad;
+  int prev1, prev2;  // the tokens before `last` (-1 = none): n-gram context of the external scorer
+  int prev3;
 };
 // External scorer = character-based back-off n-gram LM as an open-addressing hash table (ppasr_b200/decoders/ngram_lm.py):
-// token 1 = <s>, v + 2 = vocabulary id v; key = tokens packed 16 bits each (most recent in the low bits); value = (ln p, ln bo)
+// token 1 = <s>, v + 2 = vocabulary id v; key = (lo, hi): lo = the four most recent tokens packed 16 bits each (most recent in
+// the low bits), hi = the oldest token of a 5-gram (0 otherwise; array may be null for order <= 4); value = (ln p, ln bo)
 struct BeamLm {
   const unsigned long long* keys;  // null = no scorer
+  const unsigned* keys_hi;         // null = every key has hi = 0 (order <= 4)
   const float2* vals;
   const int* in_lm;                // [V] 1 if the token has a unigram
   unsigned mask;                   // capacity - 1
-  int order;                       // <= 4
+  int order;                       // <= 5
   float alpha, beta;
 };
 size_t beam_state_stride(int node_cap);

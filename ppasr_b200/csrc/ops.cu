@@ -65,7 +65,7 @@ extern "C" {
 
 const char* ppasr_b200_last_error(void) { return get_last_error(); }
 
-int ppasr_b200_abi_version(void) { return 2; }
+int ppasr_b200_abi_version(void) { return 3; }
 
 int64_t ppasr_b200_launch_count(void) { return (int64_t)launch_count(); }
 
@@ -191,13 +191,15 @@ int ppasr_b200_beam_advance(const float* probs, int32_t B, int32_t T, int32_t V,
 }
 int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t V, const int32_t* frame_lens, int32_t beam,
                                float cutoff_prob, int32_t cutoff_top_n, int32_t blank_id, void* states, int32_t max_frames,
-                               void* workspace, const uint64_t* lm_keys, const float* lm_vals, const int32_t* lm_in_vocab,
-                               int64_t lm_capacity, int32_t lm_order, float alpha, float beta, void* stream) {
+                               void* workspace, const uint64_t* lm_keys, const uint32_t* lm_keys_hi, const float* lm_vals,
+                               const int32_t* lm_in_vocab, int64_t lm_capacity, int32_t lm_order, float alpha, float beta,
+                               void* stream) {
   PPASR_REQUIRE(probs && states && workspace && lm_keys && lm_vals && lm_in_vocab, "null pointer");
   PPASR_REQUIRE(B > 0 && T > 0 && V > 1 && V + 2 < 65536, "bad sizes (the scorer packs token ids in 16 bits)");
   PPASR_REQUIRE(beam >= 1 && beam <= BEAM_MAX_BEAM, "beam_size must be in [1,512] in this build");
   PPASR_REQUIRE(cutoff_top_n >= 1 && max_frames >= 1, "cutoff_top_n and max_frames must be >= 1");
-  PPASR_REQUIRE(lm_order >= 1 && lm_order <= 4, "the scorer supports n-gram orders 1..4");
+  PPASR_REQUIRE(lm_order >= 1 && lm_order <= 5, "the scorer supports n-gram orders 1..5");
+  PPASR_REQUIRE(lm_order <= 4 || lm_keys_hi != nullptr, "order-5 tables need lm_keys_hi (the oldest token of every 5-gram)");
   PPASR_REQUIRE(lm_capacity >= 2 && (lm_capacity & (lm_capacity - 1)) == 0, "lm_capacity must be a power of two");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int top_n = cutoff_top_n < BEAM_MAX_TOPN ? cutoff_top_n : BEAM_MAX_TOPN;
@@ -207,6 +209,7 @@ int ppasr_b200_beam_advance_lm(const float* probs, int32_t B, int32_t T, int32_t
   PPASR_CUDA_CHECK(launch_ctc_prune(probs, V, B * T, cutoff_prob, top_n, cnt, cid, clp, st));
   BeamLm lm;
   lm.keys = reinterpret_cast<const unsigned long long*>(lm_keys);
+  lm.keys_hi = lm_keys_hi;
   lm.vals = reinterpret_cast<const float2*>(lm_vals);
   lm.in_lm = lm_in_vocab;
   lm.mask = (unsigned)(lm_capacity - 1);

@@ -5,7 +5,7 @@ running the CTC prefix beam search on the B200 (ppasr_b200/csrc/beam.cu) instead
 Same constructor arguments and methods (beam_search_decoder.py:9-96). Differences:
   * `language_model_path=None` (default here) decodes without an external scorer -- which the upstream C++
     supports via ext_scoring_func=None (swig_wrapper.py:35-41). With a path, the file must be an ARPA text n-gram model
-    (order <= 4) that is character based (every LM word is one vocabulary token), as the reference's Chinese setups
+    (order <= 5) that is character based (every LM word is one vocabulary token), as the reference's Chinese setups
     are; it is turned into a device hash table and scored inside the beam kernel (ppasr_b200/decoders/ngram_lm.py).
     KenLM *binary* files (.klm / trie) and word-based LMs (English, needs the dictionary FST) raise.
   * beam_size <= 512 and cutoff_top_n <= 64 in this build (the shipped configs use 300 / 40); larger values raise.
@@ -67,11 +67,12 @@ class BeamSearchDecoder:
             sc = self._ext_scorer
             if not sc.is_character_based():
                 raise UnsupportedDecoderConfig("only character-based language models are supported by the GPU scorer")
-            if sc.get_max_order() > 4:
-                raise UnsupportedDecoderConfig("n-gram order > 4 is not supported by the GPU scorer")
-            keys, vals, in_lm = sc.lm.device_tables(vocab_list)
+            if sc.get_max_order() > 5:
+                raise UnsupportedDecoderConfig("n-gram order > 5 is not supported by the GPU scorer")
+            keys, keys_hi, vals, in_lm = sc.lm.device_tables(vocab_list, with_hi=True)
             self._lm_dev = (torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(vals).cuda(),
-                            torch.from_numpy(in_lm).cuda(), int(keys.shape[0]))
+                            torch.from_numpy(in_lm).cuda(), int(keys.shape[0]),
+                            torch.from_numpy(keys_hi.view(np.int32)).cuda())
         self._stream_state = None  # persistent state of the streaming decoder (batch 1)
         self.reset_decoder()
 
@@ -91,13 +92,13 @@ class BeamSearchDecoder:
         if frame_lens is not None:
             fl = torch.as_tensor(np.asarray(frame_lens), dtype=torch.int32).cuda()
         if self._lm_dev is not None:
-            keys, vals, in_lm, cap = self._lm_dev
+            keys, vals, in_lm, cap, keys_hi = self._lm_dev
             sc = self._ext_scorer
             sc.reset_params(self.alpha, self.beta)  # beam_search_decoder.py:46-47,60-61: alpha / beta may be retuned between calls
             L.check(self.lib.ppasr_b200_beam_advance_lm(L.ptr(probs), B, T, V, L.ptr(fl), self.beam_size,
                                                         ctypes.c_float(self.cutoff_prob), self.cutoff_top_n, self.blank_id,
-                                                        L.ptr(state), max_frames, L.ptr(ws), L.ptr(keys), L.ptr(vals),
-                                                        L.ptr(in_lm), cap, sc.get_max_order(), ctypes.c_float(sc.alpha),
+                                                        L.ptr(state), max_frames, L.ptr(ws), L.ptr(keys), L.ptr(keys_hi),
+                                                        L.ptr(vals), L.ptr(in_lm), cap, sc.get_max_order(), ctypes.c_float(sc.alpha),
                                                         ctypes.c_float(sc.beta), L.stream_ptr()))
             return
         L.check(self.lib.ppasr_b200_beam_advance(L.ptr(probs), B, T, V, L.ptr(fl), self.beam_size,

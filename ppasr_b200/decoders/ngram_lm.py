@@ -11,7 +11,8 @@ third_party/ctc_decoders/scorer.cpp, recalled -- parity unpinned):
   * make_ngram(prefix): the last `order` tokens of the prefix, left-padded with <s> to `order` items.
 Only ARPA text files are read (the KenLM binary formats would need KenLM); `from_counts` builds a small model with
 absolute discounting for tests and synthetic benchmarks. `device_tables()` exports the model as an open-addressing hash
-table keyed by up to four 16-bit token ids for the GPU scorer (csrc/beam.cu).
+table keyed by up to five 16-bit token ids (the reference trains its LMs with `-o 5`, docs/beam_search.md) for the GPU scorer
+(csrc/beam.cu).
 """
 import math
 from collections import defaultdict
@@ -153,10 +154,12 @@ class NGramLM:
         return all(len(w) == 1 for w in self.vocab if w not in (START_TOKEN, END_TOKEN, UNK_TOKEN))
 
     # ---- GPU export -------------------------------------------------------------------------------------------------
-    def device_tables(self, vocab_list):
-        """Hash table keyed by token ids: id 0 = empty slot, 1 = <s>, v + 2 = vocab_list[v]. Key = ids packed 16 bits each,
-        most recent token in the low bits. Values (ln prob, ln backoff). Also returns in_lm[v] (unigram present)."""
-        assert len(vocab_list) + 2 < 65536 and self.order <= 4
+    def device_tables(self, vocab_list, with_hi=False):
+        """Hash table keyed by token ids: id 0 = empty slot, 1 = <s>, v + 2 = vocab_list[v]. Key = (lo, hi): lo = the four
+        most recent ids packed 16 bits each (most recent token in the low bits), hi = the oldest id of a 5-gram (0 for shorter
+        n-grams). Values (ln prob, ln backoff). Also returns in_lm[v] (unigram present). Returns (keys_lo, vals, in_lm) or,
+        with_hi, (keys_lo, keys_hi, vals, in_lm)."""
+        assert len(vocab_list) + 2 < 65536 and self.order <= 5
         tok = {START_TOKEN: 1}
         for v, w in enumerate(vocab_list):
             tok.setdefault(w, v + 2)
@@ -166,22 +169,26 @@ class NGramLM:
             if any(i is None for i in ids):
                 continue
             key = 0
-            for i in ids:  # oldest first -> most recent ends in the low 16 bits
+            for i in ids[-4:]:  # oldest first -> most recent ends in the low 16 bits
                 key = (key << 16) | i
-            items.append((key, p / LOG10_E, bo / LOG10_E))
+            items.append((key, ids[0] if len(ids) == 5 else 0, p / LOG10_E, bo / LOG10_E))
         cap = 1
         while cap < 2 * max(1, len(items)) + 2:
             cap *= 2
         keys = np.zeros(cap, dtype=np.uint64)
+        keys_hi = np.zeros(cap, dtype=np.uint32)
         vals = np.zeros((cap, 2), dtype=np.float32)
         mask = cap - 1
-        for key, p, bo in items:
-            slot = lm_hash64(key) & mask
+        for key, hi, p, bo in items:
+            slot = lm_hash64_2(key, hi) & mask
             while keys[slot] != 0:
                 slot = (slot + 1) & mask
             keys[slot] = key
+            keys_hi[slot] = hi
             vals[slot] = (p, bo)
         in_lm = np.array([1 if w in self.vocab else 0 for w in vocab_list], dtype=np.int32)
+        if with_hi:
+            return keys, keys_hi, vals, in_lm
         return keys, vals, in_lm
 
 
@@ -196,6 +203,11 @@ def lm_hash64(x):
     x = (x * 0xC4CEB9FE1A85EC53) & 0xFFFFFFFFFFFFFFFF
     x ^= x >> 33
     return x
+
+
+def lm_hash64_2(lo, hi):
+    """Home slot of the key (lo, hi); equals lm_hash64(lo) for n-grams of up to four tokens (hi = 0)."""
+    return lm_hash64(lo ^ ((hi * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF))
 
 
 class Scorer:

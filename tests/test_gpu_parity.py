@@ -893,6 +893,7 @@ def _toy_lm(V, order, seed=0):
 
 @pytest.mark.parametrize("T,V,beam,order,alpha,beta,temp", [
     (30, 20, 10, 4, 2.2, 4.3, 3.0), (60, 40, 20, 3, 1.0, 0.5, 4.0), (40, 30, 5, 2, 0.5, 0.0, 2.0), (25, 12, 8, 4, 2.2, 4.3, 1.0),
+    (40, 20, 10, 5, 2.2, 4.3, 2.0), (30, 15, 16, 5, 1.0, 1.0, 1.0),   # order 5: the order the reference trains its LMs with
 ])
 def test_beam_search_with_ngram_scorer_matches_oracle(lib, cuda, tmp_path, T, V, beam, order, alpha, beta, temp):
     from oracle import decoders_oracle as DO

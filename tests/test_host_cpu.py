@@ -30,7 +30,7 @@ def test_library_exports_every_header_symbol(lib):
         if s in ("ppasr_b200_last_error", "ppasr_b200_abi_version"):
             continue
         assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype in ppasr_b200/_lib.py"
-    assert lib.ppasr_b200_abi_version() == 2
+    assert lib.ppasr_b200_abi_version() == 3
 
 
 def test_config_struct_matches_header():
@@ -562,4 +562,4 @@ def test_c_abi_state_errors_and_host_helpers_without_a_gpu():
     assert 0 < lib.ppasr_b200_beam_workspace_bytes(1, 50) < lib.ppasr_b200_beam_workspace_bytes(4, 500)
     names = [lib.ppasr_b200_profile_class_name(i).decode() for i in range(lib.ppasr_b200_profile_num_classes())]
     assert len(names) == len(set(names)) >= 8 and {"fused_ffn", "attention", "qkv_gemm"} <= set(names)
-    assert lib.ppasr_b200_abi_version() == 2
+    assert lib.ppasr_b200_abi_version() == 3

@@ -378,6 +378,36 @@ def test_ngram_lm_backoff_semantics_and_arpa_roundtrip(tmp_path):
     assert occ.mean() <= 0.5 and runs.max() <= 64
 
 
+def test_ngram_lm_order5_device_table():
+    """Order 5 (what the reference's LM recipe trains, docs/beam_search.md): the device table splits a 5-gram key into the four
+    most recent tokens (64 bits) + the oldest token; every n-gram is retrievable and 5-grams do not alias their 4-gram suffix."""
+    from ppasr_b200.decoders.ngram_lm import NGramLM, LOG10_E, lm_hash64_2
+    rng = np.random.RandomState(3)
+    vocab = ["<blank>", "<unk>"] + [chr(0x4E00 + i) for i in range(30)] + ["<eos>"]
+    sents = [[vocab[2 + int(z) % 30] for z in rng.zipf(1.4, size=rng.randint(4, 14))] for _ in range(300)]
+    lm = NGramLM.from_counts(sents, order=5)
+    assert lm.order == 5 and any(len(k) == 5 for k in lm.ngrams)
+    keys, keys_hi, vals, in_lm = lm.device_tables(vocab, with_hi=True)
+    tok = {"<s>": 1, **{w: i + 2 for i, w in enumerate(vocab)}}
+    mask = len(keys) - 1
+    n5 = 0
+    for ng, (lp, bo) in lm.ngrams.items():
+        if any(w not in tok for w in ng):
+            continue
+        ids = [tok[w] for w in ng]
+        lo = 0
+        for i in ids[-4:]:
+            lo = (lo << 16) | i
+        hi = ids[0] if len(ids) == 5 else 0
+        slot = lm_hash64_2(lo, hi) & mask
+        while not (int(keys[slot]) == lo and int(keys_hi[slot]) == hi):
+            assert int(keys[slot]) != 0, ng
+            slot = (slot + 1) & mask
+        assert abs(vals[slot][0] - lp / LOG10_E) < 1e-4 and abs(vals[slot][1] - bo / LOG10_E) < 1e-4
+        n5 += len(ids) == 5
+    assert n5 > 50
+
+
 def test_oracle_beam_search_with_scorer():
     from ppasr_b200.decoders.ngram_lm import Scorer
     vocab, sents, lm = _toy_lm()
