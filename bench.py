@@ -490,6 +490,44 @@ def main():
     single = [a.elapsed_time(b) for a, b in ev]
     single_ms = sum(single) / ks
 
+    # ---- (a') the same single-batch step captured once as a CUDA graph and replayed (one graph launch per step) ----
+    graph_info = None
+    if wl.pipelined and world == 1:
+        try:
+            gs = torch.cuda.Stream(device=dev)
+            gi = torch.empty((B, Tp), dtype=torch.int32, device=dev)
+            gl = torch.empty((B,), dtype=torch.int32, device=dev)
+            gc = torch.empty((B,), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
+            eng.encode(wl.pool[0], stream=gs)
+            eng.ctc_greedy_into(gi, gl, gc, stream=gs)      # once outside the capture on this stream
+            gs.synchronize()
+            want = (gi.clone(), gl.clone())
+            eng.graph_begin(gs)
+            eng.encode(wl.pool[0], stream=gs)
+            eng.ctc_greedy_into(gi, gl, gc, stream=gs)
+            nk = eng.graph_end(gs)
+            gi.zero_()
+            torch.cuda.synchronize()
+            for _ in range(W):
+                eng.graph_launch(gs)
+            gs.synchronize()
+            same = bool(torch.equal(gi, want[0]) and torch.equal(gl, want[1]))
+            gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ks)]
+            with torch.cuda.stream(gs):
+                for k in range(ks):
+                    flush.zero_()
+                    gev[k][0].record(gs)
+                    eng.graph_launch(gs)
+                    gev[k][1].record(gs)
+            gs.synchronize()
+            gms = [a.elapsed_time(b) for a, b in gev]
+            graph_info = {"ms_per_step": sum(gms) / ks, "quantiles": quantiles(gms), "kernels_per_replay": nk,
+                          "replay_matches_direct_run": same}
+        except Exception as e:  # a driver / runtime without capture support for some launch attribute: report, do not fail
+            graph_info = {"error": str(e)[:300]}
+        torch.cuda.synchronize()
+
     # ---- (b) `value`: whole-job throughput, inputs device resident and cycling over a pool of distinct batches larger than
     #      L2 (no explicit flush). Greedy configs run the public throughput pipeline (several batches in flight on private
     #      streams); beam / chunked / DS2 configs run one batch at a time on the current stream. ----
@@ -770,6 +808,7 @@ def main():
                        "single_stream_ms_per_step": single_ms,
                        "single_stream_quantiles": quantiles(single),
                        "single_stream_note": "one batch at a time, 256 MiB memset L2 flush between steps (outside the events)",
+                       "single_stream_cuda_graph": graph_info,
                        "rtf": ms * 1e-3 / (B * conf["seconds"]), "gflop_per_step_per_gpu": conf["gflop_per_utt"] * B,
                        "ffn_variant": {"single_stream": int(lib.ppasr_b200_get_ffn_split()),
                                        "pipeline": int(os.environ.get("PPASR_B200_FFN_PIPE", "2"))},

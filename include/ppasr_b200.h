@@ -240,6 +240,18 @@ int ppasr_b200_fbank(const float* audio, int32_t B, int64_t stride, int32_t N, c
  * double-buffered serving pipeline. */
 int ppasr_b200_set_option(ppasr_b200_ctx* ctx, const char* name, int32_t value);
 
+/* ---- CUDA graph of the steady-state step ------------------------------------------------------------------------------
+ * replaces nothing in the reference (SURVEY 8d "timed region: CUDA-Graph steady state"). graph_begin puts `stream` (not the
+ * default stream) into capture; everything enqueued on it through this library until graph_end -- typically ppasr_b200_encode
+ * with device features and ppasr_b200_ctc_greedy with device outputs -- is recorded, with its programmatic-dependent-launch
+ * edges, instead of run; graph_launch replays it as ONE launch (features are re-read from the pointer given at capture time,
+ * the valid lengths from the context's pinned staging buffer). Run the step once with the same shapes before capturing; no
+ * host synchronisation or host-output call inside the capture. graph_kernels = kernels per replay. */
+int ppasr_b200_graph_begin(ppasr_b200_ctx* ctx, void* stream);
+int ppasr_b200_graph_end(ppasr_b200_ctx* ctx, void* stream);
+int ppasr_b200_graph_launch(ppasr_b200_ctx* ctx, void* stream);
+int32_t ppasr_b200_graph_kernels(const ppasr_b200_ctx* ctx);
+
 /* Per-kernel-class device timing of the model-level calls (cudaEvent pairs around every launch).
  * enable, run encode/ctc_* once, then read: counts[i] launches and total_ms[i] for class i in
  * [0, ppasr_b200_profile_num_classes()). Used by bench.py for the live roofline figure. enable = 1: every class (the

@@ -90,6 +90,10 @@ PROTOTYPES = {
     "ppasr_b200_op_attention": (c_int, [P, P, P, I, P, I, I, I, I, P, I, I, I, I, P, P]),
     "ppasr_b200_debug_copy_x": (c_int, [P, P, P]),
     "ppasr_b200_set_option": (c_int, [P, c_char_p, I]),
+    "ppasr_b200_graph_begin": (c_int, [P, P]),
+    "ppasr_b200_graph_end": (c_int, [P, P]),
+    "ppasr_b200_graph_launch": (c_int, [P, P]),
+    "ppasr_b200_graph_kernels": (c_int, [P]),
     "ppasr_b200_profile_enable": (c_int, [P, I]),
     "ppasr_b200_profile_num_classes": (c_int, []),
     "ppasr_b200_profile_class_name": (c_char_p, [I]),

@@ -17,6 +17,7 @@ void set_pdl_enabled(bool on);
 // number of kernels launched by this library (all contexts); read by bench.py for "gpu_launches"
 void count_launch();
 long long launch_count();
+void add_launches(long long n);  // kernels replayed by a CUDA graph (counted once at capture, n per replay)
 
 }  // namespace ppasr
 

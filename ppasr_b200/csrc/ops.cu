@@ -20,6 +20,7 @@ const char* get_last_error() { return g_last_error.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void add_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {

@@ -198,6 +198,15 @@ struct ppasr_b200_ctx {
   // with the tensor core's operand reads (ncu: lsu 57 % + tc 20 % of the pipe), so it is opt-in.
   bool fused_conv = false;
   bool host_sync = true;  // ctc_* with host outputs synchronise the stream before returning
+  // valid-length staging (pinned: the H2D copy may be part of a captured CUDA graph and is re-read at every replay)
+  int* h_vlen = nullptr;
+  int h_vlen_cap = 0;
+  int vlen_flip = 0;
+  // CUDA graph of a steady-state step (ppasr_b200_graph_*): everything enqueued between begin and end, replayed as one launch
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool capturing = false;
+  long long graph_kernels = 0, capture_count0 = 0;
   bool profiling = false;
   int prof_only = -1;  // >= 0: event pairs only around launches of this kernel class (undisturbed neighbours)
   struct ProfRec {
@@ -356,6 +365,9 @@ int ppasr_b200_destroy(ppasr_b200_ctx* ctx) {
   if (ctx->ss.d_step) cudaFree(ctx->ss.d_step);
   if (ctx->ds.h_state) cudaFree(ctx->ds.h_state);
   if (ctx->ds.c_state) cudaFree(ctx->ds.c_state);
+  if (ctx->h_vlen) cudaFreeHost(ctx->h_vlen);
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  if (ctx->graph) cudaGraphDestroy(ctx->graph);
   delete ctx;
   return PPASR_OK;
 }
@@ -987,7 +999,19 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
                                    feats_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   // valid subsampled frames: mask[:, :, :-2:2][:, :, :-2:2] keeps frame j iff 4*j < len (subsampling.py:115);
   // deepspeech2 uses x_len = ((len - 1) // 2 - 1) // 2 as the RNN sequence_length (deepspeech2/conv.py:20)
-  std::vector<int> vlen(B);
+  if (c->h_vlen_cap < B) {
+    if (c->capturing) {
+      set_last_error("batch size grew inside a graph capture: run the step once before ppasr_b200_graph_begin");
+      return PPASR_ERR_STATE;
+    }
+    PPASR_CUDA_CHECK(cudaStreamSynchronize(st));  // an earlier copy may still read the old staging buffer
+    if (c->h_vlen) cudaFreeHost(c->h_vlen);
+    c->h_vlen = nullptr;
+    PPASR_CUDA_CHECK(cudaMallocHost(&c->h_vlen, sizeof(int) * (size_t)B * 2));
+    c->h_vlen_cap = B;
+  }
+  // two halves used alternately: the copy of the previous call may still be in flight when the next lengths are written
+  int* vlen = c->h_vlen + (c->capturing ? 0 : ((c->vlen_flip ^= 1) ? c->h_vlen_cap : 0));
   for (int b = 0; b < B; ++b) {
     const int64_t len = lens_host ? lens_host[b] : T;
     int64_t v = ds2 ? ((len - 1) / 2 - 1) / 2 : (len + 3) / 4;
@@ -995,7 +1019,7 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
     if (v < 0) v = 0;
     vlen[b] = (int)v;
   }
-  PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  PPASR_CUDA_CHECK(cudaMemcpyAsync(p.vlen, vlen, sizeof(int) * B, cudaMemcpyHostToDevice, st));
   if (ds2) return run_encoder_ds2(c, st, false);
   if (c->cfg.model_type == 3) return run_encoder_effconf(c, st);
   return c->cfg.model_type == 1 ? run_encoder_squeezeformer(c, st) : run_encoder(c, st, false);
@@ -1409,6 +1433,46 @@ int ppasr_b200_greedy_decode(const float* probs, int32_t B, int32_t T, int32_t V
                                        nullptr, nullptr, st));
   return PPASR_OK;
 }
+
+// ---- CUDA graph of the steady-state step ------------------------------------------------------------------------------
+// begin: the stream enters capture; every call made on it until end (encode, ctc_greedy with DEVICE outputs, ...) is recorded
+// instead of run -- kernels with their programmatic-dependent-launch edges, the feature copy from the pointer passed at capture
+// time, the valid-length copy from the context's pinned staging buffer. launch replays the whole step as one graph launch.
+// The step must have run once with the same shapes before (workspace, function attributes), must not change shapes, and must not
+// synchronise or copy to pageable host memory inside the capture.
+int ppasr_b200_graph_begin(ppasr_b200_ctx* c, void* stream) {
+  PPASR_REQUIRE(c && stream, "graph capture needs a non-default stream");
+  PPASR_REQUIRE(!c->capturing && !c->profiling, "already capturing, or profiling is on");
+  PPASR_REQUIRE(c->plan.M > 0 || c->plan.B > 0, "run the step once before capturing it");
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec), c->graph_exec = nullptr;
+  if (c->graph) cudaGraphDestroy(c->graph), c->graph = nullptr;
+  PPASR_CUDA_CHECK(cudaDeviceSynchronize());  // nothing in flight still reads the staging buffers the capture will rewrite
+  PPASR_CUDA_CHECK(cudaStreamBeginCapture(reinterpret_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal));
+  c->capturing = true;
+  c->capture_count0 = launch_count();
+  return PPASR_OK;
+}
+
+int ppasr_b200_graph_end(ppasr_b200_ctx* c, void* stream) {
+  PPASR_REQUIRE(c && c->capturing, "no capture in progress");
+  c->capturing = false;
+  cudaGraph_t g = nullptr;
+  PPASR_CUDA_CHECK(cudaStreamEndCapture(reinterpret_cast<cudaStream_t>(stream), &g));
+  c->graph = g;
+  c->graph_kernels = launch_count() - c->capture_count0;
+  add_launches(-c->graph_kernels);  // recorded, not run
+  PPASR_CUDA_CHECK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+  return PPASR_OK;
+}
+
+int ppasr_b200_graph_launch(ppasr_b200_ctx* c, void* stream) {
+  PPASR_REQUIRE(c && c->graph_exec, "no captured graph (ppasr_b200_graph_begin / _end first)");
+  PPASR_CUDA_CHECK(cudaGraphLaunch(c->graph_exec, reinterpret_cast<cudaStream_t>(stream)));
+  add_launches(c->graph_kernels);
+  return PPASR_OK;
+}
+
+int32_t ppasr_b200_graph_kernels(const ppasr_b200_ctx* c) { return c ? (int32_t)c->graph_kernels : 0; }
 
 int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   PPASR_REQUIRE(c && name, "null pointer");

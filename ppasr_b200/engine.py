@@ -239,6 +239,23 @@ class ConformerEngine:
             return ids, ol, sc, fi, fp
         return ids, ol, sc
 
+    def ctc_greedy_into(self, ids, out_lens, scores, trim_to_lens=False, blank_id=0, stream=None):
+        """Fused CTC head + greedy decode into caller-owned CUDA tensors (ids int32 [B,T'], out_lens int32 [B], scores fp32 [B]):
+        no allocation, no host synchronisation -- the form a CUDA graph capture needs."""
+        L.check(self.lib.ppasr_b200_ctc_greedy(self._ctx, L.ptr(ids), L.ptr(out_lens), L.ptr(scores), None, None, 1,
+                                               int(trim_to_lens), blank_id, L.stream_ptr(stream)))
+
+    # ---- CUDA graph of the steady-state step (include/ppasr_b200.h "CUDA graph") -----------------------------------------
+    def graph_begin(self, stream):
+        L.check(self.lib.ppasr_b200_graph_begin(self._ctx, L.stream_ptr(stream)))
+
+    def graph_end(self, stream):
+        L.check(self.lib.ppasr_b200_graph_end(self._ctx, L.stream_ptr(stream)))
+        return int(self.lib.ppasr_b200_graph_kernels(self._ctx))
+
+    def graph_launch(self, stream):
+        L.check(self.lib.ppasr_b200_graph_launch(self._ctx, L.stream_ptr(stream)))
+
     def set_option(self, name, value):
         L.check(self.lib.ppasr_b200_set_option(self._ctx, name.encode(), int(value)))
 

@@ -508,6 +508,46 @@ def test_full_size_batch_matches_oracle_on_a_subset(lib, cuda):
     assert n_agree >= 0.95 * n_frames
 
 
+def test_cuda_graph_replay_matches_direct_run(lib, cuda):
+    """ppasr_b200_graph_begin / _end / _launch: the captured step (encode + fused CTC head + greedy, with the programmatic
+    dependent launch edges and the 2-CTA cluster launches) replayed on NEW feature values gives bit-identical ids / lens / scores
+    to running the same calls directly."""
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+    cfg = ConformerConfig(num_blocks=3, vocab_size=300)
+    eng = ConformerEngine(cfg, init_conformer_weights(cfg))
+    B, T = 4, 363
+    lens = [363, 200, 363, 90]
+    feats = torch.from_numpy(synthetic_fbank(B, T, seed=1)).to(cuda)
+    other = torch.from_numpy(synthetic_fbank(B, T, seed=2)).to(cuda)
+    gs = torch.cuda.Stream()
+    Tp = eng.encode(feats, lens, stream=gs).Tp
+    ids = torch.zeros((B, Tp), dtype=torch.int32, device=cuda)
+    ol = torch.zeros((B,), dtype=torch.int32, device=cuda)
+    sc = torch.zeros((B,), dtype=torch.float32, device=cuda)
+    eng.ctc_greedy_into(ids, ol, sc, trim_to_lens=True, stream=gs)
+    gs.synchronize()
+    eng.graph_begin(gs)
+    eng.encode(feats, lens, stream=gs)
+    eng.ctc_greedy_into(ids, ol, sc, trim_to_lens=True, stream=gs)
+    nk = eng.graph_end(gs)
+    assert nk > 10
+    feats.copy_(other)            # the graph re-reads the captured pointer: new values, same buffer
+    torch.cuda.synchronize()
+    n0 = lib.ppasr_b200_launch_count()
+    eng.graph_launch(gs)
+    gs.synchronize()
+    assert lib.ppasr_b200_launch_count() - n0 == nk
+    got = (ids.clone(), ol.clone(), sc.clone())
+    eng.encode(other, lens)
+    rids, rol, rsc = eng.ctc_greedy(to_host=False, trim_to_lens=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got[1], rol) and torch.equal(got[2], rsc)
+    for b in range(B):
+        assert torch.equal(got[0][b, :int(rol[b])], rids[b, :int(rol[b])])
+    eng.close()
+
+
 def test_inference_predictor_api(lib, cuda):
     """Drop-in surface: predict -> probs [B,T',V] host; predict_decode == reference greedy on those probs."""
     from oracle import decoders_oracle as DO
