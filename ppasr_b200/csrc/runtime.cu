@@ -1004,7 +1004,7 @@ int ppasr_b200_encode(ppasr_b200_ctx* c, const float* feats, int32_t feats_on_de
       set_last_error("batch size grew inside a graph capture: run the step once before ppasr_b200_graph_begin");
       return PPASR_ERR_STATE;
     }
-    PPASR_CUDA_CHECK(cudaStreamSynchronize(st));  // an earlier copy may still read the old staging buffer
+    PPASR_CUDA_CHECK(cudaDeviceSynchronize());  // an earlier copy (on any stream) may still read the old staging buffer
     if (c->h_vlen) cudaFreeHost(c->h_vlen);
     c->h_vlen = nullptr;
     PPASR_CUDA_CHECK(cudaMallocHost(&c->h_vlen, sizeof(int) * (size_t)B * 2));
