@@ -118,7 +118,7 @@ struct ppasr_b200_ctx {
   // weight tensor maps (B operands)
   CUtensorMap tm_conv2_w, tm_emb_w, tm_ctc_w, tm_pos;
   struct LayerMaps {
-    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wo, pw1, pw2, ffm_w1_128, ff_w1_128, ffm_w2s, ff_w2s;
+    CUtensorMap ffm_w1, ffm_w2, ff_w1, ff_w2, wqkv, wqkv_wide, wo, pw1, pw2, ffm_w1_128, ff_w1_128, ffm_w2s, ff_w2s;
   };
   std::vector<LayerMaps> lmaps;
   // ---- Squeezeformer (model_type 1; squeezeformer/encoder.py) ----
@@ -189,6 +189,7 @@ struct ppasr_b200_ctx {
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
   bool fused_attn_out = true;
+  bool qkv_wide = false;  // QKV GEMM with 128 x 256 tiles (experiment switch, env PPASR_B200_QKV_WIDE / option "qkv_wide")
   // causal models: depthwise conv + norm + swish computed in the chained FFN kernel's prologue. Bit-identical to the
   // stand-alone kernel but slower (2.53 vs 2.20 ms single stream, 1.45 vs 1.36 ms in throughput mode at C2): the
   // prologue (~27 us on 62 CTAs, before any MMA can start) costs more SM time than the 13 us grid-wide kernel. Opt-in.
@@ -332,6 +333,7 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   c->cfg = *cfg;
   c->layer_k.assign(cfg->n_layers, cfg->conv_kernel);
   if (const char* e = std::getenv("PPASR_B200_FUSED_DWCONV")) c->fused_dwconv = std::atoi(e) != 0;  // A/B switch for bench runs
+  if (const char* e = std::getenv("PPASR_B200_QKV_WIDE")) c->qkv_wide = std::atoi(e) != 0;
   if (cfg->model_type == 3) {
     c->eff_stride_idx = cfg->stride_layer_idx;
     c->eff_group_mask = (unsigned)cfg->group_layer_mask;
@@ -618,6 +620,7 @@ int ppasr_b200_finalize(ppasr_b200_ctx* c) {
               make_tmap_2d(&m.ff_w1_128, w.ff_w1, D, FF, (uint64_t)D * 2, 128, &err) &&
               make_tmap_2d(&m.ff_w2, w.ff_w2, FF, D, (uint64_t)FF * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.wqkv, w.wqkv, D, 3 * D, (uint64_t)D * 2, BN_NARROW, &err) &&
+              make_tmap_2d(&m.wqkv_wide, w.wqkv, D, 3 * D, (uint64_t)D * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.wo, w.wo, D, D, (uint64_t)D * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.pw1, w.pw1, D, 2 * D, (uint64_t)D * 2, BN_WIDE, &err) &&
               make_tmap_2d(&m.pw2, w.pw2, D, D, (uint64_t)D * 2, BN_WIDE, &err);
@@ -888,8 +891,15 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
       AttnParams ap{};
       ap.B = p.B, ap.H = H, ap.T1 = p.Tp, ap.D = D, ap.pos_col0 = l * D, ap.out = p.att, ap.q_rows_per_bh = p.Tp;
       if (!chunk) {
-        EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
-        { PROF(PC_QKV); PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st))); }
+        if (c->qkv_wide) {  // 128 x 256 tiles: one tile = the q, k or v third of a row tile (186 tiles instead of 372 at C2)
+          EpiQKV<BN_WIDE> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
+          PROF(PC_QKV);
+          PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.wqkv_wide, M, 3 * D, D, e, st)));
+        } else {
+          EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
+          PROF(PC_QKV);
+          PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st)));
+        }
         ap.T2 = p.Tp, ap.k_rows_per_bh = p.Tp, ap.k_row0 = 0, ap.pos_row0 = 0, ap.klens = p.vlen;
         { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st)); }
       } else {
@@ -1483,6 +1493,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   }
   if (n == "host_sync") {
     c->host_sync = value != 0;
+    return PPASR_OK;
+  }
+  if (n == "qkv_wide") {
+    c->qkv_wide = value != 0;
     return PPASR_OK;
   }
   if (n == "attn_out_v2") {  // process-wide: fused_attn_out kernel variant
