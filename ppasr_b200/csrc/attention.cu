@@ -8,8 +8,10 @@
 //
 // One CTA per (128-query tile, head, utterance). Per 128-key block:
 //   control thread : TMA loads K, P(pos), V^T tiles  -> tcgen05.mma S = Qu.K^T + Qv.P^T   (TMEM cols 0..127)
-//   128 softmax thr: thread = query row (TMEM lane). two passes over the S row in TMEM (max, then
-//                    exp2), probabilities written as bf16 into 128B-swizzled smem (K-major A operand)
+//   256 softmax thr: two threads per query row (TMEM lane): warps w and w + 4 share a lane quadrant, each owns 64 of the
+//                    128 key columns of a block and 32 of the 64 output dims. Two passes over the S row in TMEM (max --
+//                    exchanged between the two halves through shared memory -- then exp2), probabilities written as bf16
+//                    into 128B-swizzled smem (K-major A operand)
 //   control thread : tcgen05.mma O_blk = Prob . V   (TMEM cols 128..191)
 //   128 softmax thr: o_reg = o_reg * alpha + O_blk  (online soft-max rescale in registers)
 // Scores never touch HBM. smem: Q 32 KB + (K|P, reused for the probabilities) 32 KB + V^T 16 KB.
@@ -23,13 +25,14 @@ void count_launch();
 
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 128;
-constexpr int ATT_THREADS = 160;  // warps 0..3 softmax (TMEM lane quadrants), warp 4 control
+constexpr int ATT_THREADS = 288;  // warps 0..7 softmax (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8 control
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 swizzled tile = 16 KB
 constexpr int ATT_SMEM_Q = 0;
 constexpr int ATT_SMEM_KP = 2 * ATT_TILE_BYTES;         // K tile, P tile (later: probabilities half 0 / half 1)
 constexpr int ATT_SMEM_V = 4 * ATT_TILE_BYTES;          // two [64 d x 64 keys] tiles = 16 KB
 constexpr int ATT_SMEM_BAR = 5 * ATT_TILE_BYTES;
-constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128 + 1024;
+constexpr int ATT_SMEM_XCH = ATT_SMEM_BAR + 128;        // float [2][128]: row maxima / sums exchanged between the column halves
+constexpr int ATT_SMEM_TOTAL = ATT_SMEM_XCH + 1024 + 1024;
 constexpr int ATT_TMEM_COLS = 256;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -61,7 +64,7 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int klen = p.klens ? min(p.T2, __ldg(p.klens + b)) : p.T2;
   const int nblk = (p.T2 + ATT_BN - 1) / ATT_BN;
 
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     if (elect_one()) {
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
@@ -70,7 +73,7 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(bar_q_full, 1);
       mbar_init(bar_kv_full, 1);
       mbar_init(bar_s_full, 1);
-      mbar_init(bar_p_ready, 128);
+      mbar_init(bar_p_ready, 256);
       mbar_init(bar_o_full, 1);
       fence_barrier_init();
       fence_proxy_async_smem();
@@ -87,7 +90,7 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const uint32_t tmem_s = tmem_base;        // S: columns [0,128)
   const uint32_t tmem_o = tmem_base + 128;  // O_blk: columns [128,192)
 
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     // ============================ control: TMA + MMA issue ============================
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128);
@@ -134,26 +137,28 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
   } else {
-    // ============================ softmax: thread = query row ============================
-    const int quad = warp_idx;  // warps 0..3 -> TMEM lanes 32*quad ..
+    // ============================ softmax: two threads per query row ============================
+    const int quad = warp_idx & 3;   // TMEM lanes 32*quad ..
+    const int ch = warp_idx >> 2;    // column half: keys [64 ch, 64 ch + 64) of a block, output dims [32 ch, 32 ch + 32)
     const int r = quad * 32 + lane;
     const uint32_t lane_base = ((uint32_t)(quad * 32)) << 16;
+    float* xch = reinterpret_cast<float*>(smem + ATT_SMEM_XCH);  // [2][128]
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
+    float m_run = -INFINITY, l_run = 0.f;            // l_run: this thread's half of the row sum
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
 
     for (int j = 0; j < nblk; ++j) {
-      const int k0 = j * ATT_BN;
+      const int k0 = j * ATT_BN + ch * 64;
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
-      // pass 1: row maximum
+      // pass 1: maximum over this thread's 64 columns, then over the row (exchange with the other half)
       float bm = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < ATT_BN / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, rr);
+        tmem_ld_32x32b_x32(tmem_s + lane_base + ch * 64 + c * 32, rr);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -161,15 +166,19 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           bm = fmaxf(bm, valid ? __uint_as_float(rr[i]) : -INFINITY);
         }
       }
+      xch[ch * 128 + r] = bm;
+      named_bar_sync(1, 256);
+      bm = fmaxf(bm, xch[(ch ^ 1) * 128 + r]);
       const float m_new = fmaxf(m_run, bm * sc);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = exp2f(m_run - m_use);  // m_run = -inf -> 0
-      // pass 2: probabilities -> bf16, swizzled K-major A operand in smem (two 64-key halves)
+      // pass 2: probabilities -> bf16, swizzled K-major A operand in smem: this half's 64 keys are tile `ch`
       float bsum = 0.f;
+      uint8_t* tile = s_kp + ch * ATT_TILE_BYTES + r * 128;
 #pragma unroll 1
-      for (int c = 0; c < ATT_BN / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, rr);
+        tmem_ld_32x32b_x32(tmem_s + lane_base + ch * 64 + c * 32, rr);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
@@ -182,10 +191,9 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           bsum += __low2float(pb) + __high2float(pb);
           pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
         }
-        uint8_t* tile = s_kp + (c >> 1) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;  // 16-byte chunk index inside the 128-byte row
+          const int chunk = c * 4 + q4;  // 16-byte chunk index inside the 128-byte row
           *reinterpret_cast<uint4*>(tile + ((chunk ^ (r & 7)) << 4)) =
               make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
         }
@@ -195,34 +203,38 @@ rel_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_p_ready);
-      // O_blk -> registers with rescale
+      // O_blk -> registers with rescale (this thread's 32 output dims)
       mbar_wait(bar_o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, rr);
+      {
+        uint32_t ro[32];
+        tmem_ld_32x32b_x32(tmem_o + lane_base + ch * 32, ro);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(rr[i]));
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(ro[i]));
       }
       tc_fence_before();
+      named_bar_sync(1, 256);  // the exchange slots may be rewritten by the next block
     }
+    // row sum = the two halves' sums (same rescaling history: both use the row maximum)
+    xch[ch * 128 + r] = l_run;
+    named_bar_sync(1, 256);
+    l_run += xch[(ch ^ 1) * 128 + r];
     const int t = row0 + r;
     if (t < p.T1) {
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      uint32_t pk[32];
+      uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(o[2 * i] * inv, o[2 * i + 1] * inv);
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.T1 + t) * p.D + h * 64);
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(o[2 * i] * inv, o[2 * i + 1] * inv);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.T1 + t) * p.D + h * 64 + ch * 32);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     tc_fence_after();
     tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
   }
