@@ -235,7 +235,8 @@ int ppasr_b200_fbank(const float* audio, int32_t B, int64_t stride, int32_t N, c
 
 /* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels, "fused_dwconv" (default 0; causal
  * models) computes the conv module's depthwise stage in the chained FFN kernel's prologue (measured slower, kept for A/B), "fused_conv" (default 0) the
- * experimental fused conv1+conv2 front end (0 = separate kernels / GEMMs, for A/B measurements); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
+ * experimental fused conv1+conv2 front end (0 = separate kernels / GEMMs, for A/B measurements); "conv1_tc" (default 1) the first
+ * subsampling conv on the tensor cores (split-tf32, conv1_tc.cu; 0 = the CUDA-core kernel); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
  * returning -- 0 leaves the copies in flight (pinned host buffers; the caller synchronises), used by the
  * double-buffered serving pipeline. */
 int ppasr_b200_set_option(ppasr_b200_ctx* ctx, const char* name, int32_t value);
@@ -265,6 +266,10 @@ int ppasr_b200_profile_read(ppasr_b200_ctx* ctx, int32_t* counts, float* total_m
 /* Debug/inspection: copies an internal activation (fp32 residual stream x [B*T', d_model]) to the
  * device buffer `dst`. Used by the layer-wise parity tests only. */
 int ppasr_b200_debug_copy_x(ppasr_b200_ctx* ctx, float* dst_device, void* stream);
+/* The first subsampling conv's output (subsampling.py:84-85: Conv2d(1, D, 3, 2) + ReLU) as the four stride-phase images
+ * the second conv reads: bf16 [4][B*Th*FH][D], phase = 2*(t1 & 1) + (f1 & 1), row = (b*Th + t1/2)*FH + f1/2. dims
+ * receives {B, Th, FH, D}; dst_device may be null to query the dims only. Used by the front-end parity tests. */
+int ppasr_b200_debug_copy_phase(ppasr_b200_ctx* ctx, void* dst_device, int32_t* dims, void* stream);
 
 #ifdef __cplusplus
 }

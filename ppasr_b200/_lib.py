@@ -89,6 +89,7 @@ PROTOTYPES = {
     "ppasr_b200_op_fused_ffn": (c_int, [P, P, P, P, P, P, P, P, P, P, P, I, I, c_float, P]),
     "ppasr_b200_op_attention": (c_int, [P, P, P, I, P, I, I, I, I, P, I, I, I, I, P, P]),
     "ppasr_b200_debug_copy_x": (c_int, [P, P, P]),
+    "ppasr_b200_debug_copy_phase": (c_int, [P, P, P, P]),
     "ppasr_b200_set_option": (c_int, [P, c_char_p, I]),
     "ppasr_b200_graph_begin": (c_int, [P, P]),
     "ppasr_b200_graph_end": (c_int, [P, P]),

@@ -15,6 +15,11 @@ cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const 
                                    const float* bias, __nv_bfloat16* out, int B, int T, int F, int C, int T1, int F1,
                                    int Th, int FH, cudaStream_t st);
 
+// the same on the tensor cores (conv1_tc.cu): tmap_phase = 3-D map of the phase images [4][B*Th*FH][256], box 64 x 128 x 1
+cudaError_t launch_conv1_tc(const CUtensorMap& tmap_phase, const float* feats, const float* mean, const float* istd,
+                            const float* w, const float* bias, int B, int T, int F, int T1, int F1, int Th, int FH,
+                            int num_sms, cudaStream_t st);
+
 // zero_lens (nullable): output rows t >= zero_lens[b] are written as 0 (pad frames of the conv module output)
 cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
                                      const float* gamma, const float* beta, int use_layer_norm, __nv_bfloat16* out,

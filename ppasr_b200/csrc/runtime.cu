@@ -189,6 +189,7 @@ struct ppasr_b200_ctx {
   // optional per-kernel-class timing (cudaEvent pairs around every launch of the step)
   bool fused_ffn = true;
   bool fused_attn_out = true;
+  bool conv1_tc = true;   // conv1 on the tensor cores (conv1_tc.cu); 0 = the CUDA-core kernel (env PPASR_B200_CONV1_TC / option "conv1_tc")
   bool qkv_wide = false;  // QKV GEMM with 128 x 256 tiles (experiment switch, env PPASR_B200_QKV_WIDE / option "qkv_wide")
   // causal models: depthwise conv + norm + swish computed in the chained FFN kernel's prologue. Bit-identical to the
   // stand-alone kernel but slower (2.53 vs 2.20 ms single stream, 1.45 vs 1.36 ms in throughput mode at C2): the
@@ -334,6 +335,7 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   c->layer_k.assign(cfg->n_layers, cfg->conv_kernel);
   if (const char* e = std::getenv("PPASR_B200_FUSED_DWCONV")) c->fused_dwconv = std::atoi(e) != 0;  // A/B switch for bench runs
   if (const char* e = std::getenv("PPASR_B200_QKV_WIDE")) c->qkv_wide = std::atoi(e) != 0;
+  if (const char* e = std::getenv("PPASR_B200_CONV1_TC")) c->conv1_tc = std::atoi(e) != 0;
   if (cfg->model_type == 3) {
     c->eff_stride_idx = cfg->stride_layer_idx;
     c->eff_group_mask = (unsigned)cfg->group_layer_mask;
@@ -833,8 +835,12 @@ int run_subsampling_convs(ppasr_b200_ctx* c, cudaStream_t st) {
   } else {
     // CMVN + conv1 + ReLU -> stride-phase images
     { PROF(PC_CONV1);
-    PPASR_CUDA_CHECK(launch_conv1_subsample(p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.phase, p.B,
-                                            p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st)); }
+    if (c->conv1_tc && D == 256)
+      PPASR_CUDA_CHECK(launch_conv1_tc(p.tm_phase, p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.B, p.T,
+                                       cfg.feat_dim, p.T1, c->F1, p.Th, c->FH, c->sms, st));
+    else
+      PPASR_CUDA_CHECK(launch_conv1_subsample(p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.phase, p.B,
+                                              p.T, cfg.feat_dim, D, p.T1, c->F1, p.Th, c->FH, st)); }
     // conv2 + ReLU as 9 shifted GEMM taps -> c2 [M, F2*D]
     GemmShape s = make_shape(p.Mr, D, 9 * D, BN_WIDE);
     s.conv_pitch = c->FH;
@@ -1499,6 +1505,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
     c->qkv_wide = value != 0;
     return PPASR_OK;
   }
+  if (n == "conv1_tc") {
+    c->conv1_tc = value != 0;
+    return PPASR_OK;
+  }
   if (n == "attn_out_v2") {  // process-wide: fused_attn_out kernel variant
     set_attn_out_variant(value);
     return PPASR_OK;
@@ -1554,6 +1564,16 @@ int ppasr_b200_debug_copy_x(ppasr_b200_ctx* c, float* dst_device, void* stream) 
   PPASR_REQUIRE(c && dst_device && c->plan.M > 0, "encode first");
   PPASR_CUDA_CHECK(cudaMemcpyAsync(dst_device, c->plan.x, (size_t)c->plan.M * c->cfg.d_model * 4,
                                    cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return PPASR_OK;
+}
+
+int ppasr_b200_debug_copy_phase(ppasr_b200_ctx* c, void* dst_device, int32_t* dims, void* stream) {
+  PPASR_REQUIRE(c && dims && c->plan.M > 0, "encode first");
+  PPASR_REQUIRE(c->cfg.model_type != 4 && c->plan.phase != nullptr, "no conv2d subsampling front end in this model");
+  dims[0] = c->plan.B, dims[1] = c->plan.Th, dims[2] = c->FH, dims[3] = c->cfg.d_model;
+  if (dst_device)
+    PPASR_CUDA_CHECK(cudaMemcpyAsync(dst_device, c->plan.phase, (size_t)4 * c->plan.Mr * c->cfg.d_model * 2,
+                                     cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
   return PPASR_OK;
 }
 

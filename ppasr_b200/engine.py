@@ -277,6 +277,16 @@ class ConformerEngine:
         return {self.lib.ppasr_b200_profile_class_name(i).decode(): (int(counts[i]), float(ms[i]))
                 for i in range(n) if counts[i] > 0}
 
+    def debug_phase(self):
+        """conv1 output as the stride-phase images: bf16 [4, B, Th, FH, D] (ppasr_b200_debug_copy_phase)."""
+        torch = self.torch
+        dims = (ctypes.c_int32 * 4)()
+        L.check(self.lib.ppasr_b200_debug_copy_phase(self._ctx, None, dims, L.stream_ptr()))
+        B, Th, FH, D = (int(v) for v in dims)
+        out = torch.empty((4, B, Th, FH, D), dtype=torch.bfloat16, device=self.device)
+        L.check(self.lib.ppasr_b200_debug_copy_phase(self._ctx, L.ptr(out), dims, L.stream_ptr()))
+        return out
+
     def debug_x(self):
         torch = self.torch
         out = torch.empty((self.B * self.Tp, self.cfg.output_size), dtype=torch.float32, device=self.device)

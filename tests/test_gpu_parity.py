@@ -839,6 +839,7 @@ def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
         feats[b, lens[b]:] = 0
     fd = torch.from_numpy(feats).cuda()
     outs = []
+    eng.set_option("conv1_tc", 0)  # the CUDA-core conv1 is the one the fused producer mirrors instruction for instruction
     for fused in (0, 1):
         eng.set_option("fused_conv", fused)
         eng.encode(fd, lens)
@@ -846,6 +847,51 @@ def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
     torch.cuda.synchronize()
     eng.close()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("B,T,lens", [(3, 523, [523, 333, 260]), (5, 67, [67, 67, 50, 30, 67]), (2, 998, [998, 700]),
+                                      (32, 200, [200] * 32)])
+def test_conv1_phase_images_match_fp32_conv2d(lib, cuda, B, T, lens):
+    """GlobalCMVN + Conv2d(1, 256, 3, 2) + ReLU (cmvn.py:29-32, subsampling.py:84-85) as written into the stride-phase images:
+    the tensor-core kernel (split-tf32, conv1_tc.cu, default) and the CUDA-core kernel against torch fp32 conv2d. Both carry
+    fp32-accurate sums and ONE bf16 rounding, so each must sit within one bf16 ulp of the fp32 value, and the two kernels must
+    agree bit for bit on all but a few ties."""
+    import torch.nn.functional as F
+    from ppasr_b200.engine import ConformerEngine
+    from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
+    cfg = ConformerConfig(num_blocks=1, vocab_size=300)
+    w = init_conformer_weights(cfg)
+    eng = ConformerEngine(cfg, w)
+    feats = synthetic_fbank(B, T)
+    for b in range(B):
+        feats[b, lens[b]:] = 0
+    fd = torch.from_numpy(feats).cuda()
+    imgs = []
+    for tc in (0, 1):
+        eng.set_option("conv1_tc", tc)
+        eng.encode(fd, lens)
+        imgs.append(eng.debug_phase().float().cpu())
+    torch.cuda.synchronize()
+    eng.close()
+    mean = torch.from_numpy(np.asarray(w["encoder.global_cmvn.mean"], dtype=np.float32))
+    istd = torch.from_numpy(np.asarray(w["encoder.global_cmvn.istd"], dtype=np.float32))
+    xn = (torch.from_numpy(feats) - mean) * istd
+    c1 = F.relu(F.conv2d(xn.double().unsqueeze(1), torch.from_numpy(np.asarray(w["encoder.embed.conv.0.weight"])).double(),
+                         torch.from_numpy(np.asarray(w["encoder.embed.conv.0.bias"])).double(), stride=2))  # [B, 256, T1, F1]
+    _, _, T1, F1 = c1.shape
+    Th, FH = imgs[0].shape[2], imgs[0].shape[3]
+    ref = torch.zeros((4, B, Th, FH, 256), dtype=torch.float64)
+    for pt in range(2):
+        for pf in range(2):
+            sub = c1[:, :, pt::2, pf::2].permute(0, 2, 3, 1)  # [B, th, f2, C]
+            ref[2 * pt + pf, :, :sub.shape[1], :sub.shape[2]] = sub
+    for name, img in zip(("cuda-core", "tensor-core"), imgs):
+        err = (img.double() - ref).abs()
+        tol = ref.abs() * 2.0 ** -8 + 1e-5  # half a bf16 ulp (round to nearest) of the exact value
+        bad = (err > tol * 1.001).sum().item()
+        assert bad == 0, f"{name}: {bad} elements beyond one bf16 rounding of the fp64 conv (max err {err.max().item():.3e})"
+    differ = (imgs[0] != imgs[1]).float().mean().item()
+    assert differ < 1e-3, f"tensor-core and CUDA-core conv1 differ on {differ:.2e} of the elements"
 
 
 # ------------------------------------------------------------------------------------------------
