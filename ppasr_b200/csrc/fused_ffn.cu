@@ -165,7 +165,7 @@ DEVINL void dwconv_a_tiles(const FfnParams& p, int m0, int ct, int ew, int lane,
         }
         uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pk[i] = zero ? 0u : pack_bf16x2(swish_precise(v[2 * i]), swish_precise(v[2 * i + 1]));
+        for (int i = 0; i < 4; ++i) pk[i] = zero ? 0u : pack_bf16x2(swish_rcp(v[2 * i]), swish_rcp(v[2 * i + 1]));
         const int row = hf * 64 + l0 + r;
         uint8_t* atile = s_a + (lane >> 3) * FFN_TILE + row * 128;
         *reinterpret_cast<uint4*>(atile + (((lane & 7) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

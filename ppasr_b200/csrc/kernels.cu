@@ -2,6 +2,7 @@
 // fused (double) LayerNorm, CMVN + first subsampling conv, depthwise-conv + norm + Swish,
 // row soft-max, CTC greedy decode. All are HBM-bandwidth bound: coalesced 16-byte accesses,
 // warp-shuffle reductions, no re-reads.
+#include <cstdlib>
 #include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -182,10 +183,14 @@ cudaError_t launch_conv1_subsample(const float* feats, const float* mean, const 
 //   row, because the reference left-pads *before* pointwise_conv1, convolution.py:108-110),
 //   rows >= Tin read 0 (symmetric padding of the depthwise conv itself, convolution.py:47-54).
 //   Chunk mode passes Tin = lorder + Tout with lpad = 0 ("valid" convolution over [cache ; chunk]).
-// One block per (b, 32-frame tile); thread = channel for the conv, warp = row for the norm.
+// One block per (b, TT-frame tile), C * SPLIT threads: thread = (channel, 1/SPLIT of the tile's rows) for the conv -- the
+// K-1 halo rows are shared through smem, so splitting the rows costs no extra global traffic -- and warp = row for the norm.
+// The kernel is a latency chain (ncu r2_small: 1061 instructions per warp at 15 cycles each, 40 % issue utilisation), so
+// the work per thread is kept short and every constant (taps, bias, gamma, beta) is loaded before the grid dependency
+// resolves, underneath the predecessor's tail.
 // ------------------------------------------------------------------------------------------------
-template <int C, int TT, int K>
-__global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat16* __restrict__ g,
+template <int C, int TT, int K, int SPLIT>
+__global__ void __launch_bounds__(C * SPLIT) dwconv_norm_swish_kernel(const __nv_bfloat16* __restrict__ g,
                                                               const float* __restrict__ w,  // [C, K]
                                                               const float* __restrict__ bias,
                                                               const float* __restrict__ pad_left,  // [C] or null
@@ -194,24 +199,46 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
                                                               __nv_bfloat16* __restrict__ out, int Tin, int Tout,
                                                               int lpad, float eps, const int* __restrict__ zero_lens) {
   extern __shared__ uint8_t dsm[];
-  pdl_wait();
-  pdl_launch_dependents();
   constexpr int ROWS = TT + K - 1;
+  constexpr int NT = C * SPLIT;
+  constexpr int RPT = TT / SPLIT;  // conv rows per thread
+  constexpr int PER = C / 32;
+  static_assert(TT % SPLIT == 0 && NT / 32 == TT, "one warp per output row in the norm phase");
   __nv_bfloat16* sin = reinterpret_cast<__nv_bfloat16*>(dsm);                 // [ROWS][C]
   float* sout = reinterpret_cast<float*>(dsm + (size_t)ROWS * C * 2);         // [TT][C]
-  float* sw = sout + TT * C;                                                  // [C][K] staged weights
   const int tiles = (Tout + TT - 1) / TT;
   const int b = blockIdx.x / tiles;
   const int t0 = (blockIdx.x - b * tiles) * TT;
-  const int c = threadIdx.x;
-  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + ROWS) and of the weights; loads are
-  // issued in batches before the shared-memory stores so they overlap
+  const int c = threadIdx.x & (C - 1);
+  const int part = threadIdx.x / C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- constants (weights of the model: safe to read before griddepcontrol.wait) ----
+  float wk[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wk[j] = __ldg(w + c * K + j);
+  const float bs = __ldg(bias + c);
+  const float sc = use_layer_norm ? 1.f : __ldg(gamma + c);
+  const float sh = use_layer_norm ? 0.f : __ldg(beta + c);
+  float gm[PER], bt[PER];
+  if (use_layer_norm) {
+#pragma unroll
+    for (int i = 0; i < PER; i += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + lane * PER + i));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(beta + lane * PER + i));
+      gm[i] = a.x, gm[i + 1] = a.y, gm[i + 2] = a.z, gm[i + 3] = a.w;
+      bt[i] = d.x, bt[i + 1] = d.y, bt[i + 2] = d.z, bt[i + 3] = d.w;
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  const int zlen = zero_lens != nullptr ? __ldg(zero_lens + b) : 0x7fffffff;
+  // coalesced load of the input window rows [t0 - lpad, t0 - lpad + ROWS)
   {
-    constexpr int NV = (ROWS * (C / 8) + C - 1) / C;
+    constexpr int NV = (ROWS * (C / 8) + NT - 1) / NT;
     uint4 v[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int i = threadIdx.x + k * C;
+      const int i = threadIdx.x + k * NT;
       const int r = i / (C / 8), seg = i - r * (C / 8);
       const int ti = t0 - lpad + r;
       v[k] = make_uint4(0, 0, 0, 0);
@@ -226,76 +253,61 @@ __global__ void __launch_bounds__(C) dwconv_norm_swish_kernel(const __nv_bfloat1
         }
       }
     }
-    float wv[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) wv[k] = __ldg(w + threadIdx.x + k * C);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int i = threadIdx.x + k * C;
+      const int i = threadIdx.x + k * NT;
       const int r = i / (C / 8), seg = i - r * (C / 8);
       if (r < ROWS) *reinterpret_cast<uint4*>(sin + (size_t)r * C + seg * 8) = v[k];
     }
-#pragma unroll
-    for (int k = 0; k < K; ++k) sw[threadIdx.x + k * C] = wv[k];
   }
   __syncthreads();
-  // depthwise conv: thread = channel, sliding K-wide register window over time (one smem read per output)
-  float wk[K];
+  // depthwise conv: thread = (channel, rows [part*RPT, (part+1)*RPT)), sliding K-wide register window over time
+  {
+    const int r0 = part * RPT;
+    float win[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) wk[j] = sw[c * K + j];  // stride K (odd): conflict-free
-  const float bs = __ldg(bias + c);
-  const float sc = use_layer_norm ? 1.f : __ldg(gamma + c);
-  const float sh = use_layer_norm ? 0.f : __ldg(beta + c);
-  float win[K];
+    for (int j = 0; j < K - 1; ++j) win[j] = __bfloat162float(sin[(size_t)(r0 + j) * C + c]);
 #pragma unroll
-  for (int j = 0; j < K - 1; ++j) win[j] = __bfloat162float(sin[(size_t)j * C + c]);
+    for (int u = 0; u < RPT; ++u) {
+      win[(u + K - 1) % K] = __bfloat162float(sin[(size_t)(r0 + u + K - 1) * C + c]);
+      float acc = bs;
 #pragma unroll
-  for (int tb = 0; tb < TT; tb += K) {
-#pragma unroll
-    for (int u = 0; u < K; ++u) {
-      const int t = tb + u;
-      if (t < TT) {
-        win[(u + K - 1) % K] = __bfloat162float(sin[(size_t)(t + K - 1) * C + c]);
-        float acc = bs;
-#pragma unroll
-        for (int j = 0; j < K; ++j) acc = fmaf(wk[j], win[(u + j) % K], acc);
-        sout[t * C + c] = acc * sc + sh;
-      }
+      for (int j = 0; j < K; ++j) acc = fmaf(wk[j], win[(u + j) % K], acc);
+      sout[(r0 + u) * C + c] = acc * sc + sh;
     }
   }
   __syncthreads();
   // norm + swish, warp = row
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int PER = C / 32;
-  for (int t = warp; t < TT; t += C / 32) {
-    if (t0 + t >= Tout) break;
-    float v[PER];
+  const int t = warp;
+  if (t0 + t >= Tout) return;
+  float v[PER];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) v[i] = sout[t * C + lane * PER + i];
-    if (use_layer_norm) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) s += v[i];
-      const float mean = warp_sum(s) * (1.0f / C);
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const float d = v[i] - mean;
-        q += d * d;
-      }
-      const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
-#pragma unroll
-      for (int i = 0; i < PER; ++i)
-        v[i] = (v[i] - mean) * rstd * __ldg(gamma + lane * PER + i) + __ldg(beta + lane * PER + i);
-    }
-    const bool zero = zero_lens != nullptr && (t0 + t) >= __ldg(zero_lens + b);
-    uint32_t pk[PER / 2];
-#pragma unroll
-    for (int i = 0; i < PER / 2; ++i) pk[i] = zero ? 0u : pack_bf16x2(swish_precise(v[2 * i]), swish_precise(v[2 * i + 1]));
-    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * Tout + t0 + t) * C + lane * PER);
-#pragma unroll
-    for (int i = 0; i < PER / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  for (int i = 0; i < PER; i += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(sout + t * C + lane * PER + i);
+    v[i] = a.x, v[i + 1] = a.y, v[i + 2] = a.z, v[i + 3] = a.w;
   }
+  if (use_layer_norm) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = (v[i] - mean) * rstd * gm[i] + bt[i];
+  }
+  const bool zero = (t0 + t) >= zlen;
+  uint32_t pk[PER / 2];
+#pragma unroll
+  for (int i = 0; i < PER / 2; ++i) pk[i] = zero ? 0u : pack_bf16x2(swish_rcp(v[2 * i]), swish_rcp(v[2 * i + 1]));
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * Tout + t0 + t) * C + lane * PER);
+#pragma unroll
+  for (int i = 0; i < PER / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
 }
 
 cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
@@ -303,23 +315,26 @@ cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, con
                                      int B, int Tin, int Tout, int C, int K, int lpad, float eps, const int* zero_lens,
                                      cudaStream_t st) {
   if (C != 256) return cudaErrorInvalidValue;
-  constexpr int TT = 16;
-  const int tiles = (Tout + TT - 1) / TT;
-#define PPASR_DW_LAUNCH(KK)                                                                                   \
+  // 1 (default): 256 threads per 8-row tile; 2: 512 threads per 16-row tile (two row halves per channel). Both put one warp on
+  // each output row in the norm phase. C2 live: 14.0 / 14.7 us per launch (16.9 before: 16-row tiles, 256 threads, constants
+  // loaded after the grid dependency); env PPASR_B200_DW_SPLIT.
+  static const int split = [] {
+    const char* e = std::getenv("PPASR_B200_DW_SPLIT");
+    return e ? std::atoi(e) : 1;
+  }();
+#define PPASR_DW_LAUNCH(KK, TT, SPLIT)                                                                        \
   {                                                                                                           \
-    const size_t smem = (size_t)(TT + KK - 1) * C * 2 + (size_t)TT * C * 4 + (size_t)C * KK * 4;             \
-    auto kern = dwconv_norm_swish_kernel<256, TT, KK>;                                                        \
-    static bool configured = false;                                                                           \
-    if (!configured) {                                                                                        \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-      if (e != cudaSuccess) return e;                                                                         \
-      configured = true;                                                                                      \
-    }                                                                                                         \
-    cudaError_t le = launch_pdl(kern, dim3(B * tiles), dim3(256), smem, st, g, w, bias, pad_left, gamma, beta, use_layer_norm, \
-                                out, Tin, Tout, lpad, eps, zero_lens);                                       \
+    const int tiles = (Tout + TT - 1) / TT;                                                                   \
+    const size_t smem = (size_t)(TT + KK - 1) * C * 2 + (size_t)TT * C * 4;                                   \
+    auto kern = dwconv_norm_swish_kernel<256, TT, KK, SPLIT>;                                                 \
+    cudaError_t le = launch_pdl(kern, dim3(B * tiles), dim3(256 * SPLIT), smem, st, g, w, bias, pad_left, gamma, beta, \
+                                use_layer_norm, out, Tin, Tout, lpad, eps, zero_lens);                        \
     if (le != cudaSuccess) return le;                                                                         \
   }
-  if (K == 15) PPASR_DW_LAUNCH(15) else if (K == 31) PPASR_DW_LAUNCH(31) else if (K == 7) PPASR_DW_LAUNCH(7) else return cudaErrorInvalidValue;
+#define PPASR_DW_LAUNCH_K(KK) \
+  if (split == 2) PPASR_DW_LAUNCH(KK, 16, 2) else PPASR_DW_LAUNCH(KK, 8, 1)
+  if (K == 15) { PPASR_DW_LAUNCH_K(15) } else if (K == 31) { PPASR_DW_LAUNCH_K(31) } else if (K == 7) { PPASR_DW_LAUNCH_K(7) } else return cudaErrorInvalidValue;
+#undef PPASR_DW_LAUNCH_K
 #undef PPASR_DW_LAUNCH
   count_launch();
   return cudaGetLastError();

@@ -237,6 +237,8 @@ DEVINL float swish_f(float x) { return x * sigmoid_f(x); }
 // full-precision variants for the CUDA-core kernels whose output stays fp32
 DEVINL float sigmoid_precise(float x) { return 1.0f / (1.0f + __expf(-x)); }
 DEVINL float swish_precise(float x) { return x * sigmoid_precise(x); }
+// ex2 + rcp (2 ulp): for outputs that are rounded to bf16 right away (depthwise-conv module)
+DEVINL float swish_rcp(float x) { return x * __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute
 // may start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has
