@@ -78,9 +78,10 @@ DEVINL float apply_act(float v) {
 
 // Software-pipelined walk over this warp's NCH 32-column chunks: the TMEM load of chunk c+1 is in
 // flight while chunk c is processed. f(cc, r) gets the chunk's column offset inside the tile.
-template <int BLOCK_N, class F>
+template <int BLOCK_N, int PARTS = 2, class F>
 DEVINL void epi_for_chunks(uint32_t taddr, int half, F&& f) {
-  constexpr int NCH = BLOCK_N / 64;
+  constexpr int NCH = BLOCK_N / (32 * PARTS);
+  static_assert(NCH >= 1, "a column part is at least one 32-column chunk");
   const int c0 = half * NCH;
   uint32_t r[2][32];
   tmem_ld_32x32b_x32(taddr + c0 * 32, r[0]);
@@ -460,6 +461,7 @@ struct EpiGLU {
 //   vt[b,h,d,tk]     = v  (transposed so P.V^T is a K-major UMMA B operand)
 template <int BLOCK_N>
 struct EpiQKV {
+  static constexpr int kEpiWarps = 16;  // four column parts: one 32-column chunk per warp and 128-wide tile
   __nv_bfloat16* q2;
   __nv_bfloat16* kk;
   __nv_bfloat16* vt;
@@ -485,7 +487,7 @@ struct EpiQKV {
     }
     const int kb = slots ? __ldg(slots + b) : b;               // cache slot of the K / V rows
     const int kofs = kofs_b ? __ldg(kofs_b + b) : this->kofs;  // shadows the member on purpose
-    epi_for_chunks<BLOCK_N>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
+    epi_for_chunks<BLOCK_N, 4>(taddr, half, [&](int cc, const uint32_t(&r)[32]) {
       const int col = n0 + cc;
       if (row >= M || col >= 3 * D) return;
       const int which = col / D;
@@ -738,16 +740,30 @@ struct EpiUsesXbuf<Epi, decltype((void)Epi::kXbuf)> {
   static constexpr bool value = Epi::kXbuf != 0;
 };
 
+// epilogue warps per CTA: 8 (two column halves per TMEM lane quadrant) unless the epilogue asks for more. The epilogues of
+// the K = 256 GEMMs are per-warp latency chains (ncu r2_qkv: 12 cycles per instruction, 600 instructions per warp and tile,
+// 13 % tensor-pipe activity), so an epilogue with that much work per element declares kEpiWarps = 16 (four column parts).
+template <class Epi, class = void>
+struct EpiWarps {
+  static constexpr int value = GEMM_EPI_WARPS;
+};
+template <class Epi>
+struct EpiWarps<Epi, decltype((void)Epi::kEpiWarps)> {
+  static constexpr int value = Epi::kEpiWarps;
+};
+
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int STAGES, bool CONV, class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(128 + EpiWarps<Epi>::value * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmShape shape, const Epi epi) {
   using SM = GemmSmem<BLOCK_N, STAGES>;
   using ACC = GemmAcc<BLOCK_N>;
   constexpr bool XBUF = EpiUsesXbuf<Epi>::value;
+  constexpr int EPI_WARPS = EpiWarps<Epi>::value;
+  static_assert(EPI_WARPS % 4 == 0 && BLOCK_N % (8 * EPI_WARPS) == 0, "column parts of whole 32-column chunks");
   constexpr int ACC_STAGES = XBUF ? 1 : ACC::ACC_STAGES;
   static_assert(!XBUF || BLOCK_N == 256, "X buffer layout assumes 2 x 256 TMEM columns");
   static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "BLOCK_N");
@@ -778,7 +794,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS * 32);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS * 32);
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -865,7 +881,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int quad = ew & 3;  // == warp_idx % 4 : TMEM lane quadrant
     const int half = ew >> 2;
     const int lane = threadIdx.x & 31;
-    const int etid = threadIdx.x - 128;  // 0..255
+    const int etid = threadIdx.x - 128;  // 0 .. EPI_WARPS * 32
     int as = 0;
     uint32_t aphase = 0;
     int it = 0;
@@ -875,7 +891,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // stage this tile's bias slice (double buffered by tile parity; one named barrier per tile)
       float* sbias = smem_bias + (it & 1) * BLOCK_N;
       if (etid < BLOCK_N) sbias[etid] = __ldg(epi.bias + n_tile * BLOCK_N + etid);
-      named_bar_sync(1, GEMM_EPI_WARPS * 32);
+      named_bar_sync(1, EPI_WARPS * 32);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N;
       if constexpr (XBUF) epi.prefetch(taddr + BLOCK_N, m_tile * GEMM_BLOCK_M + quad * 32 + lane, half);
       mbar_wait(&tmem_full_bar[as], aphase);
@@ -914,7 +930,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tma
   const int num_tiles = shape.num_m_tiles * shape.num_n_tiles;
   if (num_tiles <= 0) return cudaSuccess;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)SM::TOTAL, stream, tmap_a, tmap_b, shape, epi);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(128 + EpiWarps<Epi>::value * 32), (size_t)SM::TOTAL, stream, tmap_a, tmap_b, shape, epi);
   count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }
