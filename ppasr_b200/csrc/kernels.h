@@ -20,6 +20,11 @@ cudaError_t launch_conv1_tc(const CUtensorMap& tmap_phase, const float* feats, c
                             const float* w, const float* bias, int B, int T, int F, int T1, int F1, int Th, int FH,
                             int num_sms, cudaStream_t st);
 
+// conv1 (as above) fused into the conv2 GEMM's A-operand producer: feats -> c2 [B*Tout*Fout, 256] (conv1_tc.cu)
+cudaError_t launch_conv_front_tc(const CUtensorMap& tmap_w2, const float* feats, const float* mean, const float* istd,
+                                 const float* w1, const float* b1, const float* b2, __nv_bfloat16* out, int B, int T, int F,
+                                 int T1, int F1, int Th, int FH, int Tout, int Fout, int num_sms, cudaStream_t st);
+
 // zero_lens (nullable): output rows t >= zero_lens[b] are written as 0 (pad frames of the conv module output)
 cudaError_t launch_dwconv_norm_swish(const __nv_bfloat16* g, const float* w, const float* bias, const float* pad_left,
                                      const float* gamma, const float* beta, int use_layer_norm, __nv_bfloat16* out,

@@ -198,7 +198,7 @@ struct ppasr_b200_ctx {
   // conv1 computed inside the conv2 GEMM's A producer (conv_front.cu). Bit-identical to the two-kernel path but slower
   // on B200 (382 us vs 145 + 145 us at C2): the producers' LDS/STS traffic shares the 128 B/clk shared-memory data pipe
   // with the tensor core's operand reads (ncu: lsu 57 % + tc 20 % of the pipe), so it is opt-in.
-  bool fused_conv = false;
+  int fused_conv = 0;  // 0: conv1 + conv2 GEMM, 1: conv_front.cu (CUDA-core producer), 2: conv_front_tc (tensor-core producer); env PPASR_B200_FUSED_CONV
   bool host_sync = true;  // ctc_* with host outputs synchronise the stream before returning
   // valid-length staging (pinned: the H2D copy may be part of a captured CUDA graph and is re-read at every replay)
   int* h_vlen = nullptr;
@@ -336,6 +336,7 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   if (const char* e = std::getenv("PPASR_B200_FUSED_DWCONV")) c->fused_dwconv = std::atoi(e) != 0;  // A/B switch for bench runs
   if (const char* e = std::getenv("PPASR_B200_QKV_WIDE")) c->qkv_wide = std::atoi(e) != 0;
   if (const char* e = std::getenv("PPASR_B200_CONV1_TC")) c->conv1_tc = std::atoi(e) != 0;
+  if (const char* e = std::getenv("PPASR_B200_FUSED_CONV")) c->fused_conv = std::atoi(e);
   if (cfg->model_type == 3) {
     c->eff_stride_idx = cfg->stride_layer_idx;
     c->eff_group_mask = (unsigned)cfg->group_layer_mask;
@@ -827,7 +828,12 @@ int run_subsampling_convs(ppasr_b200_ctx* c, cudaStream_t st) {
   Plan& p = c->plan;
   const auto& cfg = c->cfg;
   const int D = cfg.d_model;
-  if (c->fused_conv && D == 256 && c->FH == 20) {  // patch geometry of conv_front.cu assumes feat_dim 80 (pitch 20)
+  if (c->fused_conv == 2 && D == 256 && cfg.feat_dim <= 96) {
+    // CMVN + conv1 (split-tf32 GEMM) + ReLU + conv2 + ReLU in one tcgen05 kernel (conv1_tc.cu) -> c2 [M, F2*D]
+    PROF(PC_CONV_FRONT);
+    PPASR_CUDA_CHECK(launch_conv_front_tc(c->tm_conv2_w, p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, c->conv2_b,
+                                          p.c2, p.B, p.T, cfg.feat_dim, p.T1, c->F1, p.Th, c->FH, p.Tp, c->F2, c->sms, st));
+  } else if (c->fused_conv == 1 && D == 256 && c->FH == 20) {  // patch geometry of conv_front.cu assumes feat_dim 80 (pitch 20)
     // CMVN + conv1 + ReLU + conv2 + ReLU in one kernel (conv_front.cu) -> c2 [M, F2*D]
     PROF(PC_CONV_FRONT);
     PPASR_CUDA_CHECK(launch_conv_front(c->tm_conv2_w, p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, c->conv2_b,
@@ -1522,7 +1528,7 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
     return PPASR_OK;
   }
   if (n == "fused_conv") {
-    c->fused_conv = value != 0;
+    c->fused_conv = value;
     return PPASR_OK;
   }
   if (n == "fused_attn_out") {

@@ -828,8 +828,9 @@ def test_decode_pipeline_matches_sync_api(lib, cuda):
 
 @pytest.mark.parametrize("B,T,lens", [(3, 523, [523, 333, 260]), (5, 67, [67, 67, 50, 30, 67]), (1, 998, [998])])
 def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
-    """conv_front.cu (conv1 computed inside the conv2 GEMM's A producer; opt-in) == conv1 kernel + conv2 GEMM, bit for bit
-    (same fp32 FMA order, one bf16 rounding of the conv1 output in both)."""
+    """The fused front ends == the two-kernel paths they mirror, bit for bit: conv_front.cu (CUDA-core conv1 inside the conv2
+    GEMM's A producer) vs conv1_subsample + conv2 GEMM (same fp32 FMA order), and conv_front_tc (split-tf32 conv1 GEMM as the
+    producer, conv1_tc.cu) vs conv1_tc + conv2 GEMM (same MMAs in the same order)."""
     from ppasr_b200.engine import ConformerEngine
     from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
     cfg = ConformerConfig(num_blocks=1, vocab_size=300)
@@ -838,15 +839,16 @@ def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
     for b in range(B):
         feats[b, lens[b]:] = 0
     fd = torch.from_numpy(feats).cuda()
-    outs = []
-    eng.set_option("conv1_tc", 0)  # the CUDA-core conv1 is the one the fused producer mirrors instruction for instruction
-    for fused in (0, 1):
-        eng.set_option("fused_conv", fused)
-        eng.encode(fd, lens)
-        outs.append(eng.ctc_logits().float().cpu())
-    torch.cuda.synchronize()
+    for conv1_tc, fused in ((0, 1), (1, 2)):
+        outs = []
+        eng.set_option("conv1_tc", conv1_tc)
+        for f in (0, fused):
+            eng.set_option("fused_conv", f)
+            eng.encode(fd, lens)
+            outs.append(eng.ctc_logits().float().cpu())
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), f"fused_conv={fused}: max diff {(outs[0] - outs[1]).abs().max().item():.3e}"
     eng.close()
-    assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("B,T,lens", [(3, 523, [523, 333, 260]), (5, 67, [67, 67, 50, 30, 67]), (2, 998, [998, 700]),
