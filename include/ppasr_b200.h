@@ -234,8 +234,9 @@ int ppasr_b200_fbank(const float* audio, int32_t B, int64_t stride, int32_t N, c
                      void* stream);
 
 /* Switches: "fused_ffn" / "fused_attn_out" (default 1) select the fused row-tile kernels, "fused_dwconv" (default 0; causal
- * models) computes the conv module's depthwise stage in the chained FFN kernel's prologue (measured slower, kept for A/B), "fused_conv" (default 0) the
- * experimental fused conv1+conv2 front end (0 = separate kernels / GEMMs, for A/B measurements); "conv1_tc" (default 1) the first
+ * models) computes the conv module's depthwise stage in the chained FFN kernel's prologue (measured slower, kept for A/B), "fused_conv" (default 2) the
+ * subsampling front end: 2 = conv1 (split-tf32 GEMM) as the A-operand producer of the conv2 GEMM in one kernel, 0 = conv1 kernel + conv2 GEMM
+ * through the stride-phase images (bit-identical to 2 with conv1_tc = 1), 1 = the CUDA-core fused producer (slower; kept for A/B); "conv1_tc" (default 1) the first
  * subsampling conv on the tensor cores (split-tf32, conv1_tc.cu; 0 = the CUDA-core kernel); "host_sync" (default 1): ppasr_b200_ctc_greedy with host outputs synchronises the stream before
  * returning -- 0 leaves the copies in flight (pinned host buffers; the caller synchronises), used by the
  * double-buffered serving pipeline. */

@@ -198,7 +198,7 @@ struct ppasr_b200_ctx {
   // conv1 computed inside the conv2 GEMM's A producer (conv_front.cu). Bit-identical to the two-kernel path but slower
   // on B200 (382 us vs 145 + 145 us at C2): the producers' LDS/STS traffic shares the 128 B/clk shared-memory data pipe
   // with the tensor core's operand reads (ncu: lsu 57 % + tc 20 % of the pipe), so it is opt-in.
-  int fused_conv = 0;  // 0: conv1 + conv2 GEMM, 1: conv_front.cu (CUDA-core producer), 2: conv_front_tc (tensor-core producer); env PPASR_B200_FUSED_CONV
+  int fused_conv = 2;  // 2 (default): conv_front_tc (tensor-core conv1 producer inside the conv2 GEMM), 0: conv1 + conv2 GEMM, 1: conv_front.cu (CUDA-core producer); env PPASR_B200_FUSED_CONV
   bool host_sync = true;  // ctc_* with host outputs synchronise the stream before returning
   // valid-length staging (pinned: the H2D copy may be part of a captured CUDA graph and is re-read at every replay)
   int* h_vlen = nullptr;
