@@ -560,6 +560,8 @@ cudaError_t launch_argmax_rows(const float* probs, int V, int rows, int* idx, fl
 __global__ void ctc_stats_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ parg,
                                           const float* __restrict__ psum, int parts, int rows, int* __restrict__ idx,
                                           float* __restrict__ maxp) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -597,7 +599,8 @@ __global__ void ctc_stats_finalize_kernel(const float* __restrict__ pmax, const 
 cudaError_t launch_ctc_stats_finalize(const float* pmax, const int* parg, const float* psum, int parts, int rows,
                                       int* idx, float* maxp, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  ctc_stats_finalize_kernel<<<(rows + 3) / 4, 128, 0, st>>>(pmax, parg, psum, parts, rows, idx, maxp);
+  cudaError_t le = launch_pdl(ctc_stats_finalize_kernel, dim3((rows + 3) / 4), dim3(128), (size_t)0, st, pmax, parg, psum, parts, rows, idx, maxp);
+  if (le != cudaSuccess) return le;
   count_launch();
   return cudaGetLastError();
 }
@@ -610,6 +613,8 @@ __global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __
                                     const int* __restrict__ frame_lens, int blank, int* __restrict__ ids_out,
                                     int ld_out, int* __restrict__ out_len, float* __restrict__ score,
                                     float* __restrict__ score_sum, int* __restrict__ score_cnt) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -658,8 +663,9 @@ cudaError_t launch_ctc_collapse(const int* idx, const float* maxp, int B, int T,
                                 int* ids_out, int ld_out, int* out_len, float* score, float* score_sum,
                                 int* score_cnt, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  ctc_collapse_kernel<<<(B + 3) / 4, 128, 0, st>>>(idx, maxp, B, T, frame_lens, blank, ids_out, ld_out, out_len, score,
-                                                   score_sum, score_cnt);
+  cudaError_t le = launch_pdl(ctc_collapse_kernel, dim3((B + 3) / 4), dim3(128), (size_t)0, st, idx, maxp, B, T, frame_lens, blank,
+                              ids_out, ld_out, out_len, score, score_sum, score_cnt);
+  if (le != cudaSuccess) return le;
   count_launch();
   return cudaGetLastError();
 }
