@@ -440,7 +440,7 @@ def main():
     import torch
     import torch.distributed as dist
     from ppasr_b200 import _lib as L
-    from ppasr_b200.parallel import all_gather_results, detokenize
+    from ppasr_b200.parallel import all_gather_records, all_gather_results, detokenize, unpack_records
     from ppasr_b200.weights import make_vocab
 
     rank = int(os.environ.get("RANK", "0"))
@@ -535,11 +535,23 @@ def main():
     pipe = pred.pipeline(depth=depth) if wl.pipelined else None
     pool = wl.pool
 
+    # per pipeline slot: a zeroed record buffer and the gathered array (the all-gather is the only collective of the job)
+    max_local = (total_utts + world - 1) // world
+    rec_bufs, gat_bufs = {}, {}
+
+    def gather_slot(ticket):
+        ids, ol, sc = pipe.device_result(ticket)
+        st = pipe.stream(ticket)
+        key = st.cuda_stream
+        if key not in rec_bufs:
+            rec_bufs[key] = torch.zeros((max_local, lmax + 2), dtype=torch.int32, device=dev)
+            gat_bufs[key] = torch.empty((world * max_local, lmax + 2), dtype=torch.int32, device=dev)
+        with torch.cuda.stream(st):
+            return all_gather_records(ids, ol, sc, total_utts, lmax, rec=rec_bufs[key], out=gat_bufs[key])
+
     def finish(ticket):
         if world > 1:
-            ids, ol, sc = pipe.device_result(ticket)
-            with torch.cuda.stream(pipe.stream(ticket)):
-                all_gather_results(ids, ol, sc, total_utts, lmax)
+            gather_slot(ticket)
 
     def run_steps(n):
         if pipe is None:
@@ -602,33 +614,33 @@ def main():
     # of the whole job, additionally copies the gathered records back and detokenises all N x B utterances.
     brk = {"submit_ms": 0.0, "wait_d2h_ms": 0.0, "allgather_enqueue_ms": 0.0, "detok_ms": 0.0}
     pipe = pred.pipeline(depth=depth) if wl.pipelined else None
-    gathered_pin = torch.empty((total_utts, lmax + 1), dtype=torch.int32).pin_memory() if world > 1 and rank == 0 else None
+    gathered_pin = torch.empty((world * max_local, lmax + 2), dtype=torch.int32).pin_memory() if world > 1 and rank == 0 else None
 
     own_pin = (torch.empty((B, lmax), dtype=torch.int32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory()) \
-        if world > 1 else None
+        if world > 1 and rank != 0 else None
 
     def e2e_finish(ticket):
         t0 = time.perf_counter()
         if world > 1:
             dids, dol, dsc = pipe.device_result(ticket)      # device tensors (submitted with to_host=False)
+            g = gather_slot(ticket)
             with torch.cuda.stream(pipe.stream(ticket)):
-                g = all_gather_results(dids, dol, dsc, total_utts, lmax)
-                own_pin[0].copy_(dids[:, :lmax], non_blocking=True)
-                own_pin[1].copy_(dol, non_blocking=True)
                 if gathered_pin is not None:
-                    gathered_pin[:, :lmax].copy_(g[0], non_blocking=True)
-                    gathered_pin[:, lmax].copy_(g[1], non_blocking=True)
+                    gathered_pin.copy_(g, non_blocking=True)   # rank 0 consumes the whole job: ONE copy of the gathered records
+                else:
+                    own_pin[0].copy_(dids[:, :lmax], non_blocking=True)
+                    own_pin[1].copy_(dol, non_blocking=True)
             t1 = time.perf_counter()
             pipe.stream(ticket).synchronize()
-            ids, ol = own_pin[0].numpy(), own_pin[1].numpy()
+            if gathered_pin is not None:
+                ids, ol, _ = unpack_records(gathered_pin.numpy(), total_utts, world, lmax)
+            else:
+                ids, ol = own_pin[0].numpy(), own_pin[1].numpy()
         else:
             t1 = time.perf_counter()
             ids, ol, _ = pipe.result(ticket)             # synchronises the slot stream; results in pinned host buffers
         t2 = time.perf_counter()
-        texts = detokenize(ids, ol, vocab)
-        if gathered_pin is not None:
-            gp = gathered_pin.numpy()
-            texts = detokenize(gp[:, :lmax], gp[:, lmax], vocab)
+        texts = detokenize(ids, ol, vocab)   # rank 0: all N x B utterances; the other ranks: their own shard
         t3 = time.perf_counter()
         brk["allgather_enqueue_ms"] += (t1 - t0) * 1e3
         brk["wait_d2h_ms"] += (t2 - t1) * 1e3

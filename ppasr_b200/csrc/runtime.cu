@@ -190,6 +190,7 @@ struct ppasr_b200_ctx {
   bool fused_ffn = true;
   bool fused_attn_out = true;
   bool conv1_tc = true;   // conv1 on the tensor cores (conv1_tc.cu); 0 = the CUDA-core kernel (env PPASR_B200_CONV1_TC / option "conv1_tc")
+  bool qkv_co = false;    // QKV GEMM sized for two CTAs per SM (experiment switch, env PPASR_B200_QKV_CO / option "qkv_co")
   bool qkv_wide = false;  // QKV GEMM with 128 x 256 tiles (experiment switch, env PPASR_B200_QKV_WIDE / option "qkv_wide")
   // causal models: depthwise conv + norm + swish computed in the chained FFN kernel's prologue. Bit-identical to the
   // stand-alone kernel but slower (2.53 vs 2.20 ms single stream, 1.45 vs 1.36 ms in throughput mode at C2): the
@@ -335,6 +336,7 @@ int ppasr_b200_create(const ppasr_b200_config* cfg, ppasr_b200_ctx** out) {
   c->layer_k.assign(cfg->n_layers, cfg->conv_kernel);
   if (const char* e = std::getenv("PPASR_B200_FUSED_DWCONV")) c->fused_dwconv = std::atoi(e) != 0;  // A/B switch for bench runs
   if (const char* e = std::getenv("PPASR_B200_QKV_WIDE")) c->qkv_wide = std::atoi(e) != 0;
+  if (const char* e = std::getenv("PPASR_B200_QKV_CO")) c->qkv_co = std::atoi(e) != 0;
   if (const char* e = std::getenv("PPASR_B200_CONV1_TC")) c->conv1_tc = std::atoi(e) != 0;
   if (const char* e = std::getenv("PPASR_B200_FUSED_CONV")) c->fused_conv = std::atoi(e);
   if (cfg->model_type == 3) {
@@ -908,9 +910,15 @@ int run_encoder(ppasr_b200_ctx* c, cudaStream_t st, bool chunk) {
           PROF(PC_QKV);
           PPASR_CUDA_CHECK((gemm<BN_WIDE, ST_WIDE>(c, p.tm_y, m.wqkv_wide, M, 3 * D, D, e, st)));
         } else {
-          EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
-          PROF(PC_QKV);
-          PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st)));
+          if (c->qkv_co) {  // two CTAs per SM: 3-stage ring, 8 epilogue warps, <= 85 registers
+            EpiQKV<BN_NARROW, 8, 2> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
+            PROF(PC_QKV);
+            PPASR_CUDA_CHECK((gemm<BN_NARROW, 3>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st)));
+          } else {
+            EpiQKV<BN_NARROW> e{p.q2, p.kk, p.vt, w.bqkv, w.pos_u, w.pos_v, M, p.Tp, H, p.Tp, p.Tkp, 0};
+            PROF(PC_QKV);
+            PPASR_CUDA_CHECK((gemm<BN_NARROW, ST_NARROW>(c, p.tm_y, m.wqkv, M, 3 * D, D, e, st)));
+          }
         }
         ap.T2 = p.Tp, ap.k_rows_per_bh = p.Tp, ap.k_row0 = 0, ap.pos_row0 = 0, ap.klens = p.vlen;
         { PROF(PC_ATTENTION); PPASR_CUDA_CHECK(launch_rel_attention(p.tm_q, p.tm_k, c->tm_pos, p.tm_vt, ap, st)); }
@@ -1509,6 +1517,10 @@ int ppasr_b200_set_option(ppasr_b200_ctx* c, const char* name, int32_t value) {
   }
   if (n == "qkv_wide") {
     c->qkv_wide = value != 0;
+    return PPASR_OK;
+  }
+  if (n == "qkv_co") {
+    c->qkv_co = value != 0;
     return PPASR_OK;
   }
   if (n == "conv1_tc") {

@@ -14,36 +14,66 @@ def shard_range(num_items: int, world_size: int, rank: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def pack_records(ids, out_lens, scores, max_local: int, lmax: int):
-    """[max_local, lmax + 2] int32 records: ids row (zero padded), out_len, score (fp32 bit pattern)."""
+def pack_records(ids, out_lens, scores, max_local: int, lmax: int, out=None):
+    """[max_local, lmax + 2] int32 records: ids row (zero padded), out_len, score (fp32 bit pattern). `out` (optional): a
+    zero-initialised record tensor of that shape to fill in place (the serving loop keeps one per pipeline slot)."""
     import torch
-    rec = torch.zeros((max_local, lmax + 2), dtype=torch.int32, device=ids.device)
+    rec = out if out is not None else torch.zeros((max_local, lmax + 2), dtype=torch.int32, device=ids.device)
     n = ids.shape[0]
-    rec[:n, :ids.shape[1]] = ids[:, :lmax]
+    rec[:n, :min(ids.shape[1], lmax)] = ids[:, :lmax]
     rec[:n, lmax] = out_lens
     rec[:n, lmax + 1] = scores.view(torch.int32)
     return rec
+
+
+def all_gather_records(ids, out_lens, scores, num_items: int, lmax: int, group=None, rec=None, out=None):
+    """The collective itself: every rank contributes [max_local, lmax + 2] int32 records (pack_records) and receives the
+    [world * max_local, lmax + 2] concatenation on its device -- pack (3 small copies) + ONE all-gather, nothing else on the
+    stream. `rec` / `out` are optional preallocated buffers. Split it on the host with `unpack_records`."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    max_local = (num_items + world - 1) // world
+    rec = pack_records(ids, out_lens, scores, max_local, lmax, out=rec)
+    if world == 1:
+        return rec
+    if out is None:
+        out = torch.empty((world * max_local, lmax + 2), dtype=torch.int32, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    return out
+
+
+def unpack_records(records, num_items: int, world: int, lmax: int):
+    """(ids [num_items, lmax], out_lens [num_items], scores fp32 [num_items]) views / selections of a gathered record array
+    (NumPy array or torch tensor); drops the padding rows of the ranks that hold one item less."""
+    max_local = (num_items + world - 1) // world
+    if num_items != world * max_local:
+        keep = []
+        for r in range(world):
+            s, e = shard_range(num_items, world, r)
+            keep.extend(range(r * max_local, r * max_local + (e - s)))
+        records = records[keep]
+    sc = records[:, lmax + 1]
+    sc = sc.view(np.float32) if isinstance(sc, np.ndarray) else sc.contiguous().view(_torch_float32())
+    return records[:, :lmax], records[:, lmax], sc
+
+
+def _torch_float32():
+    import torch
+    return torch.float32
 
 
 def all_gather_results(ids, out_lens, scores, num_items: int, lmax: int, group=None):
     """Single collective: every rank contributes its block and receives all `num_items` results.
     ids: int32 [B_local, >=lmax] device tensor; out_lens int32 [B_local]; scores fp32 [B_local].
     Returns (ids [num_items, lmax], out_lens [num_items], scores [num_items]) on the calling device."""
-    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return ids[:, :lmax], out_lens, scores
-    max_local = (num_items + world - 1) // world
-    rec = pack_records(ids, out_lens, scores, max_local, lmax)
-    out = torch.empty((world * max_local, lmax + 2), dtype=torch.int32, device=rec.device)
-    dist.all_gather_into_tensor(out, rec, group=group)
-    rows = []
-    for r in range(world):
-        s, e = shard_range(num_items, world, r)
-        rows.append(out[r * max_local: r * max_local + (e - s)])
-    allr = torch.cat(rows, 0)
-    return allr[:, :lmax].contiguous(), allr[:, lmax].contiguous(), allr[:, lmax + 1].contiguous().view(torch.float32)
+    out = all_gather_records(ids, out_lens, scores, num_items, lmax, group=group)
+    gi, gl, gs = unpack_records(out, num_items, world, lmax)
+    return gi.contiguous(), gl.contiguous(), gs
 
 
 def detokenize(ids, out_lens, vocabulary):
