@@ -22,6 +22,7 @@
 //   warp  8   : MMA issuer (4 x tcgen05.mma kind::tf32 128x256x8 per tile), TMEM alloc (2 x 256 columns)
 // Everything is double-buffered (A tile, accumulator, output staging) so the kernel runs at the rate the 64 KB tile
 // stores drain to HBM. Rows outside the image (t1 >= T1, f1 >= F1, r >= Mr) are zero K-rows -> relu(0) = 0, as before.
+#include <mutex>
 #include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -655,12 +656,12 @@ conv_front_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, const ConvFron
 cudaError_t launch_conv_front_tc(const CUtensorMap& tmap_w2, const float* feats, const float* mean, const float* istd,
                                  const float* w1, const float* b1, const float* b2, __nv_bfloat16* out, int B, int T, int F,
                                  int T1, int F1, int Th, int FH, int Tout, int Fout, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF2_SMEM_TOTAL);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t cfg_err = cudaSuccess;
+  std::call_once(once, [] {
+    cfg_err = cudaFuncSetAttribute(conv_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF2_SMEM_TOTAL);
+  });
+  if (cfg_err != cudaSuccess) return cfg_err;
   if (F > 96) return cudaErrorInvalidValue;  // s_mean / s_istd staging
   ConvFrontTcParams p;
   p.feats = feats, p.mean = mean, p.istd = istd, p.w1 = w1, p.b1 = b1, p.b2 = b2, p.out = out;
@@ -676,12 +677,12 @@ cudaError_t launch_conv_front_tc(const CUtensorMap& tmap_w2, const float* feats,
 cudaError_t launch_conv1_tc(const CUtensorMap& tmap_phase, const float* feats, const float* mean, const float* istd,
                             const float* w, const float* bias, int B, int T, int F, int T1, int F1, int Th, int FH,
                             int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM_TOTAL);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t cfg_err = cudaSuccess;
+  std::call_once(once, [] {
+    cfg_err = cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM_TOTAL);
+  });
+  if (cfg_err != cudaSuccess) return cfg_err;
   if (F > 256) return cudaErrorInvalidValue;  // s_mean / s_istd staging
   Conv1TcParams p;
   p.feats = feats, p.mean = mean, p.istd = istd, p.w = w, p.bias = bias;
