@@ -843,7 +843,7 @@ int run_subsampling_convs(ppasr_b200_ctx* c, cudaStream_t st) {
   } else {
     // CMVN + conv1 + ReLU -> stride-phase images
     { PROF(PC_CONV1);
-    if (c->conv1_tc && D == 256)
+    if (c->conv1_tc && D == 256 && cfg.feat_dim <= 256)
       PPASR_CUDA_CHECK(launch_conv1_tc(p.tm_phase, p.feats, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, p.B, p.T,
                                        cfg.feat_dim, p.T1, c->F1, p.Th, c->FH, c->sms, st));
     else

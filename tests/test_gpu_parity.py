@@ -826,20 +826,22 @@ def test_decode_pipeline_matches_sync_api(lib, cuda):
             assert np.array_equal(ids[b, :ol[b]], rids[b, :rol[b]])
 
 
-@pytest.mark.parametrize("B,T,lens", [(3, 523, [523, 333, 260]), (5, 67, [67, 67, 50, 30, 67]), (1, 998, [998])])
-def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
+@pytest.mark.parametrize("B,T,lens,n_mels", [(3, 523, [523, 333, 260], 80), (5, 67, [67, 67, 50, 30, 67], 80), (1, 998, [998], 80),
+                                             (3, 300, [300, 211, 64], 40), (2, 131, [131, 99], 64)])
+def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens, n_mels):
     """The fused front ends == the two-kernel paths they mirror, bit for bit: conv_front.cu (CUDA-core conv1 inside the conv2
     GEMM's A producer) vs conv1_subsample + conv2 GEMM (same fp32 FMA order), and conv_front_tc (split-tf32 conv1 GEMM as the
     producer, conv1_tc.cu) vs conv1_tc + conv2 GEMM (same MMAs in the same order)."""
     from ppasr_b200.engine import ConformerEngine
     from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
-    cfg = ConformerConfig(num_blocks=1, vocab_size=300)
+    cfg = ConformerConfig(num_blocks=1, vocab_size=300, input_dim=n_mels)
     eng = ConformerEngine(cfg, init_conformer_weights(cfg))
-    feats = synthetic_fbank(B, T)
+    feats = synthetic_fbank(B, T, n_mels=n_mels)
     for b in range(B):
         feats[b, lens[b]:] = 0
     fd = torch.from_numpy(feats).cuda()
-    for conv1_tc, fused in ((0, 1), (1, 2)):
+    # conv_front.cu's patch geometry is built for 80 mel bins; the tensor-core front end takes any feature width <= 96
+    for conv1_tc, fused in (((0, 1), (1, 2)) if n_mels == 80 else ((1, 2),)):
         outs = []
         eng.set_option("conv1_tc", conv1_tc)
         for f in (0, fused):
@@ -851,9 +853,9 @@ def test_fused_conv_front_bit_identical(lib, cuda, B, T, lens):
     eng.close()
 
 
-@pytest.mark.parametrize("B,T,lens", [(3, 523, [523, 333, 260]), (5, 67, [67, 67, 50, 30, 67]), (2, 998, [998, 700]),
-                                      (32, 200, [200] * 32)])
-def test_conv1_phase_images_match_fp32_conv2d(lib, cuda, B, T, lens):
+@pytest.mark.parametrize("B,T,lens,n_mels", [(3, 523, [523, 333, 260], 80), (5, 67, [67, 67, 50, 30, 67], 80), (2, 998, [998, 700], 80),
+                                             (32, 200, [200] * 32, 80), (3, 300, [300, 211, 64], 40)])
+def test_conv1_phase_images_match_fp32_conv2d(lib, cuda, B, T, lens, n_mels):
     """GlobalCMVN + Conv2d(1, 256, 3, 2) + ReLU (cmvn.py:29-32, subsampling.py:84-85) as written into the stride-phase images:
     the tensor-core kernel (split-tf32, conv1_tc.cu, default) and the CUDA-core kernel against torch fp32 conv2d. Both carry
     fp32-accurate sums and ONE bf16 rounding, so each must sit within one bf16 ulp of the fp32 value, and the two kernels must
@@ -861,10 +863,10 @@ def test_conv1_phase_images_match_fp32_conv2d(lib, cuda, B, T, lens):
     import torch.nn.functional as F
     from ppasr_b200.engine import ConformerEngine
     from ppasr_b200.weights import ConformerConfig, init_conformer_weights, synthetic_fbank
-    cfg = ConformerConfig(num_blocks=1, vocab_size=300)
+    cfg = ConformerConfig(num_blocks=1, vocab_size=300, input_dim=n_mels)
     w = init_conformer_weights(cfg)
     eng = ConformerEngine(cfg, w)
-    feats = synthetic_fbank(B, T)
+    feats = synthetic_fbank(B, T, n_mels=n_mels)
     for b in range(B):
         feats[b, lens[b]:] = 0
     fd = torch.from_numpy(feats).cuda()
