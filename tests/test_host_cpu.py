@@ -117,7 +117,7 @@ WORKER = r'''
 import os, sys
 sys.path.insert(0, {root!r})
 import torch, torch.distributed as dist
-from ppasr_b200.parallel import shard_range, all_gather_results
+from ppasr_b200.parallel import shard_range, all_gather_results, all_gather_records, unpack_records
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
 N, L = 7, 6
@@ -128,6 +128,15 @@ sc_all = torch.rand(N, generator=g)
 s, e = shard_range(N, world, rank)
 ids, ol, sc = all_gather_results(ids_all[s:e].clone(), lens_all[s:e].clone(), sc_all[s:e].clone(), N, L)
 assert torch.equal(ids, ids_all) and torch.equal(ol, lens_all) and torch.equal(sc, sc_all), "gather mismatch"
+# the serving-loop form: preallocated record / gathered buffers reused over steps, records split on the host (NumPy)
+max_local = (N + world - 1) // world
+rec = torch.zeros((max_local, L + 2), dtype=torch.int32)
+out = torch.empty((world * max_local, L + 2), dtype=torch.int32)
+for step in range(2):
+    g2 = all_gather_records(ids_all[s:e].clone(), lens_all[s:e].clone(), sc_all[s:e].clone(), N, L, rec=rec, out=out)
+    assert g2.data_ptr() == out.data_ptr()
+    hi, hl, hs = unpack_records(g2.numpy(), N, world, L)
+    assert (hi == ids_all.numpy()).all() and (hl == lens_all.numpy()).all() and (hs == sc_all.numpy()).all(), "records mismatch"
 dist.barrier(); dist.destroy_process_group()
 print("RANK_OK", rank)
 '''
