@@ -311,8 +311,9 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmap_phase, const Conv1TcPar
 // builds), issued as two N = 128 halves ("half-taps") so that the conv1 accumulators double-buffer in 2 x 128 TMEM columns
 // next to the 256 columns of the conv2 accumulator.
 //   warp 0      : TMA producer of the conv2 weight k-blocks (3 x 32 KB ring)
-//   warp 1      : MMA issuer. Software-pipelined: MMA1(half-tap u+1) is issued before the two MMA2 k-blocks of half-tap u, so
-//                 epilogue-1 of u+1 runs underneath them
+//   warp 1      : issuer of the conv2 MMAs (bf16 128x256x16, 4 per k-block)
+//   warp 3      : issuer of the conv1 MMAs (tf32 128x128x8, 4 per half-tap); runs ahead of warp 1 by the two conv1 accumulators,
+//                 so epilogue-1 of half-tap u+1 runs underneath the conv2 k-blocks of u
 //   warp 2      : TMEM alloc (512 columns)
 //   warps 4-11  : epilogue-2: conv2 accumulator + bias -> ReLU -> bf16 -> compact c2 rows (as EpiConv2)
 //   warps 12-15 : A1 producers (thread = row), inputs of the next two taps in flight
@@ -438,14 +439,15 @@ conv_front_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, const ConvFron
         tma_load_2d(smem_b + st * CF2_B_BYTES, &tmap_w2, &b_full[st], (J % 36) * 64, 0);
       }
     }
-  } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp_idx == 3) {
+    // ===================== MMA1 issuer: the split-tf32 conv1 GEMM of every half-tap =====================
+    // A thread of its own: it runs ahead of the conv2 issuer as far as the two conv1 accumulators allow, and neither thread's
+    // mbarrier round trips delay the other's MMAs (tcgen05.commit tracks the issuing thread's MMAs only).
     if (elect_one()) {
       constexpr uint32_t idesc1 = umma_idesc_tf32(128, 128);
-      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 256);
       const uint32_t w1_addr = smem_u32(smem_w1);
       const int total = my_tiles * 18;  // half-taps
-      auto issue_mma1 = [&](int U) {
+      for (int U = 0; U < total; ++U) {
         const int Tn = U >> 1, hh = U & 1, s1 = Tn & 1, sa = U & 1;
         if (hh == 0) mbar_wait(&a1_full[s1], (Tn >> 1) & 1);
         mbar_wait(&acc1_empty[sa], ((U >> 1) & 1) ^ 1);
@@ -458,32 +460,32 @@ conv_front_tc_kernel(const __grid_constant__ CUtensorMap tmap_w2, const ConvFron
                     k != 0 ? 1u : 0u);
         umma_commit(&acc1_full[sa]);
         if (hh == 1) umma_commit(&a1_empty[s1]);
-      };
-      if (total > 0) issue_mma1(0);
-      for (int U = 0; U < total; ++U) {
-        if (U + 1 < total) issue_mma1(U + 1);
-        const int u = U % 18;
-        if (u == 0) {
-          mbar_wait(acc2_empty, ((U / 18) & 1) ^ 1);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA2 issuer: the conv2 k-blocks =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 256);
+      const int total = my_tiles * 36;  // k-blocks
+      for (int J = 0; J < total; ++J) {
+        const int kb = J % 36;
+        if (kb == 0) {
+          mbar_wait(acc2_empty, ((J / 36) & 1) ^ 1);
           tc_fence_after();
         }
+        const int sa2 = J & 3, sb = J % CF2_B_STAGES;
+        mbar_wait(&a2_full[sa2], (J >> 2) & 1);
+        mbar_wait(&b_full[sb], (J / CF2_B_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a2 + sa2 * CF2_A2_BYTES);
+        const uint32_t b_addr = smem_u32(smem_b + sb * CF2_B_BYTES);
 #pragma unroll
-        for (int kc2 = 0; kc2 < 2; ++kc2) {
-          const int J = 2 * U + kc2;
-          const int sa2 = J & 3, sb = J % CF2_B_STAGES;
-          mbar_wait(&a2_full[sa2], (J >> 2) & 1);
-          mbar_wait(&b_full[sb], (J / CF2_B_STAGES) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a2 + sa2 * CF2_A2_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + sb * CF2_B_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc2,
-                      (u | kc2 | k) != 0 ? 1u : 0u);
-          umma_commit(&a2_empty[sa2]);
-          umma_commit(&b_empty[sb]);
-        }
-        if (u == 17) umma_commit(acc2_full);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc2,
+                    (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&a2_empty[sa2]);
+        umma_commit(&b_empty[sb]);
+        if (kb == 35) umma_commit(acc2_full);
       }
     }
   } else if (warp_idx >= 4 && warp_idx < 12) {
