@@ -550,3 +550,37 @@ def test_collapse_frames_matches_reference_golden():
         assert (text2, repr(float(score2))) == (m["text"], m["score"])
     assert collapse_frames(np.zeros(4, np.int64), np.ones(4, np.float32), ["<blank>", "a"]) == (0, "")
     assert collapse_frames(np.array([1, 1, 0, 1]), np.ones(4, np.float32), ["<blank>", "a"], n_frames=0) == (0, "")
+
+
+def test_split_tf32_conv1_arithmetic_is_fp32_accurate():
+    """Numerics of the tensor-core conv1 (csrc/conv1_tc.cu): x = x_hi + x_lo, w = w_hi + w_lo with the halves rounded to tf32
+    (10 explicit mantissa bits, round to nearest, ties away: cvt.rna.tf32.f32); the GEMM carries x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+    and the bias as b_hi + b_lo. Restated in NumPy: the dropped term and the roundings leave a relative error below 2^-20 of
+    sum |x||w| -- two hundred times finer than the bf16 rounding applied to the result (2^-9) -- so the bf16 outputs agree with an
+    exact convolution on all but the rare ties. GPU side: tests/test_gpu_parity.py::test_conv1_phase_images_match_fp32_conv2d."""
+    def tf32_rna(a):
+        a = np.asarray(a, dtype=np.float32)
+        bits = a.view(np.uint32).astype(np.uint64)
+        bits = (bits + 0x1000) & 0xFFFFE000          # add half an ulp of the 13 dropped bits (ties away), truncate
+        return bits.astype(np.uint32).view(np.float32)
+
+    rng = np.random.RandomState(7)
+    x = rng.normal(0, 1, (4096, 9)).astype(np.float32)           # normalised fbank windows
+    w = (rng.normal(0, 1, (256, 9)) / 3).astype(np.float32)      # conv1 weights
+    b = rng.normal(0, 0.1, 256).astype(np.float32)
+    xh = tf32_rna(x); xl = tf32_rna(x - xh)
+    wh = tf32_rna(w); wl = tf32_rna(w - wh)
+    bh = tf32_rna(b); bl = tf32_rna(b - bh)
+    assert np.all((xh.view(np.uint32) & 0x1FFF) == 0) and np.all((wl.view(np.uint32) & 0x1FFF) == 0)
+    f = np.float64
+    got = xh.astype(f) @ wh.astype(f).T + xl.astype(f) @ wh.astype(f).T + xh.astype(f) @ wl.astype(f).T + bh.astype(f) + bl.astype(f)
+    ref = x.astype(f) @ w.astype(f).T + b.astype(f)
+    scale = np.abs(x).astype(f) @ np.abs(w).astype(f).T + np.abs(b)
+    assert np.max(np.abs(got - ref) / scale) < 2.0 ** -20
+
+    def bf16_rn(a):
+        bits = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        bits = (bits + 0x7FFF + ((bits >> 16) & 1)) & 0xFFFF0000
+        return bits.astype(np.uint32).view(np.float32)
+    same = bf16_rn(np.maximum(got, 0).astype(np.float32)) == bf16_rn(np.maximum(ref, 0).astype(np.float32))
+    assert same.mean() > 0.999
